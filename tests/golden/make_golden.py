@@ -1,0 +1,56 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Runs oracle/_ref/ref_driver (the reference's own translation units compiled against
+oracle/shim, see oracle/Makefile) with OMP_NUM_THREADS=1 on small synthetic configurations and
+packs the per-stage dumps into compressed .npz files. Only runnable where /root/reference
+exists (this container); the fixtures are what travels.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from colore_b200.inputs import RunConfig, write_inputs, write_param_file  # noqa: E402
+
+CASES = {
+    # lognormal, 1 population, intensity maps, kappa + ISW planes: every §8(a) stage once
+    "ref_n32_lognormal": RunConfig(n_grid=32, dens_type=0, nz_amplitude=60.0, imap_nside=8, imap_nchannels=4,
+                                   kappa_nside=8, isw_nside=8, seed=1003),
+    # clipped density (density.c:1034-1067), 2 populations, galaxies only -> cell-gradient RSD
+    "ref_n32_clip": RunConfig(n_grid=32, dens_type=3, nz_amplitude=40.0, n_srcs=2, seed=77),
+    # no smoothing of the potential, different grid size
+    "ref_n48_nosmooth": RunConfig(n_grid=48, dens_type=0, nz_amplitude=30.0, smooth_potential=False,
+                                  r_smooth=-1.0, seed=5),
+}
+
+
+def main():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    for name, cfg in CASES.items():
+        tmp = tempfile.mkdtemp(prefix="golden_")
+        try:
+            paths = write_inputs(os.path.join(tmp, "in"), cfg)
+            write_param_file(os.path.join(tmp, "param.cfg"), cfg, paths, os.path.join(tmp, "out"))
+            os.makedirs(os.path.join(tmp, "dump"))
+            env = dict(os.environ, OMP_NUM_THREADS="1")
+            subprocess.check_call([drv, os.path.join(tmp, "param.cfg"), os.path.join(tmp, "dump")], env=env,
+                                  stdout=subprocess.DEVNULL)
+            arrs = {f[:-4]: np.load(os.path.join(tmp, "dump", f)) for f in sorted(os.listdir(os.path.join(tmp, "dump")))}
+            out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+            np.savez_compressed(out, **arrs)
+            print(name, "->", out, f"{os.path.getsize(out) / 1e6:.2f} MB",
+                  "nsrc =", arrs.get("s4_srcs_ipix_0", np.zeros(0)).size)
+        finally:
+            shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    main()

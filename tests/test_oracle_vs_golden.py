@@ -1,0 +1,117 @@
+"""CPU suite: the C restatement (oracle/colore_oracle.c) against golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py -> oracle/_ref/ref_driver, OMP_NUM_THREADS=1).
+
+With one thread the reference's MT19937 stream order is the plain (iz,iy,ix) loop order, which the
+restatement reproduces, so every stage is compared BIT-EXACTLY (same compiler, same libm).
+The only non-bit-exact comparison would be the intensity maps under OpenMP atomics; with one
+thread they are exact too.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import NA, RNG_MT, Oracle, tables_from_dump
+
+CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth"]
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request, golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, request.param + ".npz")))
+    t = tables_from_dump(g)
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    return g, t, o
+
+
+def _fields(g, t, o):
+    dk, pk = o.fill_modes(RNG_MT, int(t["seed"]))
+    dens, npot = o.c2r(dk), o.c2r(pk)
+    o.normalize_fields(dens, npot)
+    return dens, npot
+
+
+def test_gaussian_fields_bit_exact(case):
+    g, t, o = case
+    dens, npot = _fields(g, t, o)
+    assert np.array_equal(dens, g["s1_dens_gauss"])
+    assert np.array_equal(npot, g["s1_npot"])
+    mean, s2 = o.sigma_dens(dens)
+    assert s2 == g["s1_sigma2_gauss"][0]
+    assert abs(mean) < 1e-6
+
+
+def test_physical_density_and_normalisation(case):
+    g, t, o = case
+    dens = g["s1_dens_gauss"].copy()
+    o.lognormalize(dens, g["s1_sigma2_gauss"][0], clip=(int(t["dens_type"]) == 3))
+    assert np.array_equal(dens, g["s2_dens"])
+    npop = sum(1 for k in t if k.startswith("srcs_bz_"))
+    bz = [t[f"srcs_bz_{i}"] for i in range(npop)]
+    if "imap_bz_0" in t:
+        bz.append(t["imap_bz_0"])
+    nm = o.density_normalization(dens, bz)
+    for i in range(npop):
+        assert np.array_equal(nm["norm"][i], g[f"s3_srcs_norm_{i}"])
+        assert np.array_equal(nm["ends"][i], g[f"s3_srcs_norm_ends_{i}"])
+    if "imap_bz_0" in t:
+        assert np.array_equal(nm["norm"][npop], g["s3_imap_norm_0"])
+    assert np.array_equal(nm["zends"], g["s3_znorm_ends"])
+    assert nm["hist_n"].sum() <= o.n ** 3
+
+
+def test_sources_bit_exact(case):
+    g, t, o = case
+    dens, npot = g["s2_dens"], g["s1_npot"]
+    o.set_halo(npot)
+    npop = sum(1 for k in t if k.startswith("srcs_bz_"))
+    for ipop in range(npop):
+        ends = g[f"s3_srcs_norm_ends_{ipop}"]
+        ns, tot = o.srcs_poisson(dens, t[f"srcs_nz_{ipop}"], t[f"srcs_bz_{ipop}"], g[f"s3_srcs_norm_{ipop}"],
+                                 ends[0], ends[1], RNG_MT, int(t["seed"]), ipop)
+        assert tot == g[f"s4_srcs_ipix_{ipop}"].size
+        assert ns[:, :, o.n:].sum() == 0          # padding columns never hold sources
+        pos, ipix = o.srcs_place(npot, ns, RNG_MT, int(t["seed"]), ipop)
+        assert np.array_equal(pos.ravel(), g[f"s4_srcs_pos_{ipop}"])
+        assert np.array_equal(ipix, g[f"s4_srcs_ipix_{ipop}"])
+        srcs = o.srcs_local_properties(pos)
+        ref = g[f"s5_srcs_cat_{ipop}"].reshape(-1, 9)
+        assert np.array_equal(srcs[:, :6], ref[:, :6])
+        if f"s6_srcs_cat_{ipop}" in g:
+            o.srcs_beam_rsd(npot, pos, srcs)
+            assert np.array_equal(srcs[:, :6], g[f"s6_srcs_cat_{ipop}"].reshape(-1, 9)[:, :6])
+
+
+def test_maps_bit_exact(case):
+    g, t, o = case
+    if "s6_kappa_data" not in g:
+        pytest.skip("case has no maps")
+    dens, npot = g["s2_dens"], g["s1_npot"]
+    o.set_halo(npot)
+    r0, rf = g["s4_imap_r0_0"], g["s4_imap_rf_0"]
+    nside = int(np.sqrt(g["s4_imap_data_0"].size / len(r0) / 12))
+    ends = g["s3_imap_norm_ends_0"]
+    data, nadd = o.imap(dens, npot, t["imap_tz_0"], t["imap_bz_0"], g["s3_imap_norm_0"], ends[0], ends[1],
+                        nside, r0, rf)
+    assert np.array_equal(nadd.ravel(), g["s4_imap_nadd_0"])
+    assert np.array_equal(data.ravel(), g["s4_imap_data_0"])
+    posk = g["s6_kappa_pos"].reshape(-1, 3)
+    lp, pp = o.shell_pixels(int(np.sqrt(posk.shape[0] / 12)))
+    assert np.array_equal(lp, g["s6_kappa_listpix"]) and np.array_equal(pp, posk)
+    assert np.array_equal(o.kappa(npot, posk, g["s6_kappa_rf"]).ravel(), g["s6_kappa_data"])
+    assert np.array_equal(o.isw(npot, posk, g["s6_isw_rf"]).ravel(), g["s6_isw_data"])
+
+
+def test_table_lookup_edges(case):
+    g, t, o = case
+    # cosmo.c:30-38: clamps at r<=0 and beyond the table
+    assert o.get_bg(-1.0, t["d1"], 1.0, t["d1"][-1]) == 1.0
+    assert o.get_bg(1e9, t["z"], 0.0, t["z"][-1]) == t["z"][-1]
+    r = 0.5 * (t["r"][10] + t["r"][11])
+    assert abs(o.get_bg(r, t["z"], 0.0, 0.0) - 0.5 * (t["z"][10] + t["z"][11])) < 1e-12
+    # cosmo.c:291-308: power-law extrapolation on both sides
+    lo = o.pk_linear0(t["logkmin"] - 1.0)
+    assert np.isclose(lo, t["pk_pk"][0] * 10 ** (-t["n_scal"]))
+    hi = o.pk_linear0(t["logkmax"] + 1.0)
+    assert np.isclose(hi, t["pk_pk"][-1] * 1e-3)
+    assert len(t["z"]) == NA
