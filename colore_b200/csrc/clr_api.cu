@@ -1,0 +1,411 @@
+// C ABI of colore_b200 (include/colore_b200.h): context lifetime, host<->device grid transfer,
+// orchestration of the stage kernels, and the host-side tail of compute_density_normalization.
+#include "clr_internal.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+
+static thread_local char g_err[1024] = "";
+
+void clr_set_error(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+int clr_version(void) { return 100; }
+const char *clr_last_error(void) { return g_err; }
+
+int clr_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static void copy_tab(std::vector<double> &dst, const double *src, size_t n) { dst.assign(src, src + n); }
+
+int clr_create(const clr_params *p, int device, clr_ctx **out)
+{
+  CLR_CHECK(p && out, "clr_create: null argument");
+  CLR_CHECK(clr_device_count() > device, "clr_create: CUDA device %d not available (no CPU fallback exists)", device);
+  CLR_CHECK(p->n_grid >= 16 && p->n_grid % 4 == 0, "n_grid=%d unsupported (multiple of 4, >=16)", p->n_grid);
+  CLR_CHECK(p->nz_here > 0 && p->iz0_here >= 0 && p->iz0_here + p->nz_here <= p->n_grid, "bad slab bounds");
+  CLR_CHECK(p->r_arr_r2z && p->z_arr_r2z && p->growth_d_arr && p->growth_v_arr && p->pkarr && p->logkarr,
+            "clr_create: missing tables");
+  CLR_CUDA(cudaSetDevice(device));
+  clr_ctx *c = new clr_ctx();
+  c->device = device;
+  c->p = *p;
+  cudaDeviceProp prop;
+  CLR_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CLR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CLR_CUDA(cudaEventCreate(&c->ev0)); CLR_CUDA(cudaEventCreate(&c->ev1));
+  CLR_CUDA(cudaEventCreate(&c->evp0)); CLR_CUDA(cudaEventCreate(&c->evp1));
+  // host copies of the tables
+  copy_tab(c->h_logk, p->logkarr, p->numk); copy_tab(c->h_pk, p->pkarr, p->numk);
+  copy_tab(c->h_r, p->r_arr_r2z, CLR_NA); copy_tab(c->h_z, p->z_arr_r2z, CLR_NA);
+  copy_tab(c->h_d1, p->growth_d_arr, CLR_NA);
+  copy_tab(c->h_d2, p->growth_d2_arr ? p->growth_d2_arr : p->growth_d_arr, CLR_NA);
+  copy_tab(c->h_v1, p->growth_v_arr, CLR_NA);
+  copy_tab(c->h_pd, p->growth_pd_arr ? p->growth_pd_arr : p->growth_d_arr, CLR_NA);
+  copy_tab(c->h_ih, p->ihub_arr ? p->ihub_arr : p->growth_d_arr, CLR_NA);
+  copy_tab(c->h_a2r_a, p->a_arr_a2r ? p->a_arr_a2r : p->r_arr_r2z, CLR_NA);
+  copy_tab(c->h_a2r_r, p->r_arr_a2r ? p->r_arr_a2r : p->r_arr_r2z, CLR_NA);
+  // device tables
+  CLR_CUDA(cudaMalloc(&c->d_tables, 9 * CLR_NA * sizeof(double)));
+  const std::vector<double> *tabs[9] = {&c->h_r, &c->h_z, &c->h_d1, &c->h_d2, &c->h_v1, &c->h_pd, &c->h_ih, &c->h_a2r_a, &c->h_a2r_r};
+  for (int i = 0; i < 9; i++)
+    CLR_CUDA(cudaMemcpy(c->d_tables + (size_t)i * CLR_NA, tabs[i]->data(), CLR_NA * sizeof(double), cudaMemcpyHostToDevice));
+  CLR_CUDA(cudaMalloc(&c->d_pk, 2 * (size_t)p->numk * sizeof(double)));
+  CLR_CUDA(cudaMemcpy(c->d_pk, c->h_logk.data(), p->numk * sizeof(double), cudaMemcpyHostToDevice));
+  CLR_CUDA(cudaMemcpy(c->d_pk + p->numk, c->h_pk.data(), p->numk * sizeof(double), cudaMemcpyHostToDevice));
+  // FFT master twiddles exp(+2 pi i k / n), evaluated in double
+  {
+    int n = p->n_grid;
+    std::vector<float2> w(n);
+    for (int k = 0; k < n; k++) {
+      double a = 2.0 * M_PI * k / n;
+      w[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    CLR_CUDA(cudaMalloc(&c->d_twiddle, n * sizeof(float2)));
+    CLR_CUDA(cudaMemcpy(c->d_twiddle, w.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  // grids: allocate_fftw (fourier.c:211-238): dens slab, npot slab + 2 halo planes
+  ClrDev &d = c->dev;
+  d.n = p->n_grid; d.nc = p->n_grid / 2 + 1; d.nz_here = p->nz_here; d.iz0_here = p->iz0_here;
+  d.pitch = 2 * d.nc;
+  d.bias_model = p->bias_model; d.nside_base = p->nside_base;
+  d.l_box = p->l_box;
+  for (int i = 0; i < 3; i++) d.pos_obs[i] = p->pos_obs[i];
+  d.glob_idr = p->glob_idr; d.r_tab_max = c->h_r[CLR_NA - 1];
+  d.fgrowth_0 = p->fgrowth_0; d.hubble_0 = p->hubble_0; d.OmegaM = p->OmegaM; d.r_max = p->r_max;
+  d.r_arr = c->d_tables; d.z_arr = c->d_tables + CLR_NA; d.d1_arr = c->d_tables + 2 * CLR_NA;
+  d.d2_arr = c->d_tables + 3 * CLR_NA; d.v1_arr = c->d_tables + 4 * CLR_NA; d.pd_arr = c->d_tables + 5 * CLR_NA;
+  d.ih_arr = c->d_tables + 6 * CLR_NA; d.a2r_a = c->d_tables + 7 * CLR_NA; d.a2r_r = c->d_tables + 8 * CLR_NA;
+  size_t plane = (size_t)d.pitch * d.n;
+  CLR_CUDA(cudaMalloc(&c->d_dens, plane * d.nz_here * sizeof(float)));
+  CLR_CUDA(cudaMalloc(&c->d_npot, plane * (d.nz_here + 2) * sizeof(float)));
+  d.slice_left = c->d_npot + plane * d.nz_here;
+  d.slice_right = c->d_npot + plane * (d.nz_here + 1);
+  *out = c;
+  return 0;
+}
+
+static void free_pop(clr_ctx::Pop &P)
+{
+  cudaFree(P.d_a); cudaFree(P.d_b); cudaFree(P.d_norm); cudaFree(P.d_counts);
+  cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs);
+}
+
+int clr_destroy(clr_ctx *c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
+  cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_pk);
+  cudaFree(c->d_twiddle); cudaFree(c->d_scratch);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int clr_synchronize(clr_ctx *c) { CLR_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+long long clr_launch_count(clr_ctx *c) { return c->launches; }
+
+int clr_comm_unique_id(void *id128) { (void)id128; clr_set_error("multi-GPU communicator not built yet"); return 1; }
+int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128)
+{
+  (void)id128;
+  if (nranks == 1) { c->rank = 0; c->nranks = 1; return 0; }
+  (void)rank;
+  clr_set_error("multi-GPU communicator not built yet");
+  return 1;
+}
+
+static int set_pop(clr_ctx *c, clr_ctx::Pop &P, const double *a, const double *b)
+{
+  P.h_a.assign(a, a + CLR_NA);
+  P.h_b.assign(b, b + CLR_NA);
+  if (!P.d_a) CLR_CUDA(cudaMalloc(&P.d_a, CLR_NA * sizeof(double)));
+  if (!P.d_b) CLR_CUDA(cudaMalloc(&P.d_b, CLR_NA * sizeof(double)));
+  if (!P.d_norm) CLR_CUDA(cudaMalloc(&P.d_norm, CLR_NA * sizeof(double)));
+  CLR_CUDA(cudaMemcpyAsync(P.d_a, a, CLR_NA * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(P.d_b, b, CLR_NA * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  P.set = true;
+  P.have_norm = false;
+  return 0;
+}
+
+int clr_set_srcs(clr_ctx *c, int ipop, const double *nz_arr, const double *bz_arr)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
+  return set_pop(c, c->srcs[ipop], nz_arr, bz_arr);
+}
+
+int clr_set_imap(clr_ctx *c, int ipop, const double *tz_arr, const double *bz_arr, int nside, int nr,
+                 const float *r0, const float *rf)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
+  CLR_CHECK(nside > 0 && (nside & (nside - 1)) == 0 && nr > 0, "imap: bad nside/nr");
+  clr_ctx::Pop &P = c->imap[ipop];
+  if (set_pop(c, P, tz_arr, bz_arr)) return 1;
+  P.nside = nside; P.nr = nr;
+  // imap_preproc (imap.c:105-121): shells sorted by r0
+  std::vector<int> order(nr);
+  for (int i = 0; i < nr; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return r0[a] < r0[b]; });
+  P.r0.resize(nr); P.rf.resize(nr);
+  for (int i = 0; i < nr; i++) { P.r0[i] = r0[order[i]]; P.rf[i] = rf[order[i]]; }
+  return 0;
+}
+
+static float *grid_ptr(clr_ctx *c, int which) { return which == CLR_GRID_DENS ? c->d_dens : c->d_npot; }
+
+int clr_grid_put(clr_ctx *c, int which, const float *host)
+{
+  size_t bytes = (size_t)c->dev.pitch * c->dev.n * c->dev.nz_here * sizeof(float);
+  CLR_CUDA(cudaMemcpyAsync(grid_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int clr_grid_get(clr_ctx *c, int which, float *host)
+{
+  size_t bytes = (size_t)c->dev.pitch * c->dev.n * c->dev.nz_here * sizeof(float);
+  CLR_CUDA(cudaMemcpyAsync(host, grid_ptr(c, which), bytes, cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int clr_grid_device_ptr(clr_ctx *c, int which, void **dptr) { *dptr = grid_ptr(c, which); return 0; }
+
+int clr_fill_modes(clr_ctx *c, uint32_t seed) { return clr_fields_fill(c, seed); }
+int clr_fft_c2r(clr_ctx *c, int which) { return clr_fft_c2r_impl(c, grid_ptr(c, which), 1.0, nullptr); }
+int clr_fft_r2c(clr_ctx *c, int which) { return clr_fft_r2c_impl(c, grid_ptr(c, which)); }
+int clr_update_halo(clr_ctx *c) { return clr_halo_update(c); }
+
+static void finish_moments(clr_ctx *c, const double mom[2], double *out2)
+{
+  // compute_sigma_dens (fourier.c:61-75)
+  double ng_tot = (double)c->dev.n * c->dev.n * c->dev.n;
+  double mean = mom[0] / ng_tot, s2 = mom[1] / ng_tot;
+  c->mean_gauss = mean;
+  c->sigma2_gauss = s2 - mean * mean;
+  if (out2) { out2[0] = mean; out2[1] = c->sigma2_gauss; }
+}
+
+int clr_normalize_fields(clr_ctx *c, double *out2)
+{
+  double mom[2];
+  if (clr_fields_scale_moments(c, mom)) return 1;
+  if (clr_halo_update(c)) return 1;
+  finish_moments(c, mom, out2);
+  return 0;
+}
+
+int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *out2)
+{
+  if (!inject && clr_fields_fill(c, seed)) return 1;
+  if (clr_ensure_scratch(c, 4096)) return 1;
+  CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
+  double norm = pow(sqrt(2 * M_PI) / c->p.l_box, 3);      // fourier.c:389
+  if (clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch)) return 1;   // scaling + moments fused in the x pass
+  if (clr_fft_c2r_impl(c, c->d_npot, norm, nullptr)) return 1;
+  if (clr_halo_update(c)) return 1;
+  double mom[2];
+  CLR_CUDA(cudaMemcpyAsync(mom, c->d_scratch, sizeof(mom), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  finish_moments(c, mom, out2);
+  return 0;
+}
+
+int clr_set_sigma2_gauss(clr_ctx *c, double s2) { c->sigma2_gauss = s2; return 0; }
+
+int clr_compute_physical_density_field(clr_ctx *c)
+{
+  if (c->p.dens_type == CLR_DENS_TYPE_LGNR) return clr_fields_lognormal(c, 0);
+  if (c->p.dens_type == CLR_DENS_TYPE_CLIP) return clr_fields_lognormal(c, 1);
+  clr_set_error("Density type %d not supported by the GPU path yet (LPT: see DESIGN.md)", c->p.dens_type);
+  return 1;
+}
+
+// cosmo.c:30-38 on the host copy of the tables
+static double host_lerp(const clr_ctx *c, double r, const std::vector<double> &f, double f0, double ff)
+{
+  if (r <= 0) return f0;
+  else if (r >= c->h_r[CLR_NA - 1]) return ff;
+  int ir = (int)(r * c->p.glob_idr);
+  return f[ir] + (f[ir + 1] - f[ir]) * (r - c->h_r[ir]) * c->p.glob_idr;
+}
+static double host_bg_z(const clr_ctx *c, double r) { return host_lerp(c, r, c->h_z, 0, c->h_z[CLR_NA - 1]); }
+
+// gsl linear spline evaluation (interval by bisection), used at density.c:1304-1352
+static double lin_interp(const std::vector<double> &x, const std::vector<double> &y, double xv)
+{
+  size_t lo = 0, hi = x.size() - 1;
+  while (hi - lo > 1) {
+    size_t mid = (hi + lo) >> 1;
+    if (x[mid] > xv) hi = mid; else lo = mid;
+  }
+  double h = x[hi] - x[lo];
+  double A = (x[hi] - xv) / h, B = (xv - x[lo]) / h;
+  return A * y[lo] + B * y[hi];
+}
+
+int clr_compute_density_normalization(clr_ctx *c)
+{
+  // density.c:1233-1245
+  double zmax = host_bg_z(c, (double)(c->p.l_box * 0.5));
+  int nz = (int)(zmax / 0.05) + 2;
+  double idz = (nz - 2) / zmax;
+  std::vector<clr_ctx::Pop *> pops;
+  for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->srcs[i].set) pops.push_back(&c->srcs[i]);
+  for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->imap[i].set) pops.push_back(&c->imap[i]);
+  int npop = (int)pops.size();
+  std::vector<const double *> d_bz(npop ? npop : 1);
+  for (int i = 0; i < npop; i++) d_bz[i] = pops[i]->d_b;
+  std::vector<unsigned long long> narr(nz);
+  std::vector<double> zarr(nz), barr((size_t)(npop ? npop : 1) * nz);
+  if (clr_fields_norm_hist(c, npop, d_bz.data(), nz, idz, narr.data(), zarr.data(), barr.data())) return 1;
+  // (multi-GPU: the histograms are all-reduced here, density.c:1262-1269)
+  // density.c:1272-1297
+  for (int iz = 0; iz < nz; iz++) {
+    if (narr[iz] > 0) {
+      zarr[iz] /= narr[iz];
+      for (int ip = 0; ip < npop; ip++) barr[(size_t)ip * nz + iz] = narr[iz] / barr[(size_t)ip * nz + iz];
+    }
+  }
+  zarr[0] = 0;
+  zarr[nz - 1] = host_bg_z(c, 0.5 * c->p.l_box);
+  c->z0_norm = zarr[0];
+  c->zf_norm = zarr[nz - 1];
+  for (int ip = 0; ip < npop; ip++) {
+    double *b = &barr[(size_t)ip * nz];
+    b[0] = b[1];
+    b[nz - 1] = b[nz - 2];
+    clr_ctx::Pop &P = *pops[ip];
+    P.norm_0 = b[0];
+    P.norm_f = b[nz - 1];
+    std::vector<double> yv(b, b + nz);
+    P.h_norm.resize(CLR_NA);
+    // density.c:1323-1355
+    for (int ii = 0; ii < CLR_NA; ii++) {
+      double z = host_bg_z(c, c->h_r[ii]);
+      double nm;
+      if (z < c->z0_norm) nm = P.norm_0;
+      else if (z >= c->zf_norm) nm = P.norm_f;
+      else nm = lin_interp(zarr, yv, z);
+      P.h_norm[ii] = nm;
+    }
+    CLR_CUDA(cudaMemcpyAsync(P.d_norm, P.h_norm.data(), CLR_NA * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    P.have_norm = true;
+  }
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static clr_ctx::Pop *pick_pop(clr_ctx *c, int kind, int ipop)
+{
+  if (ipop < 0 || ipop >= CLR_NPOP_MAX) return nullptr;
+  return kind == 0 ? &c->srcs[ipop] : &c->imap[ipop];
+}
+
+int clr_get_norm(clr_ctx *c, int kind, int ipop, double *norm_arr, double *ends2, double *zends2)
+{
+  clr_ctx::Pop *P = pick_pop(c, kind, ipop);
+  CLR_CHECK(P && P->have_norm, "no normalisation for population %d/%d", kind, ipop);
+  if (norm_arr) memcpy(norm_arr, P->h_norm.data(), CLR_NA * sizeof(double));
+  if (ends2) { ends2[0] = P->norm_0; ends2[1] = P->norm_f; }
+  if (zends2) { zends2[0] = c->z0_norm; zends2[1] = c->zf_norm; }
+  return 0;
+}
+
+int clr_set_norm(clr_ctx *c, int kind, int ipop, const double *norm_arr, const double *ends2)
+{
+  clr_ctx::Pop *P = pick_pop(c, kind, ipop);
+  CLR_CHECK(P && P->set, "population %d/%d not set", kind, ipop);
+  P->h_norm.assign(norm_arr, norm_arr + CLR_NA);
+  P->norm_0 = ends2[0]; P->norm_f = ends2[1];
+  CLR_CUDA(cudaMemcpyAsync(P->d_norm, norm_arr, CLR_NA * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  P->have_norm = true;
+  return 0;
+}
+
+int clr_srcs_set_cartesian(clr_ctx *c, int ipop, uint32_t seed, long long *nsrc_out)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
+  if (clr_srcs_run(c, ipop, seed)) return 1;
+  if (clr_srcs_local(c, ipop)) return 1;
+  if (nsrc_out) *nsrc_out = c->srcs[ipop].nsrc;
+  return 0;
+}
+
+int clr_srcs_get_counts(clr_ctx *c, int ipop, int32_t *nsources_padded)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  CLR_CHECK(P.d_counts, "no counts for population %d", ipop);
+  // device layout is unpadded [nz][n][n]; the reference array has the padded pitch (srcs.c:125)
+  const ClrDev &d = c->dev;
+  CLR_CUDA(cudaMemcpy2DAsync(nsources_padded, (size_t)d.pitch * sizeof(int32_t), P.d_counts, (size_t)d.n * sizeof(int32_t),
+                             (size_t)d.n * sizeof(int32_t), (size_t)d.n * d.nz_here, cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  for (long long row = 0; row < (long long)d.n * d.nz_here; row++)
+    for (int x = d.n; x < d.pitch; x++) nsources_padded[row * d.pitch + x] = 0;
+  return 0;
+}
+
+int clr_srcs_get_cartesian(clr_ctx *c, int ipop, float *pos4, int32_t *ipix)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  if (P.nsrc == 0) return 0;
+  if (pos4) CLR_CUDA(cudaMemcpyAsync(pos4, P.d_pos, (size_t)P.nsrc * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (ipix) CLR_CUDA(cudaMemcpyAsync(ipix, P.d_ipix, (size_t)P.nsrc * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  if (P.nsrc == 0) return 0;
+  CLR_CUDA(cudaMemcpyAsync(srcs9, P.d_srcs, (size_t)P.nsrc * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { return clr_srcs_beam(c, ipop); }
+
+int clr_imap_set_cartesian(clr_ctx *c, int ipop, float *data, int32_t *nadd) { return clr_maps_imap(c, ipop, data, nadd); }
+int clr_kappa_get_beam_properties(clr_ctx *c, long long num_pix, const double *pos3, int nplanes, const float *rf, float *data)
+{ return clr_maps_los(c, 0, num_pix, pos3, nplanes, rf, data); }
+int clr_isw_get_beam_properties(clr_ctx *c, long long num_pix, const double *pos3, int nplanes, const float *rf, float *data)
+{ return clr_maps_los(c, 1, num_pix, pos3, nplanes, rf, data); }
+
+int clr_timer_start(clr_ctx *c) { CLR_CUDA(cudaEventRecord(c->ev0, c->stream)); return 0; }
+int clr_timer_stop_ms(clr_ctx *c, float *ms)
+{
+  CLR_CUDA(cudaEventRecord(c->ev1, c->stream));
+  CLR_CUDA(cudaEventSynchronize(c->ev1));
+  CLR_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return 0;
+}
+int clr_set_profiling(clr_ctx *c, int on) { c->profiling = on != 0; if (on) c->stage.clear(); return 0; }
+int clr_get_stage_ms(clr_ctx *c, const char *stage, float *ms, int *launches)
+{
+  auto it = c->stage.find(stage);
+  if (it == c->stage.end()) { *ms = 0; if (launches) *launches = 0; return 0; }
+  *ms = it->second.ms;
+  if (launches) *launches = it->second.launches;
+  return 0;
+}
+
+}  // extern "C"

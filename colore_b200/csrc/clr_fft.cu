@@ -1,0 +1,463 @@
+// 3-D c2r / r2c FFT of the slab-local grid: hand-written Stockham autosort kernels for sm_100a.
+// Replaces fftw_wrap_c2r / fftw_wrap_r2c (fourier.c:81-125). No cuFFT anywhere.
+//
+// Transform definition (FFTW manual, what the reference links against): unnormalised, c2r =
+// backward (exp(+i...)), r2c = forward; half-complex last axis with n/2+1 entries; in place with
+// real rows padded to 2*(n/2+1). The c2r runs complex passes over z and y first and the
+// half-complex -> real pass over x last, so the imaginary parts of the x-DC and x-Nyquist lines
+// are dropped exactly as FFTW's rdft2 does (the reference fills those planes non-Hermitian,
+// fourier.c:325-345).
+//
+// Kernel design
+//  * One pass per axis, each pass = batched 1-D complex FFTs held in shared memory:
+//    Stockham autosort, radix-8 butterflies in registers (first stage radix 2/4/8 so that any
+//    power of two fits), 8 points per virtual thread, V virtual threads per thread.
+//  * Strided axes (y, z): a CTA owns a tile of T consecutive lines (T contiguous complex numbers
+//    per point of the line, 64 B with T=8), lane <-> line so that global accesses are coalesced
+//    along the contiguous index and shared-memory accesses are conflict free without padding.
+//  * Contiguous axis (x): lane <-> point; shared rows padded by 1 complex every 8 to spread the
+//    stride-8 first-stage stores over the banks. The real transform of length n runs as a complex
+//    transform of length n/2 plus a pre-twiddle (c2r) / post-twiddle (r2c) step.
+//  * Twiddles come from one master table exp(2*pi*i*k/n) built in double on the host; each CTA
+//    gathers the per-stage, per-thread factors once into shared memory (persistent CTAs).
+//  * The last pass of the c2r optionally fuses the (sqrt(2 pi)/L)^3 scaling and the sum / sum of
+//    squares needed by compute_sigma_dens (fourier.c:24-79, 394-397).
+#include "clr_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{ return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <int S> __device__ __forceinline__ float2 mul_i(float2 a)
+{ return S > 0 ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+template <int S> __device__ __forceinline__ void dft2(float2 &a, float2 &b)
+{
+  float2 t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+// X_k = sum_n x_n exp(S*2*pi*i*n*k/4), natural order in and out
+template <int S> __device__ __forceinline__ void dft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3)
+{
+  float2 a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = mul_i<S>(csub(x1, x3));
+  x0 = cadd(a, c); x2 = csub(a, c); x1 = cadd(b, d); x3 = csub(b, d);
+}
+template <int S> __device__ __forceinline__ void dft8(float2 (&v)[8])
+{
+  const float h = 0.70710678118654752440f;
+  float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
+  float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
+  b1 = make_float2(h * (b1.x - S * b1.y), h * (b1.y + S * b1.x));     // * exp(S*i*pi/4)
+  b2 = mul_i<S>(b2);                                                    // * exp(S*i*pi/2)
+  b3 = make_float2(h * (-b3.x - S * b3.y), h * (-b3.y + S * b3.x));   // * exp(S*3*i*pi/4)
+  dft4<S>(a0, a1, a2, a3);
+  dft4<S>(b0, b1, b2, b3);
+  v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+  v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
+}
+
+constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+template <int M> struct FftPlan {
+  static constexpr int LOG = ilog2c(M);
+  static constexpr int R0 = (LOG % 3 == 0) ? 8 : ((LOG % 3 == 1) ? 2 : 4);  // first-stage radix
+  static constexpr int NS8 = (LOG - ilog2c(R0)) / 3;                        // radix-8 stages after it
+  static constexpr int TPL = M / 8;                                         // virtual threads per line
+  static constexpr int NTW = NS8 * 7 * TPL;                                 // per-thread twiddles
+  static constexpr int LSTRIDE = M + M / 8;                                 // padded row (contiguous layout)
+};
+
+// shared-memory index of element e of line l
+template <int M, bool STRIDED, int T> __device__ __forceinline__ int sidx(int e, int l)
+{
+  return STRIDED ? e * T + l : l * FftPlan<M>::LSTRIDE + e + (e >> 3);
+}
+
+// gather the per-stage twiddles of this pass from the master table W[k] = exp(+2*pi*i*k/wn)
+template <int M, int S> __device__ __forceinline__ void load_twiddles(float2 *tw, const float2 *__restrict__ W, int wn)
+{
+  using P = FftPlan<M>;
+  for (int i = threadIdx.x; i < P::NTW; i += blockDim.x) {
+    int st = i / (7 * P::TPL);
+    int r = (i / P::TPL) % 7 + 1;
+    int jj = i % P::TPL;
+    int Ns = P::R0 << (3 * st);
+    int k = jj % Ns;
+    int t = r * k * (wn / (Ns * 8));
+    float2 w = W[t];
+    if (S < 0) w.y = -w.y;
+    tw[i] = w;
+  }
+}
+
+// first stage: inputs v[r] = element jv + r*TPL of the line; writes the stage output to shared
+template <int M, int S, bool STRIDED, int T>
+__device__ __forceinline__ void first_stage(float2 (&v)[8], float2 *s, int jv, int l)
+{
+  using P = FftPlan<M>;
+  if (P::R0 == 8) {
+    dft8<S>(v);
+    if (P::NS8 == 0) return;
+#pragma unroll
+    for (int r = 0; r < 8; r++) s[sidx<M, STRIDED, T>(8 * jv + r, l)] = v[r];
+  } else if (P::R0 == 4) {
+    dft4<S>(v[0], v[2], v[4], v[6]);
+    dft4<S>(v[1], v[3], v[5], v[7]);
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int r = 0; r < 4; r++) s[sidx<M, STRIDED, T>(4 * (jv + i * P::TPL) + r, l)] = v[i + 2 * r];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) dft2<S>(v[i], v[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) s[sidx<M, STRIDED, T>(2 * (jv + i * P::TPL) + r, l)] = v[i + 4 * r];
+  }
+}
+
+// radix-8 stage number st (0-based among the radix-8 stages that follow the first stage):
+// load from shared, twiddle, butterfly. Outputs stay in v; `store_stage` writes them back.
+template <int M, int S, bool STRIDED, int T>
+__device__ __forceinline__ void load_stage(float2 (&v)[8], const float2 *s, const float2 *tw, int st, int jv, int l)
+{
+  using P = FftPlan<M>;
+#pragma unroll
+  for (int r = 0; r < 8; r++) v[r] = s[sidx<M, STRIDED, T>(jv + r * P::TPL, l)];
+#pragma unroll
+  for (int r = 1; r < 8; r++) v[r] = cmul(v[r], tw[(st * 7 + r - 1) * P::TPL + jv]);
+  dft8<S>(v);
+}
+template <int M, bool STRIDED, int T>
+__device__ __forceinline__ void store_stage(const float2 (&v)[8], float2 *s, int st, int jv, int l)
+{
+  using P = FftPlan<M>;
+  const int Ns = P::R0 << (3 * st);
+  const int idxD = (jv / Ns) * Ns * 8 + (jv % Ns);
+#pragma unroll
+  for (int r = 0; r < 8; r++) s[sidx<M, STRIDED, T>(idxD + r * Ns, l)] = v[r];
+}
+
+// Full length-M transform of the lines held by this CTA. On entry vv[vt][r] = element
+// (j + vt*TPLV) + r*TPL of line l; on exit the same positions hold the transform (natural order).
+template <int M, int S, bool STRIDED, int T, int V>
+__device__ __forceinline__ void fft_lines(float2 (&vv)[V][8], float2 *s, const float2 *tw, int j, int l)
+{
+  using P = FftPlan<M>;
+  constexpr int TPLV = P::TPL / V;
+#pragma unroll
+  for (int vt = 0; vt < V; vt++) first_stage<M, S, STRIDED, T>(vv[vt], s, j + vt * TPLV, l);
+#pragma unroll
+  for (int st = 0; st < P::NS8; st++) {
+    __syncthreads();
+#pragma unroll
+    for (int vt = 0; vt < V; vt++) load_stage<M, S, STRIDED, T>(vv[vt], s, tw, st, j + vt * TPLV, l);
+    if (st < P::NS8 - 1) {
+      __syncthreads();
+#pragma unroll
+      for (int vt = 0; vt < V; vt++) store_stage<M, STRIDED, T>(vv[vt], s, st, j + vt * TPLV, l);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// strided pass: lines of length M, element stride e_stride, T consecutive lines per tile
+template <int M, int S, int T, int V>
+__global__ void __launch_bounds__(T * M / 8 / V)
+fft_strided_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, long long n_tiles,
+                   int tiles_per_outer, long long outer_stride, long long e_stride, int n_inner)
+{
+  using P = FftPlan<M>;
+  constexpr int TPLV = P::TPL / V;
+  extern __shared__ float2 smem[];
+  float2 *s = smem;
+  float2 *tw = smem + (P::NS8 > 0 ? M * T : 0);
+  const int tid = threadIdx.x, l = tid % T, j = tid / T;
+  load_twiddles<M, S>(tw, W, wn);
+  __syncthreads();
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    long long outer = tile / tiles_per_outer;
+    int inner0 = (int)(tile % tiles_per_outer) * T;
+    bool ok = inner0 + l < n_inner;
+    float2 *base = g + outer * outer_stride + inner0 + l;
+    float2 vv[V][8];
+#pragma unroll
+    for (int vt = 0; vt < V; vt++)
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        vv[vt][r] = ok ? base[(long long)(j + vt * TPLV + r * P::TPL) * e_stride] : make_float2(0.f, 0.f);
+    fft_lines<M, S, true, T, V>(vv, s, tw, j, l);
+    if (ok) {
+#pragma unroll
+      for (int vt = 0; vt < V; vt++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) base[(long long)(j + vt * TPLV + r * P::TPL) * e_stride] = vv[vt][r];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// x pass of the c2r: rows of nc = M+1 complex -> 2M reals, in place; M = n/2.
+// Output scaled by `norm`; MOM: accumulate sum / sum of squares (double) into mom[0..1].
+template <int M, int T, int V, bool MOM>
+__global__ void __launch_bounds__(T * M / 8 / V)
+fft_c2r_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, long long n_rows, int pitch_c,
+                 float norm, double *__restrict__ mom)
+{
+  using P = FftPlan<M>;
+  constexpr int TPLV = P::TPL / V;
+  extern __shared__ float2 smem[];
+  float2 *s = smem;
+  float2 *tw = smem + (P::NS8 > 0 ? T * P::LSTRIDE : 0);
+  float2 *wx = tw + P::NTW;   // exp(+2*pi*i*k/n), k < M
+  const int tid = threadIdx.x, j = tid % TPLV, l = tid / TPLV;
+  load_twiddles<M, +1>(tw, W, wn);
+  for (int k = tid; k < M; k += blockDim.x) wx[k] = W[k * (wn / (2 * M))];
+  __syncthreads();
+  double acc1 = 0, acc2 = 0;
+  const long long n_tiles = (n_rows + T - 1) / T;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    long long row = tile * T + l;
+    bool ok = row < n_rows;
+    float2 *X = g + row * pitch_c;
+    float2 vv[V][8];
+#pragma unroll
+    for (int vt = 0; vt < V; vt++)
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        int k = j + vt * TPLV + r * P::TPL;
+        float2 a = ok ? X[k] : make_float2(0.f, 0.f);
+        float2 b = ok ? X[M - k] : make_float2(0.f, 0.f);
+        if (k == 0) { a.y = 0.f; b.y = 0.f; }        // x-DC and x-Nyquist are taken as real
+        float2 e = make_float2(a.x + b.x, a.y - b.y);
+        float2 d = cmul(make_float2(a.x - b.x, a.y + b.y), wx[k]);
+        vv[vt][r] = make_float2(e.x - d.y, e.y + d.x);
+      }
+    if (P::NS8 == 0) __syncthreads();
+    fft_lines<M, +1, false, T, V>(vv, s, tw, j, l);
+    if (ok) {
+      float s1 = 0, s2 = 0;
+#pragma unroll
+      for (int vt = 0; vt < V; vt++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          float2 o = vv[vt][r];
+          o.x *= norm; o.y *= norm;
+          if (MOM) {
+            s1 += o.x + o.y;
+            s2 += o.x * o.x + o.y * o.y;
+          }
+          X[j + vt * TPLV + r * P::TPL] = o;
+        }
+      if (MOM) { acc1 += s1; acc2 += s2; }
+    }
+    __syncthreads();
+  }
+  if (MOM) {
+    acc1 = clr_warp_sum(acc1);
+    acc2 = clr_warp_sum(acc2);
+    __shared__ double red[2][32];
+    int w = tid >> 5, ln = tid & 31;
+    if (ln == 0) { red[0][w] = acc1; red[1][w] = acc2; }
+    __syncthreads();
+    if (w == 0) {
+      int nw = (blockDim.x + 31) >> 5;
+      double a = ln < nw ? red[0][ln] : 0, b = ln < nw ? red[1][ln] : 0;
+      a = clr_warp_sum(a); b = clr_warp_sum(b);
+      if (ln == 0) { atomicAdd(mom, a); atomicAdd(mom + 1, b); }
+    }
+  }
+}
+
+// x pass of the r2c: rows of 2M reals -> M+1 complex, in place.
+template <int M, int T, int V>
+__global__ void __launch_bounds__(T * M / 8 / V)
+fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, long long n_rows, int pitch_c)
+{
+  using P = FftPlan<M>;
+  constexpr int TPLV = P::TPL / V;
+  extern __shared__ float2 smem[];
+  float2 *s = smem;                              // always needed here (post-processing exchange)
+  float2 *tw = smem + T * P::LSTRIDE;
+  float2 *wx = tw + P::NTW;                      // exp(-2*pi*i*k/n), k < M
+  const int tid = threadIdx.x, j = tid % TPLV, l = tid / TPLV;
+  load_twiddles<M, -1>(tw, W, wn);
+  for (int k = tid; k < M; k += blockDim.x) { float2 w = W[k * (wn / (2 * M))]; w.y = -w.y; wx[k] = w; }
+  __syncthreads();
+  const long long n_tiles = (n_rows + T - 1) / T;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    long long row = tile * T + l;
+    bool ok = row < n_rows;
+    float2 *X = g + row * pitch_c;
+    float2 vv[V][8];
+#pragma unroll
+    for (int vt = 0; vt < V; vt++)
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        vv[vt][r] = ok ? X[j + vt * TPLV + r * P::TPL] : make_float2(0.f, 0.f);
+    fft_lines<M, -1, false, T, V>(vv, s, tw, j, l);
+    __syncthreads();
+#pragma unroll
+    for (int vt = 0; vt < V; vt++)
+#pragma unroll
+      for (int r = 0; r < 8; r++) s[sidx<M, false, T>(j + vt * TPLV + r * P::TPL, l)] = vv[vt][r];
+    __syncthreads();
+    if (ok) {
+#pragma unroll
+      for (int vt = 0; vt < V; vt++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          int k = j + vt * TPLV + r * P::TPL;
+          float2 zk = vv[vt][r];
+          if (k == 0) {
+            X[0] = make_float2(zk.x + zk.y, 0.f);
+            X[M] = make_float2(zk.x - zk.y, 0.f);
+          } else {
+            float2 zc = s[sidx<M, false, T>(M - k, l)];
+            zc.y = -zc.y;                                        // conj(Z[M-k])
+            float2 e = cadd(zk, zc);
+            float2 d = cmul(csub(zk, zc), wx[k]);                // (Z[k]-conj Z[M-k]) * exp(-2 pi i k/n)
+            // X[k] = 0.5*(e - i*d)
+            X[k] = make_float2(0.5f * (e.x + d.y), 0.5f * (e.y - d.x));
+          }
+        }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch
+template <int M> struct Cfg {   // tile shape per transform length
+  static constexpr int V = M >= 2048 ? 4 : (M >= 1024 ? 2 : 1);
+  static constexpr int T_STRIDED = M >= 4096 ? 4 : (M >= 256 ? 8 : (2048 / M > 64 ? 64 : 2048 / M));
+  static constexpr int T_X = M >= 2048 ? 4 : (M >= 256 ? 8 : (2048 / M > 64 ? 64 : 2048 / M));
+};
+
+template <typename K> int launch_cfg(clr_ctx *c, K kernel, int threads, size_t smem, long long n_tiles, int *grid)
+{
+  int per_sm = 0;
+  CLR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  CLR_CHECK(per_sm > 0, "FFT kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
+  long long g = (long long)per_sm * c->sm_count;
+  if (g > n_tiles) g = n_tiles;
+  *grid = (int)g;
+  return 0;
+}
+
+template <int M, int S>
+int run_strided(clr_ctx *c, float2 *g, long long n_outer, long long outer_stride, long long e_stride, int n_inner)
+{
+  using P = FftPlan<M>;
+  constexpr int T = Cfg<M>::T_STRIDED, V = Cfg<M>::V;
+  constexpr int threads = T * M / 8 / V;
+  size_t smem = ((P::NS8 > 0 ? (size_t)M * T : 0) + P::NTW) * sizeof(float2);
+  int tiles_per_outer = (n_inner + T - 1) / T;
+  long long n_tiles = n_outer * tiles_per_outer;
+  int grid;
+  auto k = fft_strided_kernel<M, S, T, V>;
+  if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
+  k<<<grid, threads, smem, c->stream>>>(g, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, outer_stride, e_stride, n_inner);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int M, bool MOM>
+int run_c2r_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c, float norm, double *mom)
+{
+  using P = FftPlan<M>;
+  constexpr int T = Cfg<M>::T_X, V = Cfg<M>::V;
+  constexpr int threads = T * M / 8 / V;
+  size_t smem = ((P::NS8 > 0 ? (size_t)T * P::LSTRIDE : 0) + P::NTW + M) * sizeof(float2);
+  int grid;
+  auto k = fft_c2r_x_kernel<M, T, V, MOM>;
+  if (launch_cfg(c, k, threads, smem, (n_rows + T - 1) / T, &grid)) return 1;
+  k<<<grid, threads, smem, c->stream>>>(g, c->d_twiddle, c->dev.n, n_rows, pitch_c, norm, mom);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int M>
+int run_r2c_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c)
+{
+  using P = FftPlan<M>;
+  constexpr int T = Cfg<M>::T_X, V = Cfg<M>::V;
+  constexpr int threads = T * M / 8 / V;
+  size_t smem = ((size_t)T * P::LSTRIDE + P::NTW + M) * sizeof(float2);
+  int grid;
+  auto k = fft_r2c_x_kernel<M, T, V>;
+  if (launch_cfg(c, k, threads, smem, (n_rows + T - 1) / T, &grid)) return 1;
+  k<<<grid, threads, smem, c->stream>>>(g, c->d_twiddle, c->dev.n, n_rows, pitch_c);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int c2r_3d(clr_ctx *c, float2 *g, float norm, double *mom)
+{
+  const long long nc = N / 2 + 1;
+  // z pass: lines along z, contiguous index = flattened (ky,kx) of a plane
+  if (run_strided<N, +1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc))) return 1;
+  // y pass: per z plane, lines along y, contiguous index = kx
+  if (run_strided<N, +1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1;
+  // x pass: half-complex -> real
+  if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)N * N, (int)nc, norm, mom);
+  return run_c2r_x<N / 2, false>(c, g, (long long)N * N, (int)nc, norm, nullptr);
+}
+
+template <int N>
+int r2c_3d(clr_ctx *c, float2 *g)
+{
+  const long long nc = N / 2 + 1;
+  if (run_r2c_x<N / 2>(c, g, (long long)N * N, (int)nc)) return 1;
+  if (run_strided<N, -1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1;
+  return run_strided<N, -1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc));
+}
+
+}  // namespace
+
+// norm multiplies the output (1.0 = plain fftw_wrap_c2r); d_moments != NULL accumulates
+// {sum, sum of squares} of the scaled output over the unpadded cells.
+int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments)
+{
+  CLR_CHECK(c->nranks == 1, "multi-GPU FFT goes through clr_fft_dist (not built in this call path)");
+  StageScope sc(c, "fft_c2r", 3);
+  float2 *g = reinterpret_cast<float2 *>(grid);
+  switch (c->dev.n) {
+    case 16: return c2r_3d<16>(c, g, (float)norm, d_moments);
+    case 32: return c2r_3d<32>(c, g, (float)norm, d_moments);
+    case 64: return c2r_3d<64>(c, g, (float)norm, d_moments);
+    case 128: return c2r_3d<128>(c, g, (float)norm, d_moments);
+    case 256: return c2r_3d<256>(c, g, (float)norm, d_moments);
+    case 512: return c2r_3d<512>(c, g, (float)norm, d_moments);
+    case 1024: return c2r_3d<1024>(c, g, (float)norm, d_moments);
+    case 2048: return c2r_3d<2048>(c, g, (float)norm, d_moments);
+    case 4096: return c2r_3d<4096>(c, g, (float)norm, d_moments);
+    default: clr_set_error("n_grid=%d: the FFT supports powers of two in [16,4096]", c->dev.n); return 1;
+  }
+}
+
+int clr_fft_r2c_impl(clr_ctx *c, float *grid)
+{
+  CLR_CHECK(c->nranks == 1, "multi-GPU FFT goes through clr_fft_dist (not built in this call path)");
+  StageScope sc(c, "fft_r2c", 3);
+  float2 *g = reinterpret_cast<float2 *>(grid);
+  switch (c->dev.n) {
+    case 16: return r2c_3d<16>(c, g);
+    case 32: return r2c_3d<32>(c, g);
+    case 64: return r2c_3d<64>(c, g);
+    case 128: return r2c_3d<128>(c, g);
+    case 256: return r2c_3d<256>(c, g);
+    case 512: return r2c_3d<512>(c, g);
+    case 1024: return r2c_3d<1024>(c, g);
+    case 2048: return r2c_3d<2048>(c, g);
+    case 4096: return r2c_3d<4096>(c, g);
+    default: clr_set_error("n_grid=%d: the FFT supports powers of two in [16,4096]", c->dev.n); return 1;
+  }
+}

@@ -1,0 +1,319 @@
+// Field kernels: Gaussian mode fill, scaling + moments, z-halo, lognormal / clip transform,
+// normalisation histogram. HBM-bound streaming kernels: 8-byte vector accesses along x (the
+// reference row pitch 2*(n/2+1) floats only guarantees 8-byte alignment), grid-stride loops sized
+// in multiples of the SM count.
+// Compiled with -fmad=false so that double-precision table lookups round exactly like the
+// reference's scalar C code (no fused multiply-add contraction).
+#include "clr_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// create_grids_fourier (fourier.c:285-359) + rng_delta_gauss (common.c:191-201) + pk_linear0
+// (cosmo.c:291-308). One thread per mode (kz_local, ky, kx<=n/2). RNG: substream
+// (seed, stream 0, global mode index), word 0 -> phase, word 1 -> modulus (phase first, as the
+// reference draws them). Arithmetic in double like the reference; the two complex64 stores per
+// mode are the only HBM traffic (8 B per real-space cell).
+__global__ void __launch_bounds__(kThreads)
+fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restrict__ npot_f, uint32_t seed,
+                  const double *__restrict__ logkarr, const double *__restrict__ pkarr, int numk, double logkmin,
+                  double logkmax, double idlogk, double n_scal, double prefac_lensing, double r2_smooth,
+                  int do_smoothing, int smooth_potential)
+{
+  const long long n_modes = (long long)d.nz_here * d.n * d.nc;
+  const double dk = 2 * 3.14159265358979323846 / d.l_box;
+  const double idk3 = 1. / (dk * dk * dk);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_modes;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(idx % d.nc);
+    long long row = idx / d.nc;
+    int jj = (int)(row % d.n);
+    int ii = (int)(row / d.n);
+    int ii_true = d.iz0_here + ii;
+    double kz = (2 * ii_true <= d.n) ? ii_true * dk : -(d.n - ii_true) * dk;
+    double ky = (2 * jj <= d.n) ? jj * dk : -(d.n - jj) * dk;
+    double kx = (2 * kk <= d.n) ? kk * dk : -(d.n - kk) * dk;
+    double k_mod2 = kx * kx + ky * ky + kz * kz;
+    float2 dk_out = make_float2(0.f, 0.f), pk_out = make_float2(0.f, 0.f);
+    if (k_mod2 > 0) {
+      double lgk = 0.5 * log10(k_mod2);
+      // pk_linear0
+      double pk;
+      int ik = (int)((lgk - logkmin) * idlogk);
+      if (ik < 0) pk = __ldg(pkarr) * pow(10., n_scal * (lgk - logkmin));
+      else if (ik < numk) {
+        double p0 = __ldg(pkarr + ik), p1 = (ik + 1 < numk) ? __ldg(pkarr + ik + 1) : p0;
+        pk = p0 + (lgk - __ldg(logkarr + ik)) * (p1 - p0) * idlogk;
+      } else pk = __ldg(pkarr + numk - 1) * pow(10., -3 * (lgk - logkmax));
+      double sigma2 = pk * idk3;
+      uint32_t w[4];
+      unsigned long long gidx = (unsigned long long)kk + (unsigned long long)d.nc * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
+      clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
+      double u1 = w[0] * (1.0 / 4294967296.0), u2 = w[1] * (1.0 / 4294967296.0);
+      double delta_mod = sqrt(-sigma2 * log(1 - u2));
+      double sn, cs;
+      sincospi(2.0 * u1, &sn, &cs);       // phase = 2*pi*u1, exact argument reduction
+      float dre = (float)(delta_mod * cs), dim = (float)(delta_mod * sn);
+      // potential from the UNSMOOTHED, already float-rounded delta_k (fourier.c:346)
+      double fac = -prefac_lensing;
+      float pre = (float)(fac * (double)dre / k_mod2), pim = (float)(fac * (double)dim / k_mod2);
+      if (do_smoothing) {
+        double sm = exp(-0.5 * r2_smooth * k_mod2);
+        dre = (float)((double)dre * sm); dim = (float)((double)dim * sm);
+        if (smooth_potential) { pre = (float)((double)pre * sm); pim = (float)((double)pim * sm); }
+      }
+      dk_out = make_float2(dre, dim);
+      pk_out = make_float2(pre, pim);
+    }
+    dens_f[idx] = dk_out;
+    npot_f[idx] = pk_out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fourier.c:394-397 scaling of both grids + compute_sigma_dens (fourier.c:24-79) as one streaming
+// pass (used when the FFT epilogue fusion is not: clr_normalize_fields on injected real fields).
+__global__ void __launch_bounds__(kThreads)
+scale_moments_kernel(const ClrDev d, float *__restrict__ dens, float *__restrict__ npot, double norm,
+                     double *__restrict__ mom)
+{
+  const int half = d.pitch / 2;                    // float2 per row, includes the padding pair
+  const long long n2 = (long long)d.nz_here * d.n * half;
+  float2 *dd = reinterpret_cast<float2 *>(dens);
+  float2 *pp = reinterpret_cast<float2 *>(npot);
+  double a1 = 0, a2 = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    int xq = (int)(i % half);
+    float2 v = dd[i], w = pp[i];
+    v.x = (float)((double)v.x * norm); v.y = (float)((double)v.y * norm);
+    w.x = (float)((double)w.x * norm); w.y = (float)((double)w.y * norm);
+    dd[i] = v; pp[i] = w;
+    if (2 * xq < d.n) {                            // padding columns do not enter the moments
+      a1 += (double)v.x + (double)v.y;
+      a2 += (double)(v.x * v.x) + (double)(v.y * v.y);
+    }
+  }
+  a1 = clr_warp_sum(a1); a2 = clr_warp_sum(a2);
+  __shared__ double red[2][kThreads / 32];
+  int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  if (ln == 0) { red[0][w] = a1; red[1][w] = a2; }
+  __syncthreads();
+  if (w == 0) {
+    double a = ln < kThreads / 32 ? red[0][ln] : 0, b = ln < kThreads / 32 ? red[1][ln] : 0;
+    a = clr_warp_sum(a); b = clr_warp_sum(b);
+    if (ln == 0) { atomicAdd(mom, a); atomicAdd(mom + 1, b); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lognormalize (density.c:1070-1103) / densclip (density.c:1034-1067): in place, cell coordinates
+// in fp32 exactly as the reference (flouble dx, x0, y0, z0), growth factor lerp and exp in double.
+__global__ void __launch_bounds__(kThreads)
+lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int clip)
+{
+  const int halfn = d.n / 2;                       // float2 per row holding real cells
+  const long long n2 = (long long)d.nz_here * d.n * halfn;
+  const float dx = d.l_box / d.n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    int xq = (int)(i % halfn);
+    long long row = i / halfn;
+    int iy = (int)(row % d.n);
+    int iz = (int)(row / d.n);
+    float z0 = (float)((iz + d.iz0_here + 0.0) * dx - d.pos_obs[2]);
+    float y0 = (float)((iy + 0.0) * dx - d.pos_obs[1]);
+    float yz = __fadd_rn(__fmul_rn(y0, y0), __fmul_rn(z0, z0));
+    float2 *p = reinterpret_cast<float2 *>(dens + row * d.pitch) + xq;
+    float2 v = *p;
+    float out[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      int ix = 2 * xq + q;
+      float x0 = (float)((ix + 0.0) * dx - d.pos_obs[0]);
+      // reference: sqrt(x0*x0+y0*y0+z0*z0) with float products, left-to-right float sums
+      float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
+      (void)yz;
+      double r = sqrt((double)r2);
+      double dg = clr_bg_d1(d, r);
+      double delta = q ? v.y : v.x;
+      double res = clip ? fmax(1 + dg * delta, 0.) - 1 : exp(dg * (delta - 0.5 * dg * sigma2)) - 1;
+      out[q] = (float)res;
+    }
+    *p = make_float2(out[0], out[1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// collect_density_normalization_from_grid (density.c:1128-1211): per redshift bin, the number of
+// cells, the sum of z and the sum of bias_model(delta, b(r)) per population. Warp-aggregated
+// shared-memory histogram (neighbouring cells mostly share a bin), one global atomic per bin and
+// CTA at the end.
+#define CLR_MAX_NORM_POP 20
+#define CLR_MAX_NZ 512
+struct NormPops { const double *bz[CLR_MAX_NORM_POP]; int npop; };
+
+__global__ void __launch_bounds__(kThreads)
+norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, int nz, double idz,
+                 unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b)
+{
+  extern __shared__ double sh[];          // [nz] z sums, [npop][nz] bias sums, then counts
+  double *s_z = sh;
+  double *s_b = sh + nz;
+  unsigned long long *s_n = reinterpret_cast<unsigned long long *>(sh + (size_t)nz * (1 + pops.npop));
+  for (int i = threadIdx.x; i < nz * (1 + pops.npop); i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) s_n[i] = 0;
+  __syncthreads();
+  const long long n_cells = (long long)d.nz_here * d.n * d.n;
+  const float dx = d.l_box / d.n;
+  const long long n_iter = (n_cells + (long long)gridDim.x * blockDim.x - 1) / ((long long)gridDim.x * blockDim.x);
+  for (long long it = 0; it < n_iter; it++) {
+    long long i = (it * gridDim.x + blockIdx.x) * (long long)blockDim.x + threadIdx.x;
+    int bin = -1;
+    double redshift = 0, dcell = 0, r = 0;
+    if (i < n_cells) {
+      int ix = (int)(i % d.n);
+      long long row = i / d.n;
+      int iy = (int)(row % d.n);
+      int iz = (int)(row / d.n);
+      float z0 = (float)((iz + d.iz0_here + 0.0) * dx - d.pos_obs[2]);
+      float y0 = (float)((iy + 0.0) * dx - d.pos_obs[1]);
+      float x0 = (float)((ix + 0.0) * dx - d.pos_obs[0]);
+      float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
+      r = sqrt((double)r2);
+      redshift = clr_bg_z(d, r);
+      int ind_z = (int)(redshift * idz) + 1;
+      if (ind_z >= 0 && ind_z < nz) { bin = ind_z; dcell = dens[row * d.pitch + ix]; }
+    }
+    // warp aggregation by bin
+    unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+      int leader = __ffs(todo) - 1;
+      int b = __shfl_sync(0xffffffffu, bin, leader);
+      bool mine = (bin == b);
+      unsigned grp = __ballot_sync(0xffffffffu, mine);
+      double zsum = clr_warp_sum(mine ? redshift : 0.);
+      if (lane == leader) { atomicAdd(&s_z[b], zsum); atomicAdd(&s_n[b], (unsigned long long)__popc(grp)); }
+      for (int ip = 0; ip < pops.npop; ip++) {
+        double bm = mine ? clr_bias_model(d.bias_model, dcell, clr_bg_bz(d, r, pops.bz[ip])) : 0.;
+        bm = clr_warp_sum(bm);
+        if (lane == leader) atomicAdd(&s_b[ip * nz + b], bm);
+      }
+      todo &= ~grp;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) {
+    if (s_n[i]) {
+      atomicAdd(&g_n[i], s_n[i]);
+      atomicAdd(&g_z[i], s_z[i]);
+      for (int ip = 0; ip < pops.npop; ip++) atomicAdd(&g_b[ip * nz + i], s_b[ip * nz + i]);
+    }
+  }
+}
+
+// z-halo of the potential for a single slab: periodic wrap (fourier.c:412-413)
+__global__ void halo_copy_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+int grid_for(clr_ctx *c, long long work_items, int per_sm)
+{
+  long long g = (work_items + kThreads - 1) / kThreads;
+  long long cap = (long long)c->sm_count * per_sm;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+int clr_ensure_scratch(clr_ctx *c, size_t bytes)
+{
+  if (bytes <= c->scratch_bytes) return 0;
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  c->d_scratch = nullptr; c->scratch_bytes = 0;
+  CLR_CUDA(cudaMalloc(&c->d_scratch, bytes));
+  c->scratch_bytes = bytes;
+  return 0;
+}
+
+int clr_fields_fill(clr_ctx *c, uint32_t seed)
+{
+  StageScope sc(c, "fill_modes", 1);
+  long long n_modes = (long long)c->dev.nz_here * c->dev.n * c->dev.nc;
+  fill_modes_kernel<<<grid_for(c, n_modes, 8), kThreads, 0, c->stream>>>(
+      c->dev, reinterpret_cast<float2 *>(c->d_dens), reinterpret_cast<float2 *>(c->d_npot), seed, c->d_pk,
+      c->d_pk + c->p.numk, c->p.numk, c->p.logkmin, c->p.logkmax, c->p.idlogk, c->p.n_scal, c->p.prefac_lensing,
+      c->p.r2_smooth, c->p.do_smoothing, c->p.smooth_potential);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clr_fields_scale_moments(clr_ctx *c, double *out2)
+{
+  if (clr_ensure_scratch(c, 4096)) return 1;
+  CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
+  double norm = pow(sqrt(2 * M_PI) / c->p.l_box, 3);
+  {
+    StageScope sc(c, "scale_moments", 1);
+    long long n2 = (long long)c->dev.nz_here * c->dev.n * (c->dev.pitch / 2);
+    scale_moments_kernel<<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->d_npot, norm, c->d_scratch);
+    CLR_CUDA(cudaGetLastError());
+  }
+  CLR_CUDA(cudaMemcpyAsync(out2, c->d_scratch, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int clr_fields_lognormal(clr_ctx *c, int clip)
+{
+  StageScope sc(c, "lognormal", 1);
+  long long n2 = (long long)c->dev.nz_here * c->dev.n * (c->dev.n / 2);
+  lognormal_kernel<<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz, double idz,
+                         unsigned long long *h_n, double *h_z, double *h_b)
+{
+  CLR_CHECK(npop <= CLR_MAX_NORM_POP && nz <= CLR_MAX_NZ, "normalisation: npop=%d nz=%d too large", npop, nz);
+  size_t nd = (size_t)nz * (2 + npop);
+  if (clr_ensure_scratch(c, nd * sizeof(double))) return 1;
+  CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
+  unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_scratch);
+  double *g_z = c->d_scratch + nz;
+  double *g_b = c->d_scratch + 2 * nz;
+  NormPops pops;
+  pops.npop = npop;
+  for (int i = 0; i < npop; i++) pops.bz[i] = d_bz[i];
+  {
+    StageScope sc(c, "norm_hist", 1);
+    long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
+    size_t smem = nd * sizeof(double);
+    norm_hist_kernel<<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
+    CLR_CUDA(cudaGetLastError());
+  }
+  CLR_CUDA(cudaMemcpyAsync(h_n, g_n, nz * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(h_z, g_z, nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (npop) CLR_CUDA(cudaMemcpyAsync(h_b, g_b, (size_t)npop * nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int clr_halo_update(clr_ctx *c)
+{
+  // single slab: slice_left = last plane, slice_right = first plane (fourier.c:412-413); they are
+  // materialised after the grid so that the stencil kernels index them like the reference.
+  CLR_CHECK(c->nranks == 1, "halo exchange over NCCL is handled by the distributed path");
+  StageScope sc(c, "halo", 2);
+  long long plane = (long long)c->dev.pitch * c->dev.n;
+  float *left = c->d_npot + (long long)c->dev.nz_here * plane;
+  float *right = left + plane;
+  halo_copy_kernel<<<grid_for(c, plane, 4), kThreads, 0, c->stream>>>(left, c->d_npot + (long long)(c->dev.nz_here - 1) * plane, plane);
+  halo_copy_kernel<<<grid_for(c, plane, 4), kThreads, 0, c->stream>>>(right, c->d_npot, plane);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,319 @@
+// colore_b200 internal declarations: context, device-side table lookups, RNG, HEALPix arithmetic.
+// sm_100a only. Reference citations are file:line under damonge/CoLoRe src/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/colore_b200.h"
+
+#define CLR_SM_COUNT_FALLBACK 148
+
+// ---------------------------------------------------------------------------------------------
+// device-visible parameter block (passed by value as __grid_constant__ where needed)
+struct ClrDev {
+  int n, nc, nz_here, iz0_here;     // grid side, n/2+1, slab
+  int pitch;                        // floats per real row = 2*nc (reference layout)
+  int bias_model, nside_base;
+  float l_box;
+  double pos_obs[3];
+  double glob_idr, r_tab_max;       // 1/dr of the NA tables; r_arr[NA-1]
+  double fgrowth_0, hubble_0, OmegaM, r_max;
+  const double *r_arr, *z_arr, *d1_arr, *d2_arr, *v1_arr, *pd_arr, *ih_arr, *a2r_a, *a2r_r;
+  const float *slice_left, *slice_right;   // z-halo planes of the potential (fourier.c:401-414)
+};
+
+struct ClrPop {           // one tracer population: tables on the NA r-grid
+  const double *nz, *bz, *norm;   // n(z) [or T(z)], b(z), normalisation
+  double norm_0, norm_f;
+};
+
+// ---------------------------------------------------------------------------------------------
+struct StageTime { float ms = 0; int launches = 0; };
+
+struct clr_ctx {
+  int device = 0, sm_count = CLR_SM_COUNT_FALLBACK;
+  cudaStream_t stream = nullptr;
+  clr_params p;                     // host copy (pointers re-targeted to host vectors below)
+  std::vector<double> h_logk, h_pk, h_r, h_z, h_d1, h_d2, h_v1, h_pd, h_ih, h_a2r_a, h_a2r_r;
+  ClrDev dev;
+  // device memory
+  float *d_dens = nullptr, *d_npot = nullptr;       // grids (+2 halo planes on npot)
+  double *d_tables = nullptr;                        // 9 x NA
+  double *d_pk = nullptr;                            // logk[numk], pk[numk]
+  float2 *d_twiddle = nullptr;                       // exp(+2*pi*i*k/n), k<n
+  double *d_scratch = nullptr;                       // reductions / histograms
+  size_t scratch_bytes = 0;
+  double sigma2_gauss = 0, mean_gauss = 0;
+  // populations
+  struct Pop {
+    bool set = false;
+    std::vector<double> h_a, h_b, h_norm;
+    double *d_a = nullptr, *d_b = nullptr, *d_norm = nullptr;
+    double norm_0 = 1, norm_f = 1;
+    bool have_norm = false;
+    // imap shells
+    int nside = 0, nr = 0;
+    std::vector<float> r0, rf;
+    // sources catalogue (device)
+    int32_t *d_counts = nullptr;
+    long long nsrc = 0;
+    float *d_pos = nullptr; int32_t *d_ipix = nullptr; float *d_srcs = nullptr;
+    size_t cap_src = 0;
+  } srcs[CLR_NPOP_MAX], imap[CLR_NPOP_MAX];
+  double z0_norm = 0, zf_norm = 0;
+  // multi-GPU
+  int rank = 0, nranks = 1;
+  void *nccl_comm = nullptr;
+  // bookkeeping
+  long long launches = 0;
+  bool profiling = false;
+  std::map<std::string, StageTime> stage;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+};
+
+void clr_set_error(const char *fmt, ...);
+#define CLR_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      clr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));  \
+      return 1;                                                                             \
+    }                                                                                       \
+  } while (0)
+#define CLR_CHECK(cond, ...)                     \
+  do {                                           \
+    if (!(cond)) { clr_set_error(__VA_ARGS__); return 1; } \
+  } while (0)
+
+// stage profiling: CUDA events around a kernel family on the context stream
+struct StageScope {
+  clr_ctx *c; const char *name; int nl;
+  StageScope(clr_ctx *ctx, const char *nm, int nlaunch) : c(ctx), name(nm), nl(nlaunch) {
+    c->launches += nl;
+    if (c->profiling) cudaEventRecord(c->evp0, c->stream);
+  }
+  ~StageScope() {
+    if (c->profiling) {
+      float ms = 0;
+      cudaEventRecord(c->evp1, c->stream);
+      cudaEventSynchronize(c->evp1);
+      cudaEventElapsedTime(&ms, c->evp0, c->evp1);
+      StageTime &s = c->stage[name];
+      s.ms += ms; s.launches += nl;
+    }
+  }
+};
+
+// kernels implemented in the other translation units
+int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments);
+int clr_fft_r2c_impl(clr_ctx *c, float *grid);
+int clr_fields_fill(clr_ctx *c, uint32_t seed);
+int clr_fields_scale_moments(clr_ctx *c, double *out2);
+int clr_fields_lognormal(clr_ctx *c, int clip);
+int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz, double idz,
+                         unsigned long long *h_n, double *h_z, double *h_b);
+int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed);
+int clr_srcs_local(clr_ctx *c, int ipop);
+int clr_srcs_beam(clr_ctx *c, int ipop);
+int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
+int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,
+                 float *h_data);
+int clr_halo_update(clr_ctx *c);
+int clr_ensure_scratch(clr_ctx *c, size_t bytes);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+#ifdef __CUDACC__
+
+// cosmo.c:30-38 f_of_r_linear
+__device__ __forceinline__ double clr_lerp(const ClrDev &d, double r, const double *__restrict__ f,
+                                           double f0, double ff)
+{
+  if (r <= 0) return f0;
+  else if (r >= d.r_tab_max) return ff;
+  int ir = (int)(r * d.glob_idr);
+  double fa = __ldg(f + ir), fb = __ldg(f + ir + 1);
+  return fa + (fb - fa) * (r - __ldg(d.r_arr + ir)) * d.glob_idr;
+}
+// cosmo.c:40-57 end values per tag
+__device__ __forceinline__ double clr_bg_z(const ClrDev &d, double r) { return clr_lerp(d, r, d.z_arr, 0.0, __ldg(d.z_arr + CLR_NA - 1)); }
+__device__ __forceinline__ double clr_bg_d1(const ClrDev &d, double r) { return clr_lerp(d, r, d.d1_arr, 1.0, __ldg(d.d1_arr + CLR_NA - 1)); }
+__device__ __forceinline__ double clr_bg_v1(const ClrDev &d, double r) { return clr_lerp(d, r, d.v1_arr, __ldg(d.v1_arr), __ldg(d.v1_arr + CLR_NA - 1)); }
+__device__ __forceinline__ double clr_bg_pd(const ClrDev &d, double r) { return clr_lerp(d, r, d.pd_arr, __ldg(d.pd_arr), __ldg(d.pd_arr + CLR_NA - 1)); }
+__device__ __forceinline__ double clr_bg_ih(const ClrDev &d, double r) { return clr_lerp(d, r, d.ih_arr, __ldg(d.ih_arr), __ldg(d.ih_arr + CLR_NA - 1)); }
+// cosmo.c:58-73
+__device__ __forceinline__ double clr_bg_nz(const ClrDev &d, double r, const double *t) { return clr_lerp(d, r, t, 0.0, 0.0); }
+__device__ __forceinline__ double clr_bg_bz(const ClrDev &d, double r, const double *t) { return clr_lerp(d, r, t, __ldg(t), 1.0); }
+
+// cosmo.c:101-112
+__device__ __forceinline__ double clr_r_of_z(const ClrDev &d, double z)
+{
+  double a = 1. / (1 + z);
+  if (a >= 1) return 0;
+  else if (a <= 0) return __ldg(d.a2r_r);
+  int ia = (int)(a * (CLR_NA - 1));
+  double r0 = __ldg(d.a2r_r + ia);
+  return r0 + (__ldg(d.a2r_r + ia + 1) - r0) * (a - __ldg(d.a2r_a + ia)) * (CLR_NA - 1.);
+}
+
+// common.h:414-431
+__device__ __forceinline__ double clr_bias_model(int model, double dd, double b)
+{
+  if (dd <= -1) return 0;
+  if (model == 2) {
+    if (dd < 0) return exp(b * dd / (1 + dd));
+    return 1 + b * dd;
+  } else if (model == 3) {
+    double v = 1 + b * dd;
+    return v > 0 ? v : 0;
+  }
+  return pow(1 + dd, b);
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter {index_lo, index_hi, block, stream}, key {seed, 0}.
+// Word j of substream (seed, stream, index) = word j%4 of block j/4. Same definition as
+// oracle/shim/gsl_shim.c:shim_philox_seek.
+__device__ __forceinline__ void clr_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct ClrStream {   // sequential reader of one counter-based substream
+  uint32_t k0, k1, i0, i1, stream, pos, buf[4];
+  __device__ __forceinline__ ClrStream(uint32_t seed, uint32_t strm, unsigned long long index)
+      : k0(seed), k1(0), i0((uint32_t)index), i1((uint32_t)(index >> 32)), stream(strm), pos(0) {}
+  __device__ __forceinline__ uint32_t next_u32()
+  {
+    if ((pos & 3) == 0) clr_philox(i0, i1, pos >> 2, stream, k0, k1, buf);
+    uint32_t w = (pos & 3) == 0 ? buf[0] : (pos & 3) == 1 ? buf[1] : (pos & 3) == 2 ? buf[2] : buf[3];
+    pos++;
+    return w;
+  }
+  // gsl_rng_uniform of mt19937: u32 / 2^32 (exact in double)
+  __device__ __forceinline__ double next() { return next_u32() * (1.0 / 4294967296.0); }
+  __device__ __forceinline__ double next_pos() { double x; do { x = next(); } while (x == 0); return x; }
+};
+
+// ---- HEALPix (Gorski et al. 2005) in the (x,y,face) formulation of the HEALPix C library -------
+__device__ __forceinline__ double clr_fmodulo(double v1, double v2)
+{
+  if (v1 >= 0) return (v1 < v2) ? v1 : fmod(v1, v2);
+  double tmp = fmod(v1, v2) + v2;
+  return (tmp == v2) ? 0. : tmp;
+}
+__device__ __forceinline__ int clr_imodulo(int v1, int v2) { int v = v1 % v2; return (v >= 0) ? v : v + v2; }
+
+// ang2pix_ring_z_phi == he_ang2pix (healpix_extra.c:141-172)
+__device__ __forceinline__ long long clr_ang2pix_ring_zphi(int nside, double z, double phi)
+{
+  const double twopi = 6.283185307179586476925286766559005768394;
+  const double twothird = 2.0 / 3.0;
+  const double inv_halfpi = 0.6366197723675813430755350534900574;
+  double za = fabs(z);
+  double tt = clr_fmodulo(phi, twopi) * inv_halfpi;
+  if (za <= twothird) {
+    double temp1 = nside * (0.5 + tt);
+    double temp2 = nside * z * 0.75;
+    int jp = (int)(temp1 - temp2);
+    int jm = (int)(temp1 + temp2);
+    int ir = nside + 1 + jp - jm;
+    int kshift = 1 - (ir & 1);
+    int ip = (jp + jm - nside + kshift + 1) / 2;
+    ip = clr_imodulo(ip, 4 * nside);
+    return (long long)nside * (nside - 1) * 2 + (long long)(ir - 1) * 4 * nside + ip;
+  } else {
+    double tp = tt - (int)(tt);
+    double tmp = nside * sqrt(3 * (1 - za));
+    int jp = (int)(tp * tmp);
+    int jm = (int)((1.0 - tp) * tmp);
+    int ir = jp + jm + 1;
+    int ip = (int)(tt * ir);
+    ip = clr_imodulo(ip, 4 * ir);
+    if (z > 0) return 2LL * ir * (ir - 1) + ip;
+    return 12LL * nside * nside - 2LL * ir * (ir + 1) + ip;
+  }
+}
+
+__device__ __forceinline__ int clr_isqrt(int v) { return (int)(sqrt(v + 0.5)); }
+__device__ __forceinline__ int clr_spread_bits(int v)
+{
+  unsigned int x = (unsigned int)v & 0xffff;
+  x = (x | (x << 8)) & 0x00ff00ff;
+  x = (x | (x << 4)) & 0x0f0f0f0f;
+  x = (x | (x << 2)) & 0x33333333;
+  x = (x | (x << 1)) & 0x55555555;
+  return (int)x;
+}
+// ring2nest for nside <= 8192 (pixel ids fit in 31 bits up to nside 8192: 12*2^26 < 2^31)
+__device__ __forceinline__ int clr_ring2nest(int nside, int pix)
+{
+  const int jrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+  const int jpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+  int iring, iphi, kshift, nr, face;
+  int ncap = 2 * nside * (nside - 1), npix = 12 * nside * nside, nl2 = 2 * nside;
+  if (pix < ncap) {
+    iring = (1 + clr_isqrt(1 + 2 * pix)) >> 1;
+    iphi = (pix + 1) - 2 * iring * (iring - 1);
+    kshift = 0; nr = iring;
+    face = (iphi - 1) / nr;
+  } else if (pix < (npix - ncap)) {
+    int ip = pix - ncap;
+    iring = ip / (4 * nside) + nside;
+    iphi = ip % (4 * nside) + 1;
+    kshift = (iring + nside) & 1;
+    nr = nside;
+    int ire = iring - nside + 1;
+    int irm = nl2 + 2 - ire;
+    int ifm = (iphi - ire / 2 + nside - 1) / nside;
+    int ifp = (iphi - irm / 2 + nside - 1) / nside;
+    if (ifp == ifm) face = (ifp == 4) ? 4 : ifp + 4;
+    else if (ifp < ifm) face = ifp;
+    else face = ifm + 8;
+  } else {
+    int ip = npix - pix;
+    iring = (1 + clr_isqrt(2 * ip - 1)) >> 1;
+    iphi = 4 * iring + 1 - (ip - 2 * iring * (iring - 1));
+    kshift = 0; nr = iring;
+    iring = 2 * nl2 - iring;
+    face = 8 + (iphi - 1) / nr;
+  }
+  int irt = iring - jrll[face] * nside + 1;
+  int ipt = 2 * iphi - jpll[face] * nr - kshift - 1;
+  if (ipt >= nl2) ipt -= 8 * nside;
+  int ix = (ipt - irt) >> 1;
+  int iy = (-(ipt + irt)) >> 1;
+  return face * nside * nside + clr_spread_bits(ix) + (clr_spread_bits(iy) << 1);
+}
+
+// srcs.c:68-85
+__device__ __forceinline__ void clr_cart2sph(double x, double y, double z, double *r, double *cth, double *phi)
+{
+  *r = sqrt(x * x + y * y + z * z);
+  if ((*r) == 0) { *cth = 1; *phi = 0; }
+  else {
+    double xn = x / (*r), yn = y / (*r);
+    *cth = z / (*r);
+    *phi = atan2(yn, xn);
+    if ((*phi) < 0) (*phi) += 2 * 3.14159265358979323846;
+  }
+}
+
+__device__ __forceinline__ double clr_warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif // __CUDACC__

@@ -1,0 +1,319 @@
+// Map kernels: intensity-map painting (scatter with atomics) and the kappa / ISW line-of-sight
+// integrals (gather with finite-difference stencils).
+// Replaces imap_set_cartesian_single (imap.c:135-245), kappa_get_beam_properties (kappa.c:78-175),
+// isw_get_beam_properties (isw.c:78-147) and the NGP branch of interpolate_from_grid /
+// get_element (beaming.c:31-181). Compiled with -fmad=false (pixel indices must match the oracle).
+//
+// Multi-GPU note: every accumulator is linear in the field, so each GPU integrates the part of
+// every ray that crosses ITS slab (interpolate_from_grid returns added=0 elsewhere, beaming.c:159)
+// and the maps are summed afterwards; the reference's ring rotation of whole slabs
+// (beaming.c:325-352) is not needed.
+#include "clr_internal.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct ImapShells { const float *r0, *rf; const int *nsub; int nr, nsub_lo, nsub_hi; };
+
+// imap.c:76-103 for contiguous sorted shells: index i with r0[i] <= r < rf[i]; -1 below the first
+// shell, nr above the last. (The reference's cached linear search returns the same index; it never
+// terminates if r falls in a gap between shells, which contiguous frequency tables never produce:
+// such points are skipped here, return -2.)
+__device__ __forceinline__ int dev_r_index(const ImapShells &sh, double r)
+{
+  if (r < (double)__ldg(sh.r0)) return -1;
+  int lo = 0, hi = sh.nr - 1;          // invariant: r0[lo] <= r
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if ((double)__ldg(sh.r0 + mid) <= r) lo = mid; else hi = mid - 1;
+  }
+  if (r < (double)__ldg(sh.rf + lo)) return lo;
+  return lo == sh.nr - 1 ? sh.nr : -2;
+}
+
+__device__ __forceinline__ double dev_get_rvel(const ClrDev &d, const float *__restrict__ npot, int ix, int iy, int iz,
+                                               double x0, double y0, double z0, double rr)
+{
+  const double idx = (double)(d.n / d.l_box);
+  const long long ngx = d.pitch, plane = ngx * d.n;
+  int ix_hi = ix + 1 == d.n ? 0 : ix + 1, ix_lo = ix == 0 ? d.n - 1 : ix - 1;
+  int iy_hi = iy + 1 == d.n ? 0 : iy + 1, iy_lo = iy == 0 ? d.n - 1 : iy - 1;
+  long long pz_hi = (iz == d.nz_here - 1) ? (long long)(d.nz_here + 1) : iz + 1;
+  long long pz_lo = (iz == 0) ? (long long)d.nz_here : iz - 1;
+  double u0 = x0 / rr, u1 = y0 / rr, u2 = z0 / rr;
+  float v0 = npot[ix_hi + iy * ngx + iz * plane] - npot[ix_lo + iy * ngx + iz * plane];
+  float v1 = npot[ix + iy_hi * ngx + iz * plane] - npot[ix + iy_lo * ngx + iz * plane];
+  float v2 = npot[ix + iy * ngx + pz_hi * plane] - npot[ix + iy * ngx + pz_lo * plane];
+  return 0.5 * idx * (v0 * u0 + v1 * u1 + v2 * u2);
+}
+
+// one thread per cell; sub-cells are painted with float / int atomics (imap.c:224-231)
+__global__ void __launch_bounds__(kThreads)
+imap_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restrict__ npot, ClrPop pop, ImapShells sh,
+            int nside, float *__restrict__ data, int *__restrict__ nadd, double rmin_here, double rmax_here)
+{
+  const long long n_cells = (long long)d.nz_here * d.n * d.n;
+  const long long num_pix = 12LL * nside * nside;
+  const double dx = (double)(d.l_box / d.n);
+  const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
+    int ix = (int)(i % d.n);
+    long long row = i / d.n;
+    int iy = (int)(row % d.n);
+    int iz = (int)(row / d.n);
+    double z0 = (iz + d.iz0_here) * dx - d.pos_obs[2];
+    double y0 = iy * dx - d.pos_obs[1];
+    double x0 = ix * dx - d.pos_obs[0];
+    double r0 = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
+    if (!(r0 <= rmax_here && r0 >= rmin_here)) continue;
+    double tmean = clr_lerp(d, r0, pop.nz, 0.0, 0.0);
+    if (!(tmean > 0)) continue;
+    double bias = clr_bg_bz(d, r0, pop.bz);
+    double dnorm = clr_lerp(d, r0, pop.norm, pop.norm_0, pop.norm_f);
+    double rvel = factor_vel * dev_get_rvel(d, npot, ix, iy, iz, x0, y0, z0, r0);
+    double dr_rsd = rvel * clr_bg_v1(d, r0) * clr_bg_ih(d, r0);
+    float temp = (float)(tmean * clr_bias_model(d.bias_model, (double)dens[row * d.pitch + ix], bias) * dnorm);
+    int irad = dev_r_index(sh, r0);
+    int nsub = irad < 0 ? sh.nsub_lo : (irad >= sh.nr ? sh.nsub_hi : __ldg(sh.nsub + irad));
+    double dx_sub = dx / nsub;
+    for (int izz = 0; izz < nsub; izz++) {
+      double z = z0 + (izz + 0.5) * dx_sub;
+      for (int iyy = 0; iyy < nsub; iyy++) {
+        double y = y0 + (iyy + 0.5) * dx_sub;
+        for (int ixx = 0; ixx < nsub; ixx++) {
+          double x = x0 + (ixx + 0.5) * dx_sub;
+          double r, cth, phi;
+          clr_cart2sph(x, y, z, &r, &cth, &phi);
+          int ir = dev_r_index(sh, r + dr_rsd);
+          if (ir >= 0 && ir < sh.nr) {
+            long long pix = clr_ang2pix_ring_zphi(nside, cth, phi);
+            atomicAdd(&data[ir * num_pix + pix], temp);
+            atomicAdd(&nadd[ir * num_pix + pix], 1);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- line-of-sight integrals ---------------------------------------------------------------------
+struct LosPlan {
+  const double *fac1, *fac2;    // kappa: r*D(1+z)*dr, r^2*D(1+z)*dr ; isw: fac1 = 2*pdot*dr
+  const int *irmin, *irmax;     // sample range of each source plane (kappa.c:99-106)
+  const double *inv_r_max;      // kappa only
+  int nplanes;
+  double dr;
+};
+
+// beaming.c:85-116: Hessian stencil of the potential at cell (ix,iy,iz_local), unnormalised
+__device__ __forceinline__ void dev_tidal(const ClrDev &d, const float *__restrict__ g, int ix, int iy, int iz, float t[6])
+{
+  const long long ngx = d.pitch, plane = ngx * d.n;
+  long long x0 = ix, xh = ix + 1 == d.n ? 0 : ix + 1, xl = ix == 0 ? d.n - 1 : ix - 1;
+  long long y0 = (long long)iy * ngx, yh = (long long)(iy + 1 == d.n ? 0 : iy + 1) * ngx, yl = (long long)(iy == 0 ? d.n - 1 : iy - 1) * ngx;
+  long long z0 = iz * plane;
+  long long zh = ((iz == d.nz_here - 1) ? (long long)(d.nz_here + 1) : iz + 1) * plane;
+  long long zl = ((iz == 0) ? (long long)d.nz_here : iz - 1) * plane;
+  float c = g[x0 + y0 + z0];
+  t[0] = (g[xh + y0 + z0] + g[xl + y0 + z0] - 2 * c);
+  t[3] = (g[x0 + yh + z0] + g[x0 + yl + z0] - 2 * c);
+  t[1] = (float)(0.25 * (double)(g[xh + yh + z0] + g[xl + yl + z0] - g[xh + yl + z0] - g[xl + yh + z0]));
+  t[5] = (g[x0 + y0 + zh] + g[x0 + y0 + zl] - 2 * c);
+  // the reference pairs the terms differently at the slab edges (beaming.c:92-107): same operands,
+  // same left-to-right order hi,lo,-,- so one expression serves the three branches
+  if (iz == d.nz_here - 1 && d.nz_here > 1) {
+    t[2] = (float)(0.25 * (double)(g[xh + y0 + zh] + g[xl + y0 + zl] - g[xh + y0 + zl] - g[xl + y0 + zh]));
+    t[4] = (float)(0.25 * (double)(g[x0 + yh + zh] + g[x0 + yl + zl] - g[x0 + yh + zl] - g[x0 + yl + zh]));
+  } else {
+    t[2] = (float)(0.25 * (double)(g[xh + y0 + zh] + g[xl + y0 + zl] - g[xh + y0 + zl] - g[xl + y0 + zh]));
+    t[4] = (float)(0.25 * (double)(g[x0 + yh + zh] + g[x0 + yl + zl] - g[x0 + yh + zl] - g[x0 + yl + zh]));
+  }
+}
+
+// NGP cell of a sample (beaming.c:148-157); returns false when the plane is not in this slab
+__device__ __forceinline__ bool dev_ngp(const ClrDev &d, const double xn[3], int c[3])
+{
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    long v = (long)(xn[ax] + 0.5);
+    if (v >= d.n) v -= d.n; else if (v < 0) v += d.n;
+    c[ax] = (int)v;
+  }
+  c[2] -= d.iz0_here;
+  return c[2] >= 0 && c[2] < d.nz_here;
+}
+
+template <bool KAPPA>
+__global__ void __launch_bounds__(kThreads)
+los_kernel(const ClrDev d, const float *__restrict__ npot, const double *__restrict__ pos, long long num_pix, LosPlan pl,
+           float *__restrict__ data)
+{
+  const double idx = (double)(d.n / d.l_box);
+  for (long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x; ip < num_pix; ip += (long long)gridDim.x * blockDim.x) {
+    double u[3] = {pos[3 * ip], pos[3 * ip + 1], pos[3 * ip + 2]};
+    double rot[6];
+    if (KAPPA) {
+      // kappa.c:128-145
+      double prefac = idx * idx;
+      double cth = u[2], sth, cph = 1, sph = 0;
+      if (cth >= 1) cth = 1;
+      if (cth <= -1) cth = -1;
+      sth = sqrt((1 - cth) * (1 + cth));
+      if (sth != 0) { cph = u[0] / sth; sph = u[1] / sth; }
+      rot[0] = (cth * cth * cph * cph + sph * sph) * prefac;
+      rot[1] = (2 * cph * sph * (cth * cth - 1)) * prefac;
+      rot[2] = (-2 * cth * sth * cph) * prefac;
+      rot[3] = (cth * cth * sph * sph + cph * cph) * prefac;
+      rot[4] = (-2 * cth * sth * sph) * prefac;
+      rot[5] = (sth * sth) * prefac;
+    }
+    double acc1 = 0, acc2 = 0;
+    for (int ipl = 0; ipl < pl.nplanes; ipl++) {
+      int irmin = __ldg(pl.irmin + ipl), irmax = __ldg(pl.irmax + ipl);
+      for (int irr = irmin; irr <= irmax; irr++) {
+        double rm = (irr + 0.5) * pl.dr;
+        double xn[3];
+        int c[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) xn[ax] = (rm * u[ax] + d.pos_obs[ax]) * idx;
+        if (dev_ngp(d, xn, c)) {
+          if (KAPPA) {
+            float t[6];
+            dev_tidal(d, npot, c[0], c[1], c[2], t);
+            double dotp = 0;
+#pragma unroll
+            for (int ax = 0; ax < 6; ax++) dotp += rot[ax] * t[ax];
+            acc1 += dotp * __ldg(pl.fac1 + irr);
+            acc2 += dotp * __ldg(pl.fac2 + irr);
+          } else {
+            float pd = npot[c[0] + (long long)c[1] * d.pitch + (long long)c[2] * d.pitch * d.n];
+            acc1 += pd * __ldg(pl.fac1 + irr);
+          }
+        }
+      }
+      float *o = data + (long long)ipl * num_pix + ip;
+      double add = KAPPA ? (acc1 - __ldg(pl.inv_r_max + ipl) * acc2) : acc1;
+      *o = (float)((double)(*o) + add);
+    }
+  }
+}
+
+int grid_for(clr_ctx *c, long long items, int per_sm)
+{
+  long long g = (items + kThreads - 1) / kThreads, cap = (long long)c->sm_count * per_sm;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+static double host_lerp(const clr_ctx *c, double r, const std::vector<double> &f, double f0, double ff)
+{
+  if (r <= 0) return f0;
+  else if (r >= c->h_r[CLR_NA - 1]) return ff;
+  int ir = (int)(r * c->p.glob_idr);
+  return f[ir] + (f[ir + 1] - f[ir]) * (r - c->h_r[ir]) * c->p.glob_idr;
+}
+
+int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd)
+{
+  clr_ctx::Pop &P = c->imap[ipop];
+  CLR_CHECK(P.set && P.nr > 0, "imap population %d not set", ipop);
+  CLR_CHECK(P.have_norm, "imap population %d has no normalisation", ipop);
+  const int nr = P.nr;
+  const long long num_pix = 12LL * P.nside * P.nside;
+  // imap.c:151-174: sub-sampling of each shell (host, double)
+  double dx = (double)(c->p.l_box / c->p.n_grid);
+  double pixel_size = sqrt(4 * M_PI / num_pix);
+  std::vector<int> nsub(nr);
+  for (int i = 0; i < nr; i++) {
+    double r0 = P.r0[i], rf = P.rf[i];
+    double vol = (rf * rf * rf - r0 * r0 * r0) * pixel_size * pixel_size / 3;
+    double sct = r0 * pixel_size, scr = rf - r0, scv = pow(vol, 0.333333);
+    double sc0 = fmin(scv, fmin(sct, scr));
+    nsub[i] = (int)(dx / sc0 + 0.5) + 1;
+  }
+  float *d_r0 = nullptr, *d_rf = nullptr, *d_data = nullptr;
+  int *d_nsub = nullptr, *d_nadd = nullptr;
+  CLR_CUDA(cudaMalloc(&d_r0, nr * sizeof(float)));
+  CLR_CUDA(cudaMalloc(&d_rf, nr * sizeof(float)));
+  CLR_CUDA(cudaMalloc(&d_nsub, nr * sizeof(int)));
+  CLR_CUDA(cudaMalloc(&d_data, (size_t)nr * num_pix * sizeof(float)));
+  CLR_CUDA(cudaMalloc(&d_nadd, (size_t)nr * num_pix * sizeof(int)));
+  CLR_CUDA(cudaMemcpyAsync(d_r0, P.r0.data(), nr * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_rf, P.rf.data(), nr * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_nsub, nsub.data(), nr * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemsetAsync(d_data, 0, (size_t)nr * num_pix * sizeof(float), c->stream));
+  CLR_CUDA(cudaMemsetAsync(d_nadd, 0, (size_t)nr * num_pix * sizeof(int), c->stream));
+  ImapShells sh{d_r0, d_rf, d_nsub, nr, nsub[0], nsub[nr - 1]};
+  ClrPop pop{P.d_a, P.d_b, P.d_norm, P.norm_0, P.norm_f};
+  {
+    StageScope sc(c, "imap_paint", 1);
+    long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
+    imap_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->d_npot, pop, sh, P.nside, d_data, d_nadd,
+                                                                      (double)P.r0[0] - 20., (double)P.rf[nr - 1] + 20.);
+    CLR_CUDA(cudaGetLastError());
+  }
+  CLR_CUDA(cudaMemcpyAsync(h_data, d_data, (size_t)nr * num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(h_nadd, d_nadd, (size_t)nr * num_pix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_r0); cudaFree(d_rf); cudaFree(d_nsub); cudaFree(d_data); cudaFree(d_nadd);
+  return 0;
+}
+
+int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf, float *h_data)
+{
+  CLR_CHECK(nplanes > 0 && nplanes <= CLR_NPLANES_MAX && num_pix > 0, "LOS maps: bad plane/pixel count");
+  // kappa.c:89-116 / isw.c:88-113: radial sampling and kernels (host, double)
+  int nr = c->p.n_grid / 2;                       // get_radial_params (common.c:333-337), NSAMP_RAD=1
+  double dr = c->p.r_max / nr, idr = 1. / dr;
+  std::vector<int> irmin(nplanes), irmax(nplanes);
+  std::vector<double> inv_r_max(nplanes), fac1(nr), fac2(nr);
+  for (int i = 0; i < nplanes; i++) {
+    int i_r_here = (int)(rf[i] * idr + 0.5);
+    inv_r_max[i] = 1. / (i_r_here * dr);
+    irmax[i] = std::min(i_r_here, nr - 1);
+  }
+  irmin[0] = 0;
+  for (int i = 1; i < nplanes; i++) irmin[i] = irmax[i - 1] + 1;
+  for (int i = 0; i < nr; i++) {
+    double rm = (i + 0.5) * dr;
+    if (which == 0) {
+      double pg = host_lerp(c, rm, c->h_d1, 1, c->h_d1[CLR_NA - 1]) * (1 + host_lerp(c, rm, c->h_z, 0, c->h_z[CLR_NA - 1]));
+      fac1[i] = rm * pg * dr;
+      fac2[i] = rm * rm * pg * dr;
+    } else {
+      fac1[i] = 2 * host_lerp(c, rm, c->h_pd, c->h_pd[0], c->h_pd[CLR_NA - 1]) * dr;
+      fac2[i] = 0;
+    }
+  }
+  double *d_pos = nullptr, *d_fac = nullptr, *d_inv = nullptr;
+  int *d_ir = nullptr;
+  float *d_data = nullptr;
+  CLR_CUDA(cudaMalloc(&d_pos, (size_t)3 * num_pix * sizeof(double)));
+  CLR_CUDA(cudaMalloc(&d_fac, (size_t)2 * nr * sizeof(double)));
+  CLR_CUDA(cudaMalloc(&d_inv, nplanes * sizeof(double)));
+  CLR_CUDA(cudaMalloc(&d_ir, 2 * nplanes * sizeof(int)));
+  CLR_CUDA(cudaMalloc(&d_data, (size_t)nplanes * num_pix * sizeof(float)));
+  CLR_CUDA(cudaMemcpyAsync(d_pos, h_pos, (size_t)3 * num_pix * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_fac, fac1.data(), nr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_fac + nr, fac2.data(), nr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_inv, inv_r_max.data(), nplanes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_ir, irmin.data(), nplanes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(d_ir + nplanes, irmax.data(), nplanes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemsetAsync(d_data, 0, (size_t)nplanes * num_pix * sizeof(float), c->stream));
+  LosPlan pl{d_fac, d_fac + nr, d_ir, d_ir + nplanes, d_inv, nplanes, dr};
+  {
+    StageScope sc(c, which == 0 ? "kappa_los" : "isw_los", 1);
+    if (which == 0)
+      los_kernel<true><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_pos, num_pix, pl, d_data);
+    else
+      los_kernel<false><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_pos, num_pix, pl, d_data);
+    CLR_CUDA(cudaGetLastError());
+  }
+  CLR_CUDA(cudaMemcpyAsync(h_data, d_data, (size_t)nplanes * num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_pos); cudaFree(d_fac); cudaFree(d_inv); cudaFree(d_ir); cudaFree(d_data);
+  return 0;
+}

@@ -1,0 +1,464 @@
+// Source catalogue kernels: per-cell Poisson sampling, ordered scan, in-cell placement + RSD +
+// base pixel, spherical properties, and the RSD estimator used under "beaming".
+// Replaces srcs_set_cartesian_single (srcs.c:120-283), srcs_get_local_properties_single
+// (srcs.c:386-416) and the RSD parts of the beam hooks (srcs.c:425-443, 486-504, 656-662).
+// Compiled with -fmad=false: counts and pixel indices must be bit-exact against the CPU oracle
+// for identical uniform draws, so double arithmetic must round like scalar C code.
+#include "clr_internal.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCellsPerThread = 4;
+constexpr int kChunk = kThreads * kCellsPerThread;   // cells per CTA chunk (flat, x fastest)
+
+// ---- gsl_ran_poisson (GSL randist/poisson.c) and its helpers, restated for the device ---------
+__device__ double dev_gamma_large(ClrStream &s, double a)
+{
+  double sqa = sqrt(2 * a - 1), x, y, v;
+  do {
+    do {
+      y = tan(3.14159265358979323846 * s.next());
+      x = sqa * y + a - 1;
+    } while (x <= 0);
+    v = s.next();
+  } while (v > (1 + y * y) * exp((a - 1) * log(x / (a - 1)) - sqa * y));
+  return x;
+}
+__device__ double dev_gamma_int(ClrStream &s, unsigned int a)
+{
+  if (a < 12) {
+    double prod = 1;
+    for (unsigned int i = 0; i < a; i++) prod *= s.next_pos();
+    return -log(prod);
+  }
+  return dev_gamma_large(s, (double)a);
+}
+__device__ double dev_stirling(double y1)
+{
+  double y2 = y1 * y1;
+  return (13860.0 - (462.0 - (132.0 - (99.0 - 140.0 / y2) / y2) / y2) / y2) / y1 / 166320.0;
+}
+// Kachitvichyanukul & Schmeiser BINV/BTPE as laid out in GSL randist/binomial_tpe.c
+__device__ unsigned int dev_binomial(ClrStream &s, double p, unsigned int n)
+{
+  int ix = 0, flipped = 0;
+  if (n == 0) return 0;
+  if (p > 0.5) { p = 1.0 - p; flipped = 1; }
+  double q = 1 - p, sr = p / q, np = n * p;
+  if (np < 14) {
+    double f0 = pow(q, (double)n);
+    bool done = false;
+    while (!done) {
+      double f = f0, u = s.next();
+      for (ix = 0; ix <= 110; ++ix) {
+        if (u < f) { done = true; break; }
+        u -= f;
+        f *= sr * (n - ix) / (ix + 1);
+      }
+    }
+  } else {
+    double ffm = np + p;
+    int m = (int)ffm;
+    double xm = m + 0.5, npq = np * q;
+    double p1 = floor(2.195 * sqrt(npq) - 4.6 * q) + 0.5;
+    double xl = xm - p1, xr = xm + p1;
+    double c = 0.134 + 20.5 / (15.3 + m);
+    double p2 = p1 * (1.0 + c + c);
+    double al = (ffm - xl) / (ffm - xl * p);
+    double lambda_l = al * (1.0 + 0.5 * al);
+    double ar = (xr - ffm) / (xr * q);
+    double lambda_r = ar * (1.0 + 0.5 * ar);
+    double p3 = p2 + c / lambda_l;
+    double p4 = p3 + c / lambda_r;
+    for (;;) {
+      double var, accept;
+      double u = s.next() * p4;
+      double v = s.next();
+      if (u <= p1) { ix = (int)(xm - p1 * v + u); break; }
+      else if (u <= p2) {
+        double x = xl + (u - p1) / c;
+        v = v * c + 1.0 - fabs(x - xm) / p1;
+        if (v > 1.0 || v <= 0.0) continue;
+        ix = (int)x;
+      } else if (u <= p3) {
+        ix = (int)(xl + log(v) / lambda_l);
+        if (ix < 0) continue;
+        v *= ((u - p2) * lambda_l);
+      } else {
+        ix = (int)(xr - log(v) / lambda_r);
+        if (ix > (double)n) continue;
+        v *= ((u - p3) * lambda_r);
+      }
+      int k = abs(ix - m);
+      if (k <= 20) {
+        double g = (n + 1) * sr, f = 1.0;
+        var = v;
+        if (m < ix) { for (int i = m + 1; i <= ix; i++) f *= (g / i - sr); }
+        else if (m > ix) { for (int i = ix + 1; i <= m; i++) f /= (g / i - sr); }
+        accept = f;
+      } else {
+        var = log(v);
+        if (k < npq / 2 - 1) {
+          double amaxp = k / npq * ((k * (k / 3.0 + 0.625) + (1.0 / 6.0)) / npq + 0.5);
+          double ynorm = -(k * k / (2.0 * npq));
+          if (var < ynorm - amaxp) break;
+          if (var > ynorm + amaxp) continue;
+        }
+        double x1 = ix + 1.0, w1 = n - ix + 1.0, f1 = m + 1.0, z1 = n + 1.0 - m;
+        accept = xm * log(f1 / x1) + (n - m + 0.5) * log(z1 / w1) + (ix - m) * log(w1 * p / (x1 * q))
+                 + dev_stirling(f1) + dev_stirling(z1) - dev_stirling(x1) - dev_stirling(w1);
+      }
+      if (var <= accept) break;
+    }
+  }
+  return flipped ? (n - ix) : (unsigned int)ix;
+}
+__device__ unsigned int dev_poisson(ClrStream &s, double mu)
+{
+  unsigned int k = 0;
+  while (mu > 10) {
+    unsigned int m = (unsigned int)(mu * (7.0 / 8.0));
+    double X = dev_gamma_int(s, m);
+    if (X >= mu) return k + dev_binomial(s, mu / X, m - 1);
+    k += m;
+    mu -= X;
+  }
+  double emu = exp(-mu), prod = 1.0;
+  do {
+    prod *= s.next();
+    k++;
+  } while (prod > emu);
+  return k - 1;
+}
+
+// ---- pass 1: lambda and Poisson count per cell (srcs.c:156-184) --------------------------------
+// counts: int32 per cell, unpadded flat order ix + n*(iy + n*iz_local); chunk_tot[chunk] = sum.
+__global__ void __launch_bounds__(kThreads)
+poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint32_t seed, int ipop,
+               int32_t *__restrict__ counts, int32_t *__restrict__ chunk_tot, long long n_cells)
+{
+  const double dx = (double)(d.l_box / d.n);       // float division, as in the reference (srcs.c:147)
+  const double cell_vol = dx * dx * dx;
+  const double rcut = (double)(d.l_box / 2) + 20.;
+  __shared__ int red[kThreads / 32];
+  for (long long chunk = blockIdx.x; chunk * kChunk < n_cells; chunk += gridDim.x) {
+    int local = 0;
+#pragma unroll
+    for (int q = 0; q < kCellsPerThread; q++) {
+      long long i = chunk * kChunk + q * kThreads + threadIdx.x;
+      if (i >= n_cells) continue;
+      int ix = (int)(i % d.n);
+      long long row = i / d.n;
+      int iy = (int)(row % d.n);
+      int iz = (int)(row / d.n);
+      double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
+      double y0 = (iy + 0.0) * dx - d.pos_obs[1];
+      double x0 = (ix + 0.0) * dx - d.pos_obs[0];
+      double r = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
+      int npp = 0;
+      if (r < rcut) {
+        double ndens = clr_bg_nz(d, r, pop.nz);
+        if (ndens > 0) {
+          double bias = clr_bg_bz(d, r, pop.bz);
+          double dnorm = clr_lerp(d, r, pop.norm, pop.norm_0, pop.norm_f);
+          double delta = dens[row * d.pitch + ix];
+          double lambda = ndens * cell_vol * clr_bias_model(d.bias_model, delta, bias) * dnorm;
+          unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
+          ClrStream s(seed, 1 + 2 * ipop, gcell);
+          npp = (int)dev_poisson(s, lambda);
+        }
+      }
+      counts[i] = npp;
+      local += npp;
+    }
+    // CTA total of the chunk
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < kThreads / 32; w++) t += red[w];
+      chunk_tot[chunk] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// exclusive scan of the chunk totals (one CTA; a few MB at most). offs[n_chunks] = grand total.
+__global__ void __launch_bounds__(1024)
+scan_chunks_kernel(const int32_t *__restrict__ tot, long long *__restrict__ offs, long long n_chunks)
+{
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  long long per = (n_chunks + 1023) / 1024;
+  long long b = t * per, e = b + per < n_chunks ? b + per : n_chunks;
+  long long s = 0;
+  for (long long i = b; i < e; i++) s += tot[i];
+  part[t] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    long long v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = t ? part[t - 1] : 0;
+  for (long long i = b; i < e; i++) { offs[i] = run; run += tot[i]; }
+  if (t == 1023) offs[n_chunks] = part[1023];
+}
+
+// srcs.c:87-118 (get_rvel): central differences of the potential, periodic in x,y, z through the
+// halo planes stored after the slab (plane nz_here = left neighbour, nz_here+1 = right neighbour)
+__device__ __forceinline__ double dev_get_rvel(const ClrDev &d, const float *__restrict__ npot, int ix, int iy, int iz,
+                                               double x0, double y0, double z0, double rr)
+{
+  const double idx = (double)(d.n / d.l_box);
+  const long long ngx = d.pitch, plane = ngx * d.n;
+  int ix_hi = ix + 1 == d.n ? 0 : ix + 1, ix_lo = ix == 0 ? d.n - 1 : ix - 1;
+  int iy_hi = iy + 1 == d.n ? 0 : iy + 1, iy_lo = iy == 0 ? d.n - 1 : iy - 1;
+  long long pz_hi = (iz == d.nz_here - 1) ? (long long)(d.nz_here + 1) : iz + 1;
+  long long pz_lo = (iz == 0) ? (long long)d.nz_here : iz - 1;
+  double u0 = x0 / rr, u1 = y0 / rr, u2 = z0 / rr;
+  float v0 = npot[ix_hi + iy * ngx + iz * plane] - npot[ix_lo + iy * ngx + iz * plane];
+  float v1 = npot[ix + iy_hi * ngx + iz * plane] - npot[ix + iy_lo * ngx + iz * plane];
+  float v2 = npot[ix + iy * ngx + pz_hi * plane] - npot[ix + iy * ngx + pz_lo * plane];
+  return 0.5 * idx * (v0 * u0 + v1 * u1 + v2 * u2);
+}
+
+// ---- pass 2: positions, RSD, base pixel (srcs.c:238-276) ---------------------------------------
+__global__ void __launch_bounds__(kThreads)
+place_kernel(const ClrDev d, const float *__restrict__ npot, const int32_t *__restrict__ counts,
+             const long long *__restrict__ chunk_offs, uint32_t seed, int ipop, float4 *__restrict__ pos,
+             int32_t *__restrict__ ipix, long long n_cells)
+{
+  const double dx = (double)(d.l_box / d.n);
+  const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
+  __shared__ int wsum[kThreads / 32];
+  for (long long chunk = blockIdx.x; chunk * kChunk < n_cells; chunk += gridDim.x) {
+    long long base = chunk_offs[chunk];
+    if (chunk_offs[chunk + 1] == base) continue;           // uniform per CTA: empty chunk
+    // thread t owns cells [4t, 4t+4) of the chunk so that the in-CTA scan follows the cell order
+    long long i0 = chunk * kChunk + (long long)threadIdx.x * kCellsPerThread;
+    int c[kCellsPerThread], tsum = 0;
+#pragma unroll
+    for (int q = 0; q < kCellsPerThread; q++) { c[q] = (i0 + q < n_cells) ? counts[i0 + q] : 0; tsum += c[q]; }
+    int incl = tsum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < w; k++) woff += wsum[k];
+    long long off = base + woff + incl - tsum;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kCellsPerThread; q++) {
+      int npp = c[q];
+      if (npp > 0) {
+        long long i = i0 + q;
+        int ix = (int)(i % d.n);
+        long long row = i / d.n;
+        int iy = (int)(row % d.n);
+        int iz = (int)(row / d.n);
+        double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
+        double y0 = (iy + 0.0) * dx - d.pos_obs[1];
+        double x0 = (ix + 0.0) * dx - d.pos_obs[0];
+        double rr = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
+        double rvel = factor_vel * dev_get_rvel(d, npot, ix, iy, iz, x0, y0, z0, rr);
+        float dz_rsd = (float)(rvel * clr_bg_v1(d, rr));
+        unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
+        ClrStream s(seed, 2 + 2 * ipop, gcell);
+        for (int ip = 0; ip < npp; ip++) {
+          float px = (float)(x0 + dx * (s.next() - 0.5));
+          float py = (float)(y0 + dx * (s.next() - 0.5));
+          float pz = (float)(z0 + dx * (s.next() - 0.5));
+          // vec2pix_ring (chealpix) on the float-rounded position, then ring2nest (srcs.c:265-270)
+          double vx = px, vy = py, vz = pz;
+          double vlen = sqrt(vx * vx + vy * vy + vz * vz);
+          long long pr = clr_ang2pix_ring_zphi(d.nside_base, vz / vlen, atan2(vy, vx));
+          pos[off] = make_float4(px, py, pz, dz_rsd);
+          ipix[off] = clr_ring2nest(d.nside_base, (int)pr);
+          off++;
+        }
+      }
+
+    }
+  }
+}
+
+// ---- srcs_get_local_properties_single (srcs.c:386-416) -----------------------------------------
+__global__ void __launch_bounds__(kThreads)
+local_props_kernel(const ClrDev d, const float4 *__restrict__ pos, float *__restrict__ srcs, long long nsrc)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nsrc; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = pos[i];
+    double r, cth, phi;
+    clr_cart2sph(p.x, p.y, p.z, &r, &cth, &phi);
+    float *o = srcs + 9 * i;
+    o[0] = (float)(57.2957795 * phi);
+    o[1] = (float)(90 - 57.2957795 * acos(cth));
+    o[2] = (float)clr_bg_z(d, r);
+    o[3] = p.w;
+    o[4] = -1.f; o[5] = -1.f; o[6] = 0.f; o[7] = 0.f; o[8] = 0.f;
+  }
+}
+
+// ---- RSD under beaming: CIC-interpolated potential gradient along the line of sight -----------
+// beaming.c:31-117 (get_element, RETURN_VEL) + beaming.c:183-265 (trilinear branch)
+__device__ __forceinline__ void dev_vel_element(const ClrDev &d, const float *__restrict__ npot, int ix, int iy, int iz, float v[3])
+{
+  const long long ngx = d.pitch, plane = ngx * d.n;
+  int ix_hi = ix + 1 == d.n ? 0 : ix + 1, ix_lo = ix == 0 ? d.n - 1 : ix - 1;
+  int iy_hi = iy + 1 == d.n ? 0 : iy + 1, iy_lo = iy == 0 ? d.n - 1 : iy - 1;
+  long long pz_hi = (iz == d.nz_here - 1) ? (long long)(d.nz_here + 1) : iz + 1;
+  long long pz_lo = (iz == 0) ? (long long)d.nz_here : iz - 1;
+  v[0] = npot[ix_hi + iy * ngx + iz * plane] - npot[ix_lo + iy * ngx + iz * plane];
+  v[1] = npot[ix + iy_hi * ngx + iz * plane] - npot[ix + iy_lo * ngx + iz * plane];
+  v[2] = npot[ix + iy * ngx + pz_hi * plane] - npot[ix + iy * ngx + pz_lo * plane];
+}
+
+__global__ void __launch_bounds__(kThreads)
+beam_rsd_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__restrict__ pos, float *__restrict__ srcs,
+                long long nsrc, int do_pre, int do_post)
+{
+  const double idx = (double)(d.n / d.l_box);
+  const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nsrc; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = pos[i];
+    float *o = srcs + 9 * i;
+    float acc = do_pre ? 0.f : o[3];
+    float pp[3] = {p.x, p.y, p.z};
+    float r2 = __fadd_rn(__fadd_rn(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y)), __fmul_rn(p.z, p.z));
+    double r = sqrt((double)r2);
+    double ir = 1. / (r > 0.001 ? r : 0.001);
+    double xn[3], u[3];
+    long ix0[3], ix1[3];
+    double h0x[3];
+    float h1x[3];
+    for (int ax = 0; ax < 3; ax++) {
+      xn[ax] = (pp[ax] + d.pos_obs[ax]) * idx;
+      u[ax] = pp[ax] * ir;
+      ix0[ax] = (long)(xn[ax]);
+      h0x[ax] = xn[ax] - ix0[ax];
+      h1x[ax] = (float)(1 - h0x[ax]);
+      ix1[ax] = ix0[ax] + 1;
+      if (ix0[ax] >= d.n) ix0[ax] -= d.n; else if (ix0[ax] < 0) ix0[ax] += d.n;
+      if (ix1[ax] >= d.n) ix1[ax] -= d.n; else if (ix1[ax] < 0) ix1[ax] += d.n;
+    }
+    ix0[2] -= d.iz0_here; ix1[2] -= d.iz0_here;
+    float v[3] = {0.f, 0.f, 0.f};
+    bool added = false;
+    for (int cz = 0; cz < 2; cz++) {
+      long izc = cz ? ix1[2] : ix0[2];
+      if (izc >= 0 && izc < d.nz_here) {
+        float w4[4], v4[4][3];
+        if (cz == 0) {
+          w4[0] = h1x[2] * h1x[1] * h1x[0]; w4[1] = (float)(h1x[2] * h1x[1] * h0x[0]);
+          w4[2] = (float)(h1x[2] * h0x[1] * h1x[0]); w4[3] = (float)(h1x[2] * h0x[1] * h0x[0]);
+        } else {
+          w4[0] = (float)(h0x[2] * h1x[1] * h1x[0]); w4[1] = (float)(h0x[2] * h1x[1] * h0x[0]);
+          w4[2] = (float)(h0x[2] * h0x[1] * h1x[0]); w4[3] = (float)(h0x[2] * h0x[1] * h0x[0]);
+        }
+        added = true;
+        dev_vel_element(d, npot, (int)ix0[0], (int)ix0[1], (int)izc, v4[0]);
+        dev_vel_element(d, npot, (int)ix1[0], (int)ix0[1], (int)izc, v4[1]);
+        dev_vel_element(d, npot, (int)ix0[0], (int)ix1[1], (int)izc, v4[2]);
+        dev_vel_element(d, npot, (int)ix1[0], (int)ix1[1], (int)izc, v4[3]);
+        for (int ax = 0; ax < 3; ax++)
+          v[ax] += (v4[0][ax] * w4[0] + v4[1][ax] * w4[1] + v4[2][ax] * w4[2] + v4[3][ax] * w4[3]);
+      }
+    }
+    if (added) {
+      float vr = (float)(0.5 * idx * (v[0] * u[0] + v[1] * u[1] + v[2] * u[2]));
+      acc += vr;
+    }
+    if (do_post) {
+      double z = o[2];
+      double rz = clr_r_of_z(d, z);
+      double vg = clr_bg_v1(d, rz);
+      acc = (float)((double)acc * (vg * factor_vel));
+    }
+    o[3] = acc;
+    if (do_pre) { o[4] = 0.f; o[5] = 0.f; }
+  }
+}
+
+int grid_for(clr_ctx *c, long long blocks, int per_sm)
+{
+  long long cap = (long long)c->sm_count * per_sm;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  CLR_CHECK(P.set, "srcs population %d has no tables (clr_set_srcs)", ipop);
+  CLR_CHECK(P.have_norm, "srcs population %d has no normalisation (clr_compute_density_normalization)", ipop);
+  const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
+  const long long n_chunks = (n_cells + kChunk - 1) / kChunk;
+  if (!P.d_counts) CLR_CUDA(cudaMalloc(&P.d_counts, n_cells * sizeof(int32_t)));
+  size_t need = (size_t)n_chunks * sizeof(int32_t) + (size_t)(n_chunks + 1) * sizeof(long long) + 64;
+  if (clr_ensure_scratch(c, need)) return 1;
+  long long *d_offs = reinterpret_cast<long long *>(c->d_scratch);
+  int32_t *d_tot = reinterpret_cast<int32_t *>(d_offs + n_chunks + 1);
+  ClrPop pop{P.d_a, P.d_b, P.d_norm, P.norm_0, P.norm_f};
+  {
+    StageScope sc(c, "srcs_poisson", 1);
+    poisson_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, pop, seed, ipop, P.d_counts, d_tot, n_cells);
+    CLR_CUDA(cudaGetLastError());
+  }
+  {
+    StageScope sc(c, "srcs_scan", 1);
+    scan_chunks_kernel<<<1, 1024, 0, c->stream>>>(d_tot, d_offs, n_chunks);
+    CLR_CUDA(cudaGetLastError());
+  }
+  long long total = 0;
+  CLR_CUDA(cudaMemcpyAsync(&total, d_offs + n_chunks, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  P.nsrc = total;
+  if ((size_t)total > P.cap_src) {
+    if (P.d_pos) cudaFree(P.d_pos);
+    if (P.d_ipix) cudaFree(P.d_ipix);
+    if (P.d_srcs) cudaFree(P.d_srcs);
+    P.d_pos = nullptr; P.d_ipix = nullptr; P.d_srcs = nullptr;
+    size_t cap = (size_t)total + (size_t)total / 16 + 1024;
+    CLR_CUDA(cudaMalloc(&P.d_pos, cap * 4 * sizeof(float)));
+    CLR_CUDA(cudaMalloc(&P.d_ipix, cap * sizeof(int32_t)));
+    CLR_CUDA(cudaMalloc(&P.d_srcs, cap * 9 * sizeof(float)));
+    P.cap_src = cap;
+  }
+  if (total > 0) {
+    StageScope sc(c, "srcs_place", 1);
+    place_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, P.d_counts, d_offs, seed, ipop,
+                                                                        reinterpret_cast<float4 *>(P.d_pos), P.d_ipix, n_cells);
+    CLR_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int clr_srcs_local(clr_ctx *c, int ipop)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  if (P.nsrc == 0) return 0;
+  StageScope sc(c, "srcs_local", 1);
+  local_props_kernel<<<grid_for(c, (P.nsrc + kThreads - 1) / kThreads, 8), kThreads, 0, c->stream>>>(
+      c->dev, reinterpret_cast<const float4 *>(P.d_pos), P.d_srcs, P.nsrc);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int clr_srcs_beam(clr_ctx *c, int ipop)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  if (P.nsrc == 0) return 0;
+  StageScope sc(c, "srcs_beam_rsd", 1);
+  beam_rsd_kernel<<<grid_for(c, (P.nsrc + kThreads - 1) / kThreads, 8), kThreads, 0, c->stream>>>(
+      c->dev, c->d_npot, reinterpret_cast<const float4 *>(P.d_pos), P.d_srcs, P.nsrc, 1, 1);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,158 @@
+/* colore_b200 -- C ABI of the B200-native density-field -> catalogue/maps path of CoLoRe.
+ *
+ * This header is the drop-in boundary: plain C, plain pointers and sizes. Each entry point
+ * names the reference function(s) it replaces (file:line under damonge/CoLoRe src/). The
+ * reference-side glue that maps `ParamCoLoRe *par` onto these calls is integration/colore_gpu_glue.c
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - All functions return 0 on success, non-zero on failure; clr_last_error() describes the last
+ *    failure of the calling thread's context. The glue maps failures to report_error(1,...)
+ *    (common.c:290-306), i.e. the reference's "print and exit(1)" behaviour.
+ *  - Host grids use the reference layout (fourier.c:46-51,328): real index
+ *    ix + 2*(N/2+1)*(iy + N*iz_local), complex index kx + (N/2+1)*(ky + N*kz_local).
+ *  - One context per process and per GPU (the reference is one `par` per MPI rank, common.c:216).
+ *  - There is NO CPU fallback: every compute entry point fails if no CUDA device is present.
+ */
+#ifndef COLORE_B200_H
+#define COLORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLR_NA 5001            /* common.h:132 */
+#define CLR_NPOP_MAX 10        /* common.h:133 */
+#define CLR_NPLANES_MAX 100    /* common.h:134 */
+
+#define CLR_GRID_DENS 0        /* par->grid_dens / grid_dens_f (common.h:283-284) */
+#define CLR_GRID_NPOT 1        /* par->grid_npot / grid_npot_f (common.h:285-286) */
+
+#define CLR_DENS_TYPE_LGNR 0   /* common.h:115-118 */
+#define CLR_DENS_TYPE_1LPT 1
+#define CLR_DENS_TYPE_2LPT 2
+#define CLR_DENS_TYPE_CLIP 3
+
+typedef struct clr_ctx clr_ctx;
+
+/* The scalar / table subset of ParamCoLoRe (common.h:220-381) that the path reads.
+ * Tables are CLR_NA doubles, copied at clr_create time. */
+typedef struct {
+  int32_t n_grid;            /* common.h:273 */
+  int32_t nz_here, iz0_here; /* common.h:275-276; init_fftw fourier.c:127-209 */
+  int32_t dens_type;         /* common.h:267 */
+  int32_t bias_model;        /* 1,2,3: _BIAS_MODEL_* of common.h:414-431 (compile-time in the reference) */
+  int32_t do_smoothing;      /* common.h:265 */
+  int32_t smooth_potential;  /* common.h:266 */
+  int32_t nside_base;        /* common.h:378, io.c:224-244 */
+  int32_t numk;              /* common.h:254 */
+  uint32_t seed_rng;         /* common.h:271 */
+  float l_box;               /* flouble, common.h:274 */
+  float reserved_;
+  double pos_obs[3];         /* common.h:294 */
+  double r2_smooth;          /* common.h:264 */
+  double prefac_lensing;     /* common.h:237 */
+  double fgrowth_0, hubble_0, OmegaM, n_scal; /* common.h:228-236 */
+  double r_max;              /* common.h:240 */
+  double glob_idr;           /* common.h:251 */
+  double logkmin, logkmax, idlogk; /* common.h:255-257 */
+  const double *logkarr, *pkarr;   /* numk entries, common.h:258-259 */
+  const double *r_arr_r2z, *z_arr_r2z, *growth_d_arr, *growth_d2_arr, *growth_v_arr,
+               *growth_pd_arr, *ihub_arr;     /* common.h:244-250 */
+  const double *a_arr_a2r, *r_arr_a2r;         /* common.h:242-243 */
+} clr_params;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int clr_version(void);
+const char *clr_last_error(void);
+/* number of visible CUDA devices (0 when none / driver missing); never fails */
+int clr_device_count(void);
+/* allocate_fftw + init_fftw (fourier.c:127-238): device grids for the slab, tables uploaded */
+int clr_create(const clr_params *p, int device, clr_ctx **out);
+/* end_fftw / param_colore_free (fourier.c:240-283, io.c:1247-1348) */
+int clr_destroy(clr_ctx *ctx);
+int clr_synchronize(clr_ctx *ctx);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+long long clr_launch_count(clr_ctx *ctx);
+
+/* ---- multi-GPU (one process per GPU; replaces mpi_init common.c:216-274) ----------------- */
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the host (torch.distributed) */
+int clr_comm_unique_id(void *id128);
+int clr_comm_init(clr_ctx *ctx, int rank, int nranks, const void *id128);
+
+/* ---- populations (cosmo.c:549-629 tables; one call per population) ---------------------- */
+int clr_set_srcs(clr_ctx *ctx, int ipop, const double *nz_arr, const double *bz_arr);
+int clr_set_imap(clr_ctx *ctx, int ipop, const double *tz_arr, const double *bz_arr,
+                 int nside, int nr, const float *r0, const float *rf);
+
+/* ---- grids: host <-> device in the reference layout ------------------------------------- */
+int clr_grid_put(clr_ctx *ctx, int which, const float *host_padded);  /* real or complex view */
+int clr_grid_get(clr_ctx *ctx, int which, float *host_padded);
+/* device pointer of a grid (for zero-copy callers that already live on the GPU) */
+int clr_grid_device_ptr(clr_ctx *ctx, int which, void **dptr);
+
+/* ---- Gaussian field (fourier.c) ---------------------------------------------------------- */
+/* create_grids_fourier (fourier.c:285-359) with the counter-based RNG stream */
+int clr_fill_modes(clr_ctx *ctx, uint32_t seed);
+/* fftw_wrap_c2r / fftw_wrap_r2c (fourier.c:81-125), in place on a device grid */
+int clr_fft_c2r(clr_ctx *ctx, int which);
+int clr_fft_r2c(clr_ctx *ctx, int which);
+/* normalisation loop + z-halo + compute_sigma_dens (fourier.c:381-416) on grids already in
+ * real space; out2 = {mean, sigma2_gauss} */
+int clr_normalize_fields(clr_ctx *ctx, double *out2);
+/* the whole of create_cartesian_fields (fourier.c:361-423). inject=0: modes from clr_fill_modes
+ * (seed); inject=1: Fourier modes already placed with clr_grid_put (the reference's own white
+ * noise). out2 = {mean, sigma2_gauss}; sigma2 is also kept in the context. */
+int clr_create_cartesian_fields(clr_ctx *ctx, uint32_t seed, int inject, double *out2);
+int clr_set_sigma2_gauss(clr_ctx *ctx, double sigma2);
+/* refresh the z-halo planes of the potential after clr_grid_put (fourier.c:401-414) */
+int clr_update_halo(clr_ctx *ctx);
+
+/* ---- physical density (density.c) -------------------------------------------------------- */
+/* compute_physical_density_field (density.c:1105-1126): lognormal / clip (LPT: see DESIGN.md) */
+int clr_compute_physical_density_field(clr_ctx *ctx);
+/* compute_density_normalization (density.c:1227-1393). Afterwards the norm tables are resident;
+ * clr_get_norm returns srcs (kind 0) / imap (kind 1) tables: norm_arr[CLR_NA], ends[2] */
+int clr_compute_density_normalization(clr_ctx *ctx);
+int clr_get_norm(clr_ctx *ctx, int kind, int ipop, double *norm_arr, double *ends2, double *zends2);
+int clr_set_norm(clr_ctx *ctx, int kind, int ipop, const double *norm_arr, const double *ends2);
+
+/* ---- sources (srcs.c) -------------------------------------------------------------------- */
+/* srcs_set_cartesian_single (srcs.c:120-283): Poisson counts, scan, positions/RSD/base pixel.
+ * nsrc_out = sources found in this slab. */
+int clr_srcs_set_cartesian(clr_ctx *ctx, int ipop, uint32_t seed, long long *nsrc_out);
+/* per-cell counts of the last clr_srcs_set_cartesian, padded reference layout (srcs.c:125) */
+int clr_srcs_get_counts(clr_ctx *ctx, int ipop, int32_t *nsources_padded);
+/* CatalogCartesian (common.h:163-167): pos[4*n] floats, ipix[n] ints */
+int clr_srcs_get_cartesian(clr_ctx *ctx, int ipop, float *pos4, int32_t *ipix);
+/* srcs_get_local_properties_single (srcs.c:386-416): Src records, 9 floats each (common.h:169-179) */
+int clr_srcs_get_local_properties(clr_ctx *ctx, int ipop, float *srcs9);
+/* RSD under beaming: srcs_beams_preproc/get_beam_properties(lines 486-504)/postproc(656-662).
+ * Updates dz_rsd (and e1=e2=0) of the resident catalogue; fetch with clr_srcs_get_local_properties */
+int clr_srcs_beam_rsd(clr_ctx *ctx, int ipop);
+
+/* ---- maps (imap.c, kappa.c, isw.c, beaming.c) --------------------------------------------- */
+/* imap_set_cartesian_single (imap.c:135-245): data[nr*12*nside^2], nadd likewise (full sky) */
+int clr_imap_set_cartesian(clr_ctx *ctx, int ipop, float *data, int32_t *nadd);
+/* kappa_beams_preproc + kappa_get_beam_properties (kappa.c:39-175) for the pixels `pos`
+ * (unit vectors, hp_shell_alloc common.c:505-552); rf sorted; data[nplanes*num_pix] */
+int clr_kappa_get_beam_properties(clr_ctx *ctx, long long num_pix, const double *pos3, int nplanes,
+                                  const float *rf, float *data);
+/* isw_get_beam_properties (isw.c:78-147) */
+int clr_isw_get_beam_properties(clr_ctx *ctx, long long num_pix, const double *pos3, int nplanes,
+                                const float *rf, float *data);
+
+/* ---- timing helpers for bench.py (CUDA events on the context's stream) -------------------- */
+int clr_timer_start(clr_ctx *ctx);
+int clr_timer_stop_ms(clr_ctx *ctx, float *ms);
+/* last duration of a named kernel family, measured with CUDA events when profiling is on */
+int clr_set_profiling(clr_ctx *ctx, int on);
+int clr_get_stage_ms(clr_ctx *ctx, const char *stage, float *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLORE_B200_H */

@@ -1,0 +1,295 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against
+  (1) the golden fixtures written by the UNMODIFIED reference (tests/golden/*.npz), and
+  (2) the CPU oracle (oracle/colore_oracle.c) on the same seeded inputs.
+
+Bar (north star): integer / index outputs (per-cell counts, pixel ids, nadd) bit-exact given
+identical uniform draws; floating-point fields within the fp32 tolerances written next to each
+assert.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import colore_b200 as cb  # noqa: E402
+from oracle.oracle import RNG_MT, RNG_PHILOX, Oracle, tables_from_dump  # noqa: E402
+
+GOLDEN = ["ref_n32_lognormal", "ref_n32_clip"]
+
+
+def _load(golden_dir, name):
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    t = tables_from_dump(g)
+    return g, t
+
+
+def _par(t, **kw):
+    return cb.ParamCoLoRe(t, int(t["n_grid"]), dens_type=int(t["dens_type"]), seed=int(t["seed"]),
+                          nside_base=int(t["nside_base"]), **kw)
+
+
+@pytest.fixture(scope="module", params=GOLDEN)
+def case(request, golden_dir):
+    g, t = _load(golden_dir, request.param)
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    par = _par(t)
+    yield g, t, o, par
+    par.free()
+
+
+def _real(a, n):
+    return a[:, :, :n]
+
+
+# ------------------------------------------------------------------------------------------ FFT
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256])
+def test_fft_c2r_r2c_vs_oracle(golden_dir, n):
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    o = Oracle(t, n)
+    par = cb.ParamCoLoRe(t, n)
+    rng = np.random.default_rng(n)
+    nc = n // 2 + 1
+    ck = (rng.standard_normal((n, n, nc)) + 1j * rng.standard_normal((n, n, nc))).astype(np.complex64)
+    par.grid_put(cb.GRID_DENS, ck)
+    cb.fftw_wrap_c2r(par, cb.GRID_DENS)
+    got = par.grid_get(cb.GRID_DENS)
+    ref = o.c2r(ck.copy())
+    scale = np.sqrt(np.mean(_real(ref, n).astype(np.float64) ** 2))
+    err = np.abs(_real(got, n) - _real(ref, n)).max() / scale
+    assert err < 2e-5, f"c2r n={n}: max error {err:.2e} of rms (fp32 tolerance 2e-5)"
+    # forward transform of a real field
+    x = np.zeros((n, n, 2 * nc), np.float32)
+    x[:, :, :n] = rng.standard_normal((n, n, n)).astype(np.float32)
+    par.grid_put(cb.GRID_NPOT, x)
+    cb.fftw_wrap_r2c(par, cb.GRID_NPOT)
+    gotk = par.grid_get(cb.GRID_NPOT).view(np.complex64)
+    refk = o.r2c(x.copy())
+    errk = np.abs(gotk - refk).max() / np.sqrt(np.mean(np.abs(refk) ** 2))
+    assert errk < 2e-5, f"r2c n={n}: max error {errk:.2e} of rms"
+    # round trip c2r(r2c(x)) = n^3 x  (size-independent property)
+    cb.fftw_wrap_c2r(par, cb.GRID_NPOT)
+    back = par.grid_get(cb.GRID_NPOT)
+    assert np.abs(_real(back, n) / n ** 3 - _real(x, n)).max() < 2e-5
+    par.free()
+
+
+def test_fft_drops_imag_of_xdc_and_nyquist(golden_dir):
+    """FFTW c2r semantics on non-Hermitian input."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    n, nc = 32, 17
+    par = cb.ParamCoLoRe(t, n)
+    rng = np.random.default_rng(5)
+    ck = (rng.standard_normal((n, n, nc)) + 1j * rng.standard_normal((n, n, nc))).astype(np.complex64)
+    par.grid_put(cb.GRID_DENS, ck)
+    cb.fftw_wrap_c2r(par, cb.GRID_DENS)
+    a = par.grid_get(cb.GRID_DENS)[:, :, :n].copy()
+    # numpy's irfftn follows the same convention (complex axes first, real axis last)
+    ref = np.fft.irfftn(ck.astype(np.complex128), s=(n, n, n), axes=(0, 1, 2)) * n ** 3
+    assert np.abs(a - ref).max() / ref.std() < 2e-5
+    par.free()
+
+
+# ------------------------------------------------------------------------------ Gaussian fields
+def test_fill_modes_vs_oracle(case):
+    g, t, o, par = case
+    dk, pk = o.fill_modes(RNG_PHILOX, int(t["seed"]))
+    cb.fill_modes(par)
+    gd = par.grid_get(cb.GRID_DENS).view(np.complex64)
+    gp = par.grid_get(cb.GRID_NPOT).view(np.complex64)
+    # double arithmetic on both sides: agreement to a few fp32 ulps of each mode
+    for got, ref in ((gd, dk), (gp, pk)):
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
+        assert rel[np.abs(ref) > 0].max() < 5e-7
+        assert np.all(got[np.abs(ref) == 0] == 0)
+
+
+def test_injected_white_noise_matches_reference(case):
+    """Reference's own MT19937 modes injected -> GPU FFT + scaling + sigma vs the reference fields."""
+    g, t, o, par = case
+    n = o.n
+    dk, pk = o.fill_modes(RNG_MT, int(t["seed"]))
+    par.grid_put(cb.GRID_DENS, dk)
+    par.grid_put(cb.GRID_NPOT, pk)
+    mean, s2 = cb.create_cartesian_fields(par, inject=True)
+    dens = par.grid_get(cb.GRID_DENS)
+    npot = par.grid_get(cb.GRID_NPOT)
+    sig = np.sqrt(g["s1_sigma2_gauss"][0])
+    assert np.abs(_real(dens, n) - _real(g["s1_dens_gauss"], n)).max() < 2e-5 * sig
+    assert np.abs(_real(npot, n) - _real(g["s1_npot"], n)).max() < 2e-5 * _real(g["s1_npot"], n).std()
+    assert abs(s2 / g["s1_sigma2_gauss"][0] - 1) < 1e-5
+    assert abs(mean) < 1e-5 * sig
+
+
+def test_own_stream_end_to_end_vs_oracle(case):
+    """GPU counter-based stream, whole create_cartesian_fields, against the oracle's Philox run."""
+    g, t, o, par = case
+    n = o.n
+    dk, pk = o.fill_modes(RNG_PHILOX, int(t["seed"]))
+    dens, npot = o.c2r(dk), o.c2r(pk)
+    o.normalize_fields(dens, npot)
+    _, s2_ref = o.sigma_dens(dens)
+    mean, s2 = cb.create_cartesian_fields(par)
+    got = par.grid_get(cb.GRID_DENS)
+    assert np.abs(_real(got, n) - _real(dens, n)).max() < 2e-5 * np.sqrt(s2_ref)
+    assert abs(s2 / s2_ref - 1) < 1e-5
+
+
+# --------------------------------------------------------------------------- physical density
+def test_physical_density_vs_reference(case):
+    g, t, o, par = case
+    n = o.n
+    par.grid_put(cb.GRID_DENS, g["s1_dens_gauss"])
+    par.set_sigma2_gauss(g["s1_sigma2_gauss"][0])
+    cb.compute_physical_density_field(par)
+    got = par.grid_get(cb.GRID_DENS)
+    ref = g["s2_dens"]
+    # same double arithmetic, CUDA exp vs glibc exp: at most 1 fp32 ulp apart
+    d = np.abs(_real(got, n).astype(np.float64) - _real(ref, n))
+    assert d.max() <= 2.5e-7 * (1 + np.abs(_real(ref, n)).max())
+    assert np.mean(_real(got, n) == _real(ref, n)) > 0.99
+
+
+def test_density_normalization_vs_reference(case):
+    g, t, o, par = case
+    par.grid_put(cb.GRID_DENS, g["s2_dens"])
+    npop = sum(1 for k in t if k.startswith("srcs_bz_"))
+    for i in range(npop):
+        par.set_srcs(i, t[f"srcs_nz_{i}"], t[f"srcs_bz_{i}"])
+    if "imap_bz_0" in t:
+        par.set_imap(0, t["imap_tz_0"], t["imap_bz_0"], 8, g["s4_imap_r0_0"], g["s4_imap_rf_0"])
+    cb.compute_density_normalization(par)
+    for i in range(npop):
+        norm, ends, zends = cb.get_norm(par, 0, i)
+        np.testing.assert_allclose(norm, g[f"s3_srcs_norm_{i}"], rtol=1e-12)
+        np.testing.assert_allclose(ends, g[f"s3_srcs_norm_ends_{i}"], rtol=1e-12)
+        np.testing.assert_allclose(zends, g["s3_znorm_ends"], rtol=1e-13, atol=0)
+    if "imap_bz_0" in t:
+        norm, ends, _ = cb.get_norm(par, 1, 0)
+        np.testing.assert_allclose(norm, g["s3_imap_norm_0"], rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------ sources
+def _setup_sources(g, t, par):
+    par.grid_put(cb.GRID_DENS, g["s2_dens"])
+    par.grid_put(cb.GRID_NPOT, g["s1_npot"])
+    par.update_halo()
+    npop = sum(1 for k in t if k.startswith("srcs_bz_"))
+    for i in range(npop):
+        par.set_srcs(i, t[f"srcs_nz_{i}"], t[f"srcs_bz_{i}"])
+        cb.set_norm(par, 0, i, g[f"s3_srcs_norm_{i}"], g[f"s3_srcs_norm_ends_{i}"])
+    return npop
+
+
+def test_sources_bit_exact_vs_oracle(case):
+    g, t, o, par = case
+    npop = _setup_sources(g, t, par)
+    o.set_halo(g["s1_npot"])
+    seed = int(t["seed"])
+    nsrc = cb.srcs_set_cartesian(par)
+    for ipop in range(npop):
+        ends = g[f"s3_srcs_norm_ends_{ipop}"]
+        ns, tot = o.srcs_poisson(g["s2_dens"], t[f"srcs_nz_{ipop}"], t[f"srcs_bz_{ipop}"], g[f"s3_srcs_norm_{ipop}"],
+                                 ends[0], ends[1], RNG_PHILOX, seed, ipop)
+        assert nsrc[ipop] == tot
+        assert np.array_equal(cb.srcs_get_counts(par, ipop), ns), "per-cell Poisson counts differ"
+        pos_ref, ipix_ref = o.srcs_place(g["s1_npot"], ns, RNG_PHILOX, seed, ipop)
+        pos, ipix = cb.srcs_get_cartesian(par, ipop)
+        assert np.array_equal(ipix, ipix_ref), "base-pixel indices differ"
+        assert np.array_equal(pos[:, :3], pos_ref[:, :3]), "in-cell positions differ"
+        np.testing.assert_allclose(pos[:, 3], pos_ref[:, 3], rtol=2e-6, atol=1e-12)
+        srcs = cb.srcs_get_local_properties(par, ipop)
+        ref = o.srcs_local_properties(pos_ref)
+        np.testing.assert_allclose(srcs[:, :3], ref[:, :3], rtol=3e-7, atol=3e-5)   # ra, dec [deg], z
+        assert np.array_equal(srcs[:, 4:6], ref[:, 4:6])
+        # statistical sanity against the reference's own MT19937 catalogue: same expected number
+        n_ref = g[f"s4_srcs_ipix_{ipop}"].size
+        assert abs(tot - n_ref) < 6 * np.sqrt(n_ref)
+
+
+def test_beam_rsd_vs_oracle(case):
+    g, t, o, par = case
+    _setup_sources(g, t, par)
+    o.set_halo(g["s1_npot"])
+    cb.srcs_set_cartesian(par)
+    pos, _ = cb.srcs_get_cartesian(par, 0)
+    before = cb.srcs_get_local_properties(par, 0)
+    cb.srcs_beams(par)
+    after = cb.srcs_get_local_properties(par, 0)
+    ref = o.srcs_beam_rsd(g["s1_npot"], pos, before.copy())
+    np.testing.assert_allclose(after[:, 3], ref[:, 3], rtol=1e-5, atol=1e-9)
+    assert np.all(after[:, 4:6] == 0)
+
+
+# --------------------------------------------------------------------------------------- maps
+def test_maps_vs_reference(golden_dir):
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    par = _par(t)
+    par.grid_put(cb.GRID_DENS, g["s2_dens"])
+    par.grid_put(cb.GRID_NPOT, g["s1_npot"])
+    par.update_halo()
+    r0, rf = g["s4_imap_r0_0"], g["s4_imap_rf_0"]
+    nside = int(np.sqrt(g["s4_imap_data_0"].size / len(r0) / 12))
+    par.set_imap(0, t["imap_tz_0"], t["imap_bz_0"], nside, r0, rf)
+    cb.set_norm(par, 1, 0, g["s3_imap_norm_0"], g["s3_imap_norm_ends_0"])
+    data, nadd = cb.imap_set_cartesian(par, 0)
+    assert np.array_equal(nadd.ravel(), g["s4_imap_nadd_0"]), "imap hit counts differ"
+    ref = g["s4_imap_data_0"].reshape(data.shape)
+    # float atomics: summation order differs (it does in the reference under OpenMP too)
+    np.testing.assert_allclose(data, ref, rtol=2e-5, atol=1e-7 * np.abs(ref).max())
+    # kappa / ISW: per-pixel double accumulators in the same order -> fp32-rounding agreement
+    listpix, pos = cb.healpix.hp_shell_pixels(int(np.sqrt(g["s6_kappa_listpix"].size / 12)), int(t["nside_base"]))
+    assert np.array_equal(listpix, g["s6_kappa_listpix"])
+    assert np.array_equal(pos.ravel(), g["s6_kappa_pos"])
+    kap = cb.kappa_get_beam_properties(par, pos, g["s6_kappa_rf"])
+    refk = g["s6_kappa_data"].reshape(kap.shape)
+    np.testing.assert_allclose(kap, refk, rtol=1e-5, atol=1e-6 * np.abs(refk).max())
+    isw = cb.isw_get_beam_properties(par, pos, g["s6_isw_rf"])
+    refi = g["s6_isw_data"].reshape(isw.shape)
+    np.testing.assert_allclose(isw, refi, rtol=1e-5, atol=1e-6 * np.abs(refi).max())
+    par.free()
+
+
+# ------------------------------------------------------------------- full-size property checks
+def test_full_size_properties(golden_dir):
+    """n_grid=512 (BASELINE config 2): properties that do not need the oracle at that size."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    n = 512
+    t = dict(t)
+    t["l_box"] = float(np.float32(2 * t["r_max"] * (1 + 2. / n)))
+    t["pos_obs"] = 0.5 * t["l_box"]
+    par = cb.ParamCoLoRe(t, n, seed=7)
+    mean, s2 = cb.create_cartesian_fields(par)
+    assert abs(mean) < 1e-4 * np.sqrt(s2) and 0.05 < s2 < 5.0
+    # Parseval-type check of sigma2 against an independent host reduction
+    dens = par.grid_get(cb.GRID_DENS)[:, :, :n]
+    assert abs(dens.astype(np.float64).var() / s2 - 1) < 1e-4
+    # r2c(c2r(.)) round trip at full size
+    x = par.grid_get(cb.GRID_NPOT)
+    cb.fftw_wrap_r2c(par, cb.GRID_NPOT)
+    cb.fftw_wrap_c2r(par, cb.GRID_NPOT)
+    y = par.grid_get(cb.GRID_NPOT)
+    assert np.abs(y[:, :, :n] / float(n) ** 3 - x[:, :, :n]).max() < 3e-5 * x[:, :, :n].std()
+    par.grid_put(cb.GRID_NPOT, x)
+    par.update_halo()
+    cb.compute_physical_density_field(par)
+    ln = par.grid_get(cb.GRID_DENS)[:, :, :n]
+    assert ln.min() > -1.0 and abs(ln.astype(np.float64).mean()) < 0.05
+    par.set_srcs(0, t["srcs_nz_0"] * 40, t["srcs_bz_0"])
+    cb.compute_density_normalization(par)
+    nsrc = cb.srcs_set_cartesian(par)[0]
+    counts = cb.srcs_get_counts(par, 0)
+    assert counts.sum() == nsrc and counts[:, :, n:].sum() == 0 and counts.min() >= 0
+    pos, ipix = cb.srcs_get_cartesian(par, 0)
+    assert ipix.min() >= 0 and ipix.max() < 48
+    # sources are ordered by cell: the running cell index of consecutive sources never decreases
+    dx = par.l_box / n
+    cell = np.rint((pos[:, :3].astype(np.float64) + 0.5 * par.l_box) / dx).astype(np.int64)
+    flat = cell[:, 0] + n * (cell[:, 1] + n * cell[:, 2])
+    # (rint can move a source sitting exactly on a cell edge; allow a handful)
+    assert np.mean(np.diff(flat) < 0) < 1e-3
+    srcs = cb.srcs_get_local_properties(par, 0)
+    assert srcs[:, 0].min() >= 0 and srcs[:, 0].max() <= 360.0 and np.abs(srcs[:, 1]).max() <= 90.0
+    assert srcs[:, 2].max() < 0.5
+    par.free()
