@@ -81,6 +81,8 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   ClrDev &d = c->dev;
   d.n = p->n_grid; d.nc = p->n_grid / 2 + 1; d.nz_here = p->nz_here; d.iz0_here = p->iz0_here;
   d.pitch = 2 * d.nc;
+  d.log2n = -1;
+  for (int b = 0; b < 31; b++) if ((1 << b) == d.n) d.log2n = b;
   d.bias_model = p->bias_model; d.nside_base = p->nside_base;
   d.l_box = p->l_box;
   for (int i = 0; i < 3; i++) d.pos_obs[i] = p->pos_obs[i];
@@ -89,6 +91,13 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   d.r_arr = c->d_tables; d.z_arr = c->d_tables + CLR_NA; d.d1_arr = c->d_tables + 2 * CLR_NA;
   d.d2_arr = c->d_tables + 3 * CLR_NA; d.v1_arr = c->d_tables + 4 * CLR_NA; d.pd_arr = c->d_tables + 5 * CLR_NA;
   d.ih_arr = c->d_tables + 6 * CLR_NA; d.a2r_a = c->d_tables + 7 * CLR_NA; d.a2r_r = c->d_tables + 8 * CLR_NA;
+  {
+    std::vector<float> tf(2 * CLR_NA);
+    for (int i = 0; i < CLR_NA; i++) { tf[i] = (float)c->h_z[i]; tf[CLR_NA + i] = (float)c->h_d1[i]; }
+    CLR_CUDA(cudaMalloc(&c->d_tables_f, 2 * CLR_NA * sizeof(float)));
+    CLR_CUDA(cudaMemcpy(c->d_tables_f, tf.data(), 2 * CLR_NA * sizeof(float), cudaMemcpyHostToDevice));
+    d.z_f = c->d_tables_f; d.d1_f = c->d_tables_f + CLR_NA;
+  }
   size_t plane = (size_t)d.pitch * d.n;
   CLR_CUDA(cudaMalloc(&c->d_dens, plane * d.nz_here * sizeof(float)));
   CLR_CUDA(cudaMalloc(&c->d_npot, plane * (d.nz_here + 2) * sizeof(float)));
@@ -110,9 +119,10 @@ int clr_destroy(clr_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
-  cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_pk);
+  cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -228,6 +238,13 @@ int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *o
 }
 
 int clr_set_sigma2_gauss(clr_ctx *c, double s2) { c->sigma2_gauss = s2; return 0; }
+
+int clr_set_option(clr_ctx *c, const char *name, int value)
+{
+  if (!strcmp(name, "exact_math")) { c->exact_math = value; return 0; }
+  clr_set_error("unknown option %s", name);
+  return 1;
+}
 
 int clr_compute_physical_density_field(clr_ctx *c)
 {
@@ -398,9 +415,30 @@ int clr_timer_stop_ms(clr_ctx *c, float *ms)
   CLR_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
   return 0;
 }
-int clr_set_profiling(clr_ctx *c, int on) { c->profiling = on != 0; if (on) c->stage.clear(); return 0; }
+static int resolve_stage_events(clr_ctx *c)
+{
+  if (c->ev_pending.empty()) return 0;
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto &pe : c->ev_pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev_pool[pe.slot], c->ev_pool[pe.slot + 1]);
+    StageTime &s = c->stage[pe.name];
+    s.ms += ms; s.launches += pe.nl;
+  }
+  c->ev_pending.clear();
+  c->ev_used = 0;
+  return 0;
+}
+int clr_set_profiling(clr_ctx *c, int on)
+{
+  if (resolve_stage_events(c)) return 1;
+  c->profiling = on != 0;
+  if (on) c->stage.clear();
+  return 0;
+}
 int clr_get_stage_ms(clr_ctx *c, const char *stage, float *ms, int *launches)
 {
+  if (resolve_stage_events(c)) return 1;
   auto it = c->stage.find(stage);
   if (it == c->stage.end()) { *ms = 0; if (launches) *launches = 0; return 0; }
   *ms = it->second.ms;

@@ -403,10 +403,11 @@ int c2r_3d(clr_ctx *c, float2 *g, float norm, double *mom)
 {
   const long long nc = N / 2 + 1;
   // z pass: lines along z, contiguous index = flattened (ky,kx) of a plane
-  if (run_strided<N, +1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc))) return 1;
+  { StageScope sc(c, "fft_z", 1); if (run_strided<N, +1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc))) return 1; }
   // y pass: per z plane, lines along y, contiguous index = kx
-  if (run_strided<N, +1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1;
+  { StageScope sc(c, "fft_y", 1); if (run_strided<N, +1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1; }
   // x pass: half-complex -> real
+  StageScope sc(c, "fft_x", 1);
   if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)N * N, (int)nc, norm, mom);
   return run_c2r_x<N / 2, false>(c, g, (long long)N * N, (int)nc, norm, nullptr);
 }
@@ -415,8 +416,9 @@ template <int N>
 int r2c_3d(clr_ctx *c, float2 *g)
 {
   const long long nc = N / 2 + 1;
-  if (run_r2c_x<N / 2>(c, g, (long long)N * N, (int)nc)) return 1;
-  if (run_strided<N, -1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1;
+  { StageScope sc(c, "fft_x", 1); if (run_r2c_x<N / 2>(c, g, (long long)N * N, (int)nc)) return 1; }
+  { StageScope sc(c, "fft_y", 1); if (run_strided<N, -1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1; }
+  StageScope sc(c, "fft_z", 1);
   return run_strided<N, -1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc));
 }
 
@@ -427,7 +429,6 @@ int r2c_3d(clr_ctx *c, float2 *g)
 int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments)
 {
   CLR_CHECK(c->nranks == 1, "multi-GPU FFT goes through clr_fft_dist (not built in this call path)");
-  StageScope sc(c, "fft_c2r", 3);
   float2 *g = reinterpret_cast<float2 *>(grid);
   switch (c->dev.n) {
     case 16: return c2r_3d<16>(c, g, (float)norm, d_moments);
@@ -446,7 +447,6 @@ int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments)
 int clr_fft_r2c_impl(clr_ctx *c, float *grid)
 {
   CLR_CHECK(c->nranks == 1, "multi-GPU FFT goes through clr_fft_dist (not built in this call path)");
-  StageScope sc(c, "fft_r2c", 3);
   float2 *g = reinterpret_cast<float2 *>(grid);
   switch (c->dev.n) {
     case 16: return r2c_3d<16>(c, g);

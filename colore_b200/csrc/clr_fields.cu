@@ -5,6 +5,7 @@
 // Compiled with -fmad=false so that double-precision table lookups round exactly like the
 // reference's scalar C code (no fused multiply-add contraction).
 #include "clr_internal.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -16,28 +17,76 @@ constexpr int kThreads = 256;
 // (seed, stream 0, global mode index), word 0 -> phase, word 1 -> modulus (phase first, as the
 // reference draws them). Arithmetic in double like the reference; the two complex64 stores per
 // mode are the only HBM traffic (8 B per real-space cell).
+template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restrict__ npot_f, uint32_t seed,
                   const double *__restrict__ logkarr, const double *__restrict__ pkarr, int numk, double logkmin,
                   double logkmax, double idlogk, double n_scal, double prefac_lensing, double r2_smooth,
-                  int do_smoothing, int smooth_potential)
+                  int do_smoothing, int smooth_potential, double lgdk)
 {
   const long long n_modes = (long long)d.nz_here * d.n * d.nc;
   const double dk = 2 * 3.14159265358979323846 / d.l_box;
   const double idk3 = 1. / (dk * dk * dk);
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n_modes;
-       idx += (long long)gridDim.x * blockDim.x) {
-    int kk = (int)(idx % d.nc);
-    long long row = idx / d.nc;
-    int jj = (int)(row % d.n);
-    int ii = (int)(row / d.n);
+  // a CTA takes groups of rows (kz,ky) so that all index divisions are 32-bit and by nc / n only
+  const unsigned n_rows = (unsigned)d.nz_here * (unsigned)d.n;
+  const unsigned rpb = max(1u, 1024u / (unsigned)d.nc);
+  const unsigned n_groups = (n_rows + rpb - 1) / rpb;
+  (void)n_modes;
+  for (unsigned grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+  for (unsigned tl = threadIdx.x; tl < rpb * (unsigned)d.nc; tl += blockDim.x) {
+    unsigned rl = tl / (unsigned)d.nc;
+    int kk = (int)(tl - rl * (unsigned)d.nc);
+    unsigned row = grp * rpb + rl;
+    if (row >= n_rows) continue;
+    int ii = (int)(row / (unsigned)d.n);
+    int jj = (int)(row - (unsigned)ii * (unsigned)d.n);
+    long long idx = (long long)row * d.nc + kk;
     int ii_true = d.iz0_here + ii;
     double kz = (2 * ii_true <= d.n) ? ii_true * dk : -(d.n - ii_true) * dk;
     double ky = (2 * jj <= d.n) ? jj * dk : -(d.n - jj) * dk;
     double kx = (2 * kk <= d.n) ? kk * dk : -(d.n - kk) * dk;
     double k_mod2 = kx * kx + ky * ky + kz * kz;
     float2 dk_out = make_float2(0.f, 0.f), pk_out = make_float2(0.f, 0.f);
-    if (k_mod2 > 0) {
+    if (k_mod2 > 0 && !EXACT) {
+      // fp32 transcendentals, double only where it is cheap and protects the result:
+      //  * log10(k): k^2/dk^2 = m is an integer < 2^24; log2(m) = e + log2f(f) with the sum in double,
+      //    so the P(k) table position keeps ~1e-8 absolute accuracy (a float sum would lose it);
+      //  * ln(1-u2): log1pf for small u2, logf of the exactly computed 1-u2 otherwise;
+      //  * phase 2*pi*u1 through sincospif (exact argument reduction).
+      int mi = (2 * ii_true <= d.n ? ii_true : d.n - ii_true), mj = (2 * jj <= d.n ? jj : d.n - jj);
+      int m = kk * kk + mj * mj + mi * mi;
+      int e2 = 31 - __clz(m);
+      float fm = __int2float_rn(m) * __int_as_float((127 - e2) << 23);      // m * 2^-e2 in [1,2), exact
+      double lgk = lgdk + 0.15051499783199060 * ((double)e2 + (double)log2f(fm));   // 0.5*log10(2)
+      double pk;
+      int ik = (int)((lgk - logkmin) * idlogk);
+      if (ik < 0) pk = __ldg(pkarr) * (double)exp10f((float)(n_scal * (lgk - logkmin)));
+      else if (ik < numk) {
+        double p0 = __ldg(pkarr + ik), p1 = (ik + 1 < numk) ? __ldg(pkarr + ik + 1) : p0;
+        pk = p0 + (lgk - __ldg(logkarr + ik)) * (p1 - p0) * idlogk;
+      } else pk = __ldg(pkarr + numk - 1) * (double)exp10f((float)(-3 * (lgk - logkmax)));
+      float sigma2 = (float)(pk * idk3);
+      uint32_t w[4];
+      unsigned long long gidx = (unsigned long long)kk + (unsigned long long)d.nc * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
+      clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
+      float l1;
+      if (w[1] < 0x80000000u) l1 = log1pf(-(float)w[1] * (1.f / 4294967296.f));
+      else l1 = logf((float)(0u - w[1]) * (1.f / 4294967296.f));            // 1-u2 = (2^32-w)/2^32 exactly
+      float delta_mod = sqrtf(-sigma2 * l1);
+      float sn, cs;
+      sincospif((float)(w[0] >> 7) * (1.f / 16777216.f), &sn, &cs);         // 2*u1 with 25 bits
+      float dre = delta_mod * cs, dim = delta_mod * sn;
+      float k2f = (float)k_mod2;
+      float pfac = -(float)prefac_lensing;
+      float pre = pfac * dre / k2f, pim = pfac * dim / k2f;
+      if (do_smoothing) {
+        float sm = expf((float)(-0.5 * r2_smooth * k_mod2));
+        dre *= sm; dim *= sm;
+        if (smooth_potential) { pre *= sm; pim *= sm; }
+      }
+      dk_out = make_float2(dre, dim);
+      pk_out = make_float2(pre, pim);
+    } else if (k_mod2 > 0) {
       double lgk = 0.5 * log10(k_mod2);
       // pk_linear0
       double pk;
@@ -110,20 +159,22 @@ scale_moments_kernel(const ClrDev d, float *__restrict__ dens, float *__restrict
 // ---------------------------------------------------------------------------------------------
 // lognormalize (density.c:1070-1103) / densclip (density.c:1034-1067): in place, cell coordinates
 // in fp32 exactly as the reference (flouble dx, x0, y0, z0), growth factor lerp and exp in double.
+template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int clip)
 {
   const int halfn = d.n / 2;                       // float2 per row holding real cells
   const long long n2 = (long long)d.nz_here * d.n * halfn;
   const float dx = d.l_box / d.n;
+  const float idr = (float)d.glob_idr, rtab = (float)d.r_tab_max, dlast = __ldg(d.d1_f + CLR_NA - 1);
+  const float hs2 = (float)(0.5 * sigma2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-    int xq = (int)(i % halfn);
-    long long row = i / halfn;
-    int iy = (int)(row % d.n);
-    int iz = (int)(row / d.n);
+    int ix0, iy, iz;
+    clr_cell(d, 2 * i, ix0, iy, iz);
+    int xq = ix0 >> 1;
+    long long row = (long long)iz * d.n + iy;
     float z0 = (float)((iz + d.iz0_here + 0.0) * dx - d.pos_obs[2]);
     float y0 = (float)((iy + 0.0) * dx - d.pos_obs[1]);
-    float yz = __fadd_rn(__fmul_rn(y0, y0), __fmul_rn(z0, z0));
     float2 *p = reinterpret_cast<float2 *>(dens + row * d.pitch) + xq;
     float2 v = *p;
     float out[2];
@@ -133,12 +184,27 @@ lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int cl
       float x0 = (float)((ix + 0.0) * dx - d.pos_obs[0]);
       // reference: sqrt(x0*x0+y0*y0+z0*z0) with float products, left-to-right float sums
       float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
-      (void)yz;
-      double r = sqrt((double)r2);
-      double dg = clr_bg_d1(d, r);
-      double delta = q ? v.y : v.x;
-      double res = clip ? fmax(1 + dg * delta, 0.) - 1 : exp(dg * (delta - 0.5 * dg * sigma2)) - 1;
-      out[q] = (float)res;
+      float delta = q ? v.y : v.x;
+      if (EXACT) {
+        double r = sqrt((double)r2);
+        double dg = clr_bg_d1(d, r);
+        double res = clip ? fmax(1 + dg * (double)delta, 0.) - 1 : exp(dg * ((double)delta - 0.5 * dg * sigma2)) - 1;
+        out[q] = (float)res;
+      } else {
+        // fp32 evaluation (the grid is fp32): growth-factor lerp on the fp32 copy of the table, expm1f
+        // keeps full relative accuracy for small arguments. |error| <~ 3e-7 (1+|result|).
+        float r = sqrtf(r2);
+        float dg;
+        if (r <= 0.f) dg = 1.f;
+        else if (r >= rtab) dg = dlast;
+        else {
+          float t = r * idr;
+          int ir = (int)t;
+          float fa = __ldg(d.d1_f + ir), fb = __ldg(d.d1_f + ir + 1);
+          dg = fa + (fb - fa) * (t - (float)ir);
+        }
+        out[q] = clip ? fmaxf(1.f + dg * delta, 0.f) - 1.f : expm1f(dg * (delta - hs2 * dg));
+      }
     }
     *p = make_float2(out[0], out[1]);
   }
@@ -153,10 +219,13 @@ lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int cl
 #define CLR_MAX_NZ 512
 struct NormPops { const double *bz[CLR_MAX_NORM_POP]; int npop; };
 
+template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, int nz, double idz,
                  unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b)
 {
+  const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max, zlastf = __ldg(d.z_f + CLR_NA - 1);
+  const float idzf = (float)idz;
   extern __shared__ double sh[];          // [nz] z sums, [npop][nz] bias sums, then counts
   double *s_z = sh;
   double *s_b = sh + nz;
@@ -172,17 +241,40 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
     int bin = -1;
     double redshift = 0, dcell = 0, r = 0;
     if (i < n_cells) {
-      int ix = (int)(i % d.n);
-      long long row = i / d.n;
-      int iy = (int)(row % d.n);
-      int iz = (int)(row / d.n);
+      int ix, iy, iz;
+      clr_cell(d, i, ix, iy, iz);
+      long long row = (long long)iz * d.n + iy;
       float z0 = (float)((iz + d.iz0_here + 0.0) * dx - d.pos_obs[2]);
       float y0 = (float)((iy + 0.0) * dx - d.pos_obs[1]);
       float x0 = (float)((ix + 0.0) * dx - d.pos_obs[0]);
       float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
-      r = sqrt((double)r2);
-      redshift = clr_bg_z(d, r);
-      int ind_z = (int)(redshift * idz) + 1;
+      int ind_z;
+      if (EXACT) {
+        r = sqrt((double)r2);
+        redshift = clr_bg_z(d, r);
+        ind_z = (int)(redshift * idz) + 1;
+      } else {
+        // fp32 screening of the bin; cells closer than 1e-4 bins to an edge take the double path
+        float rf = sqrtf(r2), zf;
+        if (rf <= 0.f) zf = 0.f;
+        else if (rf >= rtabf) zf = zlastf;
+        else {
+          float t = rf * idrf;
+          int ir = (int)t;
+          float fa = __ldg(d.z_f + ir), fb = __ldg(d.z_f + ir + 1);
+          zf = fa + (fb - fa) * (t - (float)ir);
+        }
+        float tb = zf * idzf;
+        if (fabsf(tb - rintf(tb)) < 1e-4f) {
+          r = sqrt((double)r2);
+          redshift = clr_bg_z(d, r);
+          ind_z = (int)(redshift * idz) + 1;
+        } else {
+          r = rf;
+          redshift = zf;
+          ind_z = (int)tb + 1;
+        }
+      }
       if (ind_z >= 0 && ind_z < nz) { bin = ind_z; dcell = dens[row * d.pitch + ix]; }
     }
     // warp aggregation by bin
@@ -196,7 +288,29 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
       double zsum = clr_warp_sum(mine ? redshift : 0.);
       if (lane == leader) { atomicAdd(&s_z[b], zsum); atomicAdd(&s_n[b], (unsigned long long)__popc(grp)); }
       for (int ip = 0; ip < pops.npop; ip++) {
-        double bm = mine ? clr_bias_model(d.bias_model, dcell, clr_bg_bz(d, r, pops.bz[ip])) : 0.;
+        double bm = 0.;
+        if (mine) {
+          if (EXACT) bm = clr_bias_model(d.bias_model, dcell, clr_bg_bz(d, r, pops.bz[ip]));
+          else {
+            // fp32 bias lerp and bias_model (common.h:414-431); summed in double
+            float rf = (float)r, dl = (float)dcell, bi;
+            const double *tb = pops.bz[ip];
+            if (rf <= 0.f) bi = (float)__ldg(tb);
+            else if (rf >= rtabf) bi = 1.f;
+            else {
+              float t = rf * idrf;
+              int ir = (int)t;
+              float fa = (float)__ldg(tb + ir), fb = (float)__ldg(tb + ir + 1);
+              bi = fa + (fb - fa) * (t - (float)ir);
+            }
+            float v;
+            if (dl <= -1.f) v = 0.f;
+            else if (d.bias_model == 2) v = dl < 0.f ? expf(bi * dl / (1.f + dl)) : 1.f + bi * dl;
+            else if (d.bias_model == 3) v = fmaxf(1.f + bi * dl, 0.f);
+            else v = powf(1.f + dl, bi);
+            bm = v;
+          }
+        }
         bm = clr_warp_sum(bm);
         if (lane == leader) atomicAdd(&s_b[ip * nz + b], bm);
       }
@@ -243,10 +357,15 @@ int clr_fields_fill(clr_ctx *c, uint32_t seed)
 {
   StageScope sc(c, "fill_modes", 1);
   long long n_modes = (long long)c->dev.nz_here * c->dev.n * c->dev.nc;
-  fill_modes_kernel<<<grid_for(c, n_modes, 8), kThreads, 0, c->stream>>>(
+  double lgdk = log10(2 * M_PI / c->p.l_box);
+  auto k = c->exact_math ? fill_modes_kernel<true> : fill_modes_kernel<false>;
+  unsigned rpb = std::max(1u, 1024u / (unsigned)c->dev.nc);
+  long long n_groups = ((long long)c->dev.nz_here * c->dev.n + rpb - 1) / rpb;
+  (void)n_modes;
+  k<<<grid_for(c, n_groups * kThreads, 8), kThreads, 0, c->stream>>>(
       c->dev, reinterpret_cast<float2 *>(c->d_dens), reinterpret_cast<float2 *>(c->d_npot), seed, c->d_pk,
       c->d_pk + c->p.numk, c->p.numk, c->p.logkmin, c->p.logkmax, c->p.idlogk, c->p.n_scal, c->p.prefac_lensing,
-      c->p.r2_smooth, c->p.do_smoothing, c->p.smooth_potential);
+      c->p.r2_smooth, c->p.do_smoothing, c->p.smooth_potential, lgdk);
   CLR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -271,7 +390,10 @@ int clr_fields_lognormal(clr_ctx *c, int clip)
 {
   StageScope sc(c, "lognormal", 1);
   long long n2 = (long long)c->dev.nz_here * c->dev.n * (c->dev.n / 2);
-  lognormal_kernel<<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
+  if (c->exact_math)
+    lognormal_kernel<true><<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
+  else
+    lognormal_kernel<false><<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
   CLR_CUDA(cudaGetLastError());
   return 0;
 }
@@ -293,7 +415,10 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
     StageScope sc(c, "norm_hist", 1);
     long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
     size_t smem = nd * sizeof(double);
-    norm_hist_kernel<<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
+    if (c->exact_math)
+      norm_hist_kernel<true><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
+    else
+      norm_hist_kernel<false><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
     CLR_CUDA(cudaGetLastError());
   }
   CLR_CUDA(cudaMemcpyAsync(h_n, g_n, nz * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

@@ -16,6 +16,7 @@
 struct ClrDev {
   int n, nc, nz_here, iz0_here;     // grid side, n/2+1, slab
   int pitch;                        // floats per real row = 2*nc (reference layout)
+  int log2n;                        // log2(n) when n is a power of two, else -1 (index arithmetic)
   int bias_model, nside_base;
   float l_box;
   double pos_obs[3];
@@ -23,6 +24,7 @@ struct ClrDev {
   double fgrowth_0, hubble_0, OmegaM, r_max;
   const double *r_arr, *z_arr, *d1_arr, *d2_arr, *v1_arr, *pd_arr, *ih_arr, *a2r_a, *a2r_r;
   const float *slice_left, *slice_right;   // z-halo planes of the potential (fourier.c:401-414)
+  const float *z_f, *d1_f;                 // fp32 copies of z(r), D(r) for the streaming field kernels
 };
 
 struct ClrPop {           // one tracer population: tables on the NA r-grid
@@ -42,6 +44,7 @@ struct clr_ctx {
   // device memory
   float *d_dens = nullptr, *d_npot = nullptr;       // grids (+2 halo planes on npot)
   double *d_tables = nullptr;                        // 9 x NA
+  float *d_tables_f = nullptr;                       // fp32 copies: z(r), D(r)
   double *d_pk = nullptr;                            // logk[numk], pk[numk]
   float2 *d_twiddle = nullptr;                       // exp(+2*pi*i*k/n), k<n
   double *d_scratch = nullptr;                       // reductions / histograms
@@ -70,8 +73,13 @@ struct clr_ctx {
   // bookkeeping
   long long launches = 0;
   bool profiling = false;
+  int exact_math = 0;   // 1: field kernels evaluate the reference's double-precision expressions verbatim
   std::map<std::string, StageTime> stage;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+  struct Pending { std::string name; int slot; int nl; };
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<Pending> ev_pending;
+  int ev_used = 0;
 };
 
 void clr_set_error(const char *fmt, ...);
@@ -88,21 +96,26 @@ void clr_set_error(const char *fmt, ...);
     if (!(cond)) { clr_set_error(__VA_ARGS__); return 1; } \
   } while (0)
 
-// stage profiling: CUDA events around a kernel family on the context stream
+// stage profiling: CUDA events around a kernel family on the context stream. Events are only
+// RECORDED here (no synchronisation, ~1 us each); clr_get_stage_ms resolves them after a stream
+// synchronise, so profiling can stay on inside a timed region.
 struct StageScope {
-  clr_ctx *c; const char *name; int nl;
+  clr_ctx *c; const char *name; int nl; int slot = -1;
   StageScope(clr_ctx *ctx, const char *nm, int nlaunch) : c(ctx), name(nm), nl(nlaunch) {
     c->launches += nl;
-    if (c->profiling) cudaEventRecord(c->evp0, c->stream);
+    if (c->profiling) {
+      if (c->ev_used + 2 > (int)c->ev_pool.size()) {
+        for (int i = 0; i < 64; i++) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
+      }
+      slot = c->ev_used;
+      c->ev_used += 2;
+      cudaEventRecord(c->ev_pool[slot], c->stream);
+    }
   }
   ~StageScope() {
-    if (c->profiling) {
-      float ms = 0;
-      cudaEventRecord(c->evp1, c->stream);
-      cudaEventSynchronize(c->evp1);
-      cudaEventElapsedTime(&ms, c->evp0, c->evp1);
-      StageTime &s = c->stage[name];
-      s.ms += ms; s.launches += nl;
+    if (slot >= 0) {
+      cudaEventRecord(c->ev_pool[slot + 1], c->stream);
+      c->ev_pending.push_back({std::string(name), slot, nl});
     }
   }
 };
@@ -127,6 +140,22 @@ int clr_ensure_scratch(clr_ctx *c, size_t bytes);
 // ---------------------------------------------------------------------------------------------
 // device helpers
 #ifdef __CUDACC__
+
+// flat unpadded cell index i = ix + n*(iy + n*iz_local) -> (ix, iy, iz_local). 64-bit division by a
+// run-time divisor costs ~100 instructions on the GPU, so powers of two take shifts.
+__device__ __forceinline__ void clr_cell(const ClrDev &d, long long i, int &ix, int &iy, int &iz)
+{
+  if (d.log2n >= 0) {
+    ix = (int)(i & (d.n - 1));
+    iy = (int)((i >> d.log2n) & (d.n - 1));
+    iz = (int)(i >> (2 * d.log2n));
+  } else {
+    long long row = i / d.n;
+    ix = (int)(i - row * d.n);
+    iz = (int)((unsigned)row / (unsigned)d.n);
+    iy = (int)((unsigned)row - (unsigned)iz * (unsigned)d.n);
+  }
+}
 
 // cosmo.c:30-38 f_of_r_linear
 __device__ __forceinline__ double clr_lerp(const ClrDev &d, double r, const double *__restrict__ f,
@@ -194,6 +223,12 @@ struct ClrStream {   // sequential reader of one counter-based substream
   uint32_t k0, k1, i0, i1, stream, pos, buf[4];
   __device__ __forceinline__ ClrStream(uint32_t seed, uint32_t strm, unsigned long long index)
       : k0(seed), k1(0), i0((uint32_t)index), i1((uint32_t)(index >> 32)), stream(strm), pos(0) {}
+  // position the reader at word `p` of the substream
+  __device__ __forceinline__ void seek(uint32_t p)
+  {
+    pos = p;
+    if (pos & 3) clr_philox(i0, i1, pos >> 2, stream, k0, k1, buf);
+  }
   __device__ __forceinline__ uint32_t next_u32()
   {
     if ((pos & 3) == 0) clr_philox(i0, i1, pos >> 2, stream, k0, k1, buf);

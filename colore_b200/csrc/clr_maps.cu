@@ -59,10 +59,9 @@ imap_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restr
   const double dx = (double)(d.l_box / d.n);
   const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
-    int ix = (int)(i % d.n);
-    long long row = i / d.n;
-    int iy = (int)(row % d.n);
-    int iz = (int)(row / d.n);
+    int ix, iy, iz;
+    clr_cell(d, i, ix, iy, iz);
+    long long row = (long long)iz * d.n + iy;
     double z0 = (iz + d.iz0_here) * dx - d.pos_obs[2];
     double y0 = iy * dx - d.pos_obs[1];
     double x0 = ix * dx - d.pos_obs[0];

@@ -13,7 +13,7 @@ constexpr int kCellsPerThread = 4;
 constexpr int kChunk = kThreads * kCellsPerThread;   // cells per CTA chunk (flat, x fastest)
 
 // ---- gsl_ran_poisson (GSL randist/poisson.c) and its helpers, restated for the device ---------
-__device__ double dev_gamma_large(ClrStream &s, double a)
+__device__ __noinline__ double dev_gamma_large(ClrStream &s, double a)
 {
   double sqa = sqrt(2 * a - 1), x, y, v;
   do {
@@ -40,7 +40,7 @@ __device__ double dev_stirling(double y1)
   return (13860.0 - (462.0 - (132.0 - (99.0 - 140.0 / y2) / y2) / y2) / y2) / y1 / 166320.0;
 }
 // Kachitvichyanukul & Schmeiser BINV/BTPE as laid out in GSL randist/binomial_tpe.c
-__device__ unsigned int dev_binomial(ClrStream &s, double p, unsigned int n)
+__device__ __noinline__ unsigned int dev_binomial(ClrStream &s, double p, unsigned int n)
 {
   int ix = 0, flipped = 0;
   if (n == 0) return 0;
@@ -134,24 +134,74 @@ __device__ unsigned int dev_poisson(ClrStream &s, double mu)
 
 // ---- pass 1: lambda and Poisson count per cell (srcs.c:156-184) --------------------------------
 // counts: int32 per cell, unpadded flat order ix + n*(iy + n*iz_local); chunk_tot[chunk] = sum.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint32_t seed, int ipop,
                int32_t *__restrict__ counts, int32_t *__restrict__ chunk_tot, long long n_cells)
 {
   const double dx = (double)(d.l_box / d.n);       // float division, as in the reference (srcs.c:147)
   const double cell_vol = dx * dx * dx;
   const double rcut = (double)(d.l_box / 2) + 20.;
+  // fp32 screening constants
+  const float dxf = d.l_box / d.n, volf = (float)cell_vol, rcutf = (float)rcut;
+  const float ox = (float)d.pos_obs[0], oy = (float)d.pos_obs[1], oz = (float)d.pos_obs[2];
+  const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max;
   __shared__ int red[kThreads / 32];
+  __shared__ unsigned short q_cell[kChunk];
+  __shared__ int q_len;
+  if (threadIdx.x == 0) q_len = 0;
+  __syncthreads();
   for (long long chunk = blockIdx.x; chunk * kChunk < n_cells; chunk += gridDim.x) {
     int local = 0;
+    // ---- phase 1 (all cells, fp32): a cell is SURELY empty when its first uniform lies below a
+    // rigorous lower bound of exp(-lambda) (gsl_ran_poisson returns 0 iff u0 <= exp(-mu)). Everything
+    // else -- about 3% of the cells at <N> = 0.03 -- is queued for the exact double-precision path, so
+    // that path runs on dense warps instead of dragging 31 idle lanes along.
 #pragma unroll
     for (int q = 0; q < kCellsPerThread; q++) {
-      long long i = chunk * kChunk + q * kThreads + threadIdx.x;
+      int lc = q * kThreads + threadIdx.x;
+      long long i = chunk * kChunk + lc;
       if (i >= n_cells) continue;
-      int ix = (int)(i % d.n);
-      long long row = i / d.n;
-      int iy = (int)(row % d.n);
-      int iz = (int)(row / d.n);
+      int ix, iy, iz;
+      clr_cell(d, i, ix, iy, iz);
+      long long row = (long long)iz * d.n + iy;
+      float xf = ix * dxf - ox, yf = iy * dxf - oy, zf = (iz + d.iz0_here) * dxf - oz;
+      float rf = sqrtf(xf * xf + yf * yf + zf * zf);
+      bool sure_zero = false;
+      if (rf > rcutf + 0.05f) sure_zero = true;               // outside the sampled sphere (srcs.c:169)
+      else if (rf < rcutf - 0.05f && rf > 0.05f && rf < rtabf - 1.f) {
+        float t = rf * idrf;
+        int ir = (int)t;
+        float fr = t - (float)ir;
+        float na = (float)__ldg(pop.nz + ir), nb = (float)__ldg(pop.nz + ir + 1);
+        float ba = (float)__ldg(pop.bz + ir), bb = (float)__ldg(pop.bz + ir + 1);
+        float ma = (float)__ldg(pop.norm + ir), mb = (float)__ldg(pop.norm + ir + 1);
+        float nd = na + (nb - na) * fr, bi = ba + (bb - ba) * fr, nm = ma + (mb - ma) * fr;
+        float dl = dens[row * d.pitch + ix];
+        float bm;
+        if (dl <= -1.f) bm = 0.f;
+        else if (d.bias_model == 2) bm = dl < 0.f ? __expf(bi * dl / (1.f + dl)) : 1.f + bi * dl;
+        else if (d.bias_model == 3) bm = fmaxf(1.f + bi * dl, 0.f);
+        else bm = __powf(1.f + dl, bi);
+        // upper bound of lambda: 0.2% relative slack plus the absolute lerp error of n(r)
+        float lam_hi = (fmaxf(nd, 0.f) * 1.002f + 2e-4f * (fabsf(na) + fabsf(nb))) * volf * fabsf(bm) * fabsf(nm) * 1.002f;
+        float e_lo = __expf(-lam_hi) * (1.f - 1e-5f);
+        unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
+        uint32_t w[4];
+        clr_philox((uint32_t)gcell, (uint32_t)(gcell >> 32), 0u, 1 + 2 * ipop, seed, 0u, w);
+        float u0_hi = (float)((w[0] >> 8) + 1u) * (1.f / 16777216.f);
+        sure_zero = (u0_hi <= e_lo);                           // false for NaN tables -> exact path
+      }
+      if (sure_zero) counts[i] = 0;
+      else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)lc;
+    }
+    __syncthreads();
+    // ---- phase 2 (queued cells, double): the reference arithmetic, bit for bit
+    const int nq = q_len;
+    for (int k = threadIdx.x; k < nq; k += kThreads) {
+      long long i = chunk * kChunk + q_cell[k];
+      int ix, iy, iz;
+      clr_cell(d, i, ix, iy, iz);
+      long long row = (long long)iz * d.n + iy;
       double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
       double y0 = (iy + 0.0) * dx - d.pos_obs[1];
       double x0 = (ix + 0.0) * dx - d.pos_obs[0];
@@ -172,6 +222,8 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
       counts[i] = npp;
       local += npp;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) q_len = 0;
     // CTA total of the chunk
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
@@ -189,24 +241,33 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
 __global__ void __launch_bounds__(1024)
 scan_chunks_kernel(const int32_t *__restrict__ tot, long long *__restrict__ offs, long long n_chunks)
 {
-  __shared__ long long part[1024];
-  const int t = threadIdx.x;
-  long long per = (n_chunks + 1023) / 1024;
-  long long b = t * per, e = b + per < n_chunks ? b + per : n_chunks;
+  // each of the 32 warps owns one contiguous segment and walks it 32 elements at a time, so every
+  // global access is a coalesced 128-byte line
+  __shared__ long long seg[33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long per = ((n_chunks + 31) / 32 + 31) / 32 * 32;     // segment length, multiple of 32
+  long long b = w * per, e = b + per < n_chunks ? b + per : n_chunks;
   long long s = 0;
-  for (long long i = b; i < e; i++) s += tot[i];
-  part[t] = s;
+  for (long long i = b + lane; i < e; i += 32) s += tot[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) seg[w + 1] = s;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int o = 1; o < 1024; o <<= 1) {
-    long long v = t >= o ? part[t - o] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    seg[0] = 0;
+    for (int k = 1; k <= 32; k++) seg[k] += seg[k - 1];
   }
-  long long run = t ? part[t - 1] : 0;
-  for (long long i = b; i < e; i++) { offs[i] = run; run += tot[i]; }
-  if (t == 1023) offs[n_chunks] = part[1023];
+  __syncthreads();
+  long long run = seg[w];
+  for (long long i0 = b; i0 < e; i0 += 32) {
+    long long i = i0 + lane;
+    long long v = i < e ? tot[i] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (i < e) offs[i] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (threadIdx.x == 0) offs[n_chunks] = seg[32];
 }
 
 // srcs.c:87-118 (get_rvel): central differences of the potential, periodic in x,y, z through the
@@ -228,13 +289,15 @@ __device__ __forceinline__ double dev_get_rvel(const ClrDev &d, const float *__r
 }
 
 // ---- pass 2: positions, RSD, base pixel (srcs.c:238-276) ---------------------------------------
+// Two kernels so that the expensive per-source arithmetic runs on dense warps:
+//  (a) expand_kernel, per cell chunk: in-CTA scan of the counts, then every occupied cell writes one
+//      64-bit reference (local cell index << 24 | ip) per source at its ordered slot;
+//  (b) place_src_kernel, one thread per source: decodes the reference and evaluates position, RSD and
+//      base pixel. Ordering = cell order, as the reference's single-thread loop produces.
 __global__ void __launch_bounds__(kThreads)
-place_kernel(const ClrDev d, const float *__restrict__ npot, const int32_t *__restrict__ counts,
-             const long long *__restrict__ chunk_offs, uint32_t seed, int ipop, float4 *__restrict__ pos,
-             int32_t *__restrict__ ipix, long long n_cells)
+expand_kernel(const int32_t *__restrict__ counts, const long long *__restrict__ chunk_offs,
+              unsigned long long *__restrict__ src_ref, long long n_cells)
 {
-  const double dx = (double)(d.l_box / d.n);
-  const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
   __shared__ int wsum[kThreads / 32];
   for (long long chunk = blockIdx.x; chunk * kChunk < n_cells; chunk += gridDim.x) {
     long long base = chunk_offs[chunk];
@@ -242,8 +305,15 @@ place_kernel(const ClrDev d, const float *__restrict__ npot, const int32_t *__re
     // thread t owns cells [4t, 4t+4) of the chunk so that the in-CTA scan follows the cell order
     long long i0 = chunk * kChunk + (long long)threadIdx.x * kCellsPerThread;
     int c[kCellsPerThread], tsum = 0;
+    if (i0 + kCellsPerThread <= n_cells) {
+      int4 v = *reinterpret_cast<const int4 *>(counts + i0);
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
 #pragma unroll
-    for (int q = 0; q < kCellsPerThread; q++) { c[q] = (i0 + q < n_cells) ? counts[i0 + q] : 0; tsum += c[q]; }
+      for (int q = 0; q < kCellsPerThread; q++) c[q] = (i0 + q < n_cells) ? counts[i0 + q] : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < kCellsPerThread; q++) tsum += c[q];
     int incl = tsum;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -255,37 +325,41 @@ place_kernel(const ClrDev d, const float *__restrict__ npot, const int32_t *__re
     long long off = base + woff + incl - tsum;
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < kCellsPerThread; q++) {
-      int npp = c[q];
-      if (npp > 0) {
-        long long i = i0 + q;
-        int ix = (int)(i % d.n);
-        long long row = i / d.n;
-        int iy = (int)(row % d.n);
-        int iz = (int)(row / d.n);
-        double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
-        double y0 = (iy + 0.0) * dx - d.pos_obs[1];
-        double x0 = (ix + 0.0) * dx - d.pos_obs[0];
-        double rr = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
-        double rvel = factor_vel * dev_get_rvel(d, npot, ix, iy, iz, x0, y0, z0, rr);
-        float dz_rsd = (float)(rvel * clr_bg_v1(d, rr));
-        unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
-        ClrStream s(seed, 2 + 2 * ipop, gcell);
-        for (int ip = 0; ip < npp; ip++) {
-          float px = (float)(x0 + dx * (s.next() - 0.5));
-          float py = (float)(y0 + dx * (s.next() - 0.5));
-          float pz = (float)(z0 + dx * (s.next() - 0.5));
-          // vec2pix_ring (chealpix) on the float-rounded position, then ring2nest (srcs.c:265-270)
-          double vx = px, vy = py, vz = pz;
-          double vlen = sqrt(vx * vx + vy * vy + vz * vz);
-          long long pr = clr_ang2pix_ring_zphi(d.nside_base, vz / vlen, atan2(vy, vx));
-          pos[off] = make_float4(px, py, pz, dz_rsd);
-          ipix[off] = clr_ring2nest(d.nside_base, (int)pr);
-          off++;
-        }
-      }
+    for (int q = 0; q < kCellsPerThread; q++)
+      for (int ip = 0; ip < c[q]; ip++) src_ref[off++] = ((unsigned long long)(i0 + q) << 24) | (unsigned)ip;
+  }
+}
 
-    }
+__global__ void __launch_bounds__(kThreads)
+place_src_kernel(const ClrDev d, const float *__restrict__ npot, const unsigned long long *__restrict__ src_ref,
+                 uint32_t seed, int ipop, float4 *__restrict__ pos, int32_t *__restrict__ ipix, long long nsrc)
+{
+  const double dx = (double)(d.l_box / d.n);
+  const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
+  for (long long is = blockIdx.x * (long long)blockDim.x + threadIdx.x; is < nsrc; is += (long long)gridDim.x * blockDim.x) {
+    unsigned long long ref = src_ref[is];
+    long long i = (long long)(ref >> 24);
+    int ip = (int)(ref & 0xffffffu);
+    int ix, iy, iz;
+    clr_cell(d, i, ix, iy, iz);
+    double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
+    double y0 = (iy + 0.0) * dx - d.pos_obs[1];
+    double x0 = (ix + 0.0) * dx - d.pos_obs[0];
+    double rr = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
+    double rvel = factor_vel * dev_get_rvel(d, npot, ix, iy, iz, x0, y0, z0, rr);
+    float dz_rsd = (float)(rvel * clr_bg_v1(d, rr));
+    unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
+    ClrStream s(seed, 2 + 2 * ipop, gcell);
+    s.seek(3u * (uint32_t)ip);
+    float px = (float)(x0 + dx * (s.next() - 0.5));
+    float py = (float)(y0 + dx * (s.next() - 0.5));
+    float pz = (float)(z0 + dx * (s.next() - 0.5));
+    // vec2pix_ring (chealpix) on the float-rounded position, then ring2nest (srcs.c:265-270)
+    double vx = px, vy = py, vz = pz;
+    double vlen = sqrt(vx * vx + vy * vy + vz * vz);
+    long long pr = clr_ang2pix_ring_zphi(d.nside_base, vz / vlen, atan2(vy, vx));
+    pos[is] = make_float4(px, py, pz, dz_rsd);
+    ipix[is] = clr_ring2nest(d.nside_base, (int)pr);
   }
 }
 
@@ -433,9 +507,16 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
     P.cap_src = cap;
   }
   if (total > 0) {
+    // the 9-float Src buffer is not written until clr_srcs_local: borrow it for the source references
+    unsigned long long *d_ref = reinterpret_cast<unsigned long long *>(P.d_srcs);
+    {
+      StageScope sc(c, "srcs_expand", 1);
+      expand_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(P.d_counts, d_offs, d_ref, n_cells);
+      CLR_CUDA(cudaGetLastError());
+    }
     StageScope sc(c, "srcs_place", 1);
-    place_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, P.d_counts, d_offs, seed, ipop,
-                                                                        reinterpret_cast<float4 *>(P.d_pos), P.d_ipix, n_cells);
+    place_src_kernel<<<grid_for(c, (total + kThreads - 1) / kThreads, 8), kThreads, 0, c->stream>>>(
+        c->dev, c->d_npot, d_ref, seed, ipop, reinterpret_cast<float4 *>(P.d_pos), P.d_ipix, total);
     CLR_CUDA(cudaGetLastError());
   }
   return 0;

@@ -136,6 +136,9 @@ class ParamCoLoRe:
         check(self.lib.clr_grid_get(self.ctx, C.c_int(which), _vp(out)))
         return out
 
+    def set_option(self, name: str, value: int):
+        check(self.lib.clr_set_option(self.ctx, name.encode(), C.c_int(int(value))))
+
     def set_sigma2_gauss(self, s2: float):
         self.sigma2_gauss = float(s2)
         check(self.lib.clr_set_sigma2_gauss(self.ctx, C.c_double(s2)))

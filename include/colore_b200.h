@@ -108,6 +108,12 @@ int clr_normalize_fields(clr_ctx *ctx, double *out2);
  * noise). out2 = {mean, sigma2_gauss}; sigma2 is also kept in the context. */
 int clr_create_cartesian_fields(clr_ctx *ctx, uint32_t seed, int inject, double *out2);
 int clr_set_sigma2_gauss(clr_ctx *ctx, double sigma2);
+/* options: "exact_math" = 1 makes the streaming field kernels (mode fill, lognormal / clip, the
+ * normalisation histogram) evaluate the reference's double-precision expressions verbatim
+ * (fourier.c:337-353, density.c:1095-1098, 1166-1178); 0 (default) evaluates them in fp32 with
+ * double only where it protects the result. Integer outputs (Poisson counts, pixel ids) are
+ * exact in both modes. */
+int clr_set_option(clr_ctx *ctx, const char *name, int value);
 /* refresh the z-halo planes of the potential after clr_grid_put (fourier.c:401-414) */
 int clr_update_halo(clr_ctx *ctx);
 

@@ -92,16 +92,25 @@ def test_fft_drops_imag_of_xdc_and_nyquist(golden_dir):
 
 
 # ------------------------------------------------------------------------------ Gaussian fields
-def test_fill_modes_vs_oracle(case):
+@pytest.mark.parametrize("exact", [1, 0])
+def test_fill_modes_vs_oracle(case, exact):
     g, t, o, par = case
     dk, pk = o.fill_modes(RNG_PHILOX, int(t["seed"]))
+    par.set_option("exact_math", exact)
     cb.fill_modes(par)
+    par.set_option("exact_math", 0)
     gd = par.grid_get(cb.GRID_DENS).view(np.complex64)
     gp = par.grid_get(cb.GRID_NPOT).view(np.complex64)
-    # double arithmetic on both sides: agreement to a few fp32 ulps of each mode
     for got, ref in ((gd, dk), (gp, pk)):
-        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
-        assert rel[np.abs(ref) > 0].max() < 5e-7
+        err = np.abs(got - ref)
+        big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+        if exact:
+            # double arithmetic on both sides: agreement to a few fp32 ulps of each mode
+            assert (err / np.maximum(np.abs(ref), 1e-30))[np.abs(ref) > 0].max() < 5e-7
+        else:
+            # fp32 transcendentals: 2e-6 of each significant mode, 1e-6 of the largest mode overall
+            assert (err[big] / np.abs(ref[big])).max() < 2e-6
+            assert err.max() < 1e-6 * np.abs(ref).max()
         assert np.all(got[np.abs(ref) == 0] == 0)
 
 
@@ -137,22 +146,31 @@ def test_own_stream_end_to_end_vs_oracle(case):
 
 
 # --------------------------------------------------------------------------- physical density
-def test_physical_density_vs_reference(case):
+@pytest.mark.parametrize("exact", [1, 0])
+def test_physical_density_vs_reference(case, exact):
     g, t, o, par = case
     n = o.n
     par.grid_put(cb.GRID_DENS, g["s1_dens_gauss"])
     par.set_sigma2_gauss(g["s1_sigma2_gauss"][0])
+    par.set_option("exact_math", exact)
     cb.compute_physical_density_field(par)
-    got = par.grid_get(cb.GRID_DENS)
-    ref = g["s2_dens"]
-    # same double arithmetic, CUDA exp vs glibc exp: at most 1 fp32 ulp apart
-    d = np.abs(_real(got, n).astype(np.float64) - _real(ref, n))
-    assert d.max() <= 2.5e-7 * (1 + np.abs(_real(ref, n)).max())
-    assert np.mean(_real(got, n) == _real(ref, n)) > 0.99
+    par.set_option("exact_math", 0)
+    got = _real(par.grid_get(cb.GRID_DENS), n).astype(np.float64)
+    ref = _real(g["s2_dens"], n).astype(np.float64)
+    if exact:
+        # same double arithmetic, CUDA exp vs glibc exp: at most 1 fp32 ulp apart
+        assert np.abs(got - ref).max() <= 2.5e-7 * (1 + np.abs(ref).max())
+        assert np.mean(got == ref) > 0.99
+    else:
+        # fp32 evaluation: 1e-6 relative on 1+delta (the physical density), the stated fp32 tolerance
+        assert (np.abs(got - ref) / (1 + np.abs(ref))).max() < 1e-6
 
 
-def test_density_normalization_vs_reference(case):
+@pytest.mark.parametrize("exact", [1, 0])
+def test_density_normalization_vs_reference(case, exact):
     g, t, o, par = case
+    rtol = 1e-12 if exact else 1e-6      # fp32 bias_model terms summed in double: ~1e-7 systematic
+    par.set_option("exact_math", exact)
     par.grid_put(cb.GRID_DENS, g["s2_dens"])
     npop = sum(1 for k in t if k.startswith("srcs_bz_"))
     for i in range(npop):
@@ -160,14 +178,15 @@ def test_density_normalization_vs_reference(case):
     if "imap_bz_0" in t:
         par.set_imap(0, t["imap_tz_0"], t["imap_bz_0"], 8, g["s4_imap_r0_0"], g["s4_imap_rf_0"])
     cb.compute_density_normalization(par)
+    par.set_option("exact_math", 0)
     for i in range(npop):
         norm, ends, zends = cb.get_norm(par, 0, i)
-        np.testing.assert_allclose(norm, g[f"s3_srcs_norm_{i}"], rtol=1e-12)
-        np.testing.assert_allclose(ends, g[f"s3_srcs_norm_ends_{i}"], rtol=1e-12)
+        np.testing.assert_allclose(norm, g[f"s3_srcs_norm_{i}"], rtol=rtol)
+        np.testing.assert_allclose(ends, g[f"s3_srcs_norm_ends_{i}"], rtol=rtol)
         np.testing.assert_allclose(zends, g["s3_znorm_ends"], rtol=1e-13, atol=0)
     if "imap_bz_0" in t:
         norm, ends, _ = cb.get_norm(par, 1, 0)
-        np.testing.assert_allclose(norm, g["s3_imap_norm_0"], rtol=1e-12)
+        np.testing.assert_allclose(norm, g["s3_imap_norm_0"], rtol=rtol)
 
 
 # ------------------------------------------------------------------------------------ sources
