@@ -199,17 +199,38 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    if world > 1:
-        raise SystemExit("multi-GPU slab decomposition: see DESIGN.md (not built in this revision)")
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     n = args.n_grid
     cfg = make_config(n)
     tabs = build_tables(cfg)
-    par = cb.ParamCoLoRe(tabs, n, dens_type=0, seed=cfg.seed, device=local)
+    # strong scaling: the n_grid^3 box is cut into `world` z slabs (fourier.c:172-177), one per GPU
+    nz_here, iz0_here = cb.dist.slab_bounds(n, world, rank)
+    par = cb.ParamCoLoRe(tabs, n, dens_type=0, seed=cfg.seed, device=local, nz_here=nz_here, iz0_here=iz0_here)
+    cb.dist.init_comm(par, rank, world)
     nz_tab, bz_tab = tabs["srcs_nz_0"], tabs["srcs_bz_0"]
     par.set_srcs(0, nz_tab, bz_tab)
 
@@ -217,7 +238,7 @@ def main():
     for w in range(args.warmup):
         run_step(cb, par, 100 + w, tabs)
     par.synchronize()
-    torch.cuda.synchronize()
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     par.set_profiling(True)
@@ -228,37 +249,49 @@ def main():
         # inputs (two 4.3 GB grids at 1024^3) are far larger than the 126 MB L2: no flush needed
         nsrc = run_step(cb, par, 1000 + s, tabs)
     ms_total = par.timer_stop_ms()
+    barrier()
+    ms_total = allmax(ms_total)                      # device time, max over ranks
+    nsrc_total = int(allsum(nsrc))
     launches = par.launch_count - l0
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = n ** 3 / (ms_step * 1e-3) / 1e6
-    stage_names = ["fill_modes", "fft_z", "fft_y", "fft_x", "halo", "lognormal", "norm_hist", "srcs_poisson",
-                   "srcs_scan", "srcs_place", "srcs_local"]
+    stage_names = ["fill_modes", "fft_z", "fft_a2a", "fft_y", "fft_x", "halo", "lognormal", "norm_hist", "srcs_poisson",
+                   "srcs_scan", "srcs_expand", "srcs_place", "srcs_local"]
     stages = {}
     for nm in stage_names:
         ms, nl = par.stage_ms(nm)
-        if nl:
+        if nl or ms:
             stages[nm] = {"ms_per_step": ms / args.steps, "launches_per_step": nl / args.steps}
     par.set_profiling(False)
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peak, peak_src = measured_hbm_peak()
     nc = n // 2 + 1
-    grid_bytes = 8.0 * n * n * nc          # one complex64 half-spectrum = one padded real grid
+    grid_bytes = 8.0 * n * n * nc / world   # this rank's slab of a complex64 half-spectrum / padded real grid
+    cells = float(n) ** 3 / world           # cells of this rank's slab
     alg_bytes = {                           # algorithmic bytes per LAUNCH
         "fill_modes": 2 * grid_bytes,                      # two complex grids written (8 B/cell)
         "fft_z": 2 * grid_bytes, "fft_y": 2 * grid_bytes, "fft_x": 2 * grid_bytes,   # 8 B/cell per pass
-        "lognormal": 8.0 * n ** 3, "norm_hist": 4.0 * n ** 3, "srcs_poisson": 8.0 * n ** 3,
-        "srcs_place": 4.0 * n ** 3 + 28.0 * nsrc,
+        "lognormal": 8.0 * cells, "norm_hist": 4.0 * cells, "srcs_poisson": 8.0 * cells,
+        "srcs_expand": 4.0 * cells + 8.0 * nsrc, "srcs_place": 36.0 * nsrc,
     }
-    dom = max((k for k in stages if k in alg_bytes), key=lambda k: stages[k]["ms_per_step"])
+    dom = max((k for k in stages if k in alg_bytes and stages[k]["launches_per_step"] > 0),
+              key=lambda k: stages[k]["ms_per_step"])
     per_launch_ms = stages[dom]["ms_per_step"] / stages[dom]["launches_per_step"]
     achieved = alg_bytes[dom] / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dom], "ms_per_launch": per_launch_ms}
     fft_ms = sum(stages[k]["ms_per_step"] for k in ("fft_z", "fft_y", "fft_x") if k in stages)
-    fft_gbs = 2 * 24.0 * n ** 3 / (fft_ms * 1e-3) / 1e9 if fft_ms else None
+    fft_gbs = 2 * 24.0 * cells / (fft_ms * 1e-3) / 1e9 if fft_ms else None        # per GPU
+    nvlink = None
+    if world > 1 and "fft_a2a" in stages and stages["fft_a2a"]["ms_per_step"] > 0:
+        # bytes one rank SENDS per step: 2 transforms x slab bytes x (P-1)/P
+        sent = 2 * grid_bytes * (world - 1) / world
+        nvlink = {"bytes_sent_per_rank_per_step": sent, "ms_per_step": stages["fft_a2a"]["ms_per_step"],
+                  "achieved_gbs_per_direction": sent / (stages["fft_a2a"]["ms_per_step"] * 1e-3) / 1e9,
+                  "peak_gbs_per_direction": 770.0, "peak_source": "measured peer copy (B200_PROFILING.md)"}
 
     # ---- end to end through the public API with host buffers -----------------------------------
     # inputs: the population tables from pinned host memory (H2D every step); result: the Src records
@@ -271,7 +304,7 @@ def main():
     pin_out = torch.empty((cap, 9), dtype=torch.float32).pin_memory()
     tout = pin_out.numpy()
     d2h = 0
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         par.set_srcs(0, tin[:cb._lib.NA], tin[cb._lib.NA:])
@@ -279,9 +312,9 @@ def main():
         cb.srcs_get_local_properties(par, 0, out=tout[:k])
         d2h += k * 36
     par.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    e2e = {"value": n ** 3 / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tin.nbytes),
-           "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": e2e_ms}
+    e2e_ms = allmax((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e = {"value": n ** 3 / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tin.nbytes * world),
+           "d2h_bytes_per_step": int(allsum(d2h / args.steps)), "ms_per_step": e2e_ms}
 
     # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------
     cpu = None
@@ -302,12 +335,15 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"n_grid={n} lognormal + 1 galaxy population + RSD (field->sources)",
-                       "n_grid": n, "sources_per_step": int(nsrc), "l2_policy": "inputs (8.6 GB of grids) exceed the 126 MB L2",
-                       "seed_per_step": "varies"},
+                       "n_grid": n, "sources_per_step": nsrc_total,
+                       "parallelism": f"{world} z-slab(s), one process per GPU, NCCL all-to-all in the FFT",
+                       "l2_policy": "inputs (8.6 GB of grids at 1024^3) exceed the 126 MB L2", "seed_per_step": "varies"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "fft_hbm_gbs": fft_gbs, "stages": stages, "cpu_baseline": cpu,
+            "roofline": roofline, "fft_hbm_gbs": fft_gbs, "nvlink": nvlink, "stages": stages, "cpu_baseline": cpu,
         }))
     par.free()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -81,6 +81,7 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   ClrDev &d = c->dev;
   d.n = p->n_grid; d.nc = p->n_grid / 2 + 1; d.nz_here = p->nz_here; d.iz0_here = p->iz0_here;
   d.pitch = 2 * d.nc;
+  d.nyl = d.n; d.ky0 = 0;
   d.log2n = -1;
   for (int b = 0; b < 31; b++) if ((1 << b) == d.n) d.log2n = b;
   d.bias_model = p->bias_model; d.nside_base = p->nside_base;
@@ -97,6 +98,24 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
     CLR_CUDA(cudaMalloc(&c->d_tables_f, 2 * CLR_NA * sizeof(float)));
     CLR_CUDA(cudaMemcpy(c->d_tables_f, tf.data(), 2 * CLR_NA * sizeof(float), cudaMemcpyHostToDevice));
     d.z_f = c->d_tables_f; d.d1_f = c->d_tables_f + CLR_NA;
+  }
+  {
+    // coordinate tables, evaluated with the reference's expressions (see ClrDev)
+    const int n = d.n;
+    std::vector<float> cf(3 * (size_t)n);
+    std::vector<double> cd(3 * (size_t)n);
+    const float dxf = p->l_box / n;                 // flouble dx (density.c:1079)
+    const double dxd = p->l_box / n;                // double dx from the float division (srcs.c:147)
+    for (int ax = 0; ax < 3; ax++)
+      for (int i = 0; i < n; i++) {
+        cf[(size_t)ax * n + i] = (float)((i + 0.0) * dxf - p->pos_obs[ax]);
+        cd[(size_t)ax * n + i] = (i + 0.0) * dxd - p->pos_obs[ax];
+      }
+    CLR_CUDA(cudaMalloc(&c->d_coord_f, cf.size() * sizeof(float)));
+    CLR_CUDA(cudaMalloc(&c->d_coord_d, cd.size() * sizeof(double)));
+    CLR_CUDA(cudaMemcpy(c->d_coord_f, cf.data(), cf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CLR_CUDA(cudaMemcpy(c->d_coord_d, cd.data(), cd.size() * sizeof(double), cudaMemcpyHostToDevice));
+    for (int ax = 0; ax < 3; ax++) { d.cf[ax] = c->d_coord_f + (size_t)ax * n; d.cd[ax] = c->d_coord_d + (size_t)ax * n; }
   }
   size_t plane = (size_t)d.pitch * d.n;
   CLR_CUDA(cudaMalloc(&c->d_dens, plane * d.nz_here * sizeof(float)));
@@ -118,8 +137,10 @@ int clr_destroy(clr_ctx *c)
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  clr_comm_destroy(c);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
+  cudaFree(c->d_coord_f); cudaFree(c->d_coord_d);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -131,15 +152,6 @@ int clr_destroy(clr_ctx *c)
 int clr_synchronize(clr_ctx *c) { CLR_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 long long clr_launch_count(clr_ctx *c) { return c->launches; }
 
-int clr_comm_unique_id(void *id128) { (void)id128; clr_set_error("multi-GPU communicator not built yet"); return 1; }
-int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128)
-{
-  (void)id128;
-  if (nranks == 1) { c->rank = 0; c->nranks = 1; return 0; }
-  (void)rank;
-  clr_set_error("multi-GPU communicator not built yet");
-  return 1;
-}
 
 static int set_pop(clr_ctx *c, clr_ctx::Pop &P, const double *a, const double *b)
 {
@@ -230,6 +242,7 @@ int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *o
   if (clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch)) return 1;   // scaling + moments fused in the x pass
   if (clr_fft_c2r_impl(c, c->d_npot, norm, nullptr)) return 1;
   if (clr_halo_update(c)) return 1;
+  if (clr_comm_allreduce_f64(c, c->d_scratch, 2)) return 1;            // fourier.c:69-70
   double mom[2];
   CLR_CUDA(cudaMemcpyAsync(mom, c->d_scratch, sizeof(mom), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));

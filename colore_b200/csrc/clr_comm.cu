@@ -1,0 +1,149 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink 5 / NVSwitch. Replaces the reference's MPI
+// layer (common.c:216-274 and the call sites listed in SURVEY.md section 2.3):
+//   FFTW-MPI transposes        -> one grouped ncclSend/ncclRecv all-to-all per transform (clr_fft.cu)
+//   MPI_Allreduce (2 doubles)  -> ncclAllReduce                      (fourier.c:69-70)
+//   MPI_Sendrecv z-halo        -> ncclSend/ncclRecv pair per side    (fourier.c:406-410)
+//   MPI_Allreduce histograms   -> ncclAllReduce                      (density.c:1262-1269)
+// NCCL is resolved at run time with dlopen("libnccl.so.2"): inside a torchrun process this is the
+// copy PyTorch already loaded, and a single-GPU build never needs the library at all.
+#include "clr_internal.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+namespace {
+
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl()
+{
+  if (g_nccl.h) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  CLR_CHECK(h, "cannot load libnccl.so.2: %s", dlerror());
+#define CLR_SYM(name)                                                        \
+  *(void **)(&g_nccl.name) = dlsym(h, "nccl" #name);                         \
+  CLR_CHECK(g_nccl.name, "libnccl lacks symbol nccl" #name)
+  CLR_SYM(GetUniqueId); CLR_SYM(CommInitRank); CLR_SYM(CommDestroy); CLR_SYM(Send); CLR_SYM(Recv);
+  CLR_SYM(AllReduce); CLR_SYM(GroupStart); CLR_SYM(GroupEnd); CLR_SYM(GetErrorString);
+#undef CLR_SYM
+  g_nccl.h = h;
+  return 0;
+}
+
+#define CLR_NCCL(call)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r_ = (call);                                                                   \
+    if (r_ != ncclSuccess) {                                                                    \
+      clr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_));   \
+      return 1;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+}  // namespace
+
+extern "C" int clr_comm_unique_id(void *id128)
+{
+  if (load_nccl()) return 1;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  CLR_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+extern "C" int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128)
+{
+  CLR_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "clr_comm_init: bad rank %d of %d", rank, nranks);
+  c->rank = rank; c->nranks = nranks;
+  ClrDev &d = c->dev;
+  if (nranks == 1) { d.nyl = d.n; d.ky0 = 0; return 0; }
+  CLR_CHECK(d.n % nranks == 0, "n_grid=%d is not divisible by the number of GPUs %d", d.n, nranks);
+  CLR_CHECK(d.nz_here == d.n / nranks && d.iz0_here == rank * (d.n / nranks),
+            "slab bounds (nz_here=%d, iz0_here=%d) do not match rank %d of %d", d.nz_here, d.iz0_here, rank, nranks);
+  if (load_nccl()) return 1;
+  CLR_CUDA(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  CLR_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  c->nccl_comm = comm;
+  d.nyl = d.n / nranks;
+  d.ky0 = rank * d.nyl;
+  // staging buffer of the FFT all-to-all: one slab
+  size_t bytes = (size_t)d.pitch * d.n * d.nz_here * sizeof(float);
+  CLR_CUDA(cudaMalloc(&c->d_stage, bytes));
+  return 0;
+}
+
+int clr_comm_destroy(clr_ctx *c)
+{
+  if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
+  c->nccl_comm = nullptr;
+  if (c->d_stage) cudaFree(c->d_stage);
+  c->d_stage = nullptr;
+  return 0;
+}
+
+// block b of `send` (block_floats floats) goes to rank b; block s of `recv` comes from rank s
+int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_floats)
+{
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  const float *s = static_cast<const float *>(send);
+  float *r = static_cast<float *>(recv);
+  CLR_CUDA(cudaMemcpyAsync(r + (size_t)c->rank * block_floats, s + (size_t)c->rank * block_floats,
+                           block_floats * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  CLR_NCCL(g_nccl.GroupStart());
+  for (int k = 1; k < c->nranks; k++) {
+    int to = (c->rank + k) % c->nranks, from = (c->rank - k + c->nranks) % c->nranks;
+    CLR_NCCL(g_nccl.Send(s + (size_t)to * block_floats, block_floats, ncclFloat, to, comm, c->stream));
+    CLR_NCCL(g_nccl.Recv(r + (size_t)from * block_floats, block_floats, ncclFloat, from, comm, c->stream));
+  }
+  CLR_NCCL(g_nccl.GroupEnd());
+  c->a2a_bytes += (double)block_floats * sizeof(float) * (c->nranks - 1);
+  return 0;
+}
+
+int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n)
+{
+  if (c->nranks == 1) return 0;
+  CLR_NCCL(g_nccl.AllReduce(dbuf, dbuf, n, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+  return 0;
+}
+
+int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n)
+{
+  if (c->nranks == 1) return 0;
+  CLR_NCCL(g_nccl.AllReduce(dbuf, dbuf, n, ncclUint64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+  return 0;
+}
+
+// z-halo of the potential (fourier.c:401-414): my last plane -> right neighbour's slice_left,
+// my first plane -> left neighbour's slice_right
+int clr_comm_halo(clr_ctx *c)
+{
+  const ClrDev &d = c->dev;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  size_t plane = (size_t)d.pitch * d.n;
+  int right = (c->rank + 1) % c->nranks, left = (c->rank - 1 + c->nranks) % c->nranks;
+  float *slice_left = c->d_npot + plane * d.nz_here, *slice_right = slice_left + plane;
+  CLR_NCCL(g_nccl.GroupStart());
+  CLR_NCCL(g_nccl.Send(c->d_npot + plane * (d.nz_here - 1), plane, ncclFloat, right, comm, c->stream));
+  CLR_NCCL(g_nccl.Recv(slice_left, plane, ncclFloat, left, comm, c->stream));
+  CLR_NCCL(g_nccl.Send(c->d_npot, plane, ncclFloat, left, comm, c->stream));
+  CLR_NCCL(g_nccl.Recv(slice_right, plane, ncclFloat, right, comm, c->stream));
+  CLR_NCCL(g_nccl.GroupEnd());
+  return 0;
+}

@@ -166,10 +166,22 @@ __device__ __forceinline__ void fft_lines(float2 (&vv)[V][8], float2 *s, const f
 
 // ------------------------------------------------------------------------------------------
 // strided pass: lines of length M, element stride e_stride, T consecutive lines per tile
+// Addressing of a strided line: element e lives at outer*outer_stride + (e >> lo_bits)*hi_stride +
+// (e & mask)*lo_stride (+ the contiguous index). Single-level strides use lo_bits = 31. The two-level
+// form lets the y pass of the distributed transform read straight out of the all-to-all staging
+// buffer [source rank][z_local][ky_in_source][kx] (and the r2c write straight into it), so the slab
+// transpose costs no extra pack / unpack pass over HBM.
+struct LineAddr {
+  long long outer_stride, hi_stride, lo_stride;
+  int lo_bits;
+  __device__ __forceinline__ long long off(int e) const
+  { return (long long)(e >> lo_bits) * hi_stride + (long long)(e & ((1 << lo_bits) - 1)) * lo_stride; }
+};
+
 template <int M, int S, int T, int V>
 __global__ void __launch_bounds__(T * M / 8 / V)
-fft_strided_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, long long n_tiles,
-                   int tiles_per_outer, long long outer_stride, long long e_stride, int n_inner)
+fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, const float2 *__restrict__ W, int wn,
+                   long long n_tiles, int tiles_per_outer, int n_inner)
 {
   using P = FftPlan<M>;
   constexpr int TPLV = P::TPL / V;
@@ -183,19 +195,20 @@ fft_strided_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn,
     long long outer = tile / tiles_per_outer;
     int inner0 = (int)(tile % tiles_per_outer) * T;
     bool ok = inner0 + l < n_inner;
-    float2 *base = g + outer * outer_stride + inner0 + l;
+    const float2 *bin = gin + outer * ain.outer_stride + inner0 + l;
+    float2 *bout = gout + outer * aout.outer_stride + inner0 + l;
     float2 vv[V][8];
 #pragma unroll
     for (int vt = 0; vt < V; vt++)
 #pragma unroll
       for (int r = 0; r < 8; r++)
-        vv[vt][r] = ok ? base[(long long)(j + vt * TPLV + r * P::TPL) * e_stride] : make_float2(0.f, 0.f);
+        vv[vt][r] = ok ? bin[ain.off(j + vt * TPLV + r * P::TPL)] : make_float2(0.f, 0.f);
     fft_lines<M, S, true, T, V>(vv, s, tw, j, l);
     if (ok) {
 #pragma unroll
       for (int vt = 0; vt < V; vt++)
 #pragma unroll
-        for (int r = 0; r < 8; r++) base[(long long)(j + vt * TPLV + r * P::TPL) * e_stride] = vv[vt][r];
+        for (int r = 0; r < 8; r++) bout[aout.off(j + vt * TPLV + r * P::TPL)] = vv[vt][r];
     }
     __syncthreads();
   }
@@ -352,7 +365,7 @@ template <typename K> int launch_cfg(clr_ctx *c, K kernel, int threads, size_t s
 }
 
 template <int M, int S>
-int run_strided(clr_ctx *c, float2 *g, long long n_outer, long long outer_stride, long long e_stride, int n_inner)
+int run_strided2(clr_ctx *c, const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, long long n_outer, int n_inner)
 {
   using P = FftPlan<M>;
   constexpr int T = Cfg<M>::T_STRIDED, V = Cfg<M>::V;
@@ -363,9 +376,61 @@ int run_strided(clr_ctx *c, float2 *g, long long n_outer, long long outer_stride
   int grid;
   auto k = fft_strided_kernel<M, S, T, V>;
   if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
-  k<<<grid, threads, smem, c->stream>>>(g, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, outer_stride, e_stride, n_inner);
+  k<<<grid, threads, smem, c->stream>>>(gin, gout, ain, aout, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, n_inner);
   CLR_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int M, int S>
+int run_strided(clr_ctx *c, float2 *g, long long n_outer, long long outer_stride, long long e_stride, int n_inner)
+{
+  LineAddr a{outer_stride, 0, e_stride, 31};
+  return run_strided2<M, S>(c, g, g, a, a, n_outer, n_inner);
+}
+
+// ---- slab-decomposed transform (one process per GPU) ----------------------------------------------
+// k space is held in y slabs, layout [kz][ky_local][kx] (the mode fill is layout free); real space in
+// z slabs [z_local][y][x] like the reference (fourier.c:172-177). c2r: z pass local -> ONE all-to-all
+// (block for rank h = the z planes of h: contiguous, no pack) -> y pass reading the staging buffer
+// through the two-level LineAddr and writing the natural layout -> x pass. r2c runs the mirror image.
+int ilog2_host(int v) { int b = 0; while ((1 << b) < v) b++; return b; }
+template <int M, bool MOM> int run_c2r_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c, float norm, double *mom);
+template <int M> int run_r2c_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c);
+
+template <int N>
+int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
+{
+  const long long nc = N / 2 + 1;
+  const int P = c->nranks, nzl = N / P, nyl = N / P;
+  float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
+  { StageScope sc(c, "fft_z", 1);
+    if (run_strided<N, +1>(c, g, 1, 0, (long long)nyl * nc, (int)(nyl * nc))) return 1; }
+  { StageScope sc(c, "fft_a2a", 0);
+    if (clr_comm_alltoall(c, g, stage, (size_t)nzl * nyl * nc * 2)) return 1; }
+  { StageScope sc(c, "fft_y", 1);
+    LineAddr ain{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};
+    LineAddr aout{(long long)N * nc, 0, nc, 31};
+    if (run_strided2<N, +1>(c, stage, g, ain, aout, nzl, (int)nc)) return 1; }
+  StageScope sc(c, "fft_x", 1);
+  if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)nzl * N, (int)nc, norm, mom);
+  return run_c2r_x<N / 2, false>(c, g, (long long)nzl * N, (int)nc, norm, nullptr);
+}
+
+template <int N>
+int r2c_3d_dist(clr_ctx *c, float2 *g)
+{
+  const long long nc = N / 2 + 1;
+  const int P = c->nranks, nzl = N / P, nyl = N / P;
+  float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
+  { StageScope sc(c, "fft_x", 1); if (run_r2c_x<N / 2>(c, g, (long long)nzl * N, (int)nc)) return 1; }
+  { StageScope sc(c, "fft_y", 1);
+    LineAddr ain{(long long)N * nc, 0, nc, 31};
+    LineAddr aout{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};
+    if (run_strided2<N, -1>(c, g, stage, ain, aout, nzl, (int)nc)) return 1; }
+  { StageScope sc(c, "fft_a2a", 0);
+    if (clr_comm_alltoall(c, stage, g, (size_t)nzl * nyl * nc * 2)) return 1; }
+  StageScope sc(c, "fft_z", 1);
+  return run_strided<N, -1>(c, g, 1, 0, (long long)nyl * nc, (int)(nyl * nc));
 }
 
 template <int M, bool MOM>
@@ -428,8 +493,20 @@ int r2c_3d(clr_ctx *c, float2 *g)
 // {sum, sum of squares} of the scaled output over the unpadded cells.
 int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments)
 {
-  CLR_CHECK(c->nranks == 1, "multi-GPU FFT goes through clr_fft_dist (not built in this call path)");
   float2 *g = reinterpret_cast<float2 *>(grid);
+  if (c->nranks > 1) {
+    CLR_CHECK(c->d_stage, "distributed FFT: no staging buffer (clr_comm_init first)");
+    switch (c->dev.n) {
+      case 64: return c2r_3d_dist<64>(c, g, (float)norm, d_moments);
+      case 128: return c2r_3d_dist<128>(c, g, (float)norm, d_moments);
+      case 256: return c2r_3d_dist<256>(c, g, (float)norm, d_moments);
+      case 512: return c2r_3d_dist<512>(c, g, (float)norm, d_moments);
+      case 1024: return c2r_3d_dist<1024>(c, g, (float)norm, d_moments);
+      case 2048: return c2r_3d_dist<2048>(c, g, (float)norm, d_moments);
+      case 4096: return c2r_3d_dist<4096>(c, g, (float)norm, d_moments);
+      default: clr_set_error("n_grid=%d: the distributed FFT supports powers of two in [64,4096]", c->dev.n); return 1;
+    }
+  }
   switch (c->dev.n) {
     case 16: return c2r_3d<16>(c, g, (float)norm, d_moments);
     case 32: return c2r_3d<32>(c, g, (float)norm, d_moments);
@@ -446,8 +523,20 @@ int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments)
 
 int clr_fft_r2c_impl(clr_ctx *c, float *grid)
 {
-  CLR_CHECK(c->nranks == 1, "multi-GPU FFT goes through clr_fft_dist (not built in this call path)");
   float2 *g = reinterpret_cast<float2 *>(grid);
+  if (c->nranks > 1) {
+    CLR_CHECK(c->d_stage, "distributed FFT: no staging buffer (clr_comm_init first)");
+    switch (c->dev.n) {
+      case 64: return r2c_3d_dist<64>(c, g);
+      case 128: return r2c_3d_dist<128>(c, g);
+      case 256: return r2c_3d_dist<256>(c, g);
+      case 512: return r2c_3d_dist<512>(c, g);
+      case 1024: return r2c_3d_dist<1024>(c, g);
+      case 2048: return r2c_3d_dist<2048>(c, g);
+      case 4096: return r2c_3d_dist<4096>(c, g);
+      default: clr_set_error("n_grid=%d: the distributed FFT supports powers of two in [64,4096]", c->dev.n); return 1;
+    }
+  }
   switch (c->dev.n) {
     case 16: return r2c_3d<16>(c, g);
     case 32: return r2c_3d<32>(c, g);

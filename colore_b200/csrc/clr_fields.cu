@@ -28,7 +28,9 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
   const double dk = 2 * 3.14159265358979323846 / d.l_box;
   const double idk3 = 1. / (dk * dk * dk);
   // a CTA takes groups of rows (kz,ky) so that all index divisions are 32-bit and by nc / n only
-  const unsigned n_rows = (unsigned)d.nz_here * (unsigned)d.n;
+  // k space is held as [kz][ky_local][kx] with ky in [ky0, ky0+nyl) (single GPU: nyl = n, ky0 = 0, which
+  // is the reference layout); rows = (kz, ky_local)
+  const unsigned n_rows = (unsigned)d.n * (unsigned)d.nyl;
   const unsigned rpb = max(1u, 1024u / (unsigned)d.nc);
   const unsigned n_groups = (n_rows + rpb - 1) / rpb;
   (void)n_modes;
@@ -38,10 +40,9 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
     int kk = (int)(tl - rl * (unsigned)d.nc);
     unsigned row = grp * rpb + rl;
     if (row >= n_rows) continue;
-    int ii = (int)(row / (unsigned)d.n);
-    int jj = (int)(row - (unsigned)ii * (unsigned)d.n);
+    int ii_true = (int)(row / (unsigned)d.nyl);
+    int jj = d.ky0 + (int)(row - (unsigned)ii_true * (unsigned)d.nyl);
     long long idx = (long long)row * d.nc + kk;
-    int ii_true = d.iz0_here + ii;
     double kz = (2 * ii_true <= d.n) ? ii_true * dk : -(d.n - ii_true) * dk;
     double ky = (2 * jj <= d.n) ? jj * dk : -(d.n - jj) * dk;
     double kx = (2 * kk <= d.n) ? kk * dk : -(d.n - kk) * dk;
@@ -69,9 +70,16 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
       uint32_t w[4];
       unsigned long long gidx = (unsigned long long)kk + (unsigned long long)d.nc * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
       clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
-      float l1;
-      if (w[1] < 0x80000000u) l1 = log1pf(-(float)w[1] * (1.f / 4294967296.f));
-      else l1 = logf((float)(0u - w[1]) * (1.f / 4294967296.f));            // 1-u2 = (2^32-w)/2^32 exactly
+      // ln(1-u2) without a branch: T = 2^32 - w is 1-u2 in units of 2^-32 (exact integer). logf of the
+      // float-rounded T plus the first-order term of the (exact) rounding residue keeps full relative
+      // accuracy both for u2 -> 0 (T -> 2^32, result -> 0) and u2 -> 1.
+      float l1 = 0.f;
+      if (w[1]) {
+        uint32_t T = 0u - w[1];
+        float Tf = __uint2float_rn(T);
+        float resid = (float)((long long)T - (long long)Tf);
+        l1 = logf(Tf * 2.3283064365386963e-10f) + __fdividef(resid, Tf);
+      }
       float delta_mod = sqrtf(-sigma2 * l1);
       float sn, cs;
       sincospif((float)(w[0] >> 7) * (1.f / 16777216.f), &sn, &cs);         // 2*u1 with 25 bits
@@ -173,15 +181,15 @@ lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int cl
     clr_cell(d, 2 * i, ix0, iy, iz);
     int xq = ix0 >> 1;
     long long row = (long long)iz * d.n + iy;
-    float z0 = (float)((iz + d.iz0_here + 0.0) * dx - d.pos_obs[2]);
-    float y0 = (float)((iy + 0.0) * dx - d.pos_obs[1]);
+    float z0 = __ldg(d.cf[2] + iz + d.iz0_here);
+    float y0 = __ldg(d.cf[1] + iy);
     float2 *p = reinterpret_cast<float2 *>(dens + row * d.pitch) + xq;
     float2 v = *p;
     float out[2];
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       int ix = 2 * xq + q;
-      float x0 = (float)((ix + 0.0) * dx - d.pos_obs[0]);
+      float x0 = __ldg(d.cf[0] + ix);
       // reference: sqrt(x0*x0+y0*y0+z0*z0) with float products, left-to-right float sums
       float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
       float delta = q ? v.y : v.x;
@@ -244,9 +252,9 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
       int ix, iy, iz;
       clr_cell(d, i, ix, iy, iz);
       long long row = (long long)iz * d.n + iy;
-      float z0 = (float)((iz + d.iz0_here + 0.0) * dx - d.pos_obs[2]);
-      float y0 = (float)((iy + 0.0) * dx - d.pos_obs[1]);
-      float x0 = (float)((ix + 0.0) * dx - d.pos_obs[0]);
+      float z0 = __ldg(d.cf[2] + iz + d.iz0_here);
+      float y0 = __ldg(d.cf[1] + iy);
+      float x0 = __ldg(d.cf[0] + ix);
       float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(y0, y0)), __fmul_rn(z0, z0));
       int ind_z;
       if (EXACT) {
@@ -327,6 +335,140 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
   }
 }
 
+// Fast variant of the same histogram (default path): every thread walks a run of 8 consecutive cells
+// along x and keeps the sums of its current bin in registers (bins are thick shells, a run almost
+// never crosses an edge); the run totals are merged per warp with one round of shuffles and one
+// shared-memory atomic per (warp, bin). fp32 evaluation of z(r), b(r) and bias_model; the bin index
+// falls back to the exact double expression within 1e-4 bins of an edge, so counts stay exact.
+constexpr int kRun = 8;
+constexpr int kFastPop = 4;
+struct NormPopsF { const float *bzf[kFastPop]; int npop; };
+
+__device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
+{
+  if (dl <= -1.f) return 0.f;
+  if (model == 2) return dl < 0.f ? expf(__fdividef(bi * dl, 1.f + dl)) : 1.f + bi * dl;
+  if (model == 3) return fmaxf(1.f + bi * dl, 0.f);
+  return powf(1.f + dl, bi);
+}
+
+__global__ void __launch_bounds__(kThreads)
+norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF pops, int nz, double idz,
+                      unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b)
+{
+  extern __shared__ double sh[];
+  double *s_z = sh;
+  double *s_b = sh + nz;
+  unsigned long long *s_n = reinterpret_cast<unsigned long long *>(sh + (size_t)nz * (1 + pops.npop));
+  for (int i = threadIdx.x; i < nz * (1 + pops.npop); i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) s_n[i] = 0;
+  __syncthreads();
+  const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max, zlastf = __ldg(d.z_f + CLR_NA - 1);
+  const float idzf = (float)idz;
+  const int npop = pops.npop;
+  const long long n_runs = (long long)d.nz_here * d.n * (d.n / kRun);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_iter = (n_runs + stride - 1) / stride;
+  const int lane = threadIdx.x & 31;
+  for (long long it = 0; it < n_iter; it++) {
+    long long run = it * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int curbin = -1, cnt = 0;
+    float zs = 0.f, bs[kFastPop] = {0.f, 0.f, 0.f, 0.f};
+    if (run < n_runs) {
+      int ix0, iy, iz;
+      clr_cell(d, run * kRun, ix0, iy, iz);
+      const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
+      const float yy = __fmul_rn(y0, y0), zz = __fmul_rn(z0, z0);
+      const float2 *p = reinterpret_cast<const float2 *>(dens + ((long long)iz * d.n + iy) * d.pitch + ix0);
+      float dv[kRun];
+#pragma unroll
+      for (int q = 0; q < kRun / 2; q++) { float2 v = p[q]; dv[2 * q] = v.x; dv[2 * q + 1] = v.y; }
+#pragma unroll
+      for (int q = 0; q < kRun; q++) {
+        float x0 = __ldg(d.cf[0] + ix0 + q);
+        float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
+        float rf = sqrtf(r2), zf, tr = rf * idrf;
+        int ir = (int)tr;
+        if (rf <= 0.f) zf = 0.f;
+        else if (rf >= rtabf) zf = zlastf;
+        else {
+          float fa = __ldg(d.z_f + ir), fb = __ldg(d.z_f + ir + 1);
+          zf = fa + (fb - fa) * (tr - (float)ir);
+        }
+        float tb = zf * idzf;
+        int ind_z;
+        if (fabsf(tb - rintf(tb)) < 1e-4f) {
+          double redshift = clr_bg_z(d, sqrt((double)r2));           // density.c:1166-1168 verbatim
+          ind_z = (int)(redshift * idz) + 1;
+        } else ind_z = (int)tb + 1;
+        int bin = (ind_z >= 0 && ind_z < nz) ? ind_z : -1;
+        if (bin != curbin) {
+          if (curbin >= 0 && cnt > 0) {                              // rare: the run crossed a bin edge
+            atomicAdd(&s_n[curbin], (unsigned long long)cnt);
+            atomicAdd(&s_z[curbin], (double)zs);
+#pragma unroll
+            for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) atomicAdd(&s_b[ip * nz + curbin], (double)bs[ip]);
+          }
+          curbin = bin; cnt = 0; zs = 0.f;
+#pragma unroll
+          for (int ip = 0; ip < kFastPop; ip++) bs[ip] = 0.f;
+        }
+        if (bin >= 0) {
+          cnt++;
+          zs += zf;
+#pragma unroll
+          for (int ip = 0; ip < kFastPop; ip++) {
+            if (ip < npop) {
+              float bi;
+              const float *tbz = pops.bzf[ip];
+              if (rf <= 0.f) bi = __ldg(tbz);
+              else if (rf >= rtabf) bi = 1.f;
+              else {
+                float fa = __ldg(tbz + ir), fb = __ldg(tbz + ir + 1);
+                bi = fa + (fb - fa) * (tr - (float)ir);
+              }
+              bs[ip] += bias_model_f(d.bias_model, dv[q], bi);
+            }
+          }
+        }
+      }
+    }
+    // merge the run totals of the warp, one shared atomic per distinct bin
+    unsigned todo = __ballot_sync(0xffffffffu, curbin >= 0 && cnt > 0);
+    while (todo) {
+      int leader = __ffs(todo) - 1;
+      int b = __shfl_sync(0xffffffffu, curbin, leader);
+      bool mine = (curbin == b) && cnt > 0;
+      unsigned grp = __ballot_sync(0xffffffffu, mine);
+      int csum = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
+      double zsum = clr_warp_sum(mine ? (double)zs : 0.);
+      if (lane == leader) { atomicAdd(&s_n[b], (unsigned long long)csum); atomicAdd(&s_z[b], zsum); }
+#pragma unroll
+      for (int ip = 0; ip < kFastPop; ip++) {
+        if (ip < npop) {
+          double bsum = clr_warp_sum(mine ? (double)bs[ip] : 0.);
+          if (lane == leader) atomicAdd(&s_b[ip * nz + b], bsum);
+        }
+      }
+      todo &= ~grp;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) {
+    if (s_n[i]) {
+      atomicAdd(&g_n[i], s_n[i]);
+      atomicAdd(&g_z[i], s_z[i]);
+      for (int ip = 0; ip < npop; ip++) atomicAdd(&g_b[ip * nz + i], s_b[ip * nz + i]);
+    }
+  }
+}
+
+__global__ void cvt_table_kernel(const double *__restrict__ src, float *__restrict__ dst, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+
 // z-halo of the potential for a single slab: periodic wrap (fourier.c:412-413)
 __global__ void halo_copy_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n)
 {
@@ -360,7 +502,7 @@ int clr_fields_fill(clr_ctx *c, uint32_t seed)
   double lgdk = log10(2 * M_PI / c->p.l_box);
   auto k = c->exact_math ? fill_modes_kernel<true> : fill_modes_kernel<false>;
   unsigned rpb = std::max(1u, 1024u / (unsigned)c->dev.nc);
-  long long n_groups = ((long long)c->dev.nz_here * c->dev.n + rpb - 1) / rpb;
+  long long n_groups = ((long long)c->dev.n * c->dev.nyl + rpb - 1) / rpb;
   (void)n_modes;
   k<<<grid_for(c, n_groups * kThreads, 8), kThreads, 0, c->stream>>>(
       c->dev, reinterpret_cast<float2 *>(c->d_dens), reinterpret_cast<float2 *>(c->d_npot), seed, c->d_pk,
@@ -381,6 +523,7 @@ int clr_fields_scale_moments(clr_ctx *c, double *out2)
     scale_moments_kernel<<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->d_npot, norm, c->d_scratch);
     CLR_CUDA(cudaGetLastError());
   }
+  if (clr_comm_allreduce_f64(c, c->d_scratch, 2)) return 1;
   CLR_CUDA(cudaMemcpyAsync(out2, c->d_scratch, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
@@ -403,7 +546,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
 {
   CLR_CHECK(npop <= CLR_MAX_NORM_POP && nz <= CLR_MAX_NZ, "normalisation: npop=%d nz=%d too large", npop, nz);
   size_t nd = (size_t)nz * (2 + npop);
-  if (clr_ensure_scratch(c, nd * sizeof(double))) return 1;
+  if (clr_ensure_scratch(c, nd * sizeof(double) + (size_t)kFastPop * CLR_NA * sizeof(float))) return 1;
   CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
   unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_scratch);
   double *g_z = c->d_scratch + nz;
@@ -417,10 +560,24 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
     size_t smem = nd * sizeof(double);
     if (c->exact_math)
       norm_hist_kernel<true><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
-    else
+    else if (npop <= kFastPop && c->dev.n % kRun == 0) {
+      // fp32 copies of the bias tables live behind the histograms in the scratch buffer
+      NormPopsF pf;
+      pf.npop = npop;
+      float *bzf = reinterpret_cast<float *>(c->d_scratch + nd);
+      for (int i = 0; i < npop; i++) {
+        cvt_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(d_bz[i], bzf + (size_t)i * CLR_NA, CLR_NA);
+        pf.bzf[i] = bzf + (size_t)i * CLR_NA;
+      }
+      for (int i = npop; i < kFastPop; i++) pf.bzf[i] = bzf;
+      norm_hist_fast_kernel<<<grid_for(c, n_cells / kRun, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b);
+    } else
       norm_hist_kernel<false><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
     CLR_CUDA(cudaGetLastError());
   }
+  // density.c:1262-1269: histograms summed over the slabs
+  if (clr_comm_allreduce_u64(c, g_n, nz)) return 1;
+  if (clr_comm_allreduce_f64(c, g_z, (size_t)nz * (1 + npop))) return 1;
   CLR_CUDA(cudaMemcpyAsync(h_n, g_n, nz * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaMemcpyAsync(h_z, g_z, nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (npop) CLR_CUDA(cudaMemcpyAsync(h_b, g_b, (size_t)npop * nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -432,7 +589,10 @@ int clr_halo_update(clr_ctx *c)
 {
   // single slab: slice_left = last plane, slice_right = first plane (fourier.c:412-413); they are
   // materialised after the grid so that the stencil kernels index them like the reference.
-  CLR_CHECK(c->nranks == 1, "halo exchange over NCCL is handled by the distributed path");
+  if (c->nranks > 1) {
+    StageScope sc(c, "halo", 0);
+    return clr_comm_halo(c);
+  }
   StageScope sc(c, "halo", 2);
   long long plane = (long long)c->dev.pitch * c->dev.n;
   float *left = c->d_npot + (long long)c->dev.nz_here * plane;

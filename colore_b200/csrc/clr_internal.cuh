@@ -17,6 +17,7 @@ struct ClrDev {
   int n, nc, nz_here, iz0_here;     // grid side, n/2+1, slab
   int pitch;                        // floats per real row = 2*nc (reference layout)
   int log2n;                        // log2(n) when n is a power of two, else -1 (index arithmetic)
+  int nyl, ky0;                     // k-space slab of this rank: ky in [ky0, ky0+nyl), layout [kz][ky_local][kx]
   int bias_model, nside_base;
   float l_box;
   double pos_obs[3];
@@ -25,6 +26,11 @@ struct ClrDev {
   const double *r_arr, *z_arr, *d1_arr, *d2_arr, *v1_arr, *pd_arr, *ih_arr, *a2r_a, *a2r_r;
   const float *slice_left, *slice_right;   // z-halo planes of the potential (fourier.c:401-414)
   const float *z_f, *d1_f;                 // fp32 copies of z(r), D(r) for the streaming field kernels
+  // cell-node coordinates relative to the observer, tabulated once on the host with the reference's
+  // own expressions: cf[ax][i] = (flouble)((i+0.0)*dx_f - pos_obs[ax]) (density.c:1087-1094, dx flouble)
+  // and cd[ax][i] = (i+0.0)*dx_d - pos_obs[ax] (srcs.c:159-167, dx double); i is the GLOBAL index.
+  const float *cf[3];
+  const double *cd[3];
 };
 
 struct ClrPop {           // one tracer population: tables on the NA r-grid
@@ -45,6 +51,8 @@ struct clr_ctx {
   float *d_dens = nullptr, *d_npot = nullptr;       // grids (+2 halo planes on npot)
   double *d_tables = nullptr;                        // 9 x NA
   float *d_tables_f = nullptr;                       // fp32 copies: z(r), D(r)
+  float *d_coord_f = nullptr;                        // 3 x n cell coordinates (fp32 expression)
+  double *d_coord_d = nullptr;                       // 3 x n cell coordinates (fp64 expression)
   double *d_pk = nullptr;                            // logk[numk], pk[numk]
   float2 *d_twiddle = nullptr;                       // exp(+2*pi*i*k/n), k<n
   double *d_scratch = nullptr;                       // reductions / histograms
@@ -70,6 +78,8 @@ struct clr_ctx {
   // multi-GPU
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
+  float *d_stage = nullptr;         // all-to-all staging buffer of the distributed FFT (one slab)
+  double a2a_bytes = 0;             // bytes this rank has sent through the FFT all-to-all
   // bookkeeping
   long long launches = 0;
   bool profiling = false;
@@ -135,6 +145,11 @@ int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
 int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,
                  float *h_data);
 int clr_halo_update(clr_ctx *c);
+int clr_comm_destroy(clr_ctx *c);
+int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_floats);
+int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n);
+int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n);
+int clr_comm_halo(clr_ctx *c);
 int clr_ensure_scratch(clr_ctx *c, size_t bytes);
 
 // ---------------------------------------------------------------------------------------------

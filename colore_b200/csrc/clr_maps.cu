@@ -62,9 +62,9 @@ imap_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restr
     int ix, iy, iz;
     clr_cell(d, i, ix, iy, iz);
     long long row = (long long)iz * d.n + iy;
-    double z0 = (iz + d.iz0_here) * dx - d.pos_obs[2];
-    double y0 = iy * dx - d.pos_obs[1];
-    double x0 = ix * dx - d.pos_obs[0];
+    double z0 = __ldg(d.cd[2] + iz + d.iz0_here);
+    double y0 = __ldg(d.cd[1] + iy);
+    double x0 = __ldg(d.cd[0] + ix);
     double r0 = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
     if (!(r0 <= rmax_here && r0 >= rmin_here)) continue;
     double tmean = clr_lerp(d, r0, pop.nz, 0.0, 0.0);

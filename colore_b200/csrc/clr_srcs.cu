@@ -142,8 +142,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
   const double cell_vol = dx * dx * dx;
   const double rcut = (double)(d.l_box / 2) + 20.;
   // fp32 screening constants
-  const float dxf = d.l_box / d.n, volf = (float)cell_vol, rcutf = (float)rcut;
-  const float ox = (float)d.pos_obs[0], oy = (float)d.pos_obs[1], oz = (float)d.pos_obs[2];
+  const float volf = (float)cell_vol, rcutf = (float)rcut;
   const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max;
   __shared__ int red[kThreads / 32];
   __shared__ unsigned short q_cell[kChunk];
@@ -164,7 +163,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
       int ix, iy, iz;
       clr_cell(d, i, ix, iy, iz);
       long long row = (long long)iz * d.n + iy;
-      float xf = ix * dxf - ox, yf = iy * dxf - oy, zf = (iz + d.iz0_here) * dxf - oz;
+      float xf = __ldg(d.cf[0] + ix), yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
       float rf = sqrtf(xf * xf + yf * yf + zf * zf);
       bool sure_zero = false;
       if (rf > rcutf + 0.05f) sure_zero = true;               // outside the sampled sphere (srcs.c:169)
@@ -202,9 +201,9 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
       int ix, iy, iz;
       clr_cell(d, i, ix, iy, iz);
       long long row = (long long)iz * d.n + iy;
-      double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
-      double y0 = (iy + 0.0) * dx - d.pos_obs[1];
-      double x0 = (ix + 0.0) * dx - d.pos_obs[0];
+      double z0 = __ldg(d.cd[2] + iz + d.iz0_here);
+      double y0 = __ldg(d.cd[1] + iy);
+      double x0 = __ldg(d.cd[0] + ix);
       double r = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
       int npp = 0;
       if (r < rcut) {
@@ -342,9 +341,9 @@ place_src_kernel(const ClrDev d, const float *__restrict__ npot, const unsigned 
     int ip = (int)(ref & 0xffffffu);
     int ix, iy, iz;
     clr_cell(d, i, ix, iy, iz);
-    double z0 = (iz + d.iz0_here + 0.0) * dx - d.pos_obs[2];
-    double y0 = (iy + 0.0) * dx - d.pos_obs[1];
-    double x0 = (ix + 0.0) * dx - d.pos_obs[0];
+    double z0 = __ldg(d.cd[2] + iz + d.iz0_here);
+    double y0 = __ldg(d.cd[1] + iy);
+    double x0 = __ldg(d.cd[0] + ix);
     double rr = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
     double rvel = factor_vel * dev_get_rvel(d, npot, ix, iy, iz, x0, y0, z0, rr);
     float dz_rsd = (float)(rvel * clr_bg_v1(d, rr));

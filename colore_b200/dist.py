@@ -1,0 +1,76 @@
+"""Host-side logic of the slab decomposition (one process per GPU).
+
+* ``slab_bounds``: the z-slab of a rank (init_fftw, fourier.c:172-181, for n divisible by P).
+* ``init_comm``: creates the NCCL communicator of a ``ParamCoLoRe`` from a unique id that rank 0
+  generates and ``torch.distributed`` broadcasts (replaces ``mpi_init``, common.c:216-274).
+* ``c2r_dist_numpy`` / ``r2c_dist_numpy``: a numpy restatement of the DATA MOVEMENT of the distributed
+  transform in colore_b200/csrc/clr_fft.cu (k space in y slabs ``[kz][ky_local][kx]``, one all-to-all
+  whose block for rank h is the contiguous range of z planes of h, y pass reading the staging buffer
+  ``[source][z_local][ky_in_source][kx]``). It exists so that the exchange bookkeeping can be tested
+  on CPU with gloo (tests/test_dist_host.py); it is not a compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def slab_bounds(n: int, nranks: int, rank: int):
+    """(nz_here, iz0_here) of ``rank``; n must be divisible by nranks."""
+    if n % nranks:
+        raise ValueError(f"n_grid={n} is not divisible by {nranks} GPUs")
+    nz = n // nranks
+    return nz, rank * nz
+
+
+def init_comm(par, rank: int, nranks: int):
+    """NCCL communicator for ``par`` (a pipeline.ParamCoLoRe created with this rank's slab bounds)."""
+    from ._lib import check
+    if nranks == 1:
+        check(par.lib.clr_comm_init(par.ctx, C.c_int(0), C.c_int(1), None))
+        return
+    import torch.distributed as dist
+    ident = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(par.lib.clr_comm_unique_id(ident))
+    box = [bytes(ident)]
+    dist.broadcast_object_list(box, src=0)
+    buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
+    check(par.lib.clr_comm_init(par.ctx, C.c_int(rank), C.c_int(nranks), buf))
+
+
+# ---- numpy restatement of the exchange (test support) ---------------------------------------------
+
+def kspace_slab(ck_full: np.ndarray, rank: int, nranks: int) -> np.ndarray:
+    """[kz][ky][kx] (reference layout) -> this rank's y slab [kz][ky_local][kx]."""
+    n = ck_full.shape[0]
+    nyl = n // nranks
+    return np.ascontiguousarray(ck_full[:, rank * nyl:(rank + 1) * nyl, :])
+
+
+def c2r_dist_numpy(kslab: np.ndarray, rank: int, nranks: int, alltoall) -> np.ndarray:
+    """Distributed unnormalised c2r. ``alltoall(list_of_P_blocks) -> list_of_P_blocks``."""
+    n, nyl, nc = kslab.shape
+    nzl = n // nranks
+    a = np.fft.ifft(kslab, axis=0) * n                       # z pass on [kz][ky_local][kx]
+    send = [np.ascontiguousarray(a[h * nzl:(h + 1) * nzl]) for h in range(nranks)]   # contiguous z ranges
+    recv = alltoall(send)                                     # staging [source][z_local][ky_in_source][kx]
+    stage = np.stack(recv, axis=0)
+    # y pass: element e of the line = stage[e // nyl, z_local, e % nyl, kx]  (two-level stride)
+    lines = stage.transpose(1, 0, 2, 3).reshape(nzl, n, nc)
+    b = np.fft.ifft(lines, axis=1) * n
+    # x pass: half-complex -> real, imaginary parts of DC / Nyquist dropped (numpy irfft does the same)
+    return np.fft.irfft(b, n=n, axis=2) * n
+
+
+def r2c_dist_numpy(rslab: np.ndarray, rank: int, nranks: int, alltoall) -> np.ndarray:
+    """Distributed r2c: real z slab [z_local][y][x] -> y slab of the spectrum [kz][ky_local][kx]."""
+    nzl, n, _ = rslab.shape
+    nyl = n // nranks
+    a = np.fft.rfft(rslab, axis=2)
+    b = np.fft.fft(a, axis=1)                                 # [z_local][ky][kx]
+    send = [np.ascontiguousarray(b[:, s * nyl:(s + 1) * nyl, :]) for s in range(nranks)]
+    recv = alltoall(send)                                     # block h = z planes of rank h, my ky
+    full_z = np.concatenate(recv, axis=0)                     # [kz][ky_local][kx]
+    return np.fft.fft(full_z, axis=0)

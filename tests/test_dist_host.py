@@ -1,0 +1,89 @@
+"""CPU suite, world_size 2 over gloo: the host-side logic of the slab decomposition -- slab bounds,
+the all-to-all block bookkeeping of the distributed FFT (y-slab k space, z-slab real space, staging
+buffer read with a two-level stride) and the reductions that replace MPI_Allreduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from colore_b200.dist import c2r_dist_numpy, kspace_slab, r2c_dist_numpy, slab_bounds
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _alltoall(blocks):
+    """all-to-all of numpy blocks over the default (gloo) group via point-to-point messages."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    out = [None] * world
+    out[rank] = blocks[rank]
+    reqs, bufs = [], {}
+    for k in range(1, world):
+        to, frm = (rank + k) % world, (rank - k) % world
+        ts = torch.view_as_real(torch.from_numpy(np.ascontiguousarray(blocks[to]))).contiguous()
+        tr = torch.empty_like(ts)
+        bufs[frm] = tr
+        reqs.append(dist.isend(ts, to))
+        reqs.append(dist.irecv(tr, frm))
+    for r in reqs:
+        r.wait()
+    for frm, tr in bufs.items():
+        out[frm] = torch.view_as_complex(tr).numpy()
+    return out
+
+
+def _worker(rank, world, port, n, errs):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(123)                      # same full array on every rank
+        nc = n // 2 + 1
+        ck = rng.standard_normal((n, n, nc)) + 1j * rng.standard_normal((n, n, nc))
+        nzl, iz0 = slab_bounds(n, world, rank)
+        # c2r: distributed data movement == single-process transform restricted to the slab
+        got = c2r_dist_numpy(kspace_slab(ck, rank, world), rank, world, _alltoall)
+        ref = np.fft.irfftn(ck, s=(n, n, n), axes=(0, 1, 2)) * n ** 3
+        e1 = np.abs(got - ref[iz0:iz0 + nzl]).max() / np.abs(ref).max()
+        # r2c: real z slab -> y slab of the spectrum
+        x = rng.standard_normal((n, n, n))
+        gotk = r2c_dist_numpy(x[iz0:iz0 + nzl], rank, world, _alltoall)
+        refk = np.fft.rfftn(x, axes=(0, 1, 2))
+        nyl = n // world
+        e2 = np.abs(gotk - refk[:, rank * nyl:(rank + 1) * nyl, :]).max() / np.abs(refk).max()
+        # the reductions that replace MPI_Allreduce (fourier.c:69-70, density.c:1262-1269)
+        mom = torch.tensor([ref[iz0:iz0 + nzl].sum(), (ref[iz0:iz0 + nzl] ** 2).sum()], dtype=torch.float64)
+        dist.all_reduce(mom)
+        e3 = abs(mom[1].item() / (ref ** 2).sum() - 1)
+        errs[rank] = max(e1, e2, e3)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [16, 32])
+def test_distributed_fft_bookkeeping_gloo(n):
+    world = 2
+    with mp.Manager() as m:
+        errs = m.dict()
+        mp.spawn(_worker, args=(world, _free_port(), n, errs), nprocs=world, join=True)
+        assert len(errs) == world
+        assert max(errs.values()) < 1e-12
+
+
+def test_slab_bounds():
+    assert slab_bounds(1024, 8, 3) == (128, 384)
+    assert slab_bounds(64, 1, 0) == (64, 0)
+    with pytest.raises(ValueError):
+        slab_bounds(100, 8, 0)
+    # slabs tile the grid exactly
+    for p in (1, 2, 4, 8):
+        b = [slab_bounds(256, p, r) for r in range(p)]
+        assert b[0][1] == 0 and all(b[i][1] + b[i][0] == b[i + 1][1] for i in range(p - 1))
+        assert b[-1][1] + b[-1][0] == 256
