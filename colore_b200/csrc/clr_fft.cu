@@ -179,7 +179,7 @@ struct LineAddr {
 };
 
 template <int M, int S, int T, int V>
-__global__ void __launch_bounds__(T * M / 8 / V)
+__global__ void __launch_bounds__(T * M / 8 / V, (M <= 1024 && (T * M / 8 / V) <= 512) ? 2 : 1)
 fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, const float2 *__restrict__ W, int wn,
                    long long n_tiles, int tiles_per_outer, int n_inner)
 {

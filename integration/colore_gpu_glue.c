@@ -1,0 +1,306 @@
+/* Reference-side binding of the colore_b200 C ABI.
+ *
+ * This ONE translation unit replaces fourier.c, density.c, srcs.c, imap.c, kappa.c, isw.c and
+ * beaming.c of damonge/CoLoRe in the link line: it defines exactly the functions those files export
+ * through common.h (464-543) and forwards them to include/colore_b200.h. main.c, io.c, cosmo.c,
+ * cosmo_mad.c, common.c, healpix_extra.c, predictions.c, fftlog.c (and cstm.c / lensing.c) are
+ * linked UNCHANGED, so `./CoLoRe param.cfg` stays the entry point (main.c:24-154).
+ *
+ * It is compiled against the reference's own common.h (-I<reference>/src); it contains no code of
+ * the reference. One process drives one GPU (NNodes = 1 at this boundary); the slab decomposition
+ * over several GPUs lives below the C ABI (clr_comm_init) and is driven by bench.py / torchrun.
+ *
+ * Host memory contract: par->cats_c / par->cats / shell data and nadd are
+ * host-malloc'ed with the reference's own allocators because io.c writes and frees them;
+ * par->grid_dens / grid_npot get host storage only when output_density asks for a dump.
+ */
+#include "common.h"
+#include "colore_b200.h"
+
+static clr_ctx *g_ctx = NULL;
+
+static void chk(int status)
+{
+  if (status) report_error(1, "colore_b200: %s\n", clr_last_error());
+}
+
+static size_t slab_floats(ParamCoLoRe *par)
+{
+  return (size_t)2 * (par->n_grid / 2 + 1) * par->n_grid * par->nz_here;
+}
+
+/* ------------------------------------------------------------------ fourier.c */
+void init_fftw(ParamCoLoRe *par)
+{ /* fourier.c:127-209, single-rank branch: the whole box is one slab */
+  par->nz_all = my_calloc(NNodes, sizeof(int));
+  par->iz0_all = my_calloc(NNodes, sizeof(int));
+  par->nz_here = par->n_grid;
+  par->iz0_here = 0;
+  par->nz_max = par->nz_here;
+  par->nz_all[0] = par->nz_here;
+  par->iz0_all[0] = par->iz0_here;
+}
+
+void allocate_fftw(ParamCoLoRe *par)
+{ /* fourier.c:211-238: grids live on the device; tables are uploaded once */
+  clr_params p;
+  int i;
+  memset(&p, 0, sizeof(p));
+  p.n_grid = par->n_grid; p.nz_here = par->nz_here; p.iz0_here = par->iz0_here;
+  p.dens_type = par->dens_type;
+#ifdef _BIAS_MODEL_2
+  p.bias_model = 2;
+#elif defined _BIAS_MODEL_3
+  p.bias_model = 3;
+#else
+  p.bias_model = 1;
+#endif
+  p.do_smoothing = par->do_smoothing; p.smooth_potential = par->smooth_potential;
+  p.nside_base = par->nside_base; p.numk = par->numk; p.seed_rng = par->seed_rng;
+  p.l_box = par->l_box;
+  for (i = 0; i < 3; i++) p.pos_obs[i] = par->pos_obs[i];
+  p.r2_smooth = par->r2_smooth; p.prefac_lensing = par->prefac_lensing;
+  p.fgrowth_0 = par->fgrowth_0; p.hubble_0 = par->hubble_0; p.OmegaM = par->OmegaM; p.n_scal = par->n_scal;
+  p.r_max = par->r_max; p.glob_idr = par->glob_idr;
+  p.logkmin = par->logkmin; p.logkmax = par->logkmax; p.idlogk = par->idlogk;
+  p.logkarr = par->logkarr; p.pkarr = par->pkarr;
+  p.r_arr_r2z = par->r_arr_r2z; p.z_arr_r2z = par->z_arr_r2z; p.growth_d_arr = par->growth_d_arr;
+  p.growth_d2_arr = par->growth_d2_arr; p.growth_v_arr = par->growth_v_arr;
+  p.growth_pd_arr = par->growth_pd_arr; p.ihub_arr = par->ihub_arr;
+  p.a_arr_a2r = par->a_arr_a2r; p.r_arr_a2r = par->r_arr_a2r;
+  chk(clr_create(&p, 0, &g_ctx));
+  for (i = 0; i < par->n_srcs; i++) chk(clr_set_srcs(g_ctx, i, par->srcs_nz_arr[i], par->srcs_bz_arr[i]));
+  par->grid_dens_f = NULL; par->grid_dens = NULL;
+  par->grid_npot_f = NULL; par->grid_npot = NULL;
+  if (par->output_density) { /* io.c:565-595 reads par->grid_dens on the host */
+    par->grid_dens = my_malloc(slab_floats(par) * sizeof(flouble));
+    par->grid_dens_f = (dftw_complex *)par->grid_dens;
+  }
+}
+
+void end_fftw(ParamCoLoRe *par)
+{ /* fourier.c:240-283 */
+  if (par->grid_dens != NULL) free(par->grid_dens);
+  par->grid_dens = NULL; par->grid_dens_f = NULL;
+  if (g_ctx) chk(clr_destroy(g_ctx));
+  g_ctx = NULL;
+}
+
+/* fourier.c:81-125 on HOST arrays (kept for API completeness; the GPU path never round-trips) */
+void fftw_wrap_c2r(int ng, dftw_complex *pin, flouble *pout)
+{
+  (void)ng;
+  chk(clr_grid_put(g_ctx, CLR_GRID_DENS, (const float *)pin));
+  chk(clr_fft_c2r(g_ctx, CLR_GRID_DENS));
+  chk(clr_grid_get(g_ctx, CLR_GRID_DENS, (float *)pout));
+}
+void fftw_wrap_r2c(int ng, flouble *pin, dftw_complex *pout)
+{
+  (void)ng;
+  chk(clr_grid_put(g_ctx, CLR_GRID_DENS, (const float *)pin));
+  chk(clr_fft_r2c(g_ctx, CLR_GRID_DENS));
+  chk(clr_grid_get(g_ctx, CLR_GRID_DENS, (float *)pout));
+}
+
+void create_cartesian_fields(ParamCoLoRe *par)
+{ /* fourier.c:361-423 */
+  double out[2];
+  print_info("*** Creating Gaussian density field (GPU)\n");
+  if (NodeThis == 0) timer(0);
+  chk(clr_create_cartesian_fields(g_ctx, par->seed_rng, 0, out));
+  par->sigma2_gauss = out[1];
+  if (NodeThis == 0) timer(2);
+  print_info(" <d>=%.3lE, <d^2>=%.3lE\n", out[0], sqrt(par->sigma2_gauss));
+  print_info("\n");
+  if (par->output_density) {
+    chk(clr_grid_get(g_ctx, CLR_GRID_DENS, (float *)par->grid_dens));
+    write_density_grid(par, "gaussian");
+  }
+}
+
+/* ------------------------------------------------------------------ density.c */
+void compute_physical_density_field(ParamCoLoRe *par)
+{ /* density.c:1105-1126 */
+  print_info("*** Creating physical matter density (GPU)\n");
+  if (NodeThis == 0) timer(0);
+  chk(clr_compute_physical_density_field(g_ctx));
+  chk(clr_synchronize(g_ctx));
+  if (NodeThis == 0) timer(2);
+  print_info("\n");
+  if (par->output_density) {
+    chk(clr_grid_get(g_ctx, CLR_GRID_DENS, (float *)par->grid_dens));
+    write_density_grid(par, "lightcone");
+  }
+}
+
+static void sorted_shells(HealpixShells *sh)
+{ /* kappa.c:41-56, isw.c:41-56, imap.c:107-121: radii in ascending order of r0 */
+  int i, *order = ind_sort(sh->nr, sh->r0);
+  flouble *r0 = my_malloc(sh->nr * sizeof(flouble)), *rf = my_malloc(sh->nr * sizeof(flouble));
+  memcpy(r0, sh->r0, sh->nr * sizeof(flouble));
+  memcpy(rf, sh->rf, sh->nr * sizeof(flouble));
+  for (i = 0; i < sh->nr; i++) { sh->r0[i] = r0[order[i]]; sh->rf[i] = rf[order[i]]; }
+  free(r0); free(rf); free(order);
+}
+
+void compute_density_normalization(ParamCoLoRe *par)
+{ /* density.c:1227-1393 */
+  int i;
+  double zends[2] = {0, 0};
+  print_info("*** Computing normalization of density field (GPU)\n");
+  if (NodeThis == 0) timer(0);
+  /* intensity-map populations take part in the normalisation: their shells are known by now */
+  for (i = 0; i < par->n_imap; i++) {
+    sorted_shells(par->imap[i]);
+    chk(clr_set_imap(g_ctx, i, par->imap_tz_arr[i], par->imap_bz_arr[i], par->imap[i]->nside, par->imap[i]->nr,
+                     par->imap[i]->r0, par->imap[i]->rf));
+  }
+  chk(clr_compute_density_normalization(g_ctx));
+  for (i = 0; i < par->n_srcs; i++) {
+    double ends[2];
+    par->srcs_norm_arr[i] = my_malloc(NA * sizeof(double));
+    chk(clr_get_norm(g_ctx, 0, i, par->srcs_norm_arr[i], ends, zends));
+    par->norm_srcs_0[i] = ends[0]; par->norm_srcs_f[i] = ends[1];
+  }
+  for (i = 0; i < par->n_imap; i++) {
+    double ends[2];
+    par->imap_norm_arr[i] = my_malloc(NA * sizeof(double));
+    chk(clr_get_norm(g_ctx, 1, i, par->imap_norm_arr[i], ends, zends));
+    par->norm_imap_0[i] = ends[0]; par->norm_imap_f[i] = ends[1];
+  }
+  par->z0_norm = zends[0]; par->zf_norm = zends[1];
+  if (par->n_cstm > 0) report_error(1, "custom maps are not on the GPU path\n");
+  if (NodeThis == 0) timer(2);
+  print_info("\n");
+}
+
+/* ------------------------------------------------------------------ srcs.c */
+void srcs_set_cartesian(ParamCoLoRe *par)
+{ /* srcs.c:285-294 */
+  int ipop;
+  print_info("*** Getting point sources (GPU)\n");
+  for (ipop = 0; ipop < par->n_srcs; ipop++) {
+    long long n = 0;
+    if (par->lensing_srcs[ipop] || par->skw_srcs[ipop])
+      report_error(1, "per-source lensing / skewers are not on the GPU path\n");
+    if (NodeThis == 0) timer(0);
+    chk(clr_srcs_set_cartesian(g_ctx, ipop, par->seed_rng, &n));
+    par->nsources_c_this[ipop] = (long)n;
+    print_info("   There will be %ld objects in total \n", (long)n);
+    par->cats_c[ipop] = catalog_cartesian_alloc((int)n);
+    if (n > 0) chk(clr_srcs_get_cartesian(g_ctx, ipop, par->cats_c[ipop]->pos, par->cats_c[ipop]->ipix));
+    if (NodeThis == 0) timer(2);
+  }
+  print_info("\n");
+}
+
+void srcs_distribute(ParamCoLoRe *par)
+{ /* srcs.c:375-384 with NNodes = 1: every source stays */
+  int ipop;
+  for (ipop = 0; ipop < par->n_srcs; ipop++) par->nsources_this[ipop] = par->nsources_c_this[ipop];
+}
+
+void srcs_get_local_properties(ParamCoLoRe *par)
+{ /* srcs.c:418-423 */
+  int ipop;
+  for (ipop = 0; ipop < par->n_srcs; ipop++) {
+    par->cats[ipop] = catalog_alloc(par->cats_c[ipop]->nsrc, par->lensing_srcs[ipop], par->skw_srcs[ipop],
+                                    par->skw_gauss[ipop], par->r_max, par->n_grid);
+    if (par->cats[ipop]->nsrc > 0)
+      chk(clr_srcs_get_local_properties(g_ctx, ipop, (float *)par->cats[ipop]->srcs));
+  }
+}
+
+void srcs_beams_preproc(ParamCoLoRe *par) { (void)par; }
+void srcs_get_beam_properties(ParamCoLoRe *par)
+{ /* srcs.c:452-632, RSD part: dz_rsd from the CIC-interpolated potential gradient */
+  int ipop;
+  for (ipop = 0; ipop < par->n_srcs; ipop++) {
+    chk(clr_srcs_beam_rsd(g_ctx, ipop));
+    if (par->cats[ipop]->nsrc > 0)
+      chk(clr_srcs_get_local_properties(g_ctx, ipop, (float *)par->cats[ipop]->srcs));
+  }
+}
+void srcs_beams_postproc(ParamCoLoRe *par) { (void)par; }
+
+/* ------------------------------------------------------------------ imap.c */
+void imap_set_cartesian(ParamCoLoRe *par)
+{ /* imap.c:247-256; every rank stores the full sky (imap.c:123-132) */
+  int ipop;
+  print_info("*** Filling up intensity maps (GPU)\n");
+  for (ipop = 0; ipop < par->n_imap; ipop++) {
+    HealpixShells *im = par->imap[ipop];
+    if (NodeThis == 0) timer(0);
+    im->num_pix = he_nside2npix(im->nside);
+    free(im->listpix); im->listpix = my_malloc(sizeof(long));
+    free(im->pos); im->pos = my_malloc(sizeof(double));
+    free(im->data); im->data = my_calloc(im->nr * im->num_pix, sizeof(flouble));
+    free(im->nadd); im->nadd = my_calloc(im->nr * im->num_pix, sizeof(int));
+    chk(clr_imap_set_cartesian(g_ctx, ipop, im->data, im->nadd));
+    if (NodeThis == 0) timer(2);
+  }
+  print_info("\n");
+}
+void imap_distribute(ParamCoLoRe *par) { (void)par; }
+void imap_get_local_properties(ParamCoLoRe *par) { (void)par; }
+void imap_beams_preproc(ParamCoLoRe *par) { (void)par; }
+void imap_get_beam_properties(ParamCoLoRe *par) { (void)par; }
+void imap_beams_postproc(ParamCoLoRe *par) { (void)par; }
+
+/* ------------------------------------------------------------------ kappa.c / isw.c */
+void kappa_set_cartesian(ParamCoLoRe *par) { (void)par; }
+void kappa_distribute(ParamCoLoRe *par) { (void)par; }
+void kappa_get_local_properties(ParamCoLoRe *par) { (void)par; }
+void kappa_beams_preproc(ParamCoLoRe *par)
+{ /* kappa.c:39-76 */
+  long i;
+  sorted_shells(par->kmap);
+  for (i = 0; i < par->kmap->num_pix * par->kmap->nr; i++) { par->kmap->data[i] = 0; par->kmap->nadd[i] = 1; }
+}
+void kappa_get_beam_properties(ParamCoLoRe *par)
+{ /* kappa.c:78-175 */
+  HealpixShells *k = par->kmap;
+  chk(clr_kappa_get_beam_properties(g_ctx, k->num_pix, k->pos, k->nr, k->rf, k->data));
+}
+void kappa_beams_postproc(ParamCoLoRe *par) { (void)par; }
+
+void isw_set_cartesian(ParamCoLoRe *par) { (void)par; }
+void isw_distribute(ParamCoLoRe *par) { (void)par; }
+void isw_get_local_properties(ParamCoLoRe *par) { (void)par; }
+void isw_beams_preproc(ParamCoLoRe *par)
+{ /* isw.c:39-76 */
+  long i;
+  sorted_shells(par->pd_map);
+  for (i = 0; i < par->pd_map->num_pix * par->pd_map->nr; i++) { par->pd_map->data[i] = 0; par->pd_map->nadd[i] = 1; }
+}
+void isw_get_beam_properties(ParamCoLoRe *par)
+{ /* isw.c:78-147 */
+  HealpixShells *m = par->pd_map;
+  chk(clr_isw_get_beam_properties(g_ctx, m->num_pix, m->pos, m->nr, m->rf, m->data));
+}
+void isw_beams_postproc(ParamCoLoRe *par) { (void)par; }
+
+/* ------------------------------------------------------------------ beaming.c */
+int interpolate_from_grid(ParamCoLoRe *par, double *x, flouble *d, flouble v[3], flouble t[6], flouble *pd,
+                          flouble *g, int flag_return, int interp_type)
+{ /* beaming.c:120-268 is only reached from the CPU tracers cstm.c / lensing.c, which are out of scope */
+  (void)par; (void)x; (void)d; (void)v; (void)t; (void)pd; (void)g; (void)flag_return; (void)interp_type;
+  report_error(1, "interpolate_from_grid: the grids live on the GPU; cstm / lensing tracers are not supported\n");
+  return 0;
+}
+
+void get_beam_properties(ParamCoLoRe *par)
+{ /* beaming.c:293-374 with one slab: no ring rotation, one pass over every tracer */
+  print_info("*** Getting LOS information (GPU)\n");
+  if (!par->need_beaming) { print_info("  No need!\n\n"); return; }
+  if (par->do_kappa) kappa_beams_preproc(par);
+  if (par->do_isw) isw_beams_preproc(par);
+  if (par->do_srcs) srcs_beams_preproc(par);
+  if (NodeThis == 0) timer(0);
+  if (par->do_kappa) kappa_get_beam_properties(par);
+  if (par->do_isw) isw_get_beam_properties(par);
+  if (par->do_srcs) srcs_get_beam_properties(par);
+  if (par->do_cstm) report_error(1, "custom maps are not on the GPU path\n");
+  if (NodeThis == 0) timer(2);
+  print_info("\n");
+}
