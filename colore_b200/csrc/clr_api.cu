@@ -141,6 +141,7 @@ int clr_destroy(clr_ctx *c)
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
   cudaFree(c->d_coord_f); cudaFree(c->d_coord_d);
+  for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -255,6 +256,8 @@ int clr_set_sigma2_gauss(clr_ctx *c, double s2) { c->sigma2_gauss = s2; return 0
 int clr_set_option(clr_ctx *c, const char *name, int value)
 {
   if (!strcmp(name, "exact_math")) { c->exact_math = value; return 0; }
+  if (!strcmp(name, "lpt_interp_type")) { c->lpt_interp_type = value; return 0; }
+  if (!strcmp(name, "keep_particles")) { c->keep_particles = value; return 0; }
   clr_set_error("unknown option %s", name);
   return 1;
 }
@@ -263,7 +266,9 @@ int clr_compute_physical_density_field(clr_ctx *c)
 {
   if (c->p.dens_type == CLR_DENS_TYPE_LGNR) return clr_fields_lognormal(c, 0);
   if (c->p.dens_type == CLR_DENS_TYPE_CLIP) return clr_fields_lognormal(c, 1);
-  clr_set_error("Density type %d not supported by the GPU path yet (LPT: see DESIGN.md)", c->p.dens_type);
+  if (c->p.dens_type == CLR_DENS_TYPE_1LPT) return clr_lpt_run(c, 1);
+  if (c->p.dens_type == CLR_DENS_TYPE_2LPT) return clr_lpt_run(c, 2);
+  clr_set_error("Density type %d not supported\n", c->p.dens_type);     // density.c:1119
   return 1;
 }
 
@@ -413,6 +418,7 @@ int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
 }
 
 int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { return clr_srcs_beam(c, ipop); }
+int clr_lpt_get_particles(clr_ctx *c, float *x, float *y, float *z) { return clr_lpt_particles(c, x, y, z); }
 
 int clr_imap_set_cartesian(clr_ctx *c, int ipop, float *data, int32_t *nadd) { return clr_maps_imap(c, ipop, data, nadd); }
 int clr_kappa_get_beam_properties(clr_ctx *c, long long num_pix, const double *pos3, int nplanes, const float *rf, float *data)

@@ -84,6 +84,9 @@ struct clr_ctx {
   long long launches = 0;
   bool profiling = false;
   int exact_math = 0;   // 1: field kernels evaluate the reference's double-precision expressions verbatim
+  int lpt_interp_type = 1;          // field_par.lpt_interp_type: 0 NGP, 1 CIC, 2 TSC (common.h:67-69)
+  int keep_particles = 0;           // keep the LPT particles on the device for write_lpt (io.c:619-695)
+  float *d_lpt_pos[3] = {nullptr, nullptr, nullptr};
   std::map<std::string, StageTime> stage;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
   struct Pending { std::string name; int slot; int nl; };
@@ -145,6 +148,8 @@ int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
 int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,
                  float *h_data);
 int clr_halo_update(clr_ctx *c);
+int clr_lpt_run(clr_ctx *c, int order);
+int clr_lpt_particles(clr_ctx *c, float *x, float *y, float *z);
 int clr_comm_destroy(clr_ctx *c);
 int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_floats);
 int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n);

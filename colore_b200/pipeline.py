@@ -202,6 +202,14 @@ def compute_physical_density_field(par: ParamCoLoRe):
     check(par.lib.clr_compute_physical_density_field(par.ctx))
 
 
+def lpt_get_particles(par: ParamCoLoRe):
+    """Particles of the last LPT density (x, y, z arrays); needs par.set_option("keep_particles", 1)."""
+    n = par.nz_here * par.n_grid * par.n_grid
+    x, y, z = (np.empty(n, np.float32) for _ in range(3))
+    check(par.lib.clr_lpt_get_particles(par.ctx, _vp(x), _vp(y), _vp(z)))
+    return x, y, z
+
+
 def compute_density_normalization(par: ParamCoLoRe):
     """density.c:1227-1393."""
     check(par.lib.clr_compute_density_normalization(par.ctx))

@@ -112,14 +112,20 @@ int clr_set_sigma2_gauss(clr_ctx *ctx, double sigma2);
  * normalisation histogram) evaluate the reference's double-precision expressions verbatim
  * (fourier.c:337-353, density.c:1095-1098, 1166-1178); 0 (default) evaluates them in fp32 with
  * double only where it protects the result. Integer outputs (Poisson counts, pixel ids) are
- * exact in both modes. */
+ * exact in both modes. "lpt_interp_type" = 0/1/2 (NGP/CIC/TSC, field_par.lpt_interp_type),
+ * "keep_particles" = 1 keeps the LPT particles resident for clr_lpt_get_particles. */
 int clr_set_option(clr_ctx *ctx, const char *name, int value);
 /* refresh the z-halo planes of the potential after clr_grid_put (fourier.c:401-414) */
 int clr_update_halo(clr_ctx *ctx);
 
 /* ---- physical density (density.c) -------------------------------------------------------- */
-/* compute_physical_density_field (density.c:1105-1126): lognormal / clip (LPT: see DESIGN.md) */
+/* compute_physical_density_field (density.c:1105-1126): lognormal (lognormalize, 1070-1103), clipped
+ * (densclip, 1034-1067), 1LPT (lpt_1, 376-644) and 2LPT (lpt_2, 646-1031) with the NGP / CIC / TSC mass
+ * deposits (pos_2_*, 37-188; option "lpt_interp_type"). LPT runs on one GPU per box. */
 int clr_compute_physical_density_field(clr_ctx *ctx);
+/* particle positions of the last LPT call (for write_lpt, io.c:619-695); needs option
+ * "keep_particles" = 1 before the density call. x, y, z: nz_here*n_grid^2 floats each. */
+int clr_lpt_get_particles(clr_ctx *ctx, float *x, float *y, float *z);
 /* compute_density_normalization (density.c:1227-1393). Afterwards the norm tables are resident;
  * clr_get_norm returns srcs (kind 0) / imap (kind 1) tables: norm_arr[CLR_NA], ends[2] */
 int clr_compute_density_normalization(clr_ctx *ctx);

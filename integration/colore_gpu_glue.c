@@ -69,6 +69,8 @@ void allocate_fftw(ParamCoLoRe *par)
   p.growth_pd_arr = par->growth_pd_arr; p.ihub_arr = par->ihub_arr;
   p.a_arr_a2r = par->a_arr_a2r; p.r_arr_a2r = par->r_arr_a2r;
   chk(clr_create(&p, 0, &g_ctx));
+  chk(clr_set_option(g_ctx, "lpt_interp_type", par->lpt_interp_type));
+  chk(clr_set_option(g_ctx, "keep_particles", par->output_lpt));
   for (i = 0; i < par->n_srcs; i++) chk(clr_set_srcs(g_ctx, i, par->srcs_nz_arr[i], par->srcs_bz_arr[i]));
   par->grid_dens_f = NULL; par->grid_dens = NULL;
   par->grid_npot_f = NULL; par->grid_npot = NULL;
@@ -125,6 +127,13 @@ void compute_physical_density_field(ParamCoLoRe *par)
   if (NodeThis == 0) timer(0);
   chk(clr_compute_physical_density_field(g_ctx));
   chk(clr_synchronize(g_ctx));
+  if (par->output_lpt && (par->dens_type == DENS_TYPE_1LPT || par->dens_type == DENS_TYPE_2LPT)) {
+    unsigned long long np = par->nz_here * ((long)(par->n_grid * par->n_grid));   /* density.c:563 */
+    flouble *x = my_malloc(np * sizeof(flouble)), *y = my_malloc(np * sizeof(flouble)), *z = my_malloc(np * sizeof(flouble));
+    chk(clr_lpt_get_particles(g_ctx, x, y, z));
+    write_lpt(par, np, x, y, z);
+    free(x); free(y); free(z);
+  }
   if (NodeThis == 0) timer(2);
   print_info("\n");
   if (par->output_density) {

@@ -161,6 +161,13 @@ class Oracle:
         self.par.sigma2_gauss = float(sigma2)
         self.lib.orc_lognormalize(self.pp, _fp(dens), C.c_int(int(clip)))
 
+    def lpt(self, dens: np.ndarray, order: int, interp_type: int, want_pos: bool = False):
+        """lpt_1 / lpt_2 (density.c:376-1031) in place on the Gaussian field; optionally the particles."""
+        pos = np.zeros((3, self.nz_here * self.n * self.n), np.float32) if want_pos else None
+        self.lib.orc_lpt(self.pp, C.c_int(order), C.c_int(interp_type), _fp(dens),
+                         _fp(pos) if want_pos else None)
+        return pos
+
     def density_normalization(self, dens: np.ndarray, bz_tabs: list):
         npop = len(bz_tabs)
         nz = self.lib.orc_norm_nz(self.pp)

@@ -25,6 +25,10 @@ CASES = {
                                    kappa_nside=8, isw_nside=8, seed=1003),
     # clipped density (density.c:1034-1067), 2 populations, galaxies only -> cell-gradient RSD
     "ref_n32_clip": RunConfig(n_grid=32, dens_type=3, nz_amplitude=40.0, n_srcs=2, seed=77),
+    # Lagrangian perturbation theory (density.c:376-1031): 1LPT + CIC, 2LPT + TSC, 2LPT + NGP
+    "ref_n32_1lpt_cic": RunConfig(n_grid=32, dens_type=1, lpt_interp_type=1, nz_amplitude=20.0, seed=11),
+    "ref_n32_2lpt_tsc": RunConfig(n_grid=32, dens_type=2, lpt_interp_type=2, nz_amplitude=20.0, seed=12),
+    "ref_n32_2lpt_ngp": RunConfig(n_grid=32, dens_type=2, lpt_interp_type=0, nz_amplitude=20.0, seed=13),
     # no smoothing of the potential, different grid size
     "ref_n48_nosmooth": RunConfig(n_grid=48, dens_type=0, nz_amplitude=30.0, smooth_potential=False,
                                   r_smooth=-1.0, seed=5),

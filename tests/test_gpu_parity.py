@@ -270,6 +270,56 @@ def test_maps_vs_reference(golden_dir):
     par.free()
 
 
+# ---------------------------------------------------------------------------------------- LPT
+@pytest.mark.parametrize("name", ["ref_n32_1lpt_cic", "ref_n32_2lpt_tsc", "ref_n32_2lpt_ngp"])
+def test_lpt_density_vs_reference(golden_dir, name):
+    """lpt_1 / lpt_2 + deposit (density.c:37-188, 376-1031) from the reference's Gaussian field."""
+    g, t = _load(golden_dir, name)
+    n = int(t["n_grid"])
+    o = Oracle(t, n)
+    par = _par(t)
+    par.set_option("lpt_interp_type", int(t["lpt_interp_type"]))
+    par.set_option("keep_particles", 1)
+    par.grid_put(cb.GRID_DENS, g["s1_dens_gauss"])
+    cb.compute_physical_density_field(par)
+    got = _real(par.grid_get(cb.GRID_DENS), n).astype(np.float64)
+    ref = _real(g["s2_dens"], n).astype(np.float64)
+    # particles: fp32 positions of O(1e3) Mpc/h built from fp32 FFTs -> a few ulps (1 ulp = 1.2e-4)
+    d = g["s1_dens_gauss"].copy()
+    pos_ref = o.lpt(d, int(t["dens_type"]), int(t["lpt_interp_type"]), want_pos=True)
+    x, y, z = cb.lpt_get_particles(par)
+    for a, b in zip((x, y, z), pos_ref):
+        dd = np.abs(a.astype(np.float64) - b)
+        dd = np.minimum(dd, np.abs(dd - par.l_box))          # periodic wrap
+        assert dd.max() < 2e-3, dd.max()
+    assert abs(got.sum()) < 0.5                               # mass conservation ("Total density", density.c:642)
+    if int(t["lpt_interp_type"]) == 0:
+        # NGP: a particle within rounding of a cell edge may land in the neighbour cell
+        assert np.mean(got != ref) < 1e-3
+    else:
+        assert np.abs(got - ref).max() < 2e-4                 # CIC / TSC weights are continuous in position
+    par.free()
+
+
+def test_lpt_full_flow_runs(golden_dir):
+    """2LPT at n=64 through the whole flow: density -> normalisation -> sources (BASELINE config 4 shape)."""
+    g, t = _load(golden_dir, "ref_n32_2lpt_tsc")
+    t = dict(t)
+    n = 64
+    t["l_box"] = float(np.float32(2 * t["r_max"] * (1 + 2. / n)))
+    t["pos_obs"] = 0.5 * t["l_box"]
+    par = cb.ParamCoLoRe(t, n, dens_type=2, seed=5)
+    par.set_option("lpt_interp_type", 1)
+    cb.create_cartesian_fields(par)
+    cb.compute_physical_density_field(par)
+    dens = _real(par.grid_get(cb.GRID_DENS), n)
+    assert dens.min() >= -1.0 and abs(float(dens.astype(np.float64).mean())) < 1e-5 and dens.std() > 0.01
+    par.set_srcs(0, t["srcs_nz_0"] * 50, t["srcs_bz_0"])
+    cb.compute_density_normalization(par)
+    assert cb.srcs_set_cartesian(par)[0] > 1000
+    par.free()
+
+
 # ------------------------------------------------------------------- full-size property checks
 def test_full_size_properties(golden_dir):
     """n_grid=512 (BASELINE config 2): properties that do not need the oracle at that size."""

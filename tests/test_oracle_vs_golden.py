@@ -13,7 +13,7 @@ import pytest
 
 from oracle.oracle import NA, RNG_MT, Oracle, tables_from_dump
 
-CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth"]
+CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth", "ref_n32_1lpt_cic", "ref_n32_2lpt_tsc", "ref_n32_2lpt_ngp"]
 
 
 @pytest.fixture(scope="module", params=CASES)
@@ -44,8 +44,15 @@ def test_gaussian_fields_bit_exact(case):
 def test_physical_density_and_normalisation(case):
     g, t, o = case
     dens = g["s1_dens_gauss"].copy()
-    o.lognormalize(dens, g["s1_sigma2_gauss"][0], clip=(int(t["dens_type"]) == 3))
-    assert np.array_equal(dens, g["s2_dens"])
+    if int(t["dens_type"]) in (1, 2):       # lpt_1 / lpt_2 + deposit (density.c:376-1031)
+        o.lpt(dens, int(t["dens_type"]), int(t["lpt_interp_type"]))
+        n = o.n
+        assert np.array_equal(dens[:, :, :n], g["s2_dens"][:, :, :n])
+        assert abs(dens[:, :, :n].astype(np.float64).sum()) < 1e-2       # mass conservation of the deposit
+        dens = g["s2_dens"].copy()
+    else:
+        o.lognormalize(dens, g["s1_sigma2_gauss"][0], clip=(int(t["dens_type"]) == 3))
+        assert np.array_equal(dens, g["s2_dens"])
     npop = sum(1 for k in t if k.startswith("srcs_bz_"))
     bz = [t[f"srcs_bz_{i}"] for i in range(npop)]
     if "imap_bz_0" in t:
