@@ -123,6 +123,20 @@ int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n)
   return 0;
 }
 
+// map reductions (io.c:727-735, 836-842, 974-980: MPI_Reduce of the shells): slab-local partial maps summed
+int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n)
+{
+  if (c->nranks == 1) return 0;
+  CLR_NCCL(g_nccl.AllReduce(dbuf, dbuf, n, ncclFloat, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+  return 0;
+}
+int clr_comm_allreduce_i32(clr_ctx *c, int *dbuf, size_t n)
+{
+  if (c->nranks == 1) return 0;
+  CLR_NCCL(g_nccl.AllReduce(dbuf, dbuf, n, ncclInt32, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+  return 0;
+}
+
 int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n)
 {
   if (c->nranks == 1) return 0;

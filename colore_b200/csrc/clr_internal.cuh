@@ -154,6 +154,8 @@ int clr_comm_destroy(clr_ctx *c);
 int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_floats);
 int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n);
 int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n);
+int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n);
+int clr_comm_allreduce_i32(clr_ctx *c, int *dbuf, size_t n);
 int clr_comm_halo(clr_ctx *c);
 int clr_ensure_scratch(clr_ctx *c, size_t bytes);
 

@@ -254,6 +254,9 @@ int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd)
                                                                       (double)P.r0[0] - 20., (double)P.rf[nr - 1] + 20.);
     CLR_CUDA(cudaGetLastError());
   }
+  // every GPU painted its slab into a full-sky map (imap.c:123-132); sum them (io.c:727-735)
+  if (clr_comm_allreduce_f32(c, d_data, (size_t)nr * num_pix)) return 1;
+  if (clr_comm_allreduce_i32(c, d_nadd, (size_t)nr * num_pix)) return 1;
   CLR_CUDA(cudaMemcpyAsync(h_data, d_data, (size_t)nr * num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaMemcpyAsync(h_nadd, d_nadd, (size_t)nr * num_pix * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
@@ -311,6 +314,9 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
       los_kernel<false><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_pos, num_pix, pl, d_data);
     CLR_CUDA(cudaGetLastError());
   }
+  // slab-local ray segments: the accumulators are linear in the field, so the partial maps add up to the
+  // full line-of-sight integral (replaces the ring rotation of beaming.c:325-352)
+  if (clr_comm_allreduce_f32(c, d_data, (size_t)nplanes * num_pix)) return 1;
   CLR_CUDA(cudaMemcpyAsync(h_data, d_data, (size_t)nplanes * num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_pos); cudaFree(d_fac); cudaFree(d_inv); cudaFree(d_ir); cudaFree(d_data);

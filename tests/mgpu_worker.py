@@ -87,6 +87,16 @@ def main():
     pos, ipix = cb.srcs_get_cartesian(par, 0)
     assert np.array_equal(ipix, ipix_ref) and np.array_equal(pos[:, :3], pos_ref[:, :3])
     np.testing.assert_allclose(pos[:, 3], pos_ref[:, 3], rtol=2e-6, atol=1e-12)
+    # maps: every GPU integrates the ray segments inside its slab, the partial maps are all-reduced
+    _, pix = cb.healpix.hp_shell_pixels(8, 2)
+    rf = np.sort(g["s6_kappa_rf"])
+    o.set_halo(full)
+    kap = cb.kappa_get_beam_properties(par, pix, rf)
+    kap_ref = o.kappa(full, pix, rf)
+    np.testing.assert_allclose(kap, kap_ref, rtol=2e-5, atol=2e-6 * np.abs(kap_ref).max())
+    isw = cb.isw_get_beam_properties(par, pix, rf)
+    isw_ref = o.isw(full, pix, rf)
+    np.testing.assert_allclose(isw, isw_ref, rtol=2e-5, atol=2e-6 * np.abs(isw_ref).max())
     tot_all = torch.tensor([nsrc], device="cuda")
     dist.all_reduce(tot_all)
     if rank == 0:
