@@ -31,15 +31,20 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
   // k space is held as [kz][ky_local][kx] with ky in [ky0, ky0+nyl) (single GPU: nyl = n, ky0 = 0, which
   // is the reference layout); rows = (kz, ky_local)
   const unsigned n_rows = (unsigned)d.n * (unsigned)d.nyl;
+  // rows of nc modes: the CTA takes a group of `rpb` rows; inside a group, thread t walks (row, kx) pairs
+  // with kx = t mod kxs so that no per-mode integer division is needed (kxs = blockDim / rows-in-flight)
   const unsigned rpb = max(1u, 1024u / (unsigned)d.nc);
   const unsigned n_groups = (n_rows + rpb - 1) / rpb;
   (void)n_modes;
+  // rows handled concurrently by the CTA: as many as fit with at least nc threads' worth of lanes each
+  const unsigned rows_par = min(rpb, max(1u, (unsigned)blockDim.x / (unsigned)d.nc));
+  const unsigned kxs = (unsigned)blockDim.x / rows_par;         // lanes per row
+  const unsigned my_r = threadIdx.x / kxs, my_k = threadIdx.x - my_r * kxs;
   for (unsigned grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-  for (unsigned tl = threadIdx.x; tl < rpb * (unsigned)d.nc; tl += blockDim.x) {
-    unsigned rl = tl / (unsigned)d.nc;
-    int kk = (int)(tl - rl * (unsigned)d.nc);
+  for (unsigned rl = my_r; rl < rpb; rl += rows_par)
+  for (int kk = (int)my_k; kk < d.nc; kk += (int)kxs) {
     unsigned row = grp * rpb + rl;
-    if (row >= n_rows) continue;
+    if (row >= n_rows || my_r >= rows_par) continue;
     int ii_true = (int)(row / (unsigned)d.nyl);
     int jj = d.ky0 + (int)(row - (unsigned)ii_true * (unsigned)d.nyl);
     long long idx = (long long)row * d.nc + kk;
@@ -58,7 +63,8 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
       int m = kk * kk + mj * mj + mi * mi;
       int e2 = 31 - __clz(m);
       float fm = __int2float_rn(m) * __int_as_float((127 - e2) << 23);      // m * 2^-e2 in [1,2), exact
-      double lgk = lgdk + 0.15051499783199060 * ((double)e2 + (double)log2f(fm));   // 0.5*log10(2)
+      // lg2.approx on [1,2): absolute error 2^-22, i.e. 7e-8 in log10 k
+      double lgk = lgdk + 0.15051499783199060 * ((double)e2 + (double)__log2f(fm));   // 0.5*log10(2)
       double pk;
       int ik = (int)((lgk - logkmin) * idlogk);
       if (ik < 0) pk = __ldg(pkarr) * (double)exp10f((float)(n_scal * (lgk - logkmin)));
@@ -84,11 +90,10 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
       float sn, cs;
       sincospif((float)(w[0] >> 7) * (1.f / 16777216.f), &sn, &cs);         // 2*u1 with 25 bits
       float dre = delta_mod * cs, dim = delta_mod * sn;
-      float k2f = (float)k_mod2;
-      float pfac = -(float)prefac_lensing;
-      float pre = pfac * dre / k2f, pim = pfac * dim / k2f;
+      float pk2 = -(float)prefac_lensing * __frcp_rn((float)k_mod2);
+      float pre = pk2 * dre, pim = pk2 * dim;
       if (do_smoothing) {
-        float sm = expf((float)(-0.5 * r2_smooth * k_mod2));
+        float sm = __expf((float)(-0.5 * r2_smooth * k_mod2));
         dre *= sm; dim *= sm;
         if (smooth_potential) { pre *= sm; pim *= sm; }
       }
@@ -215,6 +220,45 @@ lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int cl
       }
     }
     *p = make_float2(out[0], out[1]);
+  }
+}
+
+// Default (fp32) variant: a run of 8 consecutive cells per thread so that the index arithmetic and the
+// y/z coordinate loads are paid once per run; exp(x)-1 through ex2.approx (absolute error ~2e-7 exp(x),
+// i.e. 2e-7 relative on the physical density 1+delta, inside the stated fp32 tolerance).
+__global__ void __launch_bounds__(kThreads)
+lognormal_fast_kernel(const ClrDev d, float *__restrict__ dens, float hs2, int clip)
+{
+  const float idr = (float)d.glob_idr, rtab = (float)d.r_tab_max, dlast = __ldg(d.d1_f + CLR_NA - 1);
+  const long long n_runs = (long long)d.nz_here * d.n * (d.n / 8);
+  for (long long run = blockIdx.x * (long long)blockDim.x + threadIdx.x; run < n_runs; run += (long long)gridDim.x * blockDim.x) {
+    int ix0, iy, iz;
+    clr_cell(d, run * 8, ix0, iy, iz);
+    const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
+    const float yy = y0 * y0, zz = z0 * z0;
+    float2 *p = reinterpret_cast<float2 *>(dens + ((long long)iz * d.n + iy) * d.pitch + ix0);
+    float2 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = p[q];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      float x0 = __ldg(d.cf[0] + ix0 + q);
+      float r = sqrtf(fmaf(x0, x0, yy + zz));
+      float t = r * idr;
+      int ir = (int)t;
+      float dg;
+      if (r <= 0.f) dg = 1.f;
+      else if (r >= rtab) dg = dlast;
+      else {
+        float fa = __ldg(d.d1_f + ir), fb = __ldg(d.d1_f + ir + 1);
+        dg = fmaf(fb - fa, t - (float)ir, fa);
+      }
+      float delta = (q & 1) ? v[q >> 1].y : v[q >> 1].x;
+      float o = clip ? fmaxf(fmaf(dg, delta, 1.f), 0.f) - 1.f : __expf(dg * fmaf(-hs2, dg, delta)) - 1.f;
+      if (q & 1) v[q >> 1].y = o; else v[q >> 1].x = o;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) p[q] = v[q];
   }
 }
 
@@ -352,6 +396,7 @@ __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
   return powf(1.f + dl, bi);
 }
 
+template <int NPOP>
 __global__ void __launch_bounds__(kThreads)
 norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF pops, int nz, double idz,
                       unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b)
@@ -365,7 +410,7 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   __syncthreads();
   const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max, zlastf = __ldg(d.z_f + CLR_NA - 1);
   const float idzf = (float)idz;
-  const int npop = pops.npop;
+  constexpr int npop = NPOP;          // compile-time population count: dead per-population code folds away
   const long long n_runs = (long long)d.nz_here * d.n * (d.n / kRun);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n_iter = (n_runs + stride - 1) / stride;
@@ -535,6 +580,8 @@ int clr_fields_lognormal(clr_ctx *c, int clip)
   long long n2 = (long long)c->dev.nz_here * c->dev.n * (c->dev.n / 2);
   if (c->exact_math)
     lognormal_kernel<true><<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
+  else if (c->dev.n % 8 == 0)
+    lognormal_fast_kernel<<<grid_for(c, n2 / 4, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, (float)(0.5 * c->sigma2_gauss), clip);
   else
     lognormal_kernel<false><<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
   CLR_CUDA(cudaGetLastError());
@@ -570,7 +617,14 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
         pf.bzf[i] = bzf + (size_t)i * CLR_NA;
       }
       for (int i = npop; i < kFastPop; i++) pf.bzf[i] = bzf;
-      norm_hist_fast_kernel<<<grid_for(c, n_cells / kRun, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b);
+      int grid = grid_for(c, n_cells / kRun, 8);
+      switch (npop) {
+        case 0: norm_hist_fast_kernel<0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
+        case 1: norm_hist_fast_kernel<1><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
+        case 2: norm_hist_fast_kernel<2><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
+        case 3: norm_hist_fast_kernel<3><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
+        default: norm_hist_fast_kernel<4><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
+      }
     } else
       norm_hist_kernel<false><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
     CLR_CUDA(cudaGetLastError());

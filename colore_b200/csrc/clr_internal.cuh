@@ -243,8 +243,13 @@ __device__ __forceinline__ void clr_philox(uint32_t c0, uint32_t c1, uint32_t c2
 
 struct ClrStream {   // sequential reader of one counter-based substream
   uint32_t k0, k1, i0, i1, stream, pos, buf[4];
+  uint32_t first;            // per-cell Poisson streams: draw 0 comes from a block shared by 4 cells
+  bool first_pending;
   __device__ __forceinline__ ClrStream(uint32_t seed, uint32_t strm, unsigned long long index)
-      : k0(seed), k1(0), i0((uint32_t)index), i1((uint32_t)(index >> 32)), stream(strm), pos(0) {}
+      : k0(seed), k1(0), i0((uint32_t)index), i1((uint32_t)(index >> 32)), stream(strm), pos(0), first(0),
+        first_pending(false) {}
+  // oracle/shim/gsl_shim.c:shim_philox_seek_cell: draw 0 = `w0`, draws j>=1 = words j-1 of the substream
+  __device__ __forceinline__ void set_first(uint32_t w0) { first = w0; first_pending = true; }
   // position the reader at word `p` of the substream
   __device__ __forceinline__ void seek(uint32_t p)
   {
@@ -253,6 +258,7 @@ struct ClrStream {   // sequential reader of one counter-based substream
   }
   __device__ __forceinline__ uint32_t next_u32()
   {
+    if (first_pending) { first_pending = false; return first; }
     if ((pos & 3) == 0) clr_philox(i0, i1, pos >> 2, stream, k0, k1, buf);
     uint32_t w = (pos & 3) == 0 ? buf[0] : (pos & 3) == 1 ? buf[1] : (pos & 3) == 2 ? buf[2] : buf[3];
     pos++;

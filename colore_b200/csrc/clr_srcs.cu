@@ -133,7 +133,36 @@ __device__ unsigned int dev_poisson(ClrStream &s, double mu)
 }
 
 // ---- pass 1: lambda and Poisson count per cell (srcs.c:156-184) --------------------------------
+// fp32 screening of one cell: true when the cell is SURELY empty, i.e. its first uniform lies below a
+// rigorous lower bound of exp(-lambda) (gsl_ran_poisson returns 0 iff u0 <= exp(-mu)).
+struct ScreenK { float volf, rcutf, idrf, rtabf; int bias_model; };
+__device__ __forceinline__ bool screen_cell(const ScreenK &k, const ClrPop &pop, float r2, float dl, uint32_t word)
+{
+  float rf = sqrtf(r2);
+  if (rf > k.rcutf + 0.05f) return true;                     // outside the sampled sphere (srcs.c:169)
+  if (!(rf < k.rcutf - 0.05f && rf > 0.05f && rf < k.rtabf - 1.f)) return false;
+  float t = rf * k.idrf;
+  int ir = (int)t;
+  float fr = t - (float)ir;
+  float na = (float)__ldg(pop.nz + ir), nb = (float)__ldg(pop.nz + ir + 1);
+  float ba = (float)__ldg(pop.bz + ir), bb = (float)__ldg(pop.bz + ir + 1);
+  float ma = (float)__ldg(pop.norm + ir), mb = (float)__ldg(pop.norm + ir + 1);
+  float nd = na + (nb - na) * fr, bi = ba + (bb - ba) * fr, nm = ma + (mb - ma) * fr;
+  float bm;
+  if (dl <= -1.f) bm = 0.f;
+  else if (k.bias_model == 2) bm = dl < 0.f ? __expf(__fdividef(bi * dl, 1.f + dl)) * 1.0001f : 1.f + bi * dl;
+  else if (k.bias_model == 3) bm = fmaxf(1.f + bi * dl, 0.f);
+  else bm = __powf(1.f + dl, bi) * 1.0001f;
+  // upper bound of lambda: 0.2% relative slack plus the absolute lerp error of n(r)
+  float lam_hi = (fmaxf(nd, 0.f) * 1.002f + 2e-4f * (fabsf(na) + fabsf(nb))) * k.volf * fabsf(bm) * fabsf(nm) * 1.002f;
+  float e_lo = __expf(-lam_hi) * (1.f - 1e-5f);
+  float u0_hi = (float)((word >> 8) + 1u) * (1.f / 16777216.f);
+  return u0_hi <= e_lo;                                      // false for NaN tables -> exact path
+}
+
 // counts: int32 per cell, unpadded flat order ix + n*(iy + n*iz_local); chunk_tot[chunk] = sum.
+// RNG: the first uniform of cell g is word g&3 of the Philox block shared by cells 4(g>>2)..+3
+// (oracle/shim/gsl_shim.c:shim_philox_seek_cell), so one thread screens 4 neighbouring cells per block.
 __global__ void __launch_bounds__(kThreads, 4)
 poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint32_t seed, int ipop,
                int32_t *__restrict__ counts, int32_t *__restrict__ chunk_tot, long long n_cells)
@@ -141,9 +170,12 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
   const double dx = (double)(d.l_box / d.n);       // float division, as in the reference (srcs.c:147)
   const double cell_vol = dx * dx * dx;
   const double rcut = (double)(d.l_box / 2) + 20.;
-  // fp32 screening constants
-  const float volf = (float)cell_vol, rcutf = (float)rcut;
-  const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max;
+  ScreenK sk;
+  sk.volf = (float)cell_vol; sk.rcutf = (float)rcut;
+  sk.idrf = (float)d.glob_idr; sk.rtabf = (float)d.r_tab_max; sk.bias_model = d.bias_model;
+  const uint32_t strm = 1 + 2 * ipop;
+  const unsigned long long goff = (unsigned long long)d.n * d.n * (unsigned long long)d.iz0_here;
+  const bool rows4 = (d.n & 3) == 0;               // 4-cell groups never straddle a row
   __shared__ int red[kThreads / 32];
   __shared__ unsigned short q_cell[kChunk];
   __shared__ int q_len;
@@ -151,47 +183,50 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
   __syncthreads();
   for (long long chunk = blockIdx.x; chunk * kChunk < n_cells; chunk += gridDim.x) {
     int local = 0;
-    // ---- phase 1 (all cells, fp32): a cell is SURELY empty when its first uniform lies below a
-    // rigorous lower bound of exp(-lambda) (gsl_ran_poisson returns 0 iff u0 <= exp(-mu)). Everything
-    // else -- about 3% of the cells at <N> = 0.03 -- is queued for the exact double-precision path, so
-    // that path runs on dense warps instead of dragging 31 idle lanes along.
-#pragma unroll
-    for (int q = 0; q < kCellsPerThread; q++) {
-      int lc = q * kThreads + threadIdx.x;
-      long long i = chunk * kChunk + lc;
-      if (i >= n_cells) continue;
+    // ---- phase 1 (all cells, fp32). Everything that is not surely empty -- about 3% of the cells at
+    // <N> = 0.03 -- is queued for the exact double-precision path, so that path runs on dense warps
+    // instead of dragging 31 idle lanes along.
+    const int lc0 = threadIdx.x * kCellsPerThread;
+    const long long i0 = chunk * kChunk + lc0;
+    if (rows4 && i0 + 3 < n_cells) {
       int ix, iy, iz;
-      clr_cell(d, i, ix, iy, iz);
-      long long row = (long long)iz * d.n + iy;
-      float xf = __ldg(d.cf[0] + ix), yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
-      float rf = sqrtf(xf * xf + yf * yf + zf * zf);
-      bool sure_zero = false;
-      if (rf > rcutf + 0.05f) sure_zero = true;               // outside the sampled sphere (srcs.c:169)
-      else if (rf < rcutf - 0.05f && rf > 0.05f && rf < rtabf - 1.f) {
-        float t = rf * idrf;
-        int ir = (int)t;
-        float fr = t - (float)ir;
-        float na = (float)__ldg(pop.nz + ir), nb = (float)__ldg(pop.nz + ir + 1);
-        float ba = (float)__ldg(pop.bz + ir), bb = (float)__ldg(pop.bz + ir + 1);
-        float ma = (float)__ldg(pop.norm + ir), mb = (float)__ldg(pop.norm + ir + 1);
-        float nd = na + (nb - na) * fr, bi = ba + (bb - ba) * fr, nm = ma + (mb - ma) * fr;
-        float dl = dens[row * d.pitch + ix];
-        float bm;
-        if (dl <= -1.f) bm = 0.f;
-        else if (d.bias_model == 2) bm = dl < 0.f ? __expf(bi * dl / (1.f + dl)) : 1.f + bi * dl;
-        else if (d.bias_model == 3) bm = fmaxf(1.f + bi * dl, 0.f);
-        else bm = __powf(1.f + dl, bi);
-        // upper bound of lambda: 0.2% relative slack plus the absolute lerp error of n(r)
-        float lam_hi = (fmaxf(nd, 0.f) * 1.002f + 2e-4f * (fabsf(na) + fabsf(nb))) * volf * fabsf(bm) * fabsf(nm) * 1.002f;
-        float e_lo = __expf(-lam_hi) * (1.f - 1e-5f);
-        unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
-        uint32_t w[4];
-        clr_philox((uint32_t)gcell, (uint32_t)(gcell >> 32), 0u, 1 + 2 * ipop, seed, 0u, w);
-        float u0_hi = (float)((w[0] >> 8) + 1u) * (1.f / 16777216.f);
-        sure_zero = (u0_hi <= e_lo);                           // false for NaN tables -> exact path
+      clr_cell(d, i0, ix, iy, iz);
+      const float *drow = dens + ((long long)iz * d.n + iy) * d.pitch + ix;
+      float2 da = __ldg(reinterpret_cast<const float2 *>(drow));
+      float2 db = __ldg(reinterpret_cast<const float2 *>(drow) + 1);
+      float dl[4] = {da.x, da.y, db.x, db.y};
+      float yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
+      float4 xf4 = __ldg(reinterpret_cast<const float4 *>(d.cf[0] + ix));
+      float xf[4] = {xf4.x, xf4.y, xf4.z, xf4.w};
+      float yz2 = yf * yf + zf * zf;
+      unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
+      uint32_t w[4];
+      clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
+      unsigned pend = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (!screen_cell(sk, pop, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
+      *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
+      if (pend) {
+        int base = atomicAdd(&q_len, __popc(pend));
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (pend >> q & 1) q_cell[base++] = (unsigned short)(lc0 + q);
       }
-      if (sure_zero) counts[i] = 0;
-      else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)lc;
+    } else {
+      for (int q = 0; q < kCellsPerThread; q++) {
+        long long i = i0 + q;
+        if (i >= n_cells) break;
+        int ix, iy, iz;
+        clr_cell(d, i, ix, iy, iz);
+        float xf = __ldg(d.cf[0] + ix), yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
+        float dl = dens[((long long)iz * d.n + iy) * d.pitch + ix];
+        unsigned long long gcell = (unsigned long long)i + goff;
+        uint32_t w[4];
+        clr_philox((uint32_t)(gcell >> 2), (uint32_t)(gcell >> 34), 0u, strm | 0x80000000u, seed, 0u, w);
+        if (screen_cell(sk, pop, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
+        else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)(lc0 + q);
+      }
     }
     __syncthreads();
     // ---- phase 2 (queued cells, double): the reference arithmetic, bit for bit
@@ -213,8 +248,11 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
           double dnorm = clr_lerp(d, r, pop.norm, pop.norm_0, pop.norm_f);
           double delta = dens[row * d.pitch + ix];
           double lambda = ndens * cell_vol * clr_bias_model(d.bias_model, delta, bias) * dnorm;
-          unsigned long long gcell = (unsigned long long)ix + (unsigned long long)d.n * ((unsigned long long)iy + (unsigned long long)d.n * (iz + d.iz0_here));
-          ClrStream s(seed, 1 + 2 * ipop, gcell);
+          unsigned long long gcell = (unsigned long long)i + goff;
+          uint32_t w[4];
+          clr_philox((uint32_t)(gcell >> 2), (uint32_t)(gcell >> 34), 0u, strm | 0x80000000u, seed, 0u, w);
+          ClrStream s(seed, strm, gcell);
+          s.set_first(w[gcell & 3]);
           npp = (int)dev_poisson(s, lambda);
         }
       }

@@ -53,6 +53,19 @@ void shim_philox_seek(gsl_rng *r, unsigned long long seed, unsigned int stream, 
   r->pctr[0] = (unsigned int)index; r->pctr[1] = (unsigned int)(index >> 32);
   r->pctr[2] = 0; r->pctr[3] = stream;
   r->ppos = 0;
+  r->pfirst_pending = 0;
+}
+
+void shim_philox_seek_cell(gsl_rng *r, unsigned long long seed, unsigned int stream, unsigned long long cell)
+{
+  unsigned int ctr[4], key[2], out[4];
+  unsigned long long grp = cell >> 2;
+  key[0] = (unsigned int)seed; key[1] = (unsigned int)(seed >> 32);
+  ctr[0] = (unsigned int)grp; ctr[1] = (unsigned int)(grp >> 32); ctr[2] = 0; ctr[3] = stream | 0x80000000u;
+  shim_philox4x32_10(ctr, key, out);
+  shim_philox_seek(r, seed, stream, cell);
+  r->pfirst = out[cell & 3];
+  r->pfirst_pending = 1;
 }
 
 #define MT_N 624
@@ -83,6 +96,7 @@ unsigned long gsl_rng_get(gsl_rng *r)
   unsigned long k;
   unsigned long *mt = r->mt;
   if (r->type->kind == 2) {
+    if (r->pfirst_pending) { r->pfirst_pending = 0; r->ndraws++; return r->pfirst; }
     if ((r->ppos & 3) == 0) {
       r->pctr[2] = r->ppos >> 2;
       shim_philox4x32_10(r->pctr, r->pkey, r->pbuf);

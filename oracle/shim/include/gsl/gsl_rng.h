@@ -14,6 +14,8 @@ typedef struct gsl_rng_s {
   /* shim extension: counter-based substreams (type shim_rng_philox), see shim_philox_seek */
   unsigned int pkey[2], pctr[4], pbuf[4];
   unsigned int ppos;
+  int pfirst_pending;        /* shim_philox_seek_cell: the first draw comes from a block shared by 4 cells */
+  unsigned int pfirst;
 } gsl_rng;
 extern const gsl_rng_type *gsl_rng_mt19937;
 extern const gsl_rng_type *gsl_rng_ranlux;
@@ -23,6 +25,10 @@ extern const gsl_rng_type *gsl_rng_ranlux;
 extern const gsl_rng_type *shim_rng_philox;
 void shim_philox_seek(gsl_rng *r, unsigned long long seed, unsigned int stream, unsigned long long index);
 void shim_philox4x32_10(const unsigned int ctr[4], const unsigned int key[2], unsigned int out[4]);
+/* Per-cell Poisson substream: draw 0 = word (cell & 3) of the block {cell>>2 lo, cell>>2 hi, 0,
+ * stream | 0x80000000} (one Philox call serves the first draw of 4 neighbouring cells -- the only draw
+ * 97% of the cells ever need); draws j >= 1 = words j-1 of substream (seed, stream, cell). */
+void shim_philox_seek_cell(gsl_rng *r, unsigned long long seed, unsigned int stream, unsigned long long cell);
 gsl_rng *gsl_rng_alloc(const gsl_rng_type *T);
 void gsl_rng_set(gsl_rng *r, unsigned long seed);
 unsigned long gsl_rng_get(gsl_rng *r);
