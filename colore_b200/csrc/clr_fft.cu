@@ -59,109 +59,207 @@ template <int S> __device__ __forceinline__ void dft8(float2 (&v)[8])
   v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
 }
 
-constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
-
-template <int M> struct FftPlan {
-  static constexpr int LOG = ilog2c(M);
-  static constexpr int R0 = (LOG % 3 == 0) ? 8 : ((LOG % 3 == 1) ? 2 : 4);  // first-stage radix
-  static constexpr int NS8 = (LOG - ilog2c(R0)) / 3;                        // radix-8 stages after it
-  static constexpr int TPL = M / 8;                                         // virtual threads per line
-  static constexpr int NTW = NS8 * 7 * TPL;                                 // per-thread twiddles
-  static constexpr int LSTRIDE = M + M / 8;                                 // padded row (contiguous layout)
-};
-
-// shared-memory index of element e of line l
-template <int M, bool STRIDED, int T> __device__ __forceinline__ int sidx(int e, int l)
+// exp(S*2*pi*i*m/32) for compile-time m (folded after unrolling)
+__device__ __forceinline__ float cos32(int m)
 {
-  return STRIDED ? e * T + l : l * FftPlan<M>::LSTRIDE + e + (e >> 3);
+  m &= 31;
+  if (m > 16) m = 32 - m;
+  switch (m) {
+    case 0: return 1.f;
+    case 1: return 0.98078528040323044913f;
+    case 2: return 0.92387953251128675613f;
+    case 3: return 0.83146961230254523708f;
+    case 4: return 0.70710678118654752440f;
+    case 5: return 0.55557023301960222474f;
+    case 6: return 0.38268343236508977173f;
+    case 7: return 0.19509032201612826785f;
+    case 8: return 0.f;
+    case 9: return -0.19509032201612826785f;
+    case 10: return -0.38268343236508977173f;
+    case 11: return -0.55557023301960222474f;
+    case 12: return -0.70710678118654752440f;
+    case 13: return -0.83146961230254523708f;
+    case 14: return -0.92387953251128675613f;
+    case 15: return -0.98078528040323044913f;
+    default: return -1.f;
+  }
+}
+// a *= exp(S*2*pi*i*m/32)
+template <int S> __device__ __forceinline__ float2 rot32(float2 a, int m)
+{
+  m &= 31;
+  if (m == 0) return a;
+  if (m == 8) return mul_i<S>(a);
+  if (m == 16) return make_float2(-a.x, -a.y);
+  if (m == 24) return mul_i<-S>(a);
+  const float c = cos32(m), sn = S * cos32(m - 8);      // sin(x) = cos(x - pi/2)
+  return make_float2(a.x * c - a.y * sn, a.x * sn + a.y * c);
+}
+// R = 4 * (R/4) Cooley-Tukey step in registers, natural order in and out
+template <int S> __device__ __forceinline__ void dft16(float2 (&v)[16])
+{
+#pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) dft4<S>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+#pragma unroll
+  for (int k1 = 1; k1 < 4; k1++)
+#pragma unroll
+    for (int n2 = 1; n2 < 4; n2++) v[4 * k1 + n2] = rot32<S>(v[4 * k1 + n2], 2 * n2 * k1);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // X[k1 + 4*k2] sits at v[4*k1 + k2]: transpose the 4x4 register tile
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = a + 1; b < 4; b++) { float2 t = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = t; }
+}
+template <int S> __device__ __forceinline__ void dft32(float2 (&v)[32])
+{
+#pragma unroll
+  for (int n2 = 0; n2 < 8; n2++) dft4<S>(v[n2], v[8 + n2], v[16 + n2], v[24 + n2]);
+#pragma unroll
+  for (int k1 = 1; k1 < 4; k1++)
+#pragma unroll
+    for (int n2 = 1; n2 < 8; n2++) v[8 * k1 + n2] = rot32<S>(v[8 * k1 + n2], n2 * k1);
+  float2 o[32];
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) {
+    float2 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = v[8 * k1 + i];
+    dft8<S>(t);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) o[k1 + 4 * k2] = t[k2];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = o[i];
+}
+template <int R, int S> __device__ __forceinline__ void dftR(float2 (&t)[R])
+{
+  if constexpr (R == 8) dft8<S>(t);
+  else if constexpr (R == 16) dft16<S>(t);
+  else dft32<S>(t);
 }
 
-// gather the per-stage twiddles of this pass from the master table W[k] = exp(+2*pi*i*k/wn)
+__host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
+
+// Stage plan of a length-M transform: radices (descending) R0*R1*R2 = M, every thread owns E = R0
+// points of a line, so a 1024-point line is two radix-32 stages with ONE exchange through shared
+// memory (the exchange traffic, not the flops, is what bounds a Stockham pass on this machine).
+template <int M> struct FftPlan {
+  static constexpr int NST = M <= 32 ? 1 : (M <= 1024 ? 2 : 3);
+  static constexpr int R0 = M <= 32 ? M : (M == 64 ? 8 : (M == 128 || M == 256 ? 16 : (M <= 1024 ? 32 : 16)));
+  static constexpr int R1 = NST < 2 ? 1 : (M <= 128 ? 8 : (M <= 512 ? 16 : (M == 1024 ? 32 : 16)));
+  static constexpr int R2 = NST < 3 ? 1 : M / (R0 * R1);
+  static constexpr int E = R0;                                              // points per thread
+  static constexpr int TPL = M / E;                                         // threads per line
+  static constexpr int PADSH = ilog2c(R0);
+  static constexpr int LSTRIDE = M + (M >> PADSH);                          // padded line
+  static constexpr int NB1 = (NST >= 2 ? (E / R1) * ilog2c(R1) : 0);        // base twiddles per thread, stage 1
+  static constexpr int NB2 = (NST >= 3 ? (E / R2) * ilog2c(R2) : 0);
+  static constexpr int NTW = (NB1 + NB2) * TPL;
+  static_assert(R0 * R1 * R2 == M, "bad radix plan");
+  __host__ __device__ static constexpr int radix(int s) { return s == 0 ? R0 : (s == 1 ? R1 : R2); }
+  __host__ __device__ static constexpr int ns(int s) { return s == 0 ? 1 : (s == 1 ? R0 : R0 * R1); }
+};
+
+// shared-memory index of point p of line l. The pad of one slot every R0 points spreads the
+// first-stage stores (stride R0 between neighbouring threads) over the banks in both layouts.
+template <int M, bool STRIDED, int T> __device__ __forceinline__ int sidx(int p, int l)
+{
+  const int pp = p + (p >> FftPlan<M>::PADSH);
+  return STRIDED ? pp * T + l : l * FftPlan<M>::LSTRIDE + pp;
+}
+
+// Base twiddles of this pass from the master table W[k] = exp(+2*pi*i*k/wn): for stage s >= 1 and
+// butterfly jb the factors w^(2^q), w = exp(S*2*pi*i*(jb % Ns)/(Ns*R)). The other powers are products
+// of at most log2(R) of these (tw_apply), so every factor stays within a few ulp of the exact value.
 template <int M, int S> __device__ __forceinline__ void load_twiddles(float2 *tw, const float2 *__restrict__ W, int wn)
 {
   using P = FftPlan<M>;
   for (int i = threadIdx.x; i < P::NTW; i += blockDim.x) {
-    int st = i / (7 * P::TPL);
-    int r = (i / P::TPL) % 7 + 1;
-    int jj = i % P::TPL;
-    int Ns = P::R0 << (3 * st);
-    int k = jj % Ns;
-    int t = r * k * (wn / (Ns * 8));
+    int slot = i / P::TPL, j = i % P::TPL;
+    int s = slot < P::NB1 ? 1 : 2;
+    if (s == 2) slot -= P::NB1;
+    int R = s == 1 ? P::R1 : P::R2, Ns = s == 1 ? P::R0 : P::R0 * P::R1;
+    int lg = s == 1 ? ilog2c(P::R1) : ilog2c(P::R2);
+    int b = slot / lg, q = slot % lg;
+    int jb = j + b * P::TPL;
+    int t = ((jb % Ns) << q) * (wn / (Ns * R));
     float2 w = W[t];
     if (S < 0) w.y = -w.y;
     tw[i] = w;
   }
 }
 
-// first stage: inputs v[r] = element jv + r*TPL of the line; writes the stage output to shared
-template <int M, int S, bool STRIDED, int T>
-__device__ __forceinline__ void first_stage(float2 (&v)[8], float2 *s, int jv, int l)
+// t[r] *= w^r, r < R, from the base powers w^1, w^2, w^4, ... (stride `st` apart in shared memory)
+template <int R> __device__ __forceinline__ void tw_apply(float2 (&t)[R], const float2 *base, int st)
 {
-  using P = FftPlan<M>;
-  if (P::R0 == 8) {
-    dft8<S>(v);
-    if (P::NS8 == 0) return;
+  float2 lo[8];
+  lo[1] = base[0]; lo[2] = base[st]; lo[4] = base[2 * st];
+  lo[3] = cmul(lo[1], lo[2]); lo[5] = cmul(lo[1], lo[4]); lo[6] = cmul(lo[2], lo[4]); lo[7] = cmul(lo[3], lo[4]);
 #pragma unroll
-    for (int r = 0; r < 8; r++) s[sidx<M, STRIDED, T>(8 * jv + r, l)] = v[r];
-  } else if (P::R0 == 4) {
-    dft4<S>(v[0], v[2], v[4], v[6]);
-    dft4<S>(v[1], v[3], v[5], v[7]);
+  for (int r = 1; r < 8; r++) t[r] = cmul(t[r], lo[r]);
+  if constexpr (R >= 16) {
+    float2 w8 = base[3 * st];
+    t[8] = cmul(t[8], w8);
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int r = 1; r < 8; r++) t[8 + r] = cmul(t[8 + r], cmul(w8, lo[r]));
+    if constexpr (R == 32) {
+      float2 w16 = base[4 * st], w24 = cmul(w8, w16);
+      t[16] = cmul(t[16], w16);
+      t[24] = cmul(t[24], w24);
 #pragma unroll
-      for (int r = 0; r < 4; r++) s[sidx<M, STRIDED, T>(4 * (jv + i * P::TPL) + r, l)] = v[i + 2 * r];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) dft2<S>(v[i], v[i + 4]);
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int r = 0; r < 2; r++) s[sidx<M, STRIDED, T>(2 * (jv + i * P::TPL) + r, l)] = v[i + 4 * r];
-  }
-}
-
-// radix-8 stage number st (0-based among the radix-8 stages that follow the first stage):
-// load from shared, twiddle, butterfly. Outputs stay in v; `store_stage` writes them back.
-template <int M, int S, bool STRIDED, int T>
-__device__ __forceinline__ void load_stage(float2 (&v)[8], const float2 *s, const float2 *tw, int st, int jv, int l)
-{
-  using P = FftPlan<M>;
-#pragma unroll
-  for (int r = 0; r < 8; r++) v[r] = s[sidx<M, STRIDED, T>(jv + r * P::TPL, l)];
-#pragma unroll
-  for (int r = 1; r < 8; r++) v[r] = cmul(v[r], tw[(st * 7 + r - 1) * P::TPL + jv]);
-  dft8<S>(v);
-}
-template <int M, bool STRIDED, int T>
-__device__ __forceinline__ void store_stage(const float2 (&v)[8], float2 *s, int st, int jv, int l)
-{
-  using P = FftPlan<M>;
-  const int Ns = P::R0 << (3 * st);
-  const int idxD = (jv / Ns) * Ns * 8 + (jv % Ns);
-#pragma unroll
-  for (int r = 0; r < 8; r++) s[sidx<M, STRIDED, T>(idxD + r * Ns, l)] = v[r];
-}
-
-// Full length-M transform of the lines held by this CTA. On entry vv[vt][r] = element
-// (j + vt*TPLV) + r*TPL of line l; on exit the same positions hold the transform (natural order).
-template <int M, int S, bool STRIDED, int T, int V>
-__device__ __forceinline__ void fft_lines(float2 (&vv)[V][8], float2 *s, const float2 *tw, int j, int l)
-{
-  using P = FftPlan<M>;
-  constexpr int TPLV = P::TPL / V;
-#pragma unroll
-  for (int vt = 0; vt < V; vt++) first_stage<M, S, STRIDED, T>(vv[vt], s, j + vt * TPLV, l);
-#pragma unroll
-  for (int st = 0; st < P::NS8; st++) {
-    __syncthreads();
-#pragma unroll
-    for (int vt = 0; vt < V; vt++) load_stage<M, S, STRIDED, T>(vv[vt], s, tw, st, j + vt * TPLV, l);
-    if (st < P::NS8 - 1) {
-      __syncthreads();
-#pragma unroll
-      for (int vt = 0; vt < V; vt++) store_stage<M, STRIDED, T>(vv[vt], s, st, j + vt * TPLV, l);
+      for (int r = 1; r < 8; r++) {
+        t[16 + r] = cmul(t[16 + r], cmul(w16, lo[r]));
+        t[24 + r] = cmul(t[24 + r], cmul(w24, lo[r]));
+      }
     }
   }
+}
+
+// one stage: B = E/R butterflies per thread on the register slots b + B*r; outputs go back to the
+// same slots, and (unless it is the last stage) to their Stockham positions in shared memory
+template <int M, int S, bool STRIDED, int T, int ST>
+__device__ __forceinline__ void fft_stage(float2 (&v)[FftPlan<M>::E], float2 *s, const float2 *tw, int j, int l)
+{
+  using P = FftPlan<M>;
+  constexpr int R = P::radix(ST), B = P::E / R, Ns = P::ns(ST), LG = ilog2c(R);
+  if constexpr (ST > 0) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < P::E; i++) v[i] = s[sidx<M, STRIDED, T>(j + i * P::TPL, l)];
+  }
+#pragma unroll
+  for (int b = 0; b < B; b++) {
+    float2 t[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) t[r] = v[b + B * r];
+    if constexpr (ST > 0) tw_apply<R>(t, tw + ((ST == 1 ? 0 : P::NB1) + b * LG) * P::TPL + j, P::TPL);
+    dftR<R, S>(t);
+#pragma unroll
+    for (int r = 0; r < R; r++) v[b + B * r] = t[r];
+  }
+  if constexpr (ST < P::NST - 1) {
+    if constexpr (ST > 0) __syncthreads();
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      const int jb = j + b * P::TPL;
+      const int base = (jb / Ns) * Ns * R + (jb % Ns);
+#pragma unroll
+      for (int r = 0; r < R; r++) s[sidx<M, STRIDED, T>(base + r * Ns, l)] = v[b + B * r];
+    }
+  }
+}
+
+// Full length-M transform of the lines held by this CTA. On entry v[i] = point j + i*TPL of line l;
+// on exit the same slots hold the transform (natural order).
+template <int M, int S, bool STRIDED, int T>
+__device__ __forceinline__ void fft_lines(float2 (&v)[FftPlan<M>::E], float2 *s, const float2 *tw, int j, int l)
+{
+  using P = FftPlan<M>;
+  fft_stage<M, S, STRIDED, T, 0>(v, s, tw, j, l);
+  if constexpr (P::NST >= 2) fft_stage<M, S, STRIDED, T, 1>(v, s, tw, j, l);
+  if constexpr (P::NST >= 3) fft_stage<M, S, STRIDED, T, 2>(v, s, tw, j, l);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -178,16 +276,15 @@ struct LineAddr {
   { return (long long)(e >> lo_bits) * hi_stride + (long long)(e & ((1 << lo_bits) - 1)) * lo_stride; }
 };
 
-template <int M, int S, int T, int V>
-__global__ void __launch_bounds__(T * M / 8 / V, (M <= 1024 && (T * M / 8 / V) <= 512) ? 2 : 1)
+template <int M, int S, int T>
+__global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL <= 256) ? 2 : 1)
 fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, const float2 *__restrict__ W, int wn,
                    long long n_tiles, int tiles_per_outer, int n_inner)
 {
   using P = FftPlan<M>;
-  constexpr int TPLV = P::TPL / V;
   extern __shared__ float2 smem[];
   float2 *s = smem;
-  float2 *tw = smem + (P::NS8 > 0 ? M * T : 0);
+  float2 *tw = smem + (P::NST > 1 ? P::LSTRIDE * T : 0);
   const int tid = threadIdx.x, l = tid % T, j = tid / T;
   load_twiddles<M, S>(tw, W, wn);
   __syncthreads();
@@ -197,18 +294,13 @@ fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout,
     bool ok = inner0 + l < n_inner;
     const float2 *bin = gin + outer * ain.outer_stride + inner0 + l;
     float2 *bout = gout + outer * aout.outer_stride + inner0 + l;
-    float2 vv[V][8];
+    float2 v[P::E];
 #pragma unroll
-    for (int vt = 0; vt < V; vt++)
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        vv[vt][r] = ok ? bin[ain.off(j + vt * TPLV + r * P::TPL)] : make_float2(0.f, 0.f);
-    fft_lines<M, S, true, T, V>(vv, s, tw, j, l);
+    for (int i = 0; i < P::E; i++) v[i] = ok ? bin[ain.off(j + i * P::TPL)] : make_float2(0.f, 0.f);
+    fft_lines<M, S, true, T>(v, s, tw, j, l);
     if (ok) {
 #pragma unroll
-      for (int vt = 0; vt < V; vt++)
-#pragma unroll
-        for (int r = 0; r < 8; r++) bout[aout.off(j + vt * TPLV + r * P::TPL)] = vv[vt][r];
+      for (int i = 0; i < P::E; i++) bout[aout.off(j + i * P::TPL)] = v[i];
     }
     __syncthreads();
   }
@@ -217,18 +309,17 @@ fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout,
 // ------------------------------------------------------------------------------------------
 // x pass of the c2r: rows of nc = M+1 complex -> 2M reals, in place; M = n/2.
 // Output scaled by `norm`; MOM: accumulate sum / sum of squares (double) into mom[0..1].
-template <int M, int T, int V, bool MOM>
-__global__ void __launch_bounds__(T * M / 8 / V)
+template <int M, int T, bool MOM>
+__global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL <= 256) ? 2 : 1)
 fft_c2r_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, long long n_rows, int pitch_c,
                  float norm, double *__restrict__ mom)
 {
   using P = FftPlan<M>;
-  constexpr int TPLV = P::TPL / V;
   extern __shared__ float2 smem[];
   float2 *s = smem;
-  float2 *tw = smem + (P::NS8 > 0 ? T * P::LSTRIDE : 0);
+  float2 *tw = smem + (P::NST > 1 ? T * P::LSTRIDE : 0);
   float2 *wx = tw + P::NTW;   // exp(+2*pi*i*k/n), k < M
-  const int tid = threadIdx.x, j = tid % TPLV, l = tid / TPLV;
+  const int tid = threadIdx.x, j = tid % P::TPL, l = tid / P::TPL;
   load_twiddles<M, +1>(tw, W, wn);
   for (int k = tid; k < M; k += blockDim.x) wx[k] = W[k * (wn / (2 * M))];
   __syncthreads();
@@ -238,35 +329,30 @@ fft_c2r_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
     long long row = tile * T + l;
     bool ok = row < n_rows;
     float2 *X = g + row * pitch_c;
-    float2 vv[V][8];
+    float2 v[P::E];
 #pragma unroll
-    for (int vt = 0; vt < V; vt++)
-#pragma unroll
-      for (int r = 0; r < 8; r++) {
-        int k = j + vt * TPLV + r * P::TPL;
-        float2 a = ok ? X[k] : make_float2(0.f, 0.f);
-        float2 b = ok ? X[M - k] : make_float2(0.f, 0.f);
-        if (k == 0) { a.y = 0.f; b.y = 0.f; }        // x-DC and x-Nyquist are taken as real
-        float2 e = make_float2(a.x + b.x, a.y - b.y);
-        float2 d = cmul(make_float2(a.x - b.x, a.y + b.y), wx[k]);
-        vv[vt][r] = make_float2(e.x - d.y, e.y + d.x);
-      }
-    if (P::NS8 == 0) __syncthreads();
-    fft_lines<M, +1, false, T, V>(vv, s, tw, j, l);
+    for (int i = 0; i < P::E; i++) {
+      int k = j + i * P::TPL;
+      float2 a = ok ? X[k] : make_float2(0.f, 0.f);
+      float2 b = ok ? X[M - k] : make_float2(0.f, 0.f);
+      if (k == 0) { a.y = 0.f; b.y = 0.f; }        // x-DC and x-Nyquist are taken as real
+      float2 e = make_float2(a.x + b.x, a.y - b.y);
+      float2 d = cmul(make_float2(a.x - b.x, a.y + b.y), wx[k]);
+      v[i] = make_float2(e.x - d.y, e.y + d.x);
+    }
+    fft_lines<M, +1, false, T>(v, s, tw, j, l);
     if (ok) {
       float s1 = 0, s2 = 0;
 #pragma unroll
-      for (int vt = 0; vt < V; vt++)
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          float2 o = vv[vt][r];
-          o.x *= norm; o.y *= norm;
-          if (MOM) {
-            s1 += o.x + o.y;
-            s2 += o.x * o.x + o.y * o.y;
-          }
-          X[j + vt * TPLV + r * P::TPL] = o;
+      for (int i = 0; i < P::E; i++) {
+        float2 o = v[i];
+        o.x *= norm; o.y *= norm;
+        if (MOM) {
+          s1 += o.x + o.y;
+          s2 += o.x * o.x + o.y * o.y;
         }
+        X[j + i * P::TPL] = o;
+      }
       if (MOM) { acc1 += s1; acc2 += s2; }
     }
     __syncthreads();
@@ -288,17 +374,16 @@ fft_c2r_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
 }
 
 // x pass of the r2c: rows of 2M reals -> M+1 complex, in place.
-template <int M, int T, int V>
-__global__ void __launch_bounds__(T * M / 8 / V)
+template <int M, int T>
+__global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL <= 256) ? 2 : 1)
 fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, long long n_rows, int pitch_c)
 {
   using P = FftPlan<M>;
-  constexpr int TPLV = P::TPL / V;
   extern __shared__ float2 smem[];
   float2 *s = smem;                              // always needed here (post-processing exchange)
   float2 *tw = smem + T * P::LSTRIDE;
   float2 *wx = tw + P::NTW;                      // exp(-2*pi*i*k/n), k < M
-  const int tid = threadIdx.x, j = tid % TPLV, l = tid / TPLV;
+  const int tid = threadIdx.x, j = tid % P::TPL, l = tid / P::TPL;
   load_twiddles<M, -1>(tw, W, wn);
   for (int k = tid; k < M; k += blockDim.x) { float2 w = W[k * (wn / (2 * M))]; w.y = -w.y; wx[k] = w; }
   __syncthreads();
@@ -307,38 +392,31 @@ fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
     long long row = tile * T + l;
     bool ok = row < n_rows;
     float2 *X = g + row * pitch_c;
-    float2 vv[V][8];
+    float2 v[P::E];
 #pragma unroll
-    for (int vt = 0; vt < V; vt++)
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        vv[vt][r] = ok ? X[j + vt * TPLV + r * P::TPL] : make_float2(0.f, 0.f);
-    fft_lines<M, -1, false, T, V>(vv, s, tw, j, l);
+    for (int i = 0; i < P::E; i++) v[i] = ok ? X[j + i * P::TPL] : make_float2(0.f, 0.f);
+    fft_lines<M, -1, false, T>(v, s, tw, j, l);
     __syncthreads();
 #pragma unroll
-    for (int vt = 0; vt < V; vt++)
-#pragma unroll
-      for (int r = 0; r < 8; r++) s[sidx<M, false, T>(j + vt * TPLV + r * P::TPL, l)] = vv[vt][r];
+    for (int i = 0; i < P::E; i++) s[sidx<M, false, T>(j + i * P::TPL, l)] = v[i];
     __syncthreads();
     if (ok) {
 #pragma unroll
-      for (int vt = 0; vt < V; vt++)
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          int k = j + vt * TPLV + r * P::TPL;
-          float2 zk = vv[vt][r];
-          if (k == 0) {
-            X[0] = make_float2(zk.x + zk.y, 0.f);
-            X[M] = make_float2(zk.x - zk.y, 0.f);
-          } else {
-            float2 zc = s[sidx<M, false, T>(M - k, l)];
-            zc.y = -zc.y;                                        // conj(Z[M-k])
-            float2 e = cadd(zk, zc);
-            float2 d = cmul(csub(zk, zc), wx[k]);                // (Z[k]-conj Z[M-k]) * exp(-2 pi i k/n)
-            // X[k] = 0.5*(e - i*d)
-            X[k] = make_float2(0.5f * (e.x + d.y), 0.5f * (e.y - d.x));
-          }
+      for (int i = 0; i < P::E; i++) {
+        int k = j + i * P::TPL;
+        float2 zk = v[i];
+        if (k == 0) {
+          X[0] = make_float2(zk.x + zk.y, 0.f);
+          X[M] = make_float2(zk.x - zk.y, 0.f);
+        } else {
+          float2 zc = s[sidx<M, false, T>(M - k, l)];
+          zc.y = -zc.y;                                        // conj(Z[M-k])
+          float2 e = cadd(zk, zc);
+          float2 d = cmul(csub(zk, zc), wx[k]);                // (Z[k]-conj Z[M-k]) * exp(-2 pi i k/n)
+          // X[k] = 0.5*(e - i*d)
+          X[k] = make_float2(0.5f * (e.x + d.y), 0.5f * (e.y - d.x));
         }
+      }
     }
     __syncthreads();
   }
@@ -346,10 +424,13 @@ fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
 
 // ------------------------------------------------------------------------------------------
 // host-side dispatch
-template <int M> struct Cfg {   // tile shape per transform length
-  static constexpr int V = M >= 2048 ? 4 : (M >= 1024 ? 2 : 1);
-  static constexpr int T_STRIDED = M >= 4096 ? 4 : (M >= 256 ? 8 : (2048 / M > 64 ? 64 : 2048 / M));
-  static constexpr int T_X = M >= 2048 ? 4 : (M >= 256 ? 8 : (2048 / M > 64 ? 64 : 2048 / M));
+template <int M> struct Cfg {   // lines per CTA tile, per transform length
+  static constexpr int TPL = FftPlan<M>::TPL;
+  static constexpr int T_STRIDED = M >= 4096 ? 4 : (M == 1024 ? 16 : (256 / TPL > 64 ? 64 : (256 / TPL < 8 ? 8 : 256 / TPL)));
+  // z pass: every point of a line sits in another 2 MB page (plane stride), so wider tiles halve the
+  // TLB misses per byte
+  static constexpr int T_Z = (M == 1024 || M == 512) ? 16 : T_STRIDED;
+  static constexpr int T_X = M >= 2048 ? 4 : (256 / TPL > 64 ? 64 : 256 / TPL);
 };
 
 template <typename K> int launch_cfg(clr_ctx *c, K kernel, int threads, size_t smem, long long n_tiles, int *grid)
@@ -364,28 +445,27 @@ template <typename K> int launch_cfg(clr_ctx *c, K kernel, int threads, size_t s
   return 0;
 }
 
-template <int M, int S>
+template <int M, int S, int T = Cfg<M>::T_STRIDED>
 int run_strided2(clr_ctx *c, const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, long long n_outer, int n_inner)
 {
   using P = FftPlan<M>;
-  constexpr int T = Cfg<M>::T_STRIDED, V = Cfg<M>::V;
-  constexpr int threads = T * M / 8 / V;
-  size_t smem = ((P::NS8 > 0 ? (size_t)M * T : 0) + P::NTW) * sizeof(float2);
+  constexpr int threads = T * P::TPL;
+  size_t smem = ((P::NST > 1 ? (size_t)P::LSTRIDE * T : 0) + P::NTW) * sizeof(float2);
   int tiles_per_outer = (n_inner + T - 1) / T;
   long long n_tiles = n_outer * tiles_per_outer;
   int grid;
-  auto k = fft_strided_kernel<M, S, T, V>;
+  auto k = fft_strided_kernel<M, S, T>;
   if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
   k<<<grid, threads, smem, c->stream>>>(gin, gout, ain, aout, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, n_inner);
   CLR_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int M, int S>
+template <int M, int S, int T = Cfg<M>::T_STRIDED>
 int run_strided(clr_ctx *c, float2 *g, long long n_outer, long long outer_stride, long long e_stride, int n_inner)
 {
   LineAddr a{outer_stride, 0, e_stride, 31};
-  return run_strided2<M, S>(c, g, g, a, a, n_outer, n_inner);
+  return run_strided2<M, S, T>(c, g, g, a, a, n_outer, n_inner);
 }
 
 // ---- slab-decomposed transform (one process per GPU) ----------------------------------------------
@@ -437,11 +517,11 @@ template <int M, bool MOM>
 int run_c2r_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c, float norm, double *mom)
 {
   using P = FftPlan<M>;
-  constexpr int T = Cfg<M>::T_X, V = Cfg<M>::V;
-  constexpr int threads = T * M / 8 / V;
-  size_t smem = ((P::NS8 > 0 ? (size_t)T * P::LSTRIDE : 0) + P::NTW + M) * sizeof(float2);
+  constexpr int T = Cfg<M>::T_X;
+  constexpr int threads = T * P::TPL;
+  size_t smem = ((P::NST > 1 ? (size_t)T * P::LSTRIDE : 0) + P::NTW + M) * sizeof(float2);
   int grid;
-  auto k = fft_c2r_x_kernel<M, T, V, MOM>;
+  auto k = fft_c2r_x_kernel<M, T, MOM>;
   if (launch_cfg(c, k, threads, smem, (n_rows + T - 1) / T, &grid)) return 1;
   k<<<grid, threads, smem, c->stream>>>(g, c->d_twiddle, c->dev.n, n_rows, pitch_c, norm, mom);
   CLR_CUDA(cudaGetLastError());
@@ -452,11 +532,11 @@ template <int M>
 int run_r2c_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c)
 {
   using P = FftPlan<M>;
-  constexpr int T = Cfg<M>::T_X, V = Cfg<M>::V;
-  constexpr int threads = T * M / 8 / V;
+  constexpr int T = Cfg<M>::T_X;
+  constexpr int threads = T * P::TPL;
   size_t smem = ((size_t)T * P::LSTRIDE + P::NTW + M) * sizeof(float2);
   int grid;
-  auto k = fft_r2c_x_kernel<M, T, V>;
+  auto k = fft_r2c_x_kernel<M, T>;
   if (launch_cfg(c, k, threads, smem, (n_rows + T - 1) / T, &grid)) return 1;
   k<<<grid, threads, smem, c->stream>>>(g, c->d_twiddle, c->dev.n, n_rows, pitch_c);
   CLR_CUDA(cudaGetLastError());
@@ -468,7 +548,7 @@ int c2r_3d(clr_ctx *c, float2 *g, float norm, double *mom)
 {
   const long long nc = N / 2 + 1;
   // z pass: lines along z, contiguous index = flattened (ky,kx) of a plane
-  { StageScope sc(c, "fft_z", 1); if (run_strided<N, +1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc))) return 1; }
+  { StageScope sc(c, "fft_z", 1); if (run_strided<N, +1, Cfg<N>::T_Z>(c, g, 1, 0, (long long)N * nc, (int)(N * nc))) return 1; }
   // y pass: per z plane, lines along y, contiguous index = kx
   { StageScope sc(c, "fft_y", 1); if (run_strided<N, +1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1; }
   // x pass: half-complex -> real
@@ -484,7 +564,7 @@ int r2c_3d(clr_ctx *c, float2 *g)
   { StageScope sc(c, "fft_x", 1); if (run_r2c_x<N / 2>(c, g, (long long)N * N, (int)nc)) return 1; }
   { StageScope sc(c, "fft_y", 1); if (run_strided<N, -1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1; }
   StageScope sc(c, "fft_z", 1);
-  return run_strided<N, -1>(c, g, 1, 0, (long long)N * nc, (int)(N * nc));
+  return run_strided<N, -1, Cfg<N>::T_Z>(c, g, 1, 0, (long long)N * nc, (int)(N * nc));
 }
 
 }  // namespace
