@@ -128,7 +128,7 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
 
 static void free_pop(clr_ctx::Pop &P)
 {
-  cudaFree(P.d_a); cudaFree(P.d_b); cudaFree(P.d_norm); cudaFree(P.d_counts);
+  cudaFree(P.d_a); cudaFree(P.d_b); cudaFree(P.d_norm); cudaFree(P.d_counts); cudaFree(P.d_bound);
   cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs);
 }
 

@@ -217,18 +217,20 @@ template <int R> __device__ __forceinline__ void tw_apply(float2 (&t)[R], const 
   }
 }
 
-// one stage: B = E/R butterflies per thread on the register slots b + B*r; outputs go back to the
-// same slots, and (unless it is the last stage) to their Stockham positions in shared memory
-template <int M, int S, bool STRIDED, int T, int ST>
-__device__ __forceinline__ void fft_stage(float2 (&v)[FftPlan<M>::E], float2 *s, const float2 *tw, int j, int l)
+// One stage = B = E/R butterflies per thread on the register slots b + B*r; outputs go back to the
+// same slots and (unless it is the last stage) to their Stockham positions in shared memory.
+template <int M, bool STRIDED, int T>
+__device__ __forceinline__ void stage_load(float2 (&v)[FftPlan<M>::E], const float2 *s, int j, int l)
 {
   using P = FftPlan<M>;
-  constexpr int R = P::radix(ST), B = P::E / R, Ns = P::ns(ST), LG = ilog2c(R);
-  if constexpr (ST > 0) {
-    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < P::E; i++) v[i] = s[sidx<M, STRIDED, T>(j + i * P::TPL, l)];
-  }
+  for (int i = 0; i < P::E; i++) v[i] = s[sidx<M, STRIDED, T>(j + i * P::TPL, l)];
+}
+template <int M, int S, int ST>
+__device__ __forceinline__ void stage_math(float2 (&v)[FftPlan<M>::E], const float2 *tw, int j)
+{
+  using P = FftPlan<M>;
+  constexpr int R = P::radix(ST), B = P::E / R, LG = ilog2c(R);
 #pragma unroll
   for (int b = 0; b < B; b++) {
     float2 t[R];
@@ -239,15 +241,32 @@ __device__ __forceinline__ void fft_stage(float2 (&v)[FftPlan<M>::E], float2 *s,
 #pragma unroll
     for (int r = 0; r < R; r++) v[b + B * r] = t[r];
   }
+}
+template <int M, bool STRIDED, int T, int ST>
+__device__ __forceinline__ void stage_store(const float2 (&v)[FftPlan<M>::E], float2 *s, int j, int l)
+{
+  using P = FftPlan<M>;
+  constexpr int R = P::radix(ST), B = P::E / R, Ns = P::ns(ST);
+#pragma unroll
+  for (int b = 0; b < B; b++) {
+    const int jb = j + b * P::TPL;
+    const int base = (jb / Ns) * Ns * R + (jb % Ns);
+#pragma unroll
+    for (int r = 0; r < R; r++) s[sidx<M, STRIDED, T>(base + r * Ns, l)] = v[b + B * r];
+  }
+}
+template <int M, int S, bool STRIDED, int T, int ST>
+__device__ __forceinline__ void fft_stage(float2 (&v)[FftPlan<M>::E], float2 *s, const float2 *tw, int j, int l)
+{
+  using P = FftPlan<M>;
+  if constexpr (ST > 0) {
+    __syncthreads();
+    stage_load<M, STRIDED, T>(v, s, j, l);
+  }
+  stage_math<M, S, ST>(v, tw, j);
   if constexpr (ST < P::NST - 1) {
     if constexpr (ST > 0) __syncthreads();
-#pragma unroll
-    for (int b = 0; b < B; b++) {
-      const int jb = j + b * P::TPL;
-      const int base = (jb / Ns) * Ns * R + (jb % Ns);
-#pragma unroll
-      for (int r = 0; r < R; r++) s[sidx<M, STRIDED, T>(base + r * Ns, l)] = v[b + B * r];
-    }
+    stage_store<M, STRIDED, T, ST>(v, s, j, l);
   }
 }
 
@@ -276,6 +295,66 @@ struct LineAddr {
   { return (long long)(e >> lo_bits) * hi_stride + (long long)(e & ((1 << lo_bits) - 1)) * lo_stride; }
 };
 
+// cp.async of one 8-byte point (zero fill when !ok)
+__device__ __forceinline__ void cp_async8(float2 *dst_smem, const float2 *src, bool ok)
+{
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  int sz = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int M, int S, int T>
+struct StridedTile {
+  using P = FftPlan<M>;
+  const float2 *gin; float2 *gout; LineAddr ain, aout; int tiles_per_outer, n_inner, j, l;
+  __device__ __forceinline__ bool locate(long long tile, long long &in_off, long long &out_off) const
+  {
+    long long outer = tile / tiles_per_outer;
+    int inner0 = (int)(tile - outer * tiles_per_outer) * T;
+    in_off = outer * ain.outer_stride + inner0 + l;
+    out_off = outer * aout.outer_stride + inner0 + l;
+    return inner0 + l < n_inner;
+  }
+  // every thread copies its OWN first-stage inputs into the slots it will read them from
+  __device__ __forceinline__ void prefetch(long long tile, float2 *s) const
+  {
+    long long io, oo;
+    bool ok = locate(tile, io, oo);
+    const float2 *bin = ok ? gin + io : gin;
+    if (ain.lo_bits == 31) {             // single-level stride: step a pointer instead of 64-bit multiplies
+      const float2 *p = bin + (ok ? (long long)j * ain.lo_stride : 0);
+      const long long step = ok ? (long long)P::TPL * ain.lo_stride : 0;
+#pragma unroll
+      for (int i = 0; i < P::E; i++, p += step) cp_async8(s + sidx<M, true, T>(j + i * P::TPL, l), p, ok);
+    } else {
+#pragma unroll
+      for (int i = 0; i < P::E; i++)
+        cp_async8(s + sidx<M, true, T>(j + i * P::TPL, l), bin + (ok ? ain.off(j + i * P::TPL) : 0), ok);
+    }
+  }
+  __device__ __forceinline__ void store(long long tile, const float2 (&v)[P::E]) const
+  {
+    long long io, oo;
+    if (!locate(tile, io, oo)) return;
+    float2 *bout = gout + oo;
+    if (aout.lo_bits == 31) {
+      float2 *p = bout + (long long)j * aout.lo_stride;
+      const long long step = (long long)P::TPL * aout.lo_stride;
+#pragma unroll
+      for (int i = 0; i < P::E; i++, p += step) *p = v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < P::E; i++) bout[aout.off(j + i * P::TPL)] = v[i];
+    }
+  }
+};
+
+// Persistent CTAs, one tile of T lines at a time. The loads of the NEXT tile are issued (cp.async, each
+// thread into its own shared-memory slots) as soon as the last exchange of the current tile has been
+// read back, so they fly under the last-stage butterflies and the global stores.
+// (Tried and dropped: a separate full-tile landing buffer + half-tile exchange buffer, so that a whole
+// tile of 8-byte cp.async is always in flight -- 1.6x SLOWER at n=1024; see DESIGN.md.)
 template <int M, int S, int T>
 __global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL <= 256) ? 2 : 1)
 fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, const float2 *__restrict__ W, int wn,
@@ -284,25 +363,34 @@ fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout,
   using P = FftPlan<M>;
   extern __shared__ float2 smem[];
   float2 *s = smem;
-  float2 *tw = smem + (P::NST > 1 ? P::LSTRIDE * T : 0);
-  const int tid = threadIdx.x, l = tid % T, j = tid / T;
+  float2 *tw = smem + P::LSTRIDE * T;
+  const int tid = threadIdx.x;
+  StridedTile<M, S, T> tl{gin, gout, ain, aout, tiles_per_outer, n_inner, tid / T, tid % T};
+  const int j = tl.j, l = tl.l;
   load_twiddles<M, S>(tw, W, wn);
-  __syncthreads();
+  if (blockIdx.x < n_tiles) tl.prefetch(blockIdx.x, s);
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    long long outer = tile / tiles_per_outer;
-    int inner0 = (int)(tile % tiles_per_outer) * T;
-    bool ok = inner0 + l < n_inner;
-    const float2 *bin = gin + outer * ain.outer_stride + inner0 + l;
-    float2 *bout = gout + outer * aout.outer_stride + inner0 + l;
     float2 v[P::E];
-#pragma unroll
-    for (int i = 0; i < P::E; i++) v[i] = ok ? bin[ain.off(j + i * P::TPL)] : make_float2(0.f, 0.f);
-    fft_lines<M, S, true, T>(v, s, tw, j, l);
-    if (ok) {
-#pragma unroll
-      for (int i = 0; i < P::E; i++) bout[aout.off(j + i * P::TPL)] = v[i];
+    cp_async_wait_all();
+    stage_load<M, true, T>(v, s, j, l);                    // own slots: no barrier needed
+    if constexpr (P::NST >= 2) {
+      stage_math<M, S, 0>(v, tw, j);
+      __syncthreads();                                     // everybody has picked up its inputs (and the twiddles are in)
+      stage_store<M, true, T, 0>(v, s, j, l);
+      __syncthreads();
+      stage_load<M, true, T>(v, s, j, l);
+      if constexpr (P::NST >= 3) {
+        stage_math<M, S, 1>(v, tw, j);
+        __syncthreads();
+        stage_store<M, true, T, 1>(v, s, j, l);
+        __syncthreads();
+        stage_load<M, true, T>(v, s, j, l);
+      }
+      __syncthreads();                                     // last exchange read back: the buffer is free
     }
-    __syncthreads();
+    if (tile + gridDim.x < n_tiles) tl.prefetch(tile + gridDim.x, s);
+    stage_math<M, S, P::NST - 1>(v, tw, j);
+    tl.store(tile, v);
   }
 }
 
@@ -450,7 +538,7 @@ int run_strided2(clr_ctx *c, const float2 *gin, float2 *gout, LineAddr ain, Line
 {
   using P = FftPlan<M>;
   constexpr int threads = T * P::TPL;
-  size_t smem = ((P::NST > 1 ? (size_t)P::LSTRIDE * T : 0) + P::NTW) * sizeof(float2);
+  size_t smem = ((size_t)P::LSTRIDE * T + P::NTW) * sizeof(float2);
   int tiles_per_outer = (n_inner + T - 1) / T;
   long long n_tiles = n_outer * tiles_per_outer;
   int grid;

@@ -386,16 +386,20 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
 // falls back to the exact double expression within 1e-4 bins of an edge, so counts stay exact.
 constexpr int kRun = 8;
 constexpr int kFastPop = 4;
-struct NormPopsF { const float *bzf[kFastPop]; int npop; };
+// lerp tables {f[i], f[i+1]-f[i]} in fp32: entry 0 = z(r), entries 1.. = b(r) per population
+struct NormPopsF { const float2 *zt; const float2 *bt[kFastPop]; int npop; };
 
 __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
 {
   if (dl <= -1.f) return 0.f;
-  if (model == 2) return dl < 0.f ? expf(__fdividef(bi * dl, 1.f + dl)) : 1.f + bi * dl;
+  if (model == 2) return dl < 0.f ? __expf(bi * __fdividef(dl, 1.f + dl)) : 1.f + bi * dl;
   if (model == 3) return fmaxf(1.f + bi * dl, 0.f);
-  return powf(1.f + dl, bi);
+  return __powf(1.f + dl, bi);
 }
 
+// Every CTA walks a CONTIGUOUS range of runs (8 cells each, lane <-> run), so a thread's successive runs
+// sit two rows apart and nearly always fall into the same redshift bin (the bins are ~100 cells wide):
+// the per-thread partial sums are flushed to the shared-memory histogram only when the bin changes.
 template <int NPOP>
 __global__ void __launch_bounds__(kThreads)
 norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF pops, int nz, double idz,
@@ -408,96 +412,74 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   for (int i = threadIdx.x; i < nz * (1 + pops.npop); i += blockDim.x) sh[i] = 0;
   for (int i = threadIdx.x; i < nz; i += blockDim.x) s_n[i] = 0;
   __syncthreads();
-  const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max, zlastf = __ldg(d.z_f + CLR_NA - 1);
+  const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max;
+  const float zlastf = __ldg(&pops.zt[CLR_NA - 1].x);
   const float idzf = (float)idz;
   constexpr int npop = NPOP;          // compile-time population count: dead per-population code folds away
   const long long n_runs = (long long)d.nz_here * d.n * (d.n / kRun);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long n_iter = (n_runs + stride - 1) / stride;
-  const int lane = threadIdx.x & 31;
-  for (long long it = 0; it < n_iter; it++) {
-    long long run = it * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int curbin = -1, cnt = 0;
-    float zs = 0.f, bs[kFastPop] = {0.f, 0.f, 0.f, 0.f};
-    if (run < n_runs) {
-      int ix0, iy, iz;
-      clr_cell(d, run * kRun, ix0, iy, iz);
-      const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
-      const float yy = __fmul_rn(y0, y0), zz = __fmul_rn(z0, z0);
-      const float2 *p = reinterpret_cast<const float2 *>(dens + ((long long)iz * d.n + iy) * d.pitch + ix0);
-      float dv[kRun];
+  const long long per_cta = (n_runs + gridDim.x - 1) / gridDim.x;
+  const long long run_end = min(n_runs, (blockIdx.x + 1) * per_cta);
+  int curbin = -1, cnt = 0;
+  float zs = 0.f, bs[kFastPop] = {0.f, 0.f, 0.f, 0.f};
+  auto flush = [&]() {
+    if (curbin >= 0 && cnt > 0) {
+      atomicAdd(&s_n[curbin], (unsigned long long)cnt);
+      atomicAdd(&s_z[curbin], (double)zs);
 #pragma unroll
-      for (int q = 0; q < kRun / 2; q++) { float2 v = p[q]; dv[2 * q] = v.x; dv[2 * q + 1] = v.y; }
+      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) atomicAdd(&s_b[ip * nz + curbin], (double)bs[ip]);
+    }
+    cnt = 0; zs = 0.f;
 #pragma unroll
-      for (int q = 0; q < kRun; q++) {
-        float x0 = __ldg(d.cf[0] + ix0 + q);
-        float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
-        float rf = sqrtf(r2), zf, tr = rf * idrf;
-        int ir = (int)tr;
-        if (rf <= 0.f) zf = 0.f;
-        else if (rf >= rtabf) zf = zlastf;
-        else {
-          float fa = __ldg(d.z_f + ir), fb = __ldg(d.z_f + ir + 1);
-          zf = fa + (fb - fa) * (tr - (float)ir);
-        }
-        float tb = zf * idzf;
-        int ind_z;
-        if (fabsf(tb - rintf(tb)) < 1e-4f) {
-          double redshift = clr_bg_z(d, sqrt((double)r2));           // density.c:1166-1168 verbatim
-          ind_z = (int)(redshift * idz) + 1;
-        } else ind_z = (int)tb + 1;
-        int bin = (ind_z >= 0 && ind_z < nz) ? ind_z : -1;
-        if (bin != curbin) {
-          if (curbin >= 0 && cnt > 0) {                              // rare: the run crossed a bin edge
-            atomicAdd(&s_n[curbin], (unsigned long long)cnt);
-            atomicAdd(&s_z[curbin], (double)zs);
+    for (int ip = 0; ip < kFastPop; ip++) bs[ip] = 0.f;
+  };
+  for (long long run = blockIdx.x * per_cta + threadIdx.x; run < run_end; run += blockDim.x) {
+    int ix0, iy, iz;
+    clr_cell(d, run * kRun, ix0, iy, iz);
+    const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
+    const float yy = __fmul_rn(y0, y0), zz = __fmul_rn(z0, z0);
+    const float2 *p = reinterpret_cast<const float2 *>(dens + ((long long)iz * d.n + iy) * d.pitch + ix0);
+    float dv[kRun], xv[kRun];
 #pragma unroll
-            for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) atomicAdd(&s_b[ip * nz + curbin], (double)bs[ip]);
-          }
-          curbin = bin; cnt = 0; zs = 0.f;
+    for (int q = 0; q < kRun / 2; q++) { float2 v = p[q]; dv[2 * q] = v.x; dv[2 * q + 1] = v.y; }
+    {
+      const float4 *xp = reinterpret_cast<const float4 *>(d.cf[0] + ix0);
+      float4 xa = __ldg(xp), xb = __ldg(xp + 1);
+      xv[0] = xa.x; xv[1] = xa.y; xv[2] = xa.z; xv[3] = xa.w; xv[4] = xb.x; xv[5] = xb.y; xv[6] = xb.z; xv[7] = xb.w;
+    }
 #pragma unroll
-          for (int ip = 0; ip < kFastPop; ip++) bs[ip] = 0.f;
-        }
-        if (bin >= 0) {
-          cnt++;
-          zs += zf;
+    for (int q = 0; q < kRun; q++) {
+      float x0 = xv[q];
+      float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
+      float rf = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f, zf, tr = rf * idrf;
+      int ir = min((int)tr, CLR_NA - 2);
+      float fr = tr - (float)ir;
+      if (rf >= rtabf) zf = zlastf;
+      else { float2 t = __ldg(pops.zt + ir); zf = t.x + t.y * fr; }
+      float tb = zf * idzf;
+      int ind_z;
+      if (fabsf(tb - rintf(tb)) < 1e-4f) {
+        double redshift = clr_bg_z(d, sqrt((double)r2));           // density.c:1166-1168 verbatim
+        ind_z = (int)(redshift * idz) + 1;
+      } else ind_z = (int)tb + 1;
+      int bin = (ind_z >= 0 && ind_z < nz) ? ind_z : -1;
+      if (bin != curbin) { flush(); curbin = bin; }
+      if (bin >= 0) {
+        cnt++;
+        zs += zf;
 #pragma unroll
-          for (int ip = 0; ip < kFastPop; ip++) {
-            if (ip < npop) {
-              float bi;
-              const float *tbz = pops.bzf[ip];
-              if (rf <= 0.f) bi = __ldg(tbz);
-              else if (rf >= rtabf) bi = 1.f;
-              else {
-                float fa = __ldg(tbz + ir), fb = __ldg(tbz + ir + 1);
-                bi = fa + (fb - fa) * (tr - (float)ir);
-              }
-              bs[ip] += bias_model_f(d.bias_model, dv[q], bi);
-            }
+        for (int ip = 0; ip < kFastPop; ip++) {
+          if (ip < npop) {
+            float bi;
+            if (rf >= rtabf) bi = 1.f;
+            else { float2 t = __ldg(pops.bt[ip] + ir); bi = t.x + t.y * fr; }
+            bs[ip] += bias_model_f(d.bias_model, dv[q], bi);
           }
         }
       }
     }
-    // merge the run totals of the warp, one shared atomic per distinct bin
-    unsigned todo = __ballot_sync(0xffffffffu, curbin >= 0 && cnt > 0);
-    while (todo) {
-      int leader = __ffs(todo) - 1;
-      int b = __shfl_sync(0xffffffffu, curbin, leader);
-      bool mine = (curbin == b) && cnt > 0;
-      unsigned grp = __ballot_sync(0xffffffffu, mine);
-      int csum = __reduce_add_sync(0xffffffffu, mine ? cnt : 0);
-      double zsum = clr_warp_sum(mine ? (double)zs : 0.);
-      if (lane == leader) { atomicAdd(&s_n[b], (unsigned long long)csum); atomicAdd(&s_z[b], zsum); }
-#pragma unroll
-      for (int ip = 0; ip < kFastPop; ip++) {
-        if (ip < npop) {
-          double bsum = clr_warp_sum(mine ? (double)bs[ip] : 0.);
-          if (lane == leader) atomicAdd(&s_b[ip * nz + b], bsum);
-        }
-      }
-      todo &= ~grp;
-    }
+    if (cnt >= 4096) flush();          // keep the fp32 partial sums short
   }
+  flush();
   __syncthreads();
   for (int i = threadIdx.x; i < nz; i += blockDim.x) {
     if (s_n[i]) {
@@ -508,10 +490,13 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   }
 }
 
-__global__ void cvt_table_kernel(const double *__restrict__ src, float *__restrict__ dst, int n)
+// {f[i], f[i+1]-f[i]} in fp32 from a double table of n entries
+__global__ void lerp_table_kernel(const double *__restrict__ src, float2 *__restrict__ dst, int n)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = (float)src[i];
+  if (i >= n) return;
+  double a = src[i], b = src[i + 1 < n ? i + 1 : i];
+  dst[i] = make_float2((float)a, (float)(b - a));
 }
 
 // z-halo of the potential for a single slab: periodic wrap (fourier.c:412-413)
@@ -593,7 +578,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
 {
   CLR_CHECK(npop <= CLR_MAX_NORM_POP && nz <= CLR_MAX_NZ, "normalisation: npop=%d nz=%d too large", npop, nz);
   size_t nd = (size_t)nz * (2 + npop);
-  if (clr_ensure_scratch(c, nd * sizeof(double) + (size_t)kFastPop * CLR_NA * sizeof(float))) return 1;
+  if (clr_ensure_scratch(c, nd * sizeof(double) + (size_t)(kFastPop + 1) * CLR_NA * sizeof(float2))) return 1;
   CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
   unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_scratch);
   double *g_z = c->d_scratch + nz;
@@ -608,15 +593,17 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
     if (c->exact_math)
       norm_hist_kernel<true><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
     else if (npop <= kFastPop && c->dev.n % kRun == 0) {
-      // fp32 copies of the bias tables live behind the histograms in the scratch buffer
+      // fp32 lerp tables of z(r) and the b(r) live behind the histograms in the scratch buffer
       NormPopsF pf;
       pf.npop = npop;
-      float *bzf = reinterpret_cast<float *>(c->d_scratch + nd);
+      float2 *tab = reinterpret_cast<float2 *>(c->d_scratch + nd);
+      lerp_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, tab, CLR_NA);
+      pf.zt = tab;
       for (int i = 0; i < npop; i++) {
-        cvt_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(d_bz[i], bzf + (size_t)i * CLR_NA, CLR_NA);
-        pf.bzf[i] = bzf + (size_t)i * CLR_NA;
+        lerp_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(d_bz[i], tab + (size_t)(i + 1) * CLR_NA, CLR_NA);
+        pf.bt[i] = tab + (size_t)(i + 1) * CLR_NA;
       }
-      for (int i = npop; i < kFastPop; i++) pf.bzf[i] = bzf;
+      for (int i = npop; i < kFastPop; i++) pf.bt[i] = tab;
       int grid = grid_for(c, n_cells / kRun, 8);
       switch (npop) {
         case 0: norm_hist_fast_kernel<0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;

@@ -70,6 +70,7 @@ struct clr_ctx {
     std::vector<float> r0, rf;
     // sources catalogue (device)
     int32_t *d_counts = nullptr;
+    float *d_bound = nullptr;       // fp32 screening table of the Poisson pass (4 floats per r-bin)
     long long nsrc = 0;
     float *d_pos = nullptr; int32_t *d_ipix = nullptr; float *d_srcs = nullptr;
     size_t cap_src = 0;

@@ -134,44 +134,61 @@ __device__ unsigned int dev_poisson(ClrStream &s, double mu)
 
 // ---- pass 1: lambda and Poisson count per cell (srcs.c:156-184) --------------------------------
 // fp32 screening of one cell: true when the cell is SURELY empty, i.e. its first uniform lies below a
-// rigorous lower bound of exp(-lambda) (gsl_ran_poisson returns 0 iff u0 <= exp(-mu)).
-struct ScreenK { float volf, rcutf, idrf, rtabf; int bias_model; };
-__device__ __forceinline__ bool screen_cell(const ScreenK &k, const ClrPop &pop, float r2, float dl, uint32_t word)
+// rigorous lower bound of exp(-lambda) (gsl_ran_poisson returns 0 iff u0 <= exp(-mu)). The bound comes
+// from one float4 per r-bin (poisson_bound_kernel): {upper bound of n(r)*norm(r)*cell volume, lowest b(r),
+// highest b(r)} over the bin and its neighbours, so the fp32 bin index may be off by one.
+struct ScreenK { float rcutf, idrf, rtabf; int bias_model; };
+__device__ __forceinline__ bool screen_cell(const ScreenK &k, const float4 *__restrict__ bound, float r2, float dl,
+                                            uint32_t word)
 {
-  float rf = sqrtf(r2);
+  float rf = r2 * rsqrtf(r2);                                // NaN at r2 = 0 -> every test fails -> exact path
   if (rf > k.rcutf + 0.05f) return true;                     // outside the sampled sphere (srcs.c:169)
   if (!(rf < k.rcutf - 0.05f && rf > 0.05f && rf < k.rtabf - 1.f)) return false;
-  float t = rf * k.idrf;
-  int ir = (int)t;
-  float fr = t - (float)ir;
-  float na = (float)__ldg(pop.nz + ir), nb = (float)__ldg(pop.nz + ir + 1);
-  float ba = (float)__ldg(pop.bz + ir), bb = (float)__ldg(pop.bz + ir + 1);
-  float ma = (float)__ldg(pop.norm + ir), mb = (float)__ldg(pop.norm + ir + 1);
-  float nd = na + (nb - na) * fr, bi = ba + (bb - ba) * fr, nm = ma + (mb - ma) * fr;
-  float bm;
+  float4 e = __ldg(bound + (int)(rf * k.idrf));
+  float bm;                                                  // upper bound of |bias_model(dl, b)|, b in [e.y, e.z]
   if (dl <= -1.f) bm = 0.f;
-  else if (k.bias_model == 2) bm = dl < 0.f ? __expf(__fdividef(bi * dl, 1.f + dl)) * 1.0001f : 1.f + bi * dl;
-  else if (k.bias_model == 3) bm = fmaxf(1.f + bi * dl, 0.f);
-  else bm = __powf(1.f + dl, bi) * 1.0001f;
-  // upper bound of lambda: 0.2% relative slack plus the absolute lerp error of n(r)
-  float lam_hi = (fmaxf(nd, 0.f) * 1.002f + 2e-4f * (fabsf(na) + fabsf(nb))) * k.volf * fabsf(bm) * fabsf(nm) * 1.002f;
+  else if (k.bias_model == 2)
+    bm = dl < 0.f ? __expf(e.y * __fdividef(dl, 1.f + dl)) : fmaxf(fabsf(1.f + e.y * dl), fabsf(1.f + e.z * dl));
+  else if (k.bias_model == 3) bm = fmaxf(fmaxf(1.f + e.y * dl, 1.f + e.z * dl), 0.f);
+  else { float lg = __log2f(1.f + dl); bm = exp2f(fmaxf(e.y * lg, e.z * lg)); }
+  float lam_hi = e.x * bm * 1.001f;
   float e_lo = __expf(-lam_hi) * (1.f - 1e-5f);
   float u0_hi = (float)((word >> 8) + 1u) * (1.f / 16777216.f);
   return u0_hi <= e_lo;                                      // false for NaN tables -> exact path
+}
+
+// one entry per r-bin of the NA grid; window [ir-1, ir+2] covers an off-by-one fp32 bin index
+__global__ void poisson_bound_kernel(const ClrDev d, ClrPop pop, float vol, float4 *__restrict__ bound)
+{
+  int ir = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ir >= CLR_NA) return;
+  double a = 0, nm = fmax(fabs(pop.norm_0), fabs(pop.norm_f)), blo = 1e300, bhi = -1e300;
+  bool bad = false;
+  for (int k = ir - 1; k <= ir + 2; k++) {
+    int kk = k < 0 ? 0 : (k > CLR_NA - 1 ? CLR_NA - 1 : k);
+    double n = pop.nz[kk], m = pop.norm[kk], b = pop.bz[kk];
+    if (!(n == n) || !(m == m) || !(b == b)) bad = true;
+    a = fmax(a, fabs(n)); nm = fmax(nm, fabs(m));
+    blo = fmin(blo, b); bhi = fmax(bhi, b);
+  }
+  float4 e;
+  e.x = bad ? __int_as_float(0x7fc00000) : __double2float_ru(a * nm * (double)vol * 1.001);
+  e.y = __double2float_rd(blo); e.z = __double2float_ru(bhi); e.w = 0.f;
+  bound[ir] = e;
 }
 
 // counts: int32 per cell, unpadded flat order ix + n*(iy + n*iz_local); chunk_tot[chunk] = sum.
 // RNG: the first uniform of cell g is word g&3 of the Philox block shared by cells 4(g>>2)..+3
 // (oracle/shim/gsl_shim.c:shim_philox_seek_cell), so one thread screens 4 neighbouring cells per block.
 __global__ void __launch_bounds__(kThreads, 4)
-poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint32_t seed, int ipop,
-               int32_t *__restrict__ counts, int32_t *__restrict__ chunk_tot, long long n_cells)
+poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const float4 *__restrict__ bound,
+               uint32_t seed, int ipop, int32_t *__restrict__ counts, int32_t *__restrict__ chunk_tot, long long n_cells)
 {
   const double dx = (double)(d.l_box / d.n);       // float division, as in the reference (srcs.c:147)
   const double cell_vol = dx * dx * dx;
   const double rcut = (double)(d.l_box / 2) + 20.;
   ScreenK sk;
-  sk.volf = (float)cell_vol; sk.rcutf = (float)rcut;
+  sk.rcutf = (float)rcut;
   sk.idrf = (float)d.glob_idr; sk.rtabf = (float)d.r_tab_max; sk.bias_model = d.bias_model;
   const uint32_t strm = 1 + 2 * ipop;
   const unsigned long long goff = (unsigned long long)d.n * d.n * (unsigned long long)d.iz0_here;
@@ -205,7 +222,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
       unsigned pend = 0;
 #pragma unroll
       for (int q = 0; q < 4; q++)
-        if (!screen_cell(sk, pop, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
+        if (!screen_cell(sk, bound, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
       *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
       if (pend) {
         int base = atomicAdd(&q_len, __popc(pend));
@@ -224,7 +241,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, uint3
         unsigned long long gcell = (unsigned long long)i + goff;
         uint32_t w[4];
         clr_philox((uint32_t)(gcell >> 2), (uint32_t)(gcell >> 34), 0u, strm | 0x80000000u, seed, 0u, w);
-        if (screen_cell(sk, pop, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
+        if (screen_cell(sk, bound, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
         else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)(lc0 + q);
       }
     }
@@ -518,9 +535,18 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
   long long *d_offs = reinterpret_cast<long long *>(c->d_scratch);
   int32_t *d_tot = reinterpret_cast<int32_t *>(d_offs + n_chunks + 1);
   ClrPop pop{P.d_a, P.d_b, P.d_norm, P.norm_0, P.norm_f};
+  if (!P.d_bound) CLR_CUDA(cudaMalloc(&P.d_bound, (size_t)CLR_NA * 4 * sizeof(float)));
+  {
+    StageScope sc(c, "srcs_bound", 1);
+    const double dx = (double)(c->dev.l_box / c->dev.n);
+    poisson_bound_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev, pop, (float)(dx * dx * dx) * 1.0001f,
+                                                                      reinterpret_cast<float4 *>(P.d_bound));
+    CLR_CUDA(cudaGetLastError());
+  }
   {
     StageScope sc(c, "srcs_poisson", 1);
-    poisson_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, pop, seed, ipop, P.d_counts, d_tot, n_cells);
+    poisson_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(
+        c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound), seed, ipop, P.d_counts, d_tot, n_cells);
     CLR_CUDA(cudaGetLastError());
   }
   {
