@@ -11,6 +11,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kCellsPerThread = 4;
 constexpr int kChunk = kThreads * kCellsPerThread;   // cells per CTA chunk (flat, x fastest)
+constexpr int kSub = 8;                              // chunks a Poisson CTA screens before it runs the exact path
 
 // ---- gsl_ran_poisson (GSL randist/poisson.c) and its helpers, restated for the device ---------
 __device__ __noinline__ double dev_gamma_large(ClrStream &s, double a)
@@ -193,63 +194,72 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
   const uint32_t strm = 1 + 2 * ipop;
   const unsigned long long goff = (unsigned long long)d.n * d.n * (unsigned long long)d.iz0_here;
   const bool rows4 = (d.n & 3) == 0;               // 4-cell groups never straddle a row
-  __shared__ int red[kThreads / 32];
-  __shared__ unsigned short q_cell[kChunk];
+  // A CTA works on kSub consecutive chunks at a time: phase 1 screens all of them and queues the cells that
+  // need the exact path; phase 2 then runs over a queue long enough to fill every lane of the CTA.
+  __shared__ int sub_tot[kSub];
+  __shared__ unsigned short q_cell[kSub * kChunk];
   __shared__ int q_len;
+  const long long n_chunks = (n_cells + kChunk - 1) / kChunk;
+  const long long n_super = (n_chunks + kSub - 1) / kSub;
   if (threadIdx.x == 0) q_len = 0;
+  if (threadIdx.x < kSub) sub_tot[threadIdx.x] = 0;
   __syncthreads();
-  for (long long chunk = blockIdx.x; chunk * kChunk < n_cells; chunk += gridDim.x) {
-    int local = 0;
+  for (long long sup = blockIdx.x; sup < n_super; sup += gridDim.x) {
+    const long long cell0 = sup * kSub * kChunk;
     // ---- phase 1 (all cells, fp32). Everything that is not surely empty -- about 3% of the cells at
-    // <N> = 0.03 -- is queued for the exact double-precision path, so that path runs on dense warps
-    // instead of dragging 31 idle lanes along.
-    const int lc0 = threadIdx.x * kCellsPerThread;
-    const long long i0 = chunk * kChunk + lc0;
-    if (rows4 && i0 + 3 < n_cells) {
-      int ix, iy, iz;
-      clr_cell(d, i0, ix, iy, iz);
-      const float *drow = dens + ((long long)iz * d.n + iy) * d.pitch + ix;
-      float2 da = __ldg(reinterpret_cast<const float2 *>(drow));
-      float2 db = __ldg(reinterpret_cast<const float2 *>(drow) + 1);
-      float dl[4] = {da.x, da.y, db.x, db.y};
-      float yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
-      float4 xf4 = __ldg(reinterpret_cast<const float4 *>(d.cf[0] + ix));
-      float xf[4] = {xf4.x, xf4.y, xf4.z, xf4.w};
-      float yz2 = yf * yf + zf * zf;
-      unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
-      uint32_t w[4];
-      clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
-      unsigned pend = 0;
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (!screen_cell(sk, bound, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
-      *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
-      if (pend) {
-        int base = atomicAdd(&q_len, __popc(pend));
+    // <N> = 0.03 -- is queued for the exact double-precision path.
+#pragma unroll 1
+    for (int sub = 0; sub < kSub; sub++) {
+      const int lc0 = sub * kChunk + threadIdx.x * kCellsPerThread;
+      const long long i0 = cell0 + lc0;
+      if (i0 >= n_cells) break;
+      if (rows4 && i0 + 3 < n_cells) {
+        int ix, iy, iz;
+        clr_cell(d, i0, ix, iy, iz);
+        const float *drow = dens + ((long long)iz * d.n + iy) * d.pitch + ix;
+        float2 da = __ldg(reinterpret_cast<const float2 *>(drow));
+        float2 db = __ldg(reinterpret_cast<const float2 *>(drow) + 1);
+        float dl[4] = {da.x, da.y, db.x, db.y};
+        float yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
+        float4 xf4 = __ldg(reinterpret_cast<const float4 *>(d.cf[0] + ix));
+        float xf[4] = {xf4.x, xf4.y, xf4.z, xf4.w};
+        float yz2 = yf * yf + zf * zf;
+        unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
+        uint32_t w[4];
+        clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
+        unsigned pend = 0;
 #pragma unroll
         for (int q = 0; q < 4; q++)
-          if (pend >> q & 1) q_cell[base++] = (unsigned short)(lc0 + q);
-      }
-    } else {
-      for (int q = 0; q < kCellsPerThread; q++) {
-        long long i = i0 + q;
-        if (i >= n_cells) break;
-        int ix, iy, iz;
-        clr_cell(d, i, ix, iy, iz);
-        float xf = __ldg(d.cf[0] + ix), yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
-        float dl = dens[((long long)iz * d.n + iy) * d.pitch + ix];
-        unsigned long long gcell = (unsigned long long)i + goff;
-        uint32_t w[4];
-        clr_philox((uint32_t)(gcell >> 2), (uint32_t)(gcell >> 34), 0u, strm | 0x80000000u, seed, 0u, w);
-        if (screen_cell(sk, bound, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
-        else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)(lc0 + q);
+          if (!screen_cell(sk, bound, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
+        *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
+        if (pend) {
+          int base = atomicAdd(&q_len, __popc(pend));
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (pend >> q & 1) q_cell[base++] = (unsigned short)(lc0 + q);
+        }
+      } else {
+        for (int q = 0; q < kCellsPerThread; q++) {
+          long long i = i0 + q;
+          if (i >= n_cells) break;
+          int ix, iy, iz;
+          clr_cell(d, i, ix, iy, iz);
+          float xf = __ldg(d.cf[0] + ix), yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
+          float dl = dens[((long long)iz * d.n + iy) * d.pitch + ix];
+          unsigned long long gcell = (unsigned long long)i + goff;
+          uint32_t w[4];
+          clr_philox((uint32_t)(gcell >> 2), (uint32_t)(gcell >> 34), 0u, strm | 0x80000000u, seed, 0u, w);
+          if (screen_cell(sk, bound, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
+          else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)(lc0 + q);
+        }
       }
     }
     __syncthreads();
     // ---- phase 2 (queued cells, double): the reference arithmetic, bit for bit
     const int nq = q_len;
     for (int k = threadIdx.x; k < nq; k += kThreads) {
-      long long i = chunk * kChunk + q_cell[k];
+      const int lc = q_cell[k];
+      long long i = cell0 + lc;
       int ix, iy, iz;
       clr_cell(d, i, ix, iy, iz);
       long long row = (long long)iz * d.n + iy;
@@ -274,19 +284,15 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
         }
       }
       counts[i] = npp;
-      local += npp;
+      if (npp) atomicAdd(&sub_tot[lc / kChunk], npp);
     }
     __syncthreads();
+    if (threadIdx.x < kSub) {
+      long long chunk = sup * kSub + threadIdx.x;
+      if (chunk < n_chunks) chunk_tot[chunk] = sub_tot[threadIdx.x];
+      sub_tot[threadIdx.x] = 0;
+    }
     if (threadIdx.x == 0) q_len = 0;
-    // CTA total of the chunk
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = 0;
-      for (int w = 0; w < kThreads / 32; w++) t += red[w];
-      chunk_tot[chunk] = t;
-    }
     __syncthreads();
   }
 }
@@ -545,7 +551,7 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
   }
   {
     StageScope sc(c, "srcs_poisson", 1);
-    poisson_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(
+    poisson_kernel<<<grid_for(c, (n_chunks + kSub - 1) / kSub, 8), kThreads, 0, c->stream>>>(
         c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound), seed, ipop, P.d_counts, d_tot, n_cells);
     CLR_CUDA(cudaGetLastError());
   }
