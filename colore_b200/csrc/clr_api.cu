@@ -142,7 +142,7 @@ int clr_destroy(clr_ctx *c)
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
   cudaFree(c->d_coord_f); cudaFree(c->d_coord_d);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
-  cudaFree(c->d_twiddle); cudaFree(c->d_scratch);
+  cudaFree(c->d_twiddle); cudaFree(c->d_scratch); cudaFree(c->d_pkt); cudaFree(c->d_sincos);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);

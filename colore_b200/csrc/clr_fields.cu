@@ -135,6 +135,91 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32 mode fill (default; exact_math=0). Same draws, same formulae, but:
+//  * k^2/dk^2 = m is an integer: the P(k) table position of k = dk*sqrt(m) is
+//    t = T[e] + c1*log2(f), m = f*2^e, with T[e] tabulated in double on the host and split into an
+//    integer and a fraction, so the fp32 sum only ever carries the position INSIDE a few table bins;
+//  * P(k)/dk^3 comes from an fp32 lerp table {p_i, p_{i+1}-p_i};
+//  * the phase 2*pi*u1 (25 bits) = coarse angle from a 4096-entry table x a small-angle rotation;
+//  * row invariants are hoisted: no per-mode 64-bit or double arithmetic is left.
+struct FillFastK {
+  int e_int[26];
+  float e_frac[26];
+  float c1, nscal_c, m3_c, tmax, p_first, p_last, neg_prefac_idk2, smooth_c;
+  int numk, do_smoothing, smooth_potential;
+};
+
+__global__ void __launch_bounds__(kThreads)
+fill_modes_fast_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restrict__ npot_f, uint32_t seed,
+                       const float2 *__restrict__ pkt, const float2 *__restrict__ sct, const FillFastK k, int kxs_log2)
+{
+  const unsigned n_rows = (unsigned)d.n * (unsigned)d.nyl;          // rows (kz, ky_local) of nc modes
+  const unsigned kxs = 1u << kxs_log2, rows_par = blockDim.x >> kxs_log2;
+  const unsigned my_r = threadIdx.x >> kxs_log2, my_k = threadIdx.x & (kxs - 1);
+  for (unsigned row = blockIdx.x * rows_par + my_r; row < n_rows; row += gridDim.x * rows_par) {
+    const int ii = (int)(row / (unsigned)d.nyl);
+    const int jj = d.ky0 + (int)(row - (unsigned)ii * (unsigned)d.nyl);
+    const int mi = (2 * ii <= d.n ? ii : d.n - ii), mj = (2 * jj <= d.n ? jj : d.n - jj);
+    const int m_row = mj * mj + mi * mi;
+    const long long idx0 = (long long)row * d.nc;
+    const unsigned long long g0 = (unsigned long long)d.nc * ((unsigned long long)jj + (unsigned long long)d.n * ii);
+    for (int kk = (int)my_k; kk < d.nc; kk += (int)kxs) {
+      float2 dk_out = make_float2(0.f, 0.f), pk_out = make_float2(0.f, 0.f);
+      const int m = kk * kk + m_row;
+      if (m > 0) {
+        const int e2 = 31 - __clz(m);
+        const float mf = __int2float_rn(m);
+        const float fm = mf * __int_as_float((127 - e2) << 23);            // m * 2^-e2 in [1,2)
+        const float par = k.e_frac[e2] + k.c1 * __log2f(fm);               // >= 0
+        const float fl = floorf(par);
+        const int ik = k.e_int[e2] + (int)fl;
+        float sigma2;
+        if (ik >= 0 && ik < k.numk) {
+          float2 t = __ldg(pkt + ik);
+          sigma2 = t.x + (par - fl) * t.y;
+        } else {
+          float tf = (float)k.e_int[e2] + par;
+          sigma2 = ik < 0 ? k.p_first * exp10f(k.nscal_c * tf) : k.p_last * exp10f(k.m3_c * (tf - k.tmax));
+        }
+        const unsigned long long gidx = g0 + (unsigned)kk;
+        uint32_t w[4];
+        clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
+        // ln(1-u2): T = 2^32 - w is 1-u2 in units of 2^-32 (exact integer); logf of the float-rounded T
+        // plus the first-order term of the rounding residue keeps full relative accuracy at both ends
+        float l1 = 0.f;
+        if (w[1]) {
+          uint32_t T = 0u - w[1];
+          float Tf = __uint2float_rn(T);
+          float resid = (float)((long long)T - (long long)Tf);
+          l1 = logf(Tf * 2.3283064365386963e-10f) + __fdividef(resid, Tf);
+        }
+        const float delta_mod = sqrtf(-sigma2 * l1);
+        // phase = 2*pi*q/2^25, q = hi*2^13 + lo
+        const uint32_t q = w[0] >> 7;
+        const float2 cs_h = __ldg(sct + (q >> 13));
+        const float a = (float)(q & 8191u) * 1.872535141e-07f;                // 2*pi/2^25
+        const float a2 = a * a;
+        const float sa = a - a * a2 * 0.16666667f, ca1 = 0.5f * a2;       // sin a, 1 - cos a
+        const float cs = cs_h.x - (cs_h.x * ca1 + cs_h.y * sa);
+        const float sn = cs_h.y - (cs_h.y * ca1 - cs_h.x * sa);
+        float dre = delta_mod * cs, dim = delta_mod * sn;
+        const float pk2 = k.neg_prefac_idk2 * __frcp_rn(mf);
+        float pre = pk2 * dre, pim = pk2 * dim;
+        if (k.do_smoothing) {
+          const float sm = __expf(k.smooth_c * mf);
+          dre *= sm; dim *= sm;
+          if (k.smooth_potential) { pre *= sm; pim *= sm; }
+        }
+        dk_out = make_float2(dre, dim);
+        pk_out = make_float2(pre, pim);
+      }
+      dens_f[idx0 + kk] = dk_out;
+      npot_f[idx0 + kk] = pk_out;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // fourier.c:394-397 scaling of both grids + compute_sigma_dens (fourier.c:24-79) as one streaming
 // pass (used when the FFT epilogue fusion is not: clr_normalize_fields on injected real fields).
 __global__ void __launch_bounds__(kThreads)
@@ -525,9 +610,54 @@ int clr_ensure_scratch(clr_ctx *c, size_t bytes)
   return 0;
 }
 
+int clr_fields_fill_fast(clr_ctx *c, uint32_t seed)
+{
+  const double dk = 2 * M_PI / c->p.l_box, idk3 = 1. / (dk * dk * dk), lgdk = log10(dk);
+  const int numk = c->p.numk;
+  if (!c->d_pkt) {
+    std::vector<float2> t(numk);
+    for (int i = 0; i < numk; i++) {
+      double p0 = c->h_pk[i], p1 = i + 1 < numk ? c->h_pk[i + 1] : p0;
+      t[i] = make_float2((float)(p0 * idk3), (float)((p1 - p0) * idk3));
+    }
+    CLR_CUDA(cudaMalloc(&c->d_pkt, numk * sizeof(float2)));
+    CLR_CUDA(cudaMemcpy(c->d_pkt, t.data(), numk * sizeof(float2), cudaMemcpyHostToDevice));
+    std::vector<float2> sc(4096);
+    for (int i = 0; i < 4096; i++) sc[i] = make_float2((float)cos(2 * M_PI * i / 4096.), (float)sin(2 * M_PI * i / 4096.));
+    CLR_CUDA(cudaMalloc(&c->d_sincos, 4096 * sizeof(float2)));
+    CLR_CUDA(cudaMemcpy(c->d_sincos, sc.data(), 4096 * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  FillFastK k;
+  for (int e = 0; e < 26; e++) {
+    double v = (lgdk + 0.15051499783199060 * e - c->p.logkmin) * c->p.idlogk;
+    double fl = floor(v);
+    k.e_int[e] = (int)fl;
+    k.e_frac[e] = (float)(v - fl);
+  }
+  k.c1 = (float)(0.15051499783199060 * c->p.idlogk);
+  k.nscal_c = (float)(c->p.n_scal / c->p.idlogk);
+  k.m3_c = (float)(-3. / c->p.idlogk);
+  k.tmax = (float)((c->p.logkmax - c->p.logkmin) * c->p.idlogk);
+  k.p_first = (float)(c->h_pk[0] * idk3);
+  k.p_last = (float)(c->h_pk[numk - 1] * idk3);
+  k.neg_prefac_idk2 = (float)(-c->p.prefac_lensing / (dk * dk));
+  k.smooth_c = (float)(-0.5 * c->p.r2_smooth * dk * dk);
+  k.numk = numk; k.do_smoothing = c->p.do_smoothing; k.smooth_potential = c->p.smooth_potential;
+  int kxs_log2 = 0;
+  while ((1 << kxs_log2) < c->dev.nc && (1 << kxs_log2) < kThreads) kxs_log2++;
+  const int rows_par = kThreads >> kxs_log2;
+  long long n_rows = (long long)c->dev.n * c->dev.nyl;
+  fill_modes_fast_kernel<<<grid_for(c, (n_rows + rows_par - 1) / rows_par * kThreads, 8), kThreads, 0, c->stream>>>(
+      c->dev, reinterpret_cast<float2 *>(c->d_dens), reinterpret_cast<float2 *>(c->d_npot), seed, c->d_pkt, c->d_sincos,
+      k, kxs_log2);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int clr_fields_fill(clr_ctx *c, uint32_t seed)
 {
   StageScope sc(c, "fill_modes", 1);
+  if (!c->exact_math && 3LL * (c->dev.n / 2) * (c->dev.n / 2) < (1LL << 24)) return clr_fields_fill_fast(c, seed);
   long long n_modes = (long long)c->dev.nz_here * c->dev.n * c->dev.nc;
   double lgdk = log10(2 * M_PI / c->p.l_box);
   auto k = c->exact_math ? fill_modes_kernel<true> : fill_modes_kernel<false>;

@@ -55,6 +55,7 @@ struct clr_ctx {
   double *d_coord_d = nullptr;                       // 3 x n cell coordinates (fp64 expression)
   double *d_pk = nullptr;                            // logk[numk], pk[numk]
   float2 *d_twiddle = nullptr;                       // exp(+2*pi*i*k/n), k<n
+  float2 *d_pkt = nullptr, *d_sincos = nullptr;      // fp32 tables of the fast mode fill (clr_fields.cu)
   double *d_scratch = nullptr;                       // reductions / histograms
   size_t scratch_bytes = 0;
   double sigma2_gauss = 0, mean_gauss = 0;
