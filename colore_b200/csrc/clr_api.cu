@@ -93,11 +93,16 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   d.d2_arr = c->d_tables + 3 * CLR_NA; d.v1_arr = c->d_tables + 4 * CLR_NA; d.pd_arr = c->d_tables + 5 * CLR_NA;
   d.ih_arr = c->d_tables + 6 * CLR_NA; d.a2r_a = c->d_tables + 7 * CLR_NA; d.a2r_r = c->d_tables + 8 * CLR_NA;
   {
-    std::vector<float> tf(2 * CLR_NA);
-    for (int i = 0; i < CLR_NA; i++) { tf[i] = (float)c->h_z[i]; tf[CLR_NA + i] = (float)c->h_d1[i]; }
-    CLR_CUDA(cudaMalloc(&c->d_tables_f, 2 * CLR_NA * sizeof(float)));
-    CLR_CUDA(cudaMemcpy(c->d_tables_f, tf.data(), 2 * CLR_NA * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> tf(4 * CLR_NA);
+    for (int i = 0; i < CLR_NA; i++) {
+      tf[i] = (float)c->h_z[i]; tf[CLR_NA + i] = (float)c->h_d1[i];
+      tf[2 * CLR_NA + 2 * i] = (float)c->h_d1[i];
+      tf[2 * CLR_NA + 2 * i + 1] = (float)(c->h_d1[i + 1 < CLR_NA ? i + 1 : i] - c->h_d1[i]);
+    }
+    CLR_CUDA(cudaMalloc(&c->d_tables_f, 4 * CLR_NA * sizeof(float)));
+    CLR_CUDA(cudaMemcpy(c->d_tables_f, tf.data(), 4 * CLR_NA * sizeof(float), cudaMemcpyHostToDevice));
     d.z_f = c->d_tables_f; d.d1_f = c->d_tables_f + CLR_NA;
+    d.d1_t = reinterpret_cast<const float2 *>(c->d_tables_f + 2 * CLR_NA);
   }
   {
     // coordinate tables, evaluated with the reference's expressions (see ClrDev)

@@ -314,36 +314,48 @@ lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int cl
 __global__ void __launch_bounds__(kThreads)
 lognormal_fast_kernel(const ClrDev d, float *__restrict__ dens, float hs2, int clip)
 {
+  // a warp owns 256-cell segments of a row: lane <-> float2 number lane + 32*q, so every load / store
+  // instruction of the warp covers 256 contiguous bytes (rows are only 8-byte aligned: no float4)
   const float idr = (float)d.glob_idr, rtab = (float)d.r_tab_max, dlast = __ldg(d.d1_f + CLR_NA - 1);
-  const long long n_runs = (long long)d.nz_here * d.n * (d.n / 8);
-  for (long long run = blockIdx.x * (long long)blockDim.x + threadIdx.x; run < n_runs; run += (long long)gridDim.x * blockDim.x) {
-    int ix0, iy, iz;
-    clr_cell(d, run * 8, ix0, iy, iz);
+  const int lane = threadIdx.x & 31;
+  const unsigned spr = ((unsigned)d.n + 255u) >> 8;                     // segments per row
+  const unsigned n_seg = (unsigned)d.nz_here * (unsigned)d.n * spr;      // < 2^32 up to n = 4096
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seg < n_seg; seg += n_warps) {
+    const unsigned row = seg / spr;
+    const int s = (int)(seg - row * spr);
+    const int iz = (int)(row / (unsigned)d.n), iy = (int)(row - (unsigned)iz * (unsigned)d.n);
     const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
-    const float yy = y0 * y0, zz = z0 * z0;
-    float2 *p = reinterpret_cast<float2 *>(dens + ((long long)iz * d.n + iy) * d.pitch + ix0);
-    float2 v[4];
+    const float yz = y0 * y0 + z0 * z0;
+    const int xq0 = s * 128 + lane;                                     // float2 index inside the row
+    float2 *p = reinterpret_cast<float2 *>(dens + (long long)row * d.pitch) + xq0;
+    const float2 *xc = reinterpret_cast<const float2 *>(d.cf[0]) + xq0;
+    float2 v[4], x[4];
+    bool ok[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) v[q] = p[q];
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      float x0 = __ldg(d.cf[0] + ix0 + q);
-      float r = sqrtf(fmaf(x0, x0, yy + zz));
-      float t = r * idr;
-      int ir = (int)t;
-      float dg;
-      if (r <= 0.f) dg = 1.f;
-      else if (r >= rtab) dg = dlast;
-      else {
-        float fa = __ldg(d.d1_f + ir), fb = __ldg(d.d1_f + ir + 1);
-        dg = fmaf(fb - fa, t - (float)ir, fa);
-      }
-      float delta = (q & 1) ? v[q >> 1].y : v[q >> 1].x;
-      float o = clip ? fmaxf(fmaf(dg, delta, 1.f), 0.f) - 1.f : __expf(dg * fmaf(-hs2, dg, delta)) - 1.f;
-      if (q & 1) v[q >> 1].y = o; else v[q >> 1].x = o;
+    for (int q = 0; q < 4; q++) {
+      ok[q] = 2 * (xq0 + 32 * q) < d.n;
+      if (ok[q]) { v[q] = p[32 * q]; x[q] = __ldg(xc + 32 * q); }
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++) p[q] = v[q];
+    for (int q = 0; q < 4; q++) {
+      if (!ok[q]) continue;
+      float o[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        float x0 = h ? x[q].y : x[q].x, delta = h ? v[q].y : v[q].x;
+        float r2 = fmaf(x0, x0, yz);
+        float r = r2 * rsqrtf(r2);                                      // NaN at r2 = 0 -> dg = 1 below
+        float t = r * idr;
+        int ir = (int)t;
+        float dg;
+        if (!(r > 0.f)) dg = 1.f;
+        else if (r >= rtab) dg = dlast;
+        else { float2 e = __ldg(d.d1_t + ir); dg = fmaf(e.y, t - (float)ir, e.x); }
+        o[h] = clip ? fmaxf(fmaf(dg, delta, 1.f), 0.f) - 1.f : __expf(dg * fmaf(-hs2, dg, delta)) - 1.f;
+      }
+      p[32 * q] = make_float2(o[0], o[1]);
+    }
   }
 }
 

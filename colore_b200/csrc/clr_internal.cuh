@@ -26,6 +26,7 @@ struct ClrDev {
   const double *r_arr, *z_arr, *d1_arr, *d2_arr, *v1_arr, *pd_arr, *ih_arr, *a2r_a, *a2r_r;
   const float *slice_left, *slice_right;   // z-halo planes of the potential (fourier.c:401-414)
   const float *z_f, *d1_f;                 // fp32 copies of z(r), D(r) for the streaming field kernels
+  const float2 *d1_t;                      // {D(r_i), D(r_i+1)-D(r_i)}: one load per lerp
   // cell-node coordinates relative to the observer, tabulated once on the host with the reference's
   // own expressions: cf[ax][i] = (flouble)((i+0.0)*dx_f - pos_obs[ax]) (density.c:1087-1094, dx flouble)
   // and cd[ax][i] = (i+0.0)*dx_d - pos_obs[ax] (srcs.c:159-167, dx double); i is the GLOBAL index.
