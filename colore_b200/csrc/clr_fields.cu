@@ -513,70 +513,90 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   const float zlastf = __ldg(&pops.zt[CLR_NA - 1].x);
   const float idzf = (float)idz;
   constexpr int npop = NPOP;          // compile-time population count: dead per-population code folds away
-  const long long n_runs = (long long)d.nz_here * d.n * (d.n / kRun);
-  const long long per_cta = (n_runs + gridDim.x - 1) / gridDim.x;
-  const long long run_end = min(n_runs, (blockIdx.x + 1) * per_cta);
-  int curbin = -1, cnt = 0;
-  float zs = 0.f, bs[kFastPop] = {0.f, 0.f, 0.f, 0.f};
-  auto flush = [&]() {
-    if (curbin >= 0 && cnt > 0) {
-      atomicAdd(&s_n[curbin], (unsigned long long)cnt);
-      atomicAdd(&s_z[curbin], (double)zs);
+  // a warp owns 256-cell segments of a row (lane <-> float2 number lane + 32*q: 256 contiguous bytes per
+  // load instruction); a CTA walks a contiguous range of segments
+  const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const unsigned spr = ((unsigned)d.n + 255u) >> 8;
+  const unsigned n_seg = (unsigned)d.nz_here * (unsigned)d.n * spr;      // < 2^32 up to n = 4096
+  const unsigned per_cta = (n_seg + gridDim.x - 1) / gridDim.x;
+  const unsigned seg_end = min(n_seg, (blockIdx.x + 1) * per_cta);
+  // one set of partial sums per float2 slot q: slot (lane, q) sees the same x in successive rows, so its
+  // redshift bin (~100 cells wide) rarely changes and flushes to the shared histogram are rare
+  constexpr int NQ = kRun / 2;
+  int curbin[NQ], cnt[NQ];
+  float zs[NQ], bs[NQ][kFastPop];
 #pragma unroll
-      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) atomicAdd(&s_b[ip * nz + curbin], (double)bs[ip]);
+  for (int q = 0; q < NQ; q++) {
+    curbin[q] = -1; cnt[q] = 0; zs[q] = 0.f;
+#pragma unroll
+    for (int ip = 0; ip < kFastPop; ip++) bs[q][ip] = 0.f;
+  }
+  auto flush = [&](int q) {
+    if (curbin[q] >= 0 && cnt[q] > 0) {
+      atomicAdd(&s_n[curbin[q]], (unsigned long long)cnt[q]);
+      atomicAdd(&s_z[curbin[q]], (double)zs[q]);
+#pragma unroll
+      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) atomicAdd(&s_b[ip * nz + curbin[q]], (double)bs[q][ip]);
     }
-    cnt = 0; zs = 0.f;
+    cnt[q] = 0; zs[q] = 0.f;
 #pragma unroll
-    for (int ip = 0; ip < kFastPop; ip++) bs[ip] = 0.f;
+    for (int ip = 0; ip < kFastPop; ip++) bs[q][ip] = 0.f;
   };
-  for (long long run = blockIdx.x * per_cta + threadIdx.x; run < run_end; run += blockDim.x) {
-    int ix0, iy, iz;
-    clr_cell(d, run * kRun, ix0, iy, iz);
+  for (unsigned seg = blockIdx.x * per_cta + wip; seg < seg_end; seg += wpc) {
+    const unsigned row = seg / spr;
+    const int sg = (int)(seg - row * spr);
+    const int iz = (int)(row / (unsigned)d.n), iy = (int)(row - (unsigned)iz * (unsigned)d.n);
     const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
     const float yy = __fmul_rn(y0, y0), zz = __fmul_rn(z0, z0);
-    const float2 *p = reinterpret_cast<const float2 *>(dens + ((long long)iz * d.n + iy) * d.pitch + ix0);
-    float dv[kRun], xv[kRun];
+    const int xq0 = sg * 128 + lane;
+    const float2 *p = reinterpret_cast<const float2 *>(dens + (long long)row * d.pitch) + xq0;
+    const float2 *xc = reinterpret_cast<const float2 *>(d.cf[0]) + xq0;
+    float2 dv[NQ], xv[NQ];
+    bool ok[NQ];
 #pragma unroll
-    for (int q = 0; q < kRun / 2; q++) { float2 v = p[q]; dv[2 * q] = v.x; dv[2 * q + 1] = v.y; }
-    {
-      const float4 *xp = reinterpret_cast<const float4 *>(d.cf[0] + ix0);
-      float4 xa = __ldg(xp), xb = __ldg(xp + 1);
-      xv[0] = xa.x; xv[1] = xa.y; xv[2] = xa.z; xv[3] = xa.w; xv[4] = xb.x; xv[5] = xb.y; xv[6] = xb.z; xv[7] = xb.w;
+    for (int q = 0; q < NQ; q++) {
+      ok[q] = 2 * (xq0 + 32 * q) < d.n;
+      if (ok[q]) { dv[q] = p[32 * q]; xv[q] = __ldg(xc + 32 * q); }
     }
 #pragma unroll
-    for (int q = 0; q < kRun; q++) {
-      float x0 = xv[q];
-      float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
-      float rf = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f, zf, tr = rf * idrf;
-      int ir = min((int)tr, CLR_NA - 2);
-      float fr = tr - (float)ir;
-      if (rf >= rtabf) zf = zlastf;
-      else { float2 t = __ldg(pops.zt + ir); zf = t.x + t.y * fr; }
-      float tb = zf * idzf;
-      int ind_z;
-      if (fabsf(tb - rintf(tb)) < 1e-4f) {
-        double redshift = clr_bg_z(d, sqrt((double)r2));           // density.c:1166-1168 verbatim
-        ind_z = (int)(redshift * idz) + 1;
-      } else ind_z = (int)tb + 1;
-      int bin = (ind_z >= 0 && ind_z < nz) ? ind_z : -1;
-      if (bin != curbin) { flush(); curbin = bin; }
-      if (bin >= 0) {
-        cnt++;
-        zs += zf;
+    for (int q = 0; q < NQ; q++) {
+      if (!ok[q]) continue;
 #pragma unroll
-        for (int ip = 0; ip < kFastPop; ip++) {
-          if (ip < npop) {
-            float bi;
-            if (rf >= rtabf) bi = 1.f;
-            else { float2 t = __ldg(pops.bt[ip] + ir); bi = t.x + t.y * fr; }
-            bs[ip] += bias_model_f(d.bias_model, dv[q], bi);
+      for (int h = 0; h < 2; h++) {
+        float x0 = h ? xv[q].y : xv[q].x, dl = h ? dv[q].y : dv[q].x;
+        float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
+        float rf = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f, zf, tr = rf * idrf;
+        int ir = min((int)tr, CLR_NA - 2);
+        float fr = tr - (float)ir;
+        if (rf >= rtabf) zf = zlastf;
+        else { float2 t = __ldg(pops.zt + ir); zf = t.x + t.y * fr; }
+        float tb = zf * idzf;
+        int ind_z;
+        if (fabsf(tb - rintf(tb)) < 1e-4f) {
+          double redshift = clr_bg_z(d, sqrt((double)r2));           // density.c:1166-1168 verbatim
+          ind_z = (int)(redshift * idz) + 1;
+        } else ind_z = (int)tb + 1;
+        int bin = (ind_z >= 0 && ind_z < nz) ? ind_z : -1;
+        if (bin != curbin[q]) { flush(q); curbin[q] = bin; }
+        if (bin >= 0) {
+          cnt[q]++;
+          zs[q] += zf;
+#pragma unroll
+          for (int ip = 0; ip < kFastPop; ip++) {
+            if (ip < npop) {
+              float bi;
+              if (rf >= rtabf) bi = 1.f;
+              else { float2 t = __ldg(pops.bt[ip] + ir); bi = t.x + t.y * fr; }
+              bs[q][ip] += bias_model_f(d.bias_model, dl, bi);
+            }
           }
         }
       }
+      if (cnt[q] >= 4096) flush(q);      // keep the fp32 partial sums short
     }
-    if (cnt >= 4096) flush();          // keep the fp32 partial sums short
   }
-  flush();
+#pragma unroll
+  for (int q = 0; q < NQ; q++) flush(q);
   __syncthreads();
   for (int i = threadIdx.x; i < nz; i += blockDim.x) {
     if (s_n[i]) {
@@ -746,7 +766,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
         pf.bt[i] = tab + (size_t)(i + 1) * CLR_NA;
       }
       for (int i = npop; i < kFastPop; i++) pf.bt[i] = tab;
-      int grid = grid_for(c, n_cells / kRun, 8);
+      int grid = grid_for(c, n_cells / kRun, 8);   // 8 cells per thread and iteration
       switch (npop) {
         case 0: norm_hist_fast_kernel<0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
         case 1: norm_hist_fast_kernel<1><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
