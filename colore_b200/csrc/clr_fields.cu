@@ -502,13 +502,23 @@ __global__ void __launch_bounds__(kThreads)
 norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF pops, int nz, double idz,
                       unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b)
 {
+  // CTA histogram in shared memory, updated with 32-bit integer atomics only (the float / double / 64-bit
+  // shared atomics of sm_100 are CAS spin loops): counts as u32, sums as 64-bit fixed point (2^-20) held
+  // as {lo, hi} words with an explicit carry. Integer sums also make the result independent of the
+  // order in which the threads flush.
   extern __shared__ double sh[];
-  double *s_z = sh;
-  double *s_b = sh + nz;
-  unsigned long long *s_n = reinterpret_cast<unsigned long long *>(sh + (size_t)nz * (1 + pops.npop));
-  for (int i = threadIdx.x; i < nz * (1 + pops.npop); i += blockDim.x) sh[i] = 0;
-  for (int i = threadIdx.x; i < nz; i += blockDim.x) s_n[i] = 0;
+  unsigned *s_n = reinterpret_cast<unsigned *>(sh);                    // [nz]
+  unsigned *s_q = s_n + nz;                                            // [(1+npop)][nz][2]: z, then b per population
+  for (int i = threadIdx.x; i < nz * (3 + 2 * pops.npop); i += blockDim.x) s_n[i] = 0;
   __syncthreads();
+  auto add_fixed = [&](int slot, int bin, float v) {
+    long long f = __float2ll_rn(v * 1048576.f);
+    unsigned lo = (unsigned)f, hi = (unsigned)((unsigned long long)f >> 32);
+    unsigned *w = s_q + ((size_t)slot * nz + bin) * 2;
+    unsigned old = atomicAdd(w, lo);
+    hi += (old + lo < old) ? 1u : 0u;
+    if (hi) atomicAdd(w + 1, hi);
+  };
   const float idrf = (float)d.glob_idr, rtabf = (float)d.r_tab_max;
   const float zlastf = __ldg(&pops.zt[CLR_NA - 1].x);
   const float idzf = (float)idz;
@@ -533,10 +543,10 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   }
   auto flush = [&](int q) {
     if (curbin[q] >= 0 && cnt[q] > 0) {
-      atomicAdd(&s_n[curbin[q]], (unsigned long long)cnt[q]);
-      atomicAdd(&s_z[curbin[q]], (double)zs[q]);
+      atomicAdd(&s_n[curbin[q]], (unsigned)cnt[q]);
+      add_fixed(0, curbin[q], zs[q]);
 #pragma unroll
-      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) atomicAdd(&s_b[ip * nz + curbin[q]], (double)bs[q][ip]);
+      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) add_fixed(1 + ip, curbin[q], bs[q][ip]);
     }
     cnt[q] = 0; zs[q] = 0.f;
 #pragma unroll
@@ -600,9 +610,13 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   __syncthreads();
   for (int i = threadIdx.x; i < nz; i += blockDim.x) {
     if (s_n[i]) {
-      atomicAdd(&g_n[i], s_n[i]);
-      atomicAdd(&g_z[i], s_z[i]);
-      for (int ip = 0; ip < npop; ip++) atomicAdd(&g_b[ip * nz + i], s_b[ip * nz + i]);
+      auto fixed = [&](int slot) {
+        const unsigned *w = s_q + ((size_t)slot * nz + i) * 2;
+        return (double)(long long)(((unsigned long long)w[1] << 32) | w[0]) * (1.0 / 1048576.0);
+      };
+      atomicAdd(&g_n[i], (unsigned long long)s_n[i]);
+      atomicAdd(&g_z[i], fixed(0));
+      for (int ip = 0; ip < npop; ip++) atomicAdd(&g_b[ip * nz + i], fixed(1 + ip));
     }
   }
 }
