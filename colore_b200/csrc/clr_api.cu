@@ -47,6 +47,9 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   c->sm_count = prop.multiProcessorCount;
   CLR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CLR_CUDA(cudaEventCreate(&c->ev0)); CLR_CUDA(cudaEventCreate(&c->ev1));
+  CLR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CLR_CUDA(cudaEventCreateWithFlags(&c->ev_srcs_ready, cudaEventDisableTiming));
+  CLR_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
   CLR_CUDA(cudaEventCreate(&c->evp0)); CLR_CUDA(cudaEventCreate(&c->evp1));
   // host copies of the tables
   copy_tab(c->h_logk, p->logkarr, p->numk); copy_tab(c->h_pk, p->pkarr, p->numk);
@@ -150,12 +153,20 @@ int clr_destroy(clr_ctx *c)
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch); cudaFree(c->d_pkt); cudaFree(c->d_sincos);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_srcs_ready); cudaEventDestroy(c->ev_copy_done);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
 }
 
-int clr_synchronize(clr_ctx *c) { CLR_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+int clr_synchronize(clr_ctx *c)
+{
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->copy_stream));
+  c->copy_pending = false;
+  return 0;
+}
 long long clr_launch_count(clr_ctx *c) { return c->launches; }
 
 
@@ -263,6 +274,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "exact_math")) { c->exact_math = value; return 0; }
   if (!strcmp(name, "lpt_interp_type")) { c->lpt_interp_type = value; return 0; }
   if (!strcmp(name, "keep_particles")) { c->keep_particles = value; return 0; }
+  if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
   clr_set_error("unknown option %s", name);
   return 1;
 }
@@ -417,6 +429,16 @@ int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
 {
   clr_ctx::Pop &P = c->srcs[ipop];
   if (P.nsrc == 0) return 0;
+  if (c->async_results) {
+    // the copy runs on its own stream behind the kernels queued so far; the next run only waits for it
+    // (on the device) before it reuses the catalogue buffers. `srcs9` is valid after clr_synchronize.
+    CLR_CUDA(cudaEventRecord(c->ev_srcs_ready, c->stream));
+    CLR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_srcs_ready, 0));
+    CLR_CUDA(cudaMemcpyAsync(srcs9, P.d_srcs, (size_t)P.nsrc * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    CLR_CUDA(cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    c->copy_pending = true;
+    return 0;
+  }
   CLR_CUDA(cudaMemcpyAsync(srcs9, P.d_srcs, (size_t)P.nsrc * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -92,6 +92,11 @@ struct clr_ctx {
   float *d_lpt_pos[3] = {nullptr, nullptr, nullptr};
   std::map<std::string, StageTime> stage;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
+  // option async_results: catalogue read-back on its own stream, overlapping the next run
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_srcs_ready = nullptr, ev_copy_done = nullptr;
+  int async_results = 0;
+  bool copy_pending = false;
   struct Pending { std::string name; int slot; int nl; };
   std::vector<cudaEvent_t> ev_pool;
   std::vector<Pending> ev_pending;

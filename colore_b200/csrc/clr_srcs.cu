@@ -564,6 +564,11 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
   CLR_CUDA(cudaMemcpyAsync(&total, d_offs + n_chunks, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   P.nsrc = total;
+  if (c->copy_pending) {   // an asynchronous catalogue read-back may still be reading d_srcs
+    if ((size_t)total > P.cap_src) CLR_CUDA(cudaStreamSynchronize(c->copy_stream));
+    else CLR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+    c->copy_pending = false;
+  }
   if ((size_t)total > P.cap_src) {
     if (P.d_pos) cudaFree(P.d_pos);
     if (P.d_ipix) cudaFree(P.d_ipix);

@@ -113,7 +113,10 @@ int clr_set_sigma2_gauss(clr_ctx *ctx, double sigma2);
  * (fourier.c:337-353, density.c:1095-1098, 1166-1178); 0 (default) evaluates them in fp32 with
  * double only where it protects the result. Integer outputs (Poisson counts, pixel ids) are
  * exact in both modes. "lpt_interp_type" = 0/1/2 (NGP/CIC/TSC, field_par.lpt_interp_type),
- * "keep_particles" = 1 keeps the LPT particles resident for clr_lpt_get_particles. */
+ * "keep_particles" = 1 keeps the LPT particles resident for clr_lpt_get_particles.
+ * "async_results" = 1 makes clr_srcs_get_local_properties return as soon as the device-to-host copy is
+ * queued on a separate copy stream (the host buffer must be pinned and is valid after clr_synchronize);
+ * the next run overlaps the copy and only waits for it before it reuses the catalogue buffers. */
 int clr_set_option(clr_ctx *ctx, const char *name, int value);
 /* refresh the z-halo planes of the potential after clr_grid_put (fourier.c:401-414) */
 int clr_update_halo(clr_ctx *ctx);

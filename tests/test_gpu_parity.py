@@ -227,6 +227,25 @@ def test_sources_bit_exact_vs_oracle(case):
         assert abs(tot - n_ref) < 6 * np.sqrt(n_ref)
 
 
+def test_async_results_match_sync(case):
+    """Option async_results: the catalogue read-back overlaps the next run and returns the same records."""
+    import torch
+    g, t, o, par = case
+    _setup_sources(g, t, par)
+    cb.srcs_set_cartesian(par)
+    want = cb.srcs_get_local_properties(par, 0).copy()
+    pinned = torch.empty(want.shape, dtype=torch.float32).pin_memory()
+    out = pinned.numpy()
+    out[:] = -1
+    par.set_option("async_results", 1)
+    cb.srcs_get_local_properties(par, 0, out=out)
+    cb.srcs_set_cartesian(par)          # the next run must wait for the copy before it reuses the buffers
+    par.synchronize()
+    par.set_option("async_results", 0)
+    assert np.array_equal(out, want)
+    assert np.array_equal(cb.srcs_get_local_properties(par, 0), want)
+
+
 def test_beam_rsd_vs_oracle(case):
     g, t, o, par = case
     _setup_sources(g, t, par)
