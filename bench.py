@@ -68,12 +68,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.proc, self.lines, self.index = None, [], index
+        self.proc, self.lines, self.index, self.mark_at = None, [], index, 0
+
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.mark_at = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except OSError:
             self.proc = None
@@ -84,7 +88,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.mark_at:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -182,7 +186,7 @@ def run_step(cb, par, seed, tabs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-grid", type=int, default=1024)
@@ -235,12 +239,15 @@ def main():
     par.set_srcs(0, nz_tab, bz_tab)
 
     # ---- device-resident timing (value) ------------------------------------------------------
+    # nvidia-smi takes ~100 ms to deliver its first line: start it before the warm-up and count only the
+    # samples taken from the start of the timed regions (device-timed loop + end-to-end loop) on
+    sampler = ClockSampler(local)
+    sampler.start()
     for w in range(args.warmup):
         run_step(cb, par, 100 + w, tabs)
     par.synchronize()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     par.set_profiling(True)
     l0 = par.launch_count
     par.timer_start()
@@ -253,7 +260,6 @@ def main():
     ms_total = allmax(ms_total)                      # device time, max over ranks
     nsrc_total = int(allsum(nsrc))
     launches = par.launch_count - l0
-    clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = n ** 3 / (ms_step * 1e-3) / 1e6
     stage_names = ["fill_modes", "fft_z", "fft_a2a", "fft_y", "fft_x", "halo", "lognormal", "norm_hist", "srcs_poisson",
@@ -317,6 +323,7 @@ def main():
     par.synchronize()
     par.set_option("async_results", 0)
     e2e_ms = allmax((time.perf_counter() - t0) * 1e3 / args.steps)
+    clocks = sampler.stop()
     e2e = {"value": n ** 3 / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(tin.nbytes * world),
            "d2h_bytes_per_step": int(allsum(d2h / args.steps)), "ms_per_step": e2e_ms}
 
