@@ -446,6 +446,12 @@ int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
 
 int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { return clr_srcs_beam(c, ipop); }
 int clr_lpt_get_particles(clr_ctx *c, float *x, float *y, float *z) { return clr_lpt_particles(c, x, y, z); }
+int clr_lpt_exchange_counts(clr_ctx *c, long long *sent, long long *received)
+{
+  if (sent) *sent = c->lpt_sent;
+  if (received) *received = c->lpt_received;
+  return 0;
+}
 
 int clr_imap_set_cartesian(clr_ctx *c, int ipop, float *data, int32_t *nadd) { return clr_maps_imap(c, ipop, data, nadd); }
 int clr_kappa_get_beam_properties(clr_ctx *c, long long num_pix, const double *pos3, int nplanes, const float *rf, float *data)

@@ -116,6 +116,22 @@ int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_flo
   return 0;
 }
 
+// variable-size exchange (floats): segment h of `send` goes to rank h, segment s of `recv` comes from rank s;
+// replaces the MPI_Sendrecv ring of share_particles (density.c:300-360)
+int clr_comm_alltoallv(clr_ctx *c, const float *send, const size_t *send_off, const size_t *send_n, float *recv,
+                       const size_t *recv_off, const size_t *recv_n)
+{
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  CLR_NCCL(g_nccl.GroupStart());
+  for (int k = 1; k < c->nranks; k++) {
+    int to = (c->rank + k) % c->nranks, from = (c->rank - k + c->nranks) % c->nranks;
+    if (send_n[to]) CLR_NCCL(g_nccl.Send(send + send_off[to], send_n[to], ncclFloat, to, comm, c->stream));
+    if (recv_n[from]) CLR_NCCL(g_nccl.Recv(recv + recv_off[from], recv_n[from], ncclFloat, from, comm, c->stream));
+  }
+  CLR_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
 int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n)
 {
   if (c->nranks == 1) return 0;

@@ -90,6 +90,7 @@ struct clr_ctx {
   int lpt_interp_type = 1;          // field_par.lpt_interp_type: 0 NGP, 1 CIC, 2 TSC (common.h:67-69)
   int keep_particles = 0;           // keep the LPT particles on the device for write_lpt (io.c:619-695)
   float *d_lpt_pos[3] = {nullptr, nullptr, nullptr};
+  long long lpt_sent = 0, lpt_received = 0;   // particles shipped to / received from other slabs in the last LPT run
   std::map<std::string, StageTime> stage;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp0 = nullptr, evp1 = nullptr;
   // option async_results: catalogue read-back on its own stream, overlapping the next run
@@ -160,6 +161,8 @@ int clr_lpt_run(clr_ctx *c, int order);
 int clr_lpt_particles(clr_ctx *c, float *x, float *y, float *z);
 int clr_comm_destroy(clr_ctx *c);
 int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_floats);
+int clr_comm_alltoallv(clr_ctx *c, const float *send, const size_t *send_off, const size_t *send_n, float *recv,
+                       const size_t *recv_off, const size_t *recv_n);
 int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n);
 int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n);
 int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n);

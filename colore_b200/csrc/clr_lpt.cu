@@ -5,9 +5,13 @@
 //   x = q + D(r) psi1 + D2(r) psi2 (periodic wrap) -> deposit -> delta = n - 1
 // Work arrays follow the reference (3 extra complex fields for 1LPT, 8 for 2LPT, density.c:380-391,
 // 650-667); 1LPT writes its particles to three separate unpadded buffers instead of un-padding in place.
-// The particle exchange between slabs (share_particles, density.c:191-374) is not built: with one
-// slab per process every particle stays local; clr_compute_physical_density_field refuses LPT on more
-// than one GPU. Compiled with -fmad=false (k-space factors follow the reference's double expressions).
+// Several GPUs (share_particles, density.c:191-374): a particle is needed by every rank that owns one of
+// the z planes its deposit stencil touches. Every rank deposits its own particles into its own slab
+// straight from the particle arrays, and ships only the particles whose stencil reaches another slab:
+// count per destination -> all-reduced P x P count matrix -> pack (block-aggregated cursors) -> one grouped
+// ncclSend/ncclRecv with exact sizes -> deposit of the received particles. Unlike the reference there is no
+// lpt_buffer_fraction to tune: the buffers are sized from the counts.
+// Compiled with -fmad=false (k-space factors follow the reference's double expressions).
 #include "clr_internal.cuh"
 
 namespace {
@@ -150,16 +154,99 @@ lpt_positions_kernel(const ClrDev d, float *dens, const float *d0, const float *
   }
 }
 
+// z planes (global, wrapped) touched by the deposit stencil of a particle at height z: the same
+// expressions as in lpt_deposit_kernel below, so routing and deposit always agree
+__device__ __forceinline__ int lpt_planes(float z, int interp, int n, float i_agrid, int (&pl)[3])
+{
+  if (interp == 0) {
+    int i0 = (int)((double)(z * i_agrid) + 0.5);
+    if (i0 >= n) i0 -= n;
+    if (i0 < 0) i0 += n;
+    pl[0] = i0;
+    return 1;
+  } else if (interp == 1) {
+    float s = z * i_agrid;
+    int i0 = (int)s, i1 = i0 + 1;
+    if (i0 < 0) i0 += n;
+    if (i1 < 0) i1 += n;
+    if (i0 >= n) i0 -= n;
+    if (i1 >= n) i1 -= n;
+    pl[0] = i0; pl[1] = i1;
+    return 2;
+  }
+  float s = z * i_agrid;
+  int c0 = (int)(floorf((float)((double)s + 0.5)));
+  int cm = c0 - 1, cp = c0 + 1;
+  if (cm < 0) cm += n;
+  if (c0 < 0) c0 += n;
+  if (cp < 0) cp += n;
+  if (cm >= n) cm -= n;
+  if (c0 >= n) c0 -= n;
+  if (cp >= n) cp -= n;
+  pl[0] = cm; pl[1] = c0; pl[2] = cp;
+  return 3;
+}
+
+// Routing of the particles whose stencil reaches another rank's slab (share_particles, density.c:191-374).
+// PACK = false: cnt[h] += number of my particles rank h needs. PACK = true: copy them as (x,y,z) triplets
+// into segment h of `send` (segment offsets `off`, running cursors `cur`). Slots are reserved once per
+// block and destination, so the global atomics stay in the thousands.
+constexpr int kMaxRanks = 64;
+template <bool PACK>
+__global__ void __launch_bounds__(kThreads)
+lpt_route_kernel(const ClrDev d, const float *px, const float *py, const float *pz, long long np, int interp, int me,
+                 int nranks, unsigned long long *cnt, const unsigned long long *off, unsigned long long *cur, float *send)
+{
+  __shared__ unsigned int s_cnt[kMaxRanks];
+  __shared__ unsigned long long s_base[kMaxRanks];
+  const float i_agrid = d.n / d.l_box;
+  const int nzl = d.n / nranks;
+  const long long chunk = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < np; i0 += chunk) {
+    const long long i = i0 + threadIdx.x;
+    for (int h = threadIdx.x; h < nranks; h += blockDim.x) s_cnt[h] = 0;
+    __syncthreads();
+    int dest[3], slot[3], nd = 0;
+    float z = 0.f;
+    if (i < np) {
+      z = pz[i];
+      int pl[3];
+      int npl = lpt_planes(z, interp, d.n, i_agrid, pl);
+      for (int k = 0; k < npl; k++) {
+        int h = pl[k] / nzl;
+        bool dup = h == me;
+        for (int q = 0; q < nd; q++) dup = dup || dest[q] == h;
+        if (!dup) { dest[nd] = h; slot[nd] = (int)atomicAdd(&s_cnt[h], 1u); nd++; }
+      }
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < nranks; h += blockDim.x)
+      if (s_cnt[h]) s_base[h] = atomicAdd(PACK ? &cur[h] : &cnt[h], (unsigned long long)s_cnt[h]);
+    if (PACK) {
+      __syncthreads();
+      if (nd) {
+        float x = px[i], y = py[i];
+        for (int q = 0; q < nd; q++) {
+          float *o = send + 3 * (off[dest[q]] + s_base[dest[q]] + slot[q]);
+          o[0] = x; o[1] = y; o[2] = z;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // density.c:37-175: one thread per particle, float atomics (the reference's deposit is serial; the sum
 // order differs here, which moves the result by fp32 rounding only)
 __global__ void __launch_bounds__(kThreads)
-lpt_deposit_kernel(const ClrDev d, const float *px, const float *py, const float *pz, float *delta, long long np, int interp)
+lpt_deposit_kernel(const ClrDev d, const float *px, const float *py, const float *pz, int stride, float *delta, long long np,
+                   int interp)
 {
   const float i_agrid = d.n / d.l_box;
   const long long ngx = d.pitch;
   const int n = d.n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np; i += (long long)gridDim.x * blockDim.x) {
-    float x[3] = {px[i], py[i], pz[i]};
+    float x[3] = {px[i * stride], py[i * stride], pz[i * stride]};
     if (interp == 0) {
       int i0[3];
 #pragma unroll
@@ -257,8 +344,9 @@ int grid_for(clr_ctx *c, long long items, int per_sm)
 
 int clr_lpt_run(clr_ctx *c, int order)
 {
-  CLR_CHECK(c->nranks == 1, "LPT density on several GPUs needs the particle exchange (density.c:191-374): not built");
+  CLR_CHECK(c->nranks <= kMaxRanks, "LPT: at most %d GPUs", kMaxRanks);
   CLR_CHECK(order == 1 || order == 2, "LPT order %d", order);
+  c->lpt_sent = c->lpt_received = 0;
   CLR_CHECK(c->lpt_interp_type >= 0 && c->lpt_interp_type <= 2, "Wrong interpolation type\n");
   const ClrDev &d = c->dev;
   const size_t slab = (size_t)d.pitch * d.n * d.nz_here * sizeof(float);
@@ -267,7 +355,8 @@ int clr_lpt_run(clr_ctx *c, int order)
   float *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float *pos[3] = {nullptr, nullptr, nullptr};
   int nbuf = order == 1 ? 3 : 8;
-  auto cleanup = [&]() { for (int i = 0; i < 8; i++) cudaFree(buf[i]); };
+  float *d_send = nullptr, *d_recv = nullptr;
+  auto cleanup = [&]() { for (int i = 0; i < 8; i++) cudaFree(buf[i]); cudaFree(d_send); cudaFree(d_recv); };
   for (int i = 0; i < nbuf; i++)
     if (cudaMalloc(&buf[i], slab) != cudaSuccess) { cleanup(); clr_set_error("LPT: out of device memory (%d work fields)", nbuf); return 1; }
   LptFields f;
@@ -314,7 +403,45 @@ int clr_lpt_run(clr_ctx *c, int order)
       lpt_positions_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, c->d_dens, disp[0], disp[1], disp[2], digrad[0], digrad[1],
                                                                                digrad[2], pos[0], pos[1], pos[2], order); }
     { StageScope sc(c, "lpt_deposit", 1);
-      lpt_deposit_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, pos[0], pos[1], pos[2], c->d_dens, n_cells, c->lpt_interp_type); }
+      lpt_deposit_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, pos[0], pos[1], pos[2], 1, c->d_dens, n_cells, c->lpt_interp_type); }
+    if (c->nranks > 1) {
+      // share_particles (density.c:191-374): ship the particles whose stencil reaches another slab
+      const int P = c->nranks;
+      if (clr_ensure_scratch(c, (size_t)(P * P + 2 * P) * sizeof(unsigned long long))) break;
+      unsigned long long *d_mat = reinterpret_cast<unsigned long long *>(c->d_scratch);   // P x P counts [src][dst]
+      unsigned long long *d_off = d_mat + (size_t)P * P, *d_cur = d_off + P;
+      if (cudaMemsetAsync(d_mat, 0, (size_t)(P * P + 2 * P) * sizeof(unsigned long long), c->stream) != cudaSuccess) break;
+      { StageScope sc(c, "lpt_route", 1);
+        lpt_route_kernel<false><<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, pos[0], pos[1], pos[2], n_cells, c->lpt_interp_type, c->rank, P,
+                                                                                    d_mat + (size_t)c->rank * P, nullptr, nullptr, nullptr); }
+      if (clr_comm_allreduce_u64(c, d_mat, (size_t)P * P)) break;
+      std::vector<unsigned long long> mat((size_t)P * P);
+      if (cudaMemcpyAsync(mat.data(), d_mat, mat.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { clr_set_error("LPT: routing failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+      std::vector<unsigned long long> s_off(P + 1, 0), r_off(P + 1, 0);
+      for (int h = 0; h < P; h++) {
+        s_off[h + 1] = s_off[h] + mat[(size_t)c->rank * P + h];
+        r_off[h + 1] = r_off[h] + mat[(size_t)h * P + c->rank];
+      }
+      const unsigned long long n_send = s_off[P], n_recv = r_off[P];
+      if (cudaMalloc(&d_send, (size_t)(3 * n_send + 3) * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&d_recv, (size_t)(3 * n_recv + 3) * sizeof(float)) != cudaSuccess) {
+        clr_set_error("LPT: out of device memory (particle exchange: %llu out, %llu in)", n_send, n_recv); break; }
+      if (cudaMemcpyAsync(d_off, s_off.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+      { StageScope sc(c, "lpt_route", 1);
+        lpt_route_kernel<true><<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, pos[0], pos[1], pos[2], n_cells, c->lpt_interp_type, c->rank, P,
+                                                                                   nullptr, d_off, d_cur, d_send); }
+      std::vector<size_t> so(P), sn(P), ro(P), rn(P);
+      for (int h = 0; h < P; h++) { so[h] = 3 * s_off[h]; sn[h] = 3 * (s_off[h + 1] - s_off[h]); ro[h] = 3 * r_off[h]; rn[h] = 3 * (r_off[h + 1] - r_off[h]); }
+      { StageScope sc(c, "lpt_exchange", 0);
+        if (clr_comm_alltoallv(c, d_send, so.data(), sn.data(), d_recv, ro.data(), rn.data())) break; }
+      c->lpt_sent = (long long)n_send; c->lpt_received = (long long)n_recv;
+      if (n_recv) {
+        StageScope sc(c, "lpt_deposit", 1);
+        lpt_deposit_kernel<<<grid_for(c, (long long)n_recv, 8), kThreads, 0, c->stream>>>(d, d_recv, d_recv + 1, d_recv + 2, 3, c->d_dens, (long long)n_recv,
+                                                                                         c->lpt_interp_type);
+      }
+    }
     { StageScope sc(c, "lpt_finalize", 1);
       lpt_finalize_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, c->d_dens); }
     if (cudaGetLastError() != cudaSuccess) { clr_set_error("LPT kernel launch failed"); break; }

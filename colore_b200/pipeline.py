@@ -210,6 +210,14 @@ def lpt_get_particles(par: ParamCoLoRe):
     return x, y, z
 
 
+def lpt_exchange_counts(par: ParamCoLoRe):
+    """(sent, received): particles this rank shipped to / got from other slabs in the last LPT density
+    (share_particles, density.c:191-374)."""
+    a, b = C.c_longlong(), C.c_longlong()
+    check(par.lib.clr_lpt_exchange_counts(par.ctx, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
 def compute_density_normalization(par: ParamCoLoRe):
     """density.c:1227-1393."""
     check(par.lib.clr_compute_density_normalization(par.ctx))

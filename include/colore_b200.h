@@ -124,11 +124,15 @@ int clr_update_halo(clr_ctx *ctx);
 /* ---- physical density (density.c) -------------------------------------------------------- */
 /* compute_physical_density_field (density.c:1105-1126): lognormal (lognormalize, 1070-1103), clipped
  * (densclip, 1034-1067), 1LPT (lpt_1, 376-644) and 2LPT (lpt_2, 646-1031) with the NGP / CIC / TSC mass
- * deposits (pos_2_*, 37-188; option "lpt_interp_type"). LPT runs on one GPU per box. */
+ * deposits (pos_2_*, 37-188; option "lpt_interp_type"). On several GPUs the particles whose deposit stencil
+ * reaches another slab are exchanged over NCCL (share_particles, density.c:191-374), with buffers sized
+ * from exact counts instead of field_par.lpt_buffer_fraction. */
 int clr_compute_physical_density_field(clr_ctx *ctx);
 /* particle positions of the last LPT call (for write_lpt, io.c:619-695); needs option
  * "keep_particles" = 1 before the density call. x, y, z: nz_here*n_grid^2 floats each. */
 int clr_lpt_get_particles(clr_ctx *ctx, float *x, float *y, float *z);
+/* particles this rank shipped to / received from other slabs in the last LPT density (0 on one GPU) */
+int clr_lpt_exchange_counts(clr_ctx *ctx, long long *sent, long long *received);
 /* compute_density_normalization (density.c:1227-1393). Afterwards the norm tables are resident;
  * clr_get_norm returns srcs (kind 0) / imap (kind 1) tables: norm_arr[CLR_NA], ends[2] */
 int clr_compute_density_normalization(clr_ctx *ctx);

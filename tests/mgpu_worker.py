@@ -39,6 +39,7 @@ def main():
     d0, p0 = o.c2r(dk), o.c2r(pk)
     o.normalize_fields(d0, p0)
     _, s2_ref = o.sigma_dens(d0)
+    d_gauss = d0.copy()
 
     mean, s2 = cb.create_cartesian_fields(par)
     dens = par.grid_get(cb.GRID_DENS)
@@ -97,10 +98,35 @@ def main():
     isw = cb.isw_get_beam_properties(par, pix, rf)
     isw_ref = o.isw(full, pix, rf)
     np.testing.assert_allclose(isw, isw_ref, rtol=2e-5, atol=2e-6 * np.abs(isw_ref).max())
+    # LPT densities on slabs: distributed r2c/c2r + particle exchange between slabs (density.c:191-374)
+    # from the oracle's Gaussian field; the deposits must agree with the single-box oracle
+    lpt_sent = 0
+    for order, interp in ((1, 1), (2, 2), (2, 0)):
+        ref = d_gauss.copy()
+        o.lpt(ref, order, interp)
+        pl = cb.ParamCoLoRe(t, n, dens_type=order, seed=seed, nz_here=nzl, iz0_here=iz0, device=local)
+        cb.dist.init_comm(pl, rank, world)
+        pl.set_option("lpt_interp_type", interp)
+        pl.grid_put(cb.GRID_DENS, np.ascontiguousarray(d_gauss[sl]))
+        cb.compute_physical_density_field(pl)
+        got = pl.grid_get(cb.GRID_DENS)[:, :, :n].astype(np.float64)
+        want = ref[sl, :, :n].astype(np.float64)
+        sent, recv = cb.lpt_exchange_counts(pl)
+        lpt_sent += sent
+        tot = torch.tensor([got.sum(), float(sent), float(recv)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        assert abs(tot[0].item()) < 0.5, tot                      # mass conservation over all slabs
+        assert tot[1].item() == tot[2].item() and (interp == 0 or tot[1].item() > 0), tot   # NGP: coarse cells may keep every particle home
+        if interp == 0:
+            assert np.mean(got != want) < 1e-3, (rank, order, np.mean(got != want))
+        else:
+            assert np.abs(got - want).max() < 3e-4, (rank, order, interp, np.abs(got - want).max())
+        pl.free()
     tot_all = torch.tensor([nsrc], device="cuda")
     dist.all_reduce(tot_all)
     if rank == 0:
-        print(f"MGPU OK world={world} n={n} field_err={e_d:.2e} roundtrip={e_rt:.2e} nsrc_total={int(tot_all.item())}")
+        print(f"MGPU OK world={world} n={n} field_err={e_d:.2e} roundtrip={e_rt:.2e} nsrc_total={int(tot_all.item())} "
+              f"lpt_particles_shipped_rank0={lpt_sent}")
     par.free()
     dist.destroy_process_group()
 
