@@ -11,7 +11,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libcolore_b200.so")
+# COLORE_B200_LIB: another build of the SAME library (kernel-variant experiments, tools/fft_bench.py)
+SO_PATH = os.environ.get("COLORE_B200_LIB") or os.path.join(HERE, "libcolore_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "colore_b200.h")
 NA = 5001
 

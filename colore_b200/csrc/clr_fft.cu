@@ -142,13 +142,19 @@ template <int R, int S> __device__ __forceinline__ void dftR(float2 (&t)[R])
 
 __host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c(v >> 1); }
 
+// kernel-variant experiments (tools/fft_bench.py builds the library with -DCLR_FFT_VARIANT=k)
+#ifndef CLR_FFT_VARIANT
+#define CLR_FFT_VARIANT 0
+#endif
+
 // Stage plan of a length-M transform: radices (descending) R0*R1*R2 = M, every thread owns E = R0
 // points of a line, so a 1024-point line is two radix-32 stages with ONE exchange through shared
 // memory (the exchange traffic, not the flops, is what bounds a Stockham pass on this machine).
 template <int M> struct FftPlan {
   static constexpr int NST = M <= 32 ? 1 : (M <= 1024 ? 2 : 3);
-  static constexpr int R0 = M <= 32 ? M : (M == 64 ? 8 : (M == 128 || M == 256 ? 16 : (M <= 1024 ? 32 : 16)));
-  static constexpr int R1 = NST < 2 ? 1 : (M <= 128 ? 8 : (M <= 512 ? 16 : (M == 1024 ? 32 : 16)));
+  static constexpr bool WIDE3 = (CLR_FFT_VARIANT == 1 || CLR_FFT_VARIANT == 2) && M == 2048;   // 32 x 8 x 8
+  static constexpr int R0 = M <= 32 ? M : (M == 64 ? 8 : (M == 128 || M == 256 ? 16 : (M <= 1024 || WIDE3 ? 32 : 16)));
+  static constexpr int R1 = NST < 2 ? 1 : (M <= 128 ? 8 : (M <= 512 ? 16 : (M == 1024 ? 32 : (WIDE3 ? 8 : 16))));
   static constexpr int R2 = NST < 3 ? 1 : M / (R0 * R1);
   static constexpr int E = R0;                                              // points per thread
   static constexpr int TPL = M / E;                                         // threads per line
@@ -353,10 +359,14 @@ struct StridedTile {
 // Persistent CTAs, one tile of T lines at a time. The loads of the NEXT tile are issued (cp.async, each
 // thread into its own shared-memory slots) as soon as the last exchange of the current tile has been
 // read back, so they fly under the last-stage butterflies and the global stores.
+// (Measured, round 1: a strided pass moves ~35 G contiguous runs/s whatever the run length -- 32 B runs
+// 1.16 TB/s, 64 B 2.3 TB/s, 128 B 4.1 TB/s on the z pass, where every point of a line sits in another 2 MB
+// page -- and cp.async .L2::128B / .L2::256B prefetch hints change nothing, so the limit is per-request
+// (translation), not DRAM row activation: tiles are as wide as shared memory allows.)
 // (Tried and dropped: a separate full-tile landing buffer + half-tile exchange buffer, so that a whole
 // tile of 8-byte cp.async is always in flight -- 1.6x SLOWER at n=1024; see DESIGN.md.)
 template <int M, int S, int T>
-__global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL <= 256) ? 2 : 1)
+__global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL * FftPlan<M>::E <= 8192) ? 2 : 1)
 fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, const float2 *__restrict__ W, int wn,
                    long long n_tiles, int tiles_per_outer, int n_inner)
 {
@@ -514,10 +524,12 @@ fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
 // host-side dispatch
 template <int M> struct Cfg {   // lines per CTA tile, per transform length
   static constexpr int TPL = FftPlan<M>::TPL;
-  static constexpr int T_STRIDED = M >= 4096 ? 4 : (M == 1024 ? 16 : (256 / TPL > 64 ? 64 : (256 / TPL < 8 ? 8 : 256 / TPL)));
+  static constexpr int T_DEF = M >= 4096 ? 4 : (M == 1024 ? 16 : (256 / TPL > 64 ? 64 : (256 / TPL < 8 ? 8 : 256 / TPL)));
+  static constexpr int T_STRIDED = (M == 2048 && (CLR_FFT_VARIANT == 2 || CLR_FFT_VARIANT == 3)) ? 4
+                                   : ((M == 1024 && CLR_FFT_VARIANT >= 1) ? 8 : T_DEF);
   // z pass: every point of a line sits in another 2 MB page (plane stride), so wider tiles halve the
   // TLB misses per byte
-  static constexpr int T_Z = (M == 1024 || M == 512) ? 16 : T_STRIDED;
+  static constexpr int T_Z = ((M == 1024 && CLR_FFT_VARIANT == 0) || M == 512) ? 16 : T_STRIDED;
   static constexpr int T_X = M >= 2048 ? 4 : (256 / TPL > 64 ? 64 : 256 / TPL);
 };
 

@@ -49,6 +49,21 @@ __device__ __forceinline__ double dev_get_rvel(const ClrDev &d, const float *__r
   return 0.5 * idx * (v0 * u0 + v1 * u1 + v2 * u2);
 }
 
+// one sub-cell, the reference's double arithmetic verbatim (imap.c:214-231)
+__device__ __forceinline__ void imap_subcell_exact(const ImapShells &sh, int nside, long long num_pix, double x, double y,
+                                                   double z, double dr_rsd, float temp, float *__restrict__ data,
+                                                   int *__restrict__ nadd)
+{
+  double r, cth, phi;
+  clr_cart2sph(x, y, z, &r, &cth, &phi);
+  int ir = dev_r_index(sh, r + dr_rsd);
+  if (ir >= 0 && ir < sh.nr) {
+    long long pix = clr_ang2pix_ring_zphi(nside, cth, phi);
+    atomicAdd(&data[ir * num_pix + pix], temp);
+    atomicAdd(&nadd[ir * num_pix + pix], 1);
+  }
+}
+
 // one thread per cell; sub-cells are painted with float / int atomics (imap.c:224-231)
 __global__ void __launch_bounds__(kThreads)
 imap_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restrict__ npot, ClrPop pop, ImapShells sh,
@@ -83,17 +98,168 @@ imap_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restr
         double y = y0 + (iyy + 0.5) * dx_sub;
         for (int ixx = 0; ixx < nsub; ixx++) {
           double x = x0 + (ixx + 0.5) * dx_sub;
-          double r, cth, phi;
-          clr_cart2sph(x, y, z, &r, &cth, &phi);
-          int ir = dev_r_index(sh, r + dr_rsd);
-          if (ir >= 0 && ir < sh.nr) {
-            long long pix = clr_ang2pix_ring_zphi(nside, cth, phi);
-            atomicAdd(&data[ir * num_pix + pix], temp);
-            atomicAdd(&nadd[ir * num_pix + pix], 1);
+          imap_subcell_exact(sh, nside, num_pix, x, y, z, dr_rsd, temp, data, nadd);
+        }
+      }
+    }
+  }
+}
+
+// ---- fp32-screened painter (default path) ---------------------------------------------------------
+// The per-cell quantities (temperature, RSD shift, sub-sampling) keep the reference's double arithmetic; the
+// per-SUB-CELL work -- 4*10^9 (r, cos theta, phi) -> (shell, pixel) evaluations at 1024^3 -- runs in fp32 with
+// rigorous margins: whenever r + dr_rsd lies within kMarginR of a shell edge, or one of the floor() arguments
+// of ang2pix_ring lies within `margin` of an integer (fp32 error budget: 2e-6 * nside), the sub-cell is queued
+// in shared memory and the CTA re-does it with imap_subcell_exact on dense warps. Shell and pixel indices
+// (hence the hit counts) are therefore bit-identical to the double path.
+constexpr int kImapQCap = 6144;
+constexpr float kMarginR = 5e-3f;      // Mpc/h: fp32 ulp of r ~ 1200 is 1.2e-4, rsqrt.approx adds 3e-4
+
+__device__ __forceinline__ int fast_r_index(const float *s_r0, const float *s_rf, int nr, float r, bool &sure)
+{
+  if (r < s_r0[0]) { if (s_r0[0] - r < kMarginR) sure = false; return -1; }
+  int lo = 0, hi = nr - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (s_r0[mid] <= r) lo = mid; else hi = mid - 1;
+  }
+  if (r - s_r0[lo] < kMarginR || fabsf(r - s_rf[lo]) < kMarginR) sure = false;
+  if (lo + 1 < nr && s_r0[lo + 1] - r < kMarginR) sure = false;
+  if (r < s_rf[lo]) return lo;
+  return lo == nr - 1 ? nr : -2;
+}
+
+__device__ __forceinline__ bool near_int(float v, float fl, float margin) { return v - fl < margin || fl + 1.f - v < margin; }
+
+// ang2pix_ring_z_phi in fp32 (same formulae as clr_ang2pix_ring_zphi); 1-|z| from (x^2+y^2)/(r(r+|z|)) so that
+// the polar caps keep full relative accuracy
+__device__ __forceinline__ long long fast_ang2pix(int nside, float nsf, float x, float y, float z, float r2, float rinv,
+                                                  float margin, bool &sure)
+{
+  const float cth = z * rinv, za = fabsf(cth);
+  float tt = atan2f(y, x) * 0.6366197723675814f;
+  if (tt < 0.f) tt += 4.f;
+  if (fabsf(za - 0.66666667f) < 4e-6f) sure = false;
+  if (za <= 0.66666667f) {
+    float t1 = nsf * (0.5f + tt), t2 = nsf * cth * 0.75f;
+    float a = t1 - t2, b = t1 + t2, fa = floorf(a), fb = floorf(b);
+    if (near_int(a, fa, margin) || near_int(b, fb, margin)) sure = false;
+    int jp = (int)fa, jm = (int)fb;
+    int ir = nside + 1 + jp - jm;
+    int kshift = 1 - (ir & 1);
+    int ip = (jp + jm - nside + kshift + 1) / 2;
+    ip = clr_imodulo(ip, 4 * nside);
+    return (long long)nside * (nside - 1) * 2 + (long long)(ir - 1) * 4 * nside + ip;
+  }
+  float ftt = floorf(tt), tp = tt - ftt;
+  if (tp < 2e-5f || tp > 1.f - 2e-5f || tt >= 4.f) sure = false;
+  float rr = r2 * rinv;
+  float omz = (x * x + y * y) / (rr * (rr + fabsf(z)));
+  float tmp = nsf * sqrtf(3.f * omz);
+  float a = tp * tmp, b = (1.f - tp) * tmp, fa = floorf(a), fb = floorf(b);
+  if (near_int(a, fa, margin) || near_int(b, fb, margin)) sure = false;
+  int jp = (int)fa, jm = (int)fb;
+  int ir = jp + jm + 1;
+  float c = tt * (float)ir, fc = floorf(c);
+  if (near_int(c, fc, margin)) sure = false;
+  int ip = clr_imodulo((int)fc, 4 * ir);
+  if (z > 0.f) return 2LL * ir * (ir - 1) + ip;
+  return 12LL * nside * nside - 2LL * ir * (ir + 1) + ip;
+}
+
+struct ImapCell { double x0, y0, z0, dr_rsd; float temp; int nsub; };
+
+__global__ void __launch_bounds__(kThreads)
+imap_fast_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restrict__ npot, ClrPop pop, ImapShells sh,
+                 int nside, float *__restrict__ data, int *__restrict__ nadd, double rmin_here, double rmax_here)
+{
+  extern __shared__ unsigned char smem_raw[];
+  ImapCell *s_cell = reinterpret_cast<ImapCell *>(smem_raw);                       // [kThreads]
+  unsigned *s_q = reinterpret_cast<unsigned *>(s_cell + kThreads);                // [kImapQCap]
+  float *s_r0 = reinterpret_cast<float *>(s_q + kImapQCap), *s_rf = s_r0 + sh.nr;  // [nr] each
+  __shared__ int q_len;
+  for (int i = threadIdx.x; i < sh.nr; i += blockDim.x) { s_r0[i] = sh.r0[i]; s_rf[i] = sh.rf[i]; }
+  if (threadIdx.x == 0) q_len = 0;
+  __syncthreads();
+  const long long n_cells = (long long)d.nz_here * d.n * d.n;
+  const long long num_pix = 12LL * nside * nside;
+  const double dx = (double)(d.l_box / d.n);
+  const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
+  const float nsf = (float)nside, margin = 8e-6f * nsf;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_iter = (n_cells + stride - 1) / stride;
+  for (long long it = 0; it < n_iter; it++) {
+    const long long i = it * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int nsub = 0;
+    double x0 = 0, y0 = 0, z0 = 0, dr_rsd = 0;
+    float temp = 0.f;
+    if (i < n_cells) {
+      int ix, iy, iz;
+      clr_cell(d, i, ix, iy, iz);
+      z0 = __ldg(d.cd[2] + iz + d.iz0_here);
+      y0 = __ldg(d.cd[1] + iy);
+      x0 = __ldg(d.cd[0] + ix);
+      double r0 = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
+      if (r0 <= rmax_here && r0 >= rmin_here) {
+        double tmean = clr_lerp(d, r0, pop.nz, 0.0, 0.0);
+        if (tmean > 0) {
+          double bias = clr_bg_bz(d, r0, pop.bz);
+          double dnorm = clr_lerp(d, r0, pop.norm, pop.norm_0, pop.norm_f);
+          double rvel = factor_vel * dev_get_rvel(d, npot, ix, iy, iz, x0, y0, z0, r0);
+          dr_rsd = rvel * clr_bg_v1(d, r0) * clr_bg_ih(d, r0);
+          temp = (float)(tmean * clr_bias_model(d.bias_model, (double)dens[((long long)iz * d.n + iy) * d.pitch + ix], bias) * dnorm);
+          int irad = dev_r_index(sh, r0);
+          nsub = irad < 0 ? sh.nsub_lo : (irad >= sh.nr ? sh.nsub_hi : __ldg(sh.nsub + irad));
+        }
+      }
+    }
+    s_cell[threadIdx.x] = ImapCell{x0, y0, z0, dr_rsd, temp, nsub};
+    if (nsub > 0) {
+      const double dx_sub = dx / nsub;
+      const float drf = (float)dr_rsd;
+      for (int izz = 0; izz < nsub; izz++) {
+        const float z = (float)(z0 + (izz + 0.5) * dx_sub);
+        for (int iyy = 0; iyy < nsub; iyy++) {
+          const float y = (float)(y0 + (iyy + 0.5) * dx_sub);
+          const float yz2 = y * y + z * z;
+          for (int ixx = 0; ixx < nsub; ixx++) {
+            const float x = (float)(x0 + (ixx + 0.5) * dx_sub);
+            const float r2 = fmaf(x, x, yz2);
+            const float rinv = rsqrtf(r2);
+            bool sure = r2 > 1e-6f && nsub < 256;
+            int ir = fast_r_index(s_r0, s_rf, sh.nr, r2 * rinv + drf, sure);
+            long long pix = 0;
+            if (!sure || (ir >= 0 && ir < sh.nr)) pix = fast_ang2pix(nside, nsf, x, y, z, r2, rinv, margin, sure);
+            if (sure) {
+              if (ir >= 0 && ir < sh.nr) {
+                atomicAdd(&data[ir * num_pix + pix], temp);
+                atomicAdd(&nadd[ir * num_pix + pix], 1);
+              }
+            } else {
+              int slot = nsub < 256 ? atomicAdd(&q_len, 1) : kImapQCap;
+              if (slot < kImapQCap) s_q[slot] = ((unsigned)threadIdx.x << 24) | (unsigned)((izz * nsub + iyy) * nsub + ixx);
+              else imap_subcell_exact(sh, nside, num_pix, x0 + (ixx + 0.5) * dx_sub, y0 + (iyy + 0.5) * dx_sub,
+                                      z0 + (izz + 0.5) * dx_sub, dr_rsd, temp, data, nadd);
+            }
           }
         }
       }
     }
+    __syncthreads();
+    // deferred sub-cells: the reference's double arithmetic on dense warps
+    const int nq = min(q_len, kImapQCap);
+    for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+      const unsigned e = s_q[k];
+      const ImapCell c = s_cell[e >> 24];
+      const int sub = (int)(e & 0xffffffu);
+      const int ixx = sub % c.nsub, iyy = (sub / c.nsub) % c.nsub, izz = sub / (c.nsub * c.nsub);
+      const double dx_sub = dx / c.nsub;
+      imap_subcell_exact(sh, nside, num_pix, c.x0 + (ixx + 0.5) * dx_sub, c.y0 + (iyy + 0.5) * dx_sub,
+                         c.z0 + (izz + 0.5) * dx_sub, c.dr_rsd, c.temp, data, nadd);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) q_len = 0;
+    __syncthreads();
   }
 }
 
@@ -104,6 +270,10 @@ struct LosPlan {
   const double *inv_r_max;      // kappa only
   int nplanes;
   double dr;
+  // several GPUs: a ray only meets this slab for r*u_z in [za, zb) (Mpc/h, observer frame); `restrict_z`
+  // is set when no sample of any ray can wrap around the box, so the bound is safe
+  int restrict_z;
+  double za, zb;
 };
 
 // beaming.c:85-116: Hessian stencil of the potential at cell (ix,iy,iz_local), unnormalised
@@ -169,8 +339,20 @@ los_kernel(const ClrDev d, const float *__restrict__ npot, const double *__restr
       rot[5] = (sth * sth) * prefac;
     }
     double acc1 = 0, acc2 = 0;
+    // samples whose NGP plane can lie in this slab: r_m * u_z in [za, zb), widened by one sample each side;
+    // the exact test (dev_ngp) still decides inside the window
+    int win_lo = 0, win_hi = 0x7fffffff;
+    if (pl.restrict_z) {
+      double ra, rb;
+      if (fabs(u[2]) < 1e-12) { ra = (pl.za <= 0 && pl.zb > 0) ? -1e300 : 1e300; rb = (pl.za <= 0 && pl.zb > 0) ? 1e300 : -1e300; }
+      else if (u[2] > 0) { ra = pl.za / u[2]; rb = pl.zb / u[2]; }
+      else { ra = pl.zb / u[2]; rb = pl.za / u[2]; }
+      double lo = floor(ra / pl.dr - 0.5) - 1, hi = ceil(rb / pl.dr - 0.5) + 1;
+      win_lo = lo < 0 ? 0 : (lo > 2e9 ? 0x7fffffff : (int)lo);
+      win_hi = hi < 0 ? -1 : (hi > 2e9 ? 0x7fffffff : (int)hi);
+    }
     for (int ipl = 0; ipl < pl.nplanes; ipl++) {
-      int irmin = __ldg(pl.irmin + ipl), irmax = __ldg(pl.irmax + ipl);
+      int irmin = max(__ldg(pl.irmin + ipl), win_lo), irmax = min(__ldg(pl.irmax + ipl), win_hi);
       for (int irr = irmin; irr <= irmax; irr++) {
         double rm = (irr + 0.5) * pl.dr;
         double xn[3];
@@ -250,8 +432,15 @@ int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd)
   {
     StageScope sc(c, "imap_paint", 1);
     long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
-    imap_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->d_npot, pop, sh, P.nside, d_data, d_nadd,
-                                                                      (double)P.r0[0] - 20., (double)P.rf[nr - 1] + 20.);
+    if (c->exact_math)
+      imap_kernel<<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->d_npot, pop, sh, P.nside, d_data, d_nadd,
+                                                                        (double)P.r0[0] - 20., (double)P.rf[nr - 1] + 20.);
+    else {
+      size_t smem = kThreads * sizeof(ImapCell) + kImapQCap * sizeof(unsigned) + 2 * (size_t)nr * sizeof(float);
+      CLR_CUDA(cudaFuncSetAttribute(imap_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      imap_fast_kernel<<<grid_for(c, n_cells, 4), kThreads, smem, c->stream>>>(c->dev, c->d_dens, c->d_npot, pop, sh, P.nside, d_data,
+                                                                                d_nadd, (double)P.r0[0] - 20., (double)P.rf[nr - 1] + 20.);
+    }
     CLR_CUDA(cudaGetLastError());
   }
   // every GPU painted its slab into a full-sky map (imap.c:123-132); sum them (io.c:727-735)
@@ -305,7 +494,18 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
   CLR_CUDA(cudaMemcpyAsync(d_ir, irmin.data(), nplanes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CLR_CUDA(cudaMemcpyAsync(d_ir + nplanes, irmax.data(), nplanes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CLR_CUDA(cudaMemsetAsync(d_data, 0, (size_t)nplanes * num_pix * sizeof(float), c->stream));
-  LosPlan pl{d_fac, d_fac + nr, d_ir, d_ir + nplanes, d_inv, nplanes, dr};
+  LosPlan pl{d_fac, d_fac + nr, d_ir, d_ir + nplanes, d_inv, nplanes, dr, 0, 0., 0.};
+  if (c->nranks > 1) {
+    // NGP plane of a sample = (long)((r*u_z + pos_obs_z)*idx + 0.5) (beaming.c:148-157); it lies in this slab iff
+    // r*u_z in [(iz0-0.5)/idx - pos_obs_z, (iz0+nz-0.5)/idx - pos_obs_z) provided no sample wraps around the box
+    const double idx = (double)(c->p.n_grid / c->p.l_box);
+    double far = (nr * dr + fabs(c->p.pos_obs[2])) * idx + 0.5, near = (c->p.pos_obs[2] - nr * dr) * idx + 0.5;
+    if (far < c->p.n_grid && near >= 0) {
+      pl.restrict_z = 1;
+      pl.za = (c->dev.iz0_here - 0.5) / idx - c->p.pos_obs[2];
+      pl.zb = (c->dev.iz0_here + c->dev.nz_here - 0.5) / idx - c->p.pos_obs[2];
+    }
+  }
   {
     StageScope sc(c, which == 0 ? "kappa_los" : "isw_los", 1);
     if (which == 0)

@@ -261,9 +261,11 @@ def test_beam_rsd_vs_oracle(case):
 
 
 # --------------------------------------------------------------------------------------- maps
-def test_maps_vs_reference(golden_dir):
+@pytest.mark.parametrize("exact", [1, 0])
+def test_maps_vs_reference(golden_dir, exact):
     g, t = _load(golden_dir, "ref_n32_lognormal")
     par = _par(t)
+    par.set_option("exact_math", exact)      # 0: fp32-screened painter (default), 1: the double kernel
     par.grid_put(cb.GRID_DENS, g["s2_dens"])
     par.grid_put(cb.GRID_NPOT, g["s1_npot"])
     par.update_halo()
@@ -286,6 +288,30 @@ def test_maps_vs_reference(golden_dir):
     isw = cb.isw_get_beam_properties(par, pos, g["s6_isw_rf"])
     refi = g["s6_isw_data"].reshape(isw.shape)
     np.testing.assert_allclose(isw, refi, rtol=1e-5, atol=1e-6 * np.abs(refi).max())
+    par.free()
+
+
+def test_imap_fast_painter_equals_exact(golden_dir):
+    """The fp32-screened painter defers every sub-cell that is close to a pixel / shell edge to the double
+    path, so hit counts must be IDENTICAL to the all-double kernel (imap.c:135-245) at any size."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    t = dict(t)
+    n = 128
+    t["l_box"] = float(np.float32(2 * t["r_max"] * (1 + 2. / n)))
+    t["pos_obs"] = 0.5 * t["l_box"]
+    par = cb.ParamCoLoRe(t, n, seed=11)
+    cb.create_cartesian_fields(par)
+    cb.compute_physical_density_field(par)
+    edges = np.linspace(0.12 * t["r_max"], 0.97 * t["r_max"], 13).astype(np.float32)
+    res = {}
+    for nside in (64, 256):
+        par.set_imap(0, t["imap_tz_0"], t["imap_bz_0"], nside, edges[:-1], edges[1:])
+        cb.compute_density_normalization(par)
+        for exact in (1, 0):
+            par.set_option("exact_math", exact)
+            res[exact] = cb.imap_set_cartesian(par, 0)
+        assert res[0][1].sum() > 5 * n ** 3 and np.array_equal(res[0][1], res[1][1]), nside
+        np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5, atol=1e-7 * np.abs(res[1][0]).max())
     par.free()
 
 
