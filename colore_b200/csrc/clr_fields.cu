@@ -345,14 +345,12 @@ lognormal_fast_kernel(const ClrDev d, float *__restrict__ dens, float hs2, int c
       for (int h = 0; h < 2; h++) {
         float x0 = h ? x[q].y : x[q].x, delta = h ? v[q].y : v[q].x;
         float r2 = fmaf(x0, x0, yz);
-        float r = r2 * rsqrtf(r2);                                      // NaN at r2 = 0 -> dg = 1 below
-        float t = r * idr;
-        int ir = (int)t;
-        float dg;
-        if (!(r > 0.f)) dg = 1.f;
-        else if (r >= rtab) dg = dlast;
-        else { float2 e = __ldg(d.d1_t + ir); dg = fmaf(e.y, t - (float)ir, e.x); }
-        o[h] = clip ? fmaxf(fmaf(dg, delta, 1.f), 0.f) - 1.f : __expf(dg * fmaf(-hs2, dg, delta)) - 1.f;
+        float r = clr_sqrt_fast(r2);                                    // 0 at r2 = 0 -> D(r_0) = 1
+        float t = fminf(r * idr, (float)(CLR_NA - 2) + 0.5f);
+        float m = clr_floor_magic(t);
+        float2 e = __ldg(d.d1_t + clr_magic_int(m));
+        float dg = r >= rtab ? dlast : fmaf(e.y, t - (m - 8388608.f), e.x);
+        o[h] = clip ? fmaxf(fmaf(dg, delta, 1.f), 0.f) - 1.f : clr_ex2_fast(1.4426950408889634f * dg * fmaf(-hs2, dg, delta)) - 1.f;
       }
       p[32 * q] = make_float2(o[0], o[1]);
     }
@@ -484,12 +482,17 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
 constexpr int kRun = 8;
 constexpr int kFastPop = 4;
 // lerp tables {f[i], f[i+1]-f[i]} in fp32: entry 0 = z(r), entries 1.. = b(r) per population
-struct NormPopsF { const float2 *zt; const float2 *bt[kFastPop]; int npop; };
+struct NormPopsF { const float2 *zt; const float4 *zb; const float2 *bt[kFastPop]; int npop; };
 
 __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
 {
+  // branch free on the data (delta < 0 for ~60 % of the cells: both sides would run in every warp anyway)
+  if (model == 2) {
+    float e = clr_ex2_fast(1.4426950408889634f * bi * dl * clr_rcp_fast(fmaxf(1.f + dl, 1e-30f)));
+    float v = dl < 0.f ? e : fmaf(bi, dl, 1.f);
+    return dl <= -1.f ? 0.f : v;
+  }
   if (dl <= -1.f) return 0.f;
-  if (model == 2) return dl < 0.f ? __expf(bi * __fdividef(dl, 1.f + dl)) : 1.f + bi * dl;
   if (model == 3) return fmaxf(1.f + bi * dl, 0.f);
   return __powf(1.f + dl, bi);
 }
@@ -571,35 +574,56 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
       if (!ok[q]) continue;
+      // phase A, branch free: bin, z and bias_model of the two cells of the slot
+      int bin2[2];
+      float zf2[2], bm2[2][kFastPop];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         float x0 = h ? xv[q].y : xv[q].x, dl = h ? dv[q].y : dv[q].x;
         float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
-        float rf = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f, zf, tr = rf * idrf;
-        int ir = min((int)tr, CLR_NA - 2);
-        float fr = tr - (float)ir;
-        if (rf >= rtabf) zf = zlastf;
-        else { float2 t = __ldg(pops.zt + ir); zf = t.x + t.y * fr; }
+        float rf = clr_sqrt_fast(r2);
+        float tr = fminf(rf * idrf, (float)(CLR_NA - 2) + 0.5f);
+        float mr = clr_floor_magic(tr);
+        int ir = clr_magic_int(mr);
+        float fr = tr - (mr - 8388608.f);
+        // pops.zb: {z_i, z_i+1 - z_i, b_i, b_i+1 - b_i} of the first population: one 16-byte load per cell
+        float4 tz = __ldg(pops.zb + ir);
+        const bool past = rf >= rtabf;
+        float zf = past ? zlastf : fmaf(tz.y, fr, tz.x);
         float tb = zf * idzf;
-        int ind_z;
-        if (fabsf(tb - rintf(tb)) < 1e-4f) {
-          double redshift = clr_bg_z(d, sqrt((double)r2));           // density.c:1166-1168 verbatim
+        float tbn = __fadd_rn(__fadd_rn(tb, 12582912.f), -12582912.f);   // nearest integer, conversion-free
+        int ind_z = clr_magic_int(clr_floor_magic(tb)) + 1;              // tb >= 0
+        if (fabsf(tb - tbn) < 1e-4f) {                                   // ~2e-4 of the cells: exact edge decision
+          double redshift = clr_bg_z(d, sqrt((double)r2));              // density.c:1166-1168 verbatim
           ind_z = (int)(redshift * idz) + 1;
-        } else ind_z = (int)tb + 1;
-        int bin = (ind_z >= 0 && ind_z < nz) ? ind_z : -1;
-        if (bin != curbin[q]) { flush(q); curbin[q] = bin; }
-        if (bin >= 0) {
-          cnt[q]++;
-          zs[q] += zf;
+        }
+        bin2[h] = ((unsigned)ind_z < (unsigned)nz) ? ind_z : -1;
+        zf2[h] = zf;
 #pragma unroll
-          for (int ip = 0; ip < kFastPop; ip++) {
-            if (ip < npop) {
-              float bi;
-              if (rf >= rtabf) bi = 1.f;
-              else { float2 t = __ldg(pops.bt[ip] + ir); bi = t.x + t.y * fr; }
-              bs[q][ip] += bias_model_f(d.bias_model, dl, bi);
-            }
+        for (int ip = 0; ip < kFastPop; ip++) {
+          bm2[h][ip] = 0.f;
+          if (ip < npop) {
+            float bi;
+            if (ip == 0) bi = past ? 1.f : fmaf(tz.w, fr, tz.z);
+            else { float2 t = __ldg(pops.bt[ip] + ir); bi = past ? 1.f : fmaf(t.y, fr, t.x); }
+            bm2[h][ip] = bias_model_f(d.bias_model, dl, bi);
           }
+        }
+      }
+      // phase B: both cells in the slot's current bin (the common case) -> plain register sums
+      if (bin2[0] == curbin[q] && bin2[1] == curbin[q]) {
+        cnt[q] += 2;
+        zs[q] += zf2[0] + zf2[1];
+#pragma unroll
+        for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) bs[q][ip] += bm2[0][ip] + bm2[1][ip];
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (bin2[h] != curbin[q]) { flush(q); curbin[q] = bin2[h]; }
+          cnt[q]++;
+          zs[q] += zf2[h];
+#pragma unroll
+          for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) bs[q][ip] += bm2[h][ip];
         }
       }
       if (cnt[q] >= 4096) flush(q);      // keep the fp32 partial sums short
@@ -619,6 +643,16 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
       for (int ip = 0; ip < npop; ip++) atomicAdd(&g_b[ip * nz + i], fixed(1 + ip));
     }
   }
+}
+
+// {z[i], z[i+1]-z[i], b[i], b[i+1]-b[i]}: redshift and first-population bias lerp entries side by side
+__global__ void lerp_table2_kernel(const double *__restrict__ za, const double *__restrict__ ba, float4 *__restrict__ dst, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j = i + 1 < n ? i + 1 : i;
+  double z0 = za[i], z1 = za[j], b0 = ba ? ba[i] : 1., b1 = ba ? ba[j] : 1.;
+  dst[i] = make_float4((float)z0, (float)(z1 - z0), (float)b0, (float)(b1 - b0));
 }
 
 // {f[i], f[i+1]-f[i]} in fp32 from a double table of n entries
@@ -754,7 +788,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
 {
   CLR_CHECK(npop <= CLR_MAX_NORM_POP && nz <= CLR_MAX_NZ, "normalisation: npop=%d nz=%d too large", npop, nz);
   size_t nd = (size_t)nz * (2 + npop);
-  if (clr_ensure_scratch(c, nd * sizeof(double) + (size_t)(kFastPop + 1) * CLR_NA * sizeof(float2))) return 1;
+  if (clr_ensure_scratch(c, nd * sizeof(double) + (size_t)(kFastPop + 3) * CLR_NA * sizeof(float2) + 64)) return 1;
   CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
   unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_scratch);
   double *g_z = c->d_scratch + nz;
@@ -780,6 +814,9 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
         pf.bt[i] = tab + (size_t)(i + 1) * CLR_NA;
       }
       for (int i = npop; i < kFastPop; i++) pf.bt[i] = tab;
+      float4 *tab4 = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(tab + (size_t)(kFastPop + 1) * CLR_NA) + 15) & ~(uintptr_t)15);
+      lerp_table2_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, npop ? d_bz[0] : nullptr, tab4, CLR_NA);
+      pf.zb = tab4;
       int grid = grid_for(c, n_cells / kRun, 8);   // 8 cells per thread and iteration
       switch (npop) {
         case 0: norm_hist_fast_kernel<0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;

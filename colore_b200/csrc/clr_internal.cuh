@@ -384,6 +384,23 @@ __device__ __forceinline__ void clr_cart2sph(double x, double y, double z, doubl
   }
 }
 
+// Conversion-free floor for 0 <= t < 2^23: adding 2^23 with round-toward-zero leaves floor(t) in the mantissa.
+// F2I / I2F / FRND all issue on the quarter-rate XU pipe shared with rsqrt / ex2 / rcp; these forms stay on
+// the FMA and ALU pipes. m = clr_floor_magic(t): index = clr_magic_int(m), (float)index = m - 2^23.
+__device__ __forceinline__ float clr_floor_magic(float t) { return __fadd_rz(t, 8388608.f); }
+__device__ __forceinline__ int clr_magic_int(float m) { return __float_as_int(m) & 0x7fffff; }
+// r = sqrt(r2) through one MUFU.RSQ (rsqrtf() adds a denormal-scaling sequence); exact 0 at r2 = 0
+__device__ __forceinline__ float clr_sqrt_fast(float r2)
+{
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(r2, 1e-30f)));
+  return r2 * y;
+}
+
+// single-MUFU forms (the libdevice __expf / __fdividef wrap the MUFU in denormal-range scaling sequences)
+__device__ __forceinline__ float clr_ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float clr_rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 __device__ __forceinline__ double clr_warp_sum(double v)
 {
 #pragma unroll

@@ -142,18 +142,18 @@ struct ScreenK { float rcutf, idrf, rtabf; int bias_model; };
 __device__ __forceinline__ bool screen_cell(const ScreenK &k, const float4 *__restrict__ bound, float r2, float dl,
                                             uint32_t word)
 {
-  float rf = r2 * rsqrtf(r2);                                // NaN at r2 = 0 -> every test fails -> exact path
+  float rf = clr_sqrt_fast(r2);                              // 0 at r2 = 0 -> fails rf > 0.05 -> exact path
   if (rf > k.rcutf + 0.05f) return true;                     // outside the sampled sphere (srcs.c:169)
   if (!(rf < k.rcutf - 0.05f && rf > 0.05f && rf < k.rtabf - 1.f)) return false;
-  float4 e = __ldg(bound + (int)(rf * k.idrf));
+  float4 e = __ldg(bound + clr_magic_int(clr_floor_magic(rf * k.idrf)));
   float bm;                                                  // upper bound of |bias_model(dl, b)|, b in [e.y, e.z]
   if (dl <= -1.f) bm = 0.f;
   else if (k.bias_model == 2)
-    bm = dl < 0.f ? __expf(e.y * __fdividef(dl, 1.f + dl)) : fmaxf(fabsf(1.f + e.y * dl), fabsf(1.f + e.z * dl));
+    bm = dl < 0.f ? clr_ex2_fast(1.4426951f * e.y * dl * clr_rcp_fast(1.f + dl)) : fmaxf(fabsf(1.f + e.y * dl), fabsf(1.f + e.z * dl));
   else if (k.bias_model == 3) bm = fmaxf(fmaxf(1.f + e.y * dl, 1.f + e.z * dl), 0.f);
   else { float lg = __log2f(1.f + dl); bm = exp2f(fmaxf(e.y * lg, e.z * lg)); }
   float lam_hi = e.x * bm * 1.001f;
-  float e_lo = __expf(-lam_hi) * (1.f - 1e-5f);
+  float e_lo = clr_ex2_fast(-1.4426951f * lam_hi) * (1.f - 1e-5f);
   float u0_hi = (float)((word >> 8) + 1u) * (1.f / 16777216.f);
   return u0_hi <= e_lo;                                      // false for NaN tables -> exact path
 }

@@ -193,6 +193,25 @@ def main():
             assert np.isfinite(m).all() and m.std() > 0
             out[name] = {"nside": args.kappa_nside, "kernel_ms_max": allmax(kms), "api_wall_ms": wall * 1e3,
                          "map_rms": float(m.astype(np.float64).std())}
+    if args.imap_nside:
+        nu_rest = 1420.405
+        edges = np.linspace(nu_rest / 1.4, nu_rest / 1.05, 21)
+        zf, z0 = nu_rest / edges[:-1] - 1, nu_rest / edges[1:] - 1
+        r0 = np.interp(z0, t["z"], t["r"]).astype(np.float32)
+        rfi = np.interp(zf, t["z"], t["r"]).astype(np.float32)
+        par.set_imap(0, np.full(cb._lib.NA, 0.05), 1.0 + 0.5 * np.asarray(t["z"]), args.imap_nside, r0, rfi)
+        cb.compute_density_normalization(par)
+        barrier()
+        par.set_profiling(True)
+        t0 = time.perf_counter()
+        data, nadd = cb.imap_set_cartesian(par, 0)
+        wall = allmax(time.perf_counter() - t0)
+        kms, _ = par.stage_ms("imap_paint")
+        par.set_profiling(False)
+        hits = float(nadd.astype(np.int64).sum())       # maps are all-reduced: every rank holds the full sky
+        assert hits > 0 and np.isfinite(data).all()
+        out["imap_paint"] = {"nside": args.imap_nside, "channels": 20, "subcell_hits": hits, "kernel_ms_max": allmax(kms),
+                             "api_wall_ms": wall * 1e3}
     if rank == 0:
         print(json.dumps(out))
     par.free()
