@@ -292,10 +292,18 @@ def main():
     fft_ms = sum(stages[k]["ms_per_step"] for k in ("fft_z", "fft_y", "fft_x") if k in stages)
     fft_gbs = 2 * 24.0 * cells / (fft_ms * 1e-3) / 1e9 if fft_ms else None        # per GPU
     nvlink = None
-    if world > 1 and "fft_a2a" in stages and stages["fft_a2a"]["ms_per_step"] > 0:
+    if world > 1 and cb.dist.transpose_mode(par) == "p2p-fused":
+        # the transpose is fused into the z pass: its stores go straight to the destination GPU over NVLink,
+        # so the bytes below travel DURING that kernel (time = the whole fused pass incl. its two barriers)
+        sent = 2 * grid_bytes * (world - 1) / world
+        nvlink = {"transpose": "p2p-fused (peer stores from the FFT z pass)", "bytes_sent_per_rank_per_step": sent,
+                  "ms_per_step": stages["fft_z"]["ms_per_step"],
+                  "achieved_gbs_per_direction": sent / (stages["fft_z"]["ms_per_step"] * 1e-3) / 1e9,
+                  "peak_gbs_per_direction": 770.0, "peak_source": "measured peer copy (B200_PROFILING.md)"}
+    elif world > 1 and "fft_a2a" in stages and stages["fft_a2a"]["ms_per_step"] > 0:
         # bytes one rank SENDS per step: 2 transforms x slab bytes x (P-1)/P
         sent = 2 * grid_bytes * (world - 1) / world
-        nvlink = {"bytes_sent_per_rank_per_step": sent, "ms_per_step": stages["fft_a2a"]["ms_per_step"],
+        nvlink = {"transpose": "nccl all-to-all", "bytes_sent_per_rank_per_step": sent, "ms_per_step": stages["fft_a2a"]["ms_per_step"],
                   "achieved_gbs_per_direction": sent / (stages["fft_a2a"]["ms_per_step"] * 1e-3) / 1e9,
                   "peak_gbs_per_direction": 770.0, "peak_source": "measured peer copy (B200_PROFILING.md)"}
 
@@ -347,7 +355,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"n_grid={n} lognormal + 1 galaxy population + RSD (field->sources)",
                        "n_grid": n, "sources_per_step": nsrc_total,
-                       "parallelism": f"{world} z-slab(s), one process per GPU, NCCL all-to-all in the FFT",
+                       "parallelism": f"{world} z-slab(s), one process per GPU, FFT slab transpose: "
+                                      + (cb.dist.transpose_mode(par) if world > 1 else "none"),
                        "l2_policy": "inputs (8.6 GB of grids at 1024^3) exceed the 126 MB L2", "seed_per_step": "varies"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "fft_hbm_gbs": fft_gbs, "nvlink": nvlink, "stages": stages, "cpu_baseline": cpu,

@@ -21,6 +21,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -37,7 +38,7 @@ int load_nccl()
   *(void **)(&g_nccl.name) = dlsym(h, "nccl" #name);                         \
   CLR_CHECK(g_nccl.name, "libnccl lacks symbol nccl" #name)
   CLR_SYM(GetUniqueId); CLR_SYM(CommInitRank); CLR_SYM(CommDestroy); CLR_SYM(Send); CLR_SYM(Recv);
-  CLR_SYM(AllReduce); CLR_SYM(GroupStart); CLR_SYM(GroupEnd); CLR_SYM(GetErrorString);
+  CLR_SYM(AllReduce); CLR_SYM(AllGather); CLR_SYM(GroupStart); CLR_SYM(GroupEnd); CLR_SYM(GetErrorString);
 #undef CLR_SYM
   g_nccl.h = h;
   return 0;
@@ -85,6 +86,44 @@ extern "C" int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128
   // staging buffer of the FFT all-to-all: one slab
   size_t bytes = (size_t)d.pitch * d.n * d.nz_here * sizeof(float);
   CLR_CUDA(cudaMalloc(&c->d_stage, bytes));
+  CLR_CUDA(cudaMalloc(&c->d_barrier, sizeof(int)));
+  CLR_CUDA(cudaMemset(c->d_barrier, 0, sizeof(int)));
+  // Peer mapping of the staging buffers (CUDA IPC; the GPUs of one node see each other over NVLink / NVSwitch).
+  // Handles travel through an ncclAllGather. If any rank cannot map a peer, every rank falls back to the NCCL
+  // all-to-all (the decision is all-reduced so that the ranks never disagree).
+  int ok = nranks <= CLR_MAX_PEERS ? 1 : 0;
+  cudaIpcMemHandle_t mine;
+  if (ok && cudaIpcGetMemHandle(&mine, c->d_stage) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  unsigned char *d_h = nullptr;
+  CLR_CUDA(cudaMalloc(&d_h, (size_t)nranks * sizeof(cudaIpcMemHandle_t)));
+  CLR_CUDA(cudaMemset(d_h, 0, (size_t)nranks * sizeof(cudaIpcMemHandle_t)));
+  if (ok) CLR_CUDA(cudaMemcpy(d_h + (size_t)rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  CLR_NCCL(g_nccl.AllGather(d_h + (size_t)rank * sizeof(mine), d_h, sizeof(mine), ncclChar, comm, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<cudaIpcMemHandle_t> all(nranks);
+  CLR_CUDA(cudaMemcpy(all.data(), d_h, (size_t)nranks * sizeof(mine), cudaMemcpyDeviceToHost));
+  cudaFree(d_h);
+  for (int h = 0; h < nranks && ok; h++) {
+    if (h == rank) { c->peer_stage[h] = c->d_stage; continue; }
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[h], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    c->peer_stage[h] = static_cast<float *>(ptr);
+  }
+  CLR_CUDA(cudaMemcpy(c->d_barrier, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  CLR_NCCL(g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMin, comm, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  CLR_CUDA(cudaMemcpy(&ok, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost));
+  c->p2p = ok != 0;
+  return 0;
+}
+
+extern "C" int clr_comm_p2p(clr_ctx *c) { return c->p2p && c->p2p_enabled ? 1 : 0; }
+
+// all ranks have finished everything queued on their streams so far (tiny all-reduce, stream ordered)
+int clr_comm_barrier(clr_ctx *c)
+{
+  if (c->nranks == 1) return 0;
+  CLR_NCCL(g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMax, (ncclComm_t)c->nccl_comm, c->stream));
   return 0;
 }
 
@@ -92,8 +131,15 @@ int clr_comm_destroy(clr_ctx *c)
 {
   if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
   c->nccl_comm = nullptr;
+  for (int h = 0; h < CLR_MAX_PEERS; h++) {
+    if (c->peer_stage[h] && c->peer_stage[h] != c->d_stage) cudaIpcCloseMemHandle(c->peer_stage[h]);
+    c->peer_stage[h] = nullptr;
+  }
+  c->p2p = false;
   if (c->d_stage) cudaFree(c->d_stage);
   c->d_stage = nullptr;
+  if (c->d_barrier) cudaFree(c->d_barrier);
+  c->d_barrier = nullptr;
   return 0;
 }
 

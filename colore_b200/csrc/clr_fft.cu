@@ -310,10 +310,25 @@ __device__ __forceinline__ void cp_async8(float2 *dst_smem, const float2 *src, b
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Peer-memory output: element e of a line is stored on rank e >> aout.lo_bits, at peers.p[rank] (that rank's
+// staging buffer, already offset to the block reserved for this source rank) + the usual in-rank offset.
+struct PeerPtrs { float2 *p[CLR_MAX_PEERS]; };
+
 template <int M, int S, int T>
 struct StridedTile {
   using P = FftPlan<M>;
   const float2 *gin; float2 *gout; LineAddr ain, aout; int tiles_per_outer, n_inner, j, l;
+  __device__ __forceinline__ void store_peer(long long tile, const float2 (&v)[P::E], const PeerPtrs &peers) const
+  {
+    long long io, oo;
+    if (!locate(tile, io, oo)) return;
+    const int mask = (1 << aout.lo_bits) - 1;
+#pragma unroll
+    for (int i = 0; i < P::E; i++) {
+      const int e = j + i * P::TPL;
+      peers.p[e >> aout.lo_bits][oo + (long long)(e & mask) * aout.lo_stride] = v[i];
+    }
+  }
   __device__ __forceinline__ bool locate(long long tile, long long &in_off, long long &out_off) const
   {
     long long outer = tile / tiles_per_outer;
@@ -365,10 +380,10 @@ struct StridedTile {
 // (translation), not DRAM row activation: tiles are as wide as shared memory allows.)
 // (Tried and dropped: a separate full-tile landing buffer + half-tile exchange buffer, so that a whole
 // tile of 8-byte cp.async is always in flight -- 1.6x SLOWER at n=1024; see DESIGN.md.)
-template <int M, int S, int T>
+template <int M, int S, int T, bool PEER>
 __global__ void __launch_bounds__(T * FftPlan<M>::TPL, (T * FftPlan<M>::TPL * FftPlan<M>::E <= 8192) ? 2 : 1)
 fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, const float2 *__restrict__ W, int wn,
-                   long long n_tiles, int tiles_per_outer, int n_inner)
+                   long long n_tiles, int tiles_per_outer, int n_inner, const __grid_constant__ PeerPtrs peers)
 {
   using P = FftPlan<M>;
   extern __shared__ float2 smem[];
@@ -400,7 +415,8 @@ fft_strided_kernel(const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout,
     }
     if (tile + gridDim.x < n_tiles) tl.prefetch(tile + gridDim.x, s);
     stage_math<M, S, P::NST - 1>(v, tw, j);
-    tl.store(tile, v);
+    if constexpr (PEER) tl.store_peer(tile, v, peers);
+    else tl.store(tile, v);
   }
 }
 
@@ -546,7 +562,8 @@ template <typename K> int launch_cfg(clr_ctx *c, K kernel, int threads, size_t s
 }
 
 template <int M, int S, int T = Cfg<M>::T_STRIDED>
-int run_strided2(clr_ctx *c, const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, long long n_outer, int n_inner)
+int run_strided2(clr_ctx *c, const float2 *gin, float2 *gout, LineAddr ain, LineAddr aout, long long n_outer, int n_inner,
+                 const PeerPtrs *peers = nullptr)
 {
   using P = FftPlan<M>;
   constexpr int threads = T * P::TPL;
@@ -554,11 +571,25 @@ int run_strided2(clr_ctx *c, const float2 *gin, float2 *gout, LineAddr ain, Line
   int tiles_per_outer = (n_inner + T - 1) / T;
   long long n_tiles = n_outer * tiles_per_outer;
   int grid;
-  auto k = fft_strided_kernel<M, S, T>;
-  if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
-  k<<<grid, threads, smem, c->stream>>>(gin, gout, ain, aout, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, n_inner);
+  if (peers) {
+    auto k = fft_strided_kernel<M, S, T, true>;
+    if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
+    k<<<grid, threads, smem, c->stream>>>(gin, gout, ain, aout, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, n_inner, *peers);
+  } else {
+    auto k = fft_strided_kernel<M, S, T, false>;
+    if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
+    k<<<grid, threads, smem, c->stream>>>(gin, gout, ain, aout, c->d_twiddle, c->dev.n, n_tiles, tiles_per_outer, n_inner, PeerPtrs{});
+  }
   CLR_CUDA(cudaGetLastError());
   return 0;
+}
+
+// staging-buffer pointers of every rank, offset to the block this rank writes (block index = source rank)
+PeerPtrs peer_blocks(clr_ctx *c, size_t block_float2)
+{
+  PeerPtrs pp{};
+  for (int h = 0; h < c->nranks; h++) pp.p[h] = reinterpret_cast<float2 *>(c->peer_stage[h]) + (size_t)c->rank * block_float2;
+  return pp;
 }
 
 template <int M, int S, int T = Cfg<M>::T_STRIDED>
@@ -583,10 +614,24 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
   const long long nc = N / 2 + 1;
   const int P = c->nranks, nzl = N / P, nyl = N / P;
   float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
-  { StageScope sc(c, "fft_z", 1);
-    if (run_strided<N, +1>(c, g, 1, 0, (long long)nyl * nc, (int)(nyl * nc))) return 1; }
-  { StageScope sc(c, "fft_a2a", 0);
-    if (clr_comm_alltoall(c, g, stage, (size_t)nzl * nyl * nc * 2)) return 1; }
+  if (c->p2p && c->p2p_enabled) {
+    // z pass with the slab transpose fused into its stores: plane z of the result belongs to rank z / nzl and is
+    // written straight into that rank's staging buffer over NVLink (block = source rank), tile by tile while
+    // the next tile is being transformed. Barriers: nobody still reads its staging buffer / everything arrived.
+    StageScope sc(c, "fft_z", 1);
+    if (clr_comm_barrier(c)) return 1;
+    PeerPtrs pp = peer_blocks(c, (size_t)nzl * nyl * nc);
+    LineAddr ain{0, 0, (long long)nyl * nc, 31};
+    LineAddr aout{0, 0, (long long)nyl * nc, ilog2_host(nzl)};
+    if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
+    if (clr_comm_barrier(c)) return 1;
+    c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1);
+  } else {
+    { StageScope sc(c, "fft_z", 1);
+      if (run_strided<N, +1>(c, g, 1, 0, (long long)nyl * nc, (int)(nyl * nc))) return 1; }
+    { StageScope sc(c, "fft_a2a", 0);
+      if (clr_comm_alltoall(c, g, stage, (size_t)nzl * nyl * nc * 2)) return 1; }
+  }
   { StageScope sc(c, "fft_y", 1);
     LineAddr ain{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};
     LineAddr aout{(long long)N * nc, 0, nc, 31};
@@ -603,6 +648,20 @@ int r2c_3d_dist(clr_ctx *c, float2 *g)
   const int P = c->nranks, nzl = N / P, nyl = N / P;
   float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
   { StageScope sc(c, "fft_x", 1); if (run_r2c_x<N / 2>(c, g, (long long)nzl * N, (int)nc)) return 1; }
+  if (c->p2p && c->p2p_enabled) {
+    // y pass storing ky block s straight into rank s's staging buffer; the z pass then runs staging -> grid
+    { StageScope sc(c, "fft_y", 1);
+      if (clr_comm_barrier(c)) return 1;
+      PeerPtrs pp = peer_blocks(c, (size_t)nzl * nyl * nc);
+      LineAddr ain{(long long)N * nc, 0, nc, 31};
+      LineAddr aout{(long long)nyl * nc, 0, nc, ilog2_host(nyl)};
+      if (run_strided2<N, -1>(c, g, nullptr, ain, aout, nzl, (int)nc, &pp)) return 1;
+      if (clr_comm_barrier(c)) return 1;
+      c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1); }
+    StageScope sc(c, "fft_z", 1);
+    LineAddr a{0, 0, (long long)nyl * nc, 31};
+    return run_strided2<N, -1>(c, stage, g, a, a, 1, (int)(nyl * nc));
+  }
   { StageScope sc(c, "fft_y", 1);
     LineAddr ain{(long long)N * nc, 0, nc, 31};
     LineAddr aout{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};

@@ -10,6 +10,7 @@
 #include "../../include/colore_b200.h"
 
 #define CLR_SM_COUNT_FALLBACK 148
+#define CLR_MAX_PEERS 16
 
 // ---------------------------------------------------------------------------------------------
 // device-visible parameter block (passed by value as __grid_constant__ where needed)
@@ -82,6 +83,12 @@ struct clr_ctx {
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
   float *d_stage = nullptr;         // all-to-all staging buffer of the distributed FFT (one slab)
+  // peer-memory transpose: every rank's staging buffer mapped into this process (CUDA IPC over NVLink), so the
+  // FFT pass that produces the data stores it straight into the destination GPU (no separate all-to-all)
+  float *peer_stage[CLR_MAX_PEERS] = {nullptr};
+  bool p2p = false;
+  int p2p_enabled = 1;              // option "p2p_fused"
+  int *d_barrier = nullptr;
   double a2a_bytes = 0;             // bytes this rank has sent through the FFT all-to-all
   // bookkeeping
   long long launches = 0;
@@ -163,6 +170,7 @@ int clr_comm_destroy(clr_ctx *c);
 int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_floats);
 int clr_comm_alltoallv(clr_ctx *c, const float *send, const size_t *send_off, const size_t *send_n, float *recv,
                        const size_t *recv_off, const size_t *recv_n);
+int clr_comm_barrier(clr_ctx *c);
 int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n);
 int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n);
 int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n);

@@ -38,6 +38,15 @@ def init_comm(par, rank: int, nranks: int):
     dist.broadcast_object_list(box, src=0)
     buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
     check(par.lib.clr_comm_init(par.ctx, C.c_int(rank), C.c_int(nranks), buf))
+    import os
+    if os.environ.get("COLORE_B200_P2P", "1") == "0":      # force the NCCL all-to-all (comparison runs)
+        par.set_option("p2p_fused", 0)
+
+
+def transpose_mode(par) -> str:
+    """How the slab transpose of the distributed FFT runs: peer-memory stores fused into the producing
+    pass ("p2p-fused") or an NCCL all-to-all ("nccl")."""
+    return "p2p-fused" if par.lib.clr_comm_p2p(par.ctx) == 1 else "nccl"
 
 
 # ---- numpy restatement of the exchange (test support) ---------------------------------------------

@@ -82,6 +82,10 @@ long long clr_launch_count(clr_ctx *ctx);
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host (torch.distributed) */
 int clr_comm_unique_id(void *id128);
 int clr_comm_init(clr_ctx *ctx, int rank, int nranks, const void *id128);
+/* 1 when the slab transpose of the distributed FFT runs as peer-memory stores fused into the producing pass
+ * (every rank mapped every other rank's staging buffer over CUDA IPC), 0 when it runs as an NCCL all-to-all.
+ * Option "p2p_fused" = 0 forces the NCCL path (clr_set_option). */
+int clr_comm_p2p(clr_ctx *ctx);
 
 /* ---- populations (cosmo.c:549-629 tables; one call per population) ---------------------- */
 int clr_set_srcs(clr_ctx *ctx, int ipop, const double *nz_arr, const double *bz_arr);

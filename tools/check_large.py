@@ -77,7 +77,8 @@ def main():
     par = cb.ParamCoLoRe(t, n, dens_type=args.dens_type, seed=cfg.seed, device=local, nz_here=nzl, iz0_here=iz0)
     cb.dist.init_comm(par, rank, world)
     par.set_srcs(0, t["srcs_nz_0"], t["srcs_bz_0"])
-    out = {"n_grid": n, "n_gpus": world, "dens_type": args.dens_type}
+    out = {"n_grid": n, "n_gpus": world, "dens_type": args.dens_type,
+           "transpose": cb.dist.transpose_mode(par) if world > 1 else "none"}
     nfl = nzl * n * 2 * par.nc
 
     def dev_view(which):
@@ -173,7 +174,10 @@ def main():
     if "lognormal" in stages:
         out["lognormal_hbm_gbs_per_gpu"] = 8.0 * cells_rank / (stages["lognormal"]["ms_per_step"] * 1e-3) / 1e9
         out["lognormal_frac_of_hbm_peak"] = out["lognormal_hbm_gbs_per_gpu"] / peak
-    if "fft_a2a" in stages and world > 1:
+    if out["transpose"] == "p2p-fused":
+        sent = nfft * 8.0 * n * n * par.nc / world * (world - 1) / world
+        out["nvlink_gbs_per_direction_during_fused_pass"] = sent / (stages["fft_z"]["ms_per_step"] * 1e-3) / 1e9
+    elif "fft_a2a" in stages and world > 1:
         sent = nfft * 8.0 * n * n * par.nc / world * (world - 1) / world
         out["a2a_gbs_per_direction"] = sent / (stages["fft_a2a"]["ms_per_step"] * 1e-3) / 1e9
 
