@@ -142,20 +142,25 @@ struct ScreenK { float rcutf, idrf, rtabf; int bias_model; };
 __device__ __forceinline__ bool screen_cell(const ScreenK &k, const float4 *__restrict__ bound, float r2, float dl,
                                             uint32_t word)
 {
-  float rf = clr_sqrt_fast(r2);                              // 0 at r2 = 0 -> fails rf > 0.05 -> exact path
-  if (rf > k.rcutf + 0.05f) return true;                     // outside the sampled sphere (srcs.c:169)
-  if (!(rf < k.rcutf - 0.05f && rf > 0.05f && rf < k.rtabf - 1.f)) return false;
-  float4 e = __ldg(bound + clr_magic_int(clr_floor_magic(rf * k.idrf)));
+  // branch free (the tests below are data dependent and would diverge in nearly every warp)
+  const float rf = clr_sqrt_fast(r2);
+  const bool outside = rf > k.rcutf + 0.05f;                 // outside the sampled sphere (srcs.c:169)
+  if (outside) return true;                                  // box corners: spatially coherent early out
+  const bool inside = rf < k.rcutf - 0.05f && rf > 0.05f && rf < k.rtabf - 1.f;   // else: exact path decides
+  const float4 e = __ldg(bound + clr_magic_int(clr_floor_magic(fminf(rf * k.idrf, (float)(CLR_NA - 1)))));
   float bm;                                                  // upper bound of |bias_model(dl, b)|, b in [e.y, e.z]
-  if (dl <= -1.f) bm = 0.f;
-  else if (k.bias_model == 2)
-    bm = dl < 0.f ? clr_ex2_fast(1.4426951f * e.y * dl * clr_rcp_fast(1.f + dl)) : fmaxf(fabsf(1.f + e.y * dl), fabsf(1.f + e.z * dl));
-  else if (k.bias_model == 3) bm = fmaxf(fmaxf(1.f + e.y * dl, 1.f + e.z * dl), 0.f);
-  else { float lg = __log2f(1.f + dl); bm = exp2f(fmaxf(e.y * lg, e.z * lg)); }
-  float lam_hi = e.x * bm * 1.001f;
-  float e_lo = clr_ex2_fast(-1.4426951f * lam_hi) * (1.f - 1e-5f);
-  float u0_hi = (float)((word >> 8) + 1u) * (1.f / 16777216.f);
-  return u0_hi <= e_lo;                                      // false for NaN tables -> exact path
+  if (k.bias_model == 2) {
+    const float ex = clr_ex2_fast(1.4426951f * e.y * dl * clr_rcp_fast(fmaxf(1.f + dl, 1e-30f)));
+    const float li = fmaxf(fabsf(fmaf(e.y, dl, 1.f)), fabsf(fmaf(e.z, dl, 1.f)));
+    bm = dl < 0.f ? ex : li;
+  } else if (k.bias_model == 3) bm = fmaxf(fmaxf(1.f + e.y * dl, 1.f + e.z * dl), 0.f);
+  else { float lg = __log2f(fmaxf(1.f + dl, 1e-30f)); bm = exp2f(fmaxf(e.y * lg, e.z * lg)); }
+  bm = dl <= -1.f ? 0.f : bm;
+  const float lam_hi = e.x * bm * 1.001f;
+  const float e_lo = clr_ex2_fast(-1.4426951f * lam_hi) * (1.f - 1e-5f);
+  // upper bound of the first uniform from its top 23 bits, conversion free: ((word >> 9) + 1) * 2^-23 >= u0
+  const float u0_hi = (__uint_as_float(0x4B000000u | (word >> 9)) - 8388607.f) * 1.1920928955078125e-07f;
+  return outside || (inside && u0_hi <= e_lo);               // NaN tables: comparison false -> exact path
 }
 
 // one entry per r-bin of the NA grid; window [ir-1, ir+2] covers an off-by-one fp32 bin index
