@@ -430,31 +430,48 @@ fft_c2r_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
 {
   using P = FftPlan<M>;
   extern __shared__ float2 smem[];
+  // s: landing area of the raw rows (M+1 complex each, row stride LSTRIDE) AND exchange buffer of the stages
   float2 *s = smem;
-  float2 *tw = smem + (P::NST > 1 ? T * P::LSTRIDE : 0);
+  float2 *tw = smem + T * P::LSTRIDE;
   float2 *wx = tw + P::NTW;   // exp(+2*pi*i*k/n), k < M
   const int tid = threadIdx.x, j = tid % P::TPL, l = tid / P::TPL;
   load_twiddles<M, +1>(tw, W, wn);
   for (int k = tid; k < M; k += blockDim.x) wx[k] = W[k * (wn / (2 * M))];
-  __syncthreads();
   double acc1 = 0, acc2 = 0;
   const long long n_tiles = (n_rows + T - 1) / T;
+  // every element of a row is fetched ONCE, contiguously, with cp.async (the half-complex combination below
+  // needs X[k] and X[M-k]); the next tile's rows are in flight while this tile's results are stored
+  auto prefetch = [&](long long tile) {
+    const long long row = tile * T + l;
+    const bool ok = row < n_rows;
+    const float2 *X = g + (ok ? row : 0) * pitch_c;
+    float2 *dst = s + l * P::LSTRIDE;
+#pragma unroll
+    for (int i = 0; i < P::E; i++) cp_async8(dst + j + i * P::TPL, X + j + i * P::TPL, ok);
+    if (j == 0) cp_async8(dst + M, X + M, ok);
+  };
+  if (blockIdx.x < n_tiles) prefetch(blockIdx.x);
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    long long row = tile * T + l;
-    bool ok = row < n_rows;
+    const long long row = tile * T + l;
+    const bool ok = row < n_rows;
     float2 *X = g + row * pitch_c;
     float2 v[P::E];
+    cp_async_wait_all();
+    __syncthreads();                                 // the rows have landed (and, first time, the twiddles)
+    const float2 *raw = s + l * P::LSTRIDE;
 #pragma unroll
     for (int i = 0; i < P::E; i++) {
       int k = j + i * P::TPL;
-      float2 a = ok ? X[k] : make_float2(0.f, 0.f);
-      float2 b = ok ? X[M - k] : make_float2(0.f, 0.f);
+      float2 a = raw[k], b = raw[M - k];
       if (k == 0) { a.y = 0.f; b.y = 0.f; }        // x-DC and x-Nyquist are taken as real
       float2 e = make_float2(a.x + b.x, a.y - b.y);
       float2 d = cmul(make_float2(a.x - b.x, a.y + b.y), wx[k]);
       v[i] = make_float2(e.x - d.y, e.y + d.x);
     }
+    if constexpr (P::NST > 1) __syncthreads();      // everybody has picked up its inputs: s is the exchange buffer now
     fft_lines<M, +1, false, T>(v, s, tw, j, l);
+    __syncthreads();                                 // last exchange read back: s is free for the next rows
+    if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x);
     if (ok) {
       float s1 = 0, s2 = 0;
 #pragma unroll
@@ -469,7 +486,6 @@ fft_c2r_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
       }
       if (MOM) { acc1 += s1; acc2 += s2; }
     }
-    __syncthreads();
   }
   if (MOM) {
     acc1 = clr_warp_sum(acc1);
@@ -678,7 +694,7 @@ int run_c2r_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c, float norm, 
   using P = FftPlan<M>;
   constexpr int T = Cfg<M>::T_X;
   constexpr int threads = T * P::TPL;
-  size_t smem = ((P::NST > 1 ? (size_t)T * P::LSTRIDE : 0) + P::NTW + M) * sizeof(float2);
+  size_t smem = ((size_t)T * P::LSTRIDE + P::NTW + M) * sizeof(float2);
   int grid;
   auto k = fft_c2r_x_kernel<M, T, MOM>;
   if (launch_cfg(c, k, threads, smem, (n_rows + T - 1) / T, &grid)) return 1;

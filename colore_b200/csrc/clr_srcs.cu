@@ -302,37 +302,67 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
   }
 }
 
-// exclusive scan of the chunk totals (one CTA; a few MB at most). offs[n_chunks] = grand total.
-__global__ void __launch_bounds__(1024)
-scan_chunks_kernel(const int32_t *__restrict__ tot, long long *__restrict__ offs, long long n_chunks)
+// exclusive scan of the chunk totals, offs[n_chunks] = grand total. Two launches over kScanBlocks contiguous
+// segments: (1) segment sums, (2) every CTA scans the kScanBlocks sums in shared memory to get its base, then
+// scans its own segment (a single 1024-thread CTA took 0.42 ms for the 10^6 chunks of a 1024^3 grid).
+constexpr int kScanBlocks = 256;
+__global__ void __launch_bounds__(256)
+scan_sums_kernel(const int32_t *__restrict__ tot, long long *__restrict__ seg_sum, long long n_chunks)
 {
-  // each of the 32 warps owns one contiguous segment and walks it 32 elements at a time, so every
-  // global access is a coalesced 128-byte line
-  __shared__ long long seg[33];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  long long per = ((n_chunks + 31) / 32 + 31) / 32 * 32;     // segment length, multiple of 32
-  long long b = w * per, e = b + per < n_chunks ? b + per : n_chunks;
-  long long s = 0;
-  for (long long i = b + lane; i < e; i += 32) s += tot[i];
+  const long long per = (n_chunks + kScanBlocks - 1) / kScanBlocks;
+  const long long b = blockIdx.x * per, e = b + per < n_chunks ? b + per : n_chunks;
+  long long sum = 0;
+  for (long long i = b + threadIdx.x; i < e; i += blockDim.x) sum += tot[i];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) seg[w + 1] = s;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __shared__ long long ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
   __syncthreads();
   if (threadIdx.x == 0) {
-    seg[0] = 0;
-    for (int k = 1; k <= 32; k++) seg[k] += seg[k - 1];
+    long long t = 0;
+    for (int k = 0; k < 8; k++) t += ws[k];
+    seg_sum[blockIdx.x] = t;
   }
-  __syncthreads();
-  long long run = seg[w];
-  for (long long i0 = b; i0 < e; i0 += 32) {
-    long long i = i0 + lane;
+}
+__global__ void __launch_bounds__(256)
+scan_chunks_kernel(const int32_t *__restrict__ tot, const long long *__restrict__ seg_sum, long long *__restrict__ offs,
+                   long long n_chunks)
+{
+  __shared__ long long base_s, ws[8];
+  // base of this segment = sum of the earlier segment sums
+  {
+    long long v = threadIdx.x < blockIdx.x ? seg_sum[threadIdx.x] : 0;      // kScanBlocks == blockDim.x
+    long long all = seg_sum[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+    __shared__ long long wa[8];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = v; wa[threadIdx.x >> 5] = all; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0, ta = 0;
+      for (int k = 0; k < 8; k++) { t += ws[k]; ta += wa[k]; }
+      base_s = t;
+      if (blockIdx.x == 0) offs[n_chunks] = ta;
+    }
+    __syncthreads();
+  }
+  const long long per = (n_chunks + kScanBlocks - 1) / kScanBlocks;
+  const long long b = blockIdx.x * per, e = b + per < n_chunks ? b + per : n_chunks;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long run = base_s;
+  for (long long i0 = b; i0 < e; i0 += blockDim.x) {
+    const long long i = i0 + threadIdx.x;
     long long v = i < e ? tot[i] : 0, incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-    if (i < e) offs[i] = run + incl - v;
-    run += __shfl_sync(0xffffffffu, incl, 31);
+    __syncthreads();
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    long long woff = 0, blk = 0;
+    for (int k = 0; k < 8; k++) { long long t = ws[k]; if (k < w) woff += t; blk += t; }
+    if (i < e) offs[i] = run + woff + incl - v;
+    run += blk;
   }
-  if (threadIdx.x == 0) offs[n_chunks] = seg[32];
 }
 
 // srcs.c:87-118 (get_rvel): central differences of the potential, periodic in x,y, z through the
@@ -432,16 +462,28 @@ place_src_kernel(const ClrDev d, const float *__restrict__ npot, const unsigned 
 __global__ void __launch_bounds__(kThreads)
 local_props_kernel(const ClrDev d, const float4 *__restrict__ pos, float *__restrict__ srcs, long long nsrc)
 {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nsrc; i += (long long)gridDim.x * blockDim.x) {
-    float4 p = pos[i];
-    double r, cth, phi;
-    clr_cart2sph(p.x, p.y, p.z, &r, &cth, &phi);
-    float *o = srcs + 9 * i;
-    o[0] = (float)(57.2957795 * phi);
-    o[1] = (float)(90 - 57.2957795 * acos(cth));
-    o[2] = (float)clr_bg_z(d, r);
-    o[3] = p.w;
-    o[4] = -1.f; o[5] = -1.f; o[6] = 0.f; o[7] = 0.f; o[8] = 0.f;
+  // the Src record is 9 floats (36 B): written directly, a warp store would touch 36 sectors for 128 useful
+  // bytes, so the CTA assembles its 256 records in shared memory and streams them out as contiguous floats
+  __shared__ float rec[kThreads * 9];
+  const long long n_blocks = (nsrc + kThreads - 1) / kThreads;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long i = blk * kThreads + threadIdx.x;
+    if (i < nsrc) {
+      float4 p = pos[i];
+      double r, cth, phi;
+      clr_cart2sph(p.x, p.y, p.z, &r, &cth, &phi);
+      float *o = rec + 9 * threadIdx.x;
+      o[0] = (float)(57.2957795 * phi);
+      o[1] = (float)(90 - 57.2957795 * acos(cth));
+      o[2] = (float)clr_bg_z(d, r);
+      o[3] = p.w;
+      o[4] = -1.f; o[5] = -1.f; o[6] = 0.f; o[7] = 0.f; o[8] = 0.f;
+    }
+    __syncthreads();
+    const long long base = blk * kThreads * 9;
+    const long long lim = (nsrc - blk * kThreads < kThreads ? nsrc - blk * kThreads : kThreads) * 9;
+    for (int k = threadIdx.x; k < lim; k += kThreads) srcs[base + k] = rec[k];
+    __syncthreads();
   }
 }
 
@@ -541,7 +583,8 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
   const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
   const long long n_chunks = (n_cells + kChunk - 1) / kChunk;
   if (!P.d_counts) CLR_CUDA(cudaMalloc(&P.d_counts, n_cells * sizeof(int32_t)));
-  size_t need = (size_t)n_chunks * sizeof(int32_t) + (size_t)(n_chunks + 1) * sizeof(long long) + 64;
+  size_t need = (size_t)(n_chunks + 2) / 2 * sizeof(long long) + (size_t)(n_chunks + 1) * sizeof(long long) +
+                (size_t)kScanBlocks * sizeof(long long) + 64;
   if (clr_ensure_scratch(c, need)) return 1;
   long long *d_offs = reinterpret_cast<long long *>(c->d_scratch);
   int32_t *d_tot = reinterpret_cast<int32_t *>(d_offs + n_chunks + 1);
@@ -561,8 +604,10 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
     CLR_CUDA(cudaGetLastError());
   }
   {
-    StageScope sc(c, "srcs_scan", 1);
-    scan_chunks_kernel<<<1, 1024, 0, c->stream>>>(d_tot, d_offs, n_chunks);
+    StageScope sc(c, "srcs_scan", 2);
+    long long *d_seg = d_offs + n_chunks + 1 + (n_chunks + 2) / 2;   // behind offs[] and tot[]
+    scan_sums_kernel<<<kScanBlocks, 256, 0, c->stream>>>(d_tot, d_seg, n_chunks);
+    scan_chunks_kernel<<<kScanBlocks, 256, 0, c->stream>>>(d_tot, d_seg, d_offs, n_chunks);
     CLR_CUDA(cudaGetLastError());
   }
   long long total = 0;
