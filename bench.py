@@ -286,8 +286,13 @@ def main():
               key=lambda k: stages[k]["ms_per_step"])
     per_launch_ms = stages[dom]["ms_per_step"] / stages[dom]["launches_per_step"]
     achieved = alg_bytes[dom] / (per_launch_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of THIS
+    # workload (n_grid=1024, one GPU): profiles/r1_ncu_top_kernels_v8_full.csv (Poisson: ..._v4_full.csv)
+    ncu_traffic = {"fill_modes": 9.33e9, "fft_z": 8.55e9, "fft_y": 8.55e9, "fft_x": 8.56e9, "lognormal": 8.58e9,
+                   "norm_hist": 4.33e9, "srcs_poisson": 9.32e9, "srcs_expand": 3.72e9, "srcs_place": 5.81e9}
+    traffic = ncu_traffic.get(dom) if (n == 1024 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dom], "ms_per_launch": per_launch_ms}
     fft_ms = sum(stages[k]["ms_per_step"] for k in ("fft_z", "fft_y", "fft_x") if k in stages)
     fft_gbs = 2 * 24.0 * cells / (fft_ms * 1e-3) / 1e9 if fft_ms else None        # per GPU

@@ -523,9 +523,11 @@ __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
   return __powf(1.f + dl, bi);
 }
 
-// Every CTA walks a CONTIGUOUS range of runs (8 cells each, lane <-> run), so a thread's successive runs
-// sit two rows apart and nearly always fall into the same redshift bin (the bins are ~100 cells wide):
-// the per-thread partial sums are flushed to the shared-memory histogram only when the bin changes.
+// Column-strip walk: a warp owns a strip of 64 cells along x (lane <-> one float2) and walks DOWN the rows of a
+// contiguous row range, so a lane's x never changes, y moves one cell per step and its redshift bin (a ~60-cell
+// thick shell) changes every ~60 steps: the lane keeps {count, sum z, sum bias_model} of its current bin in
+// registers and touches the shared-memory histogram only when the bin changes. The 8 warps of a CTA take 8
+// neighbouring strips of the same rows (2 KB contiguous per row step).
 template <int NPOP>
 __global__ void __launch_bounds__(kThreads)
 norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF pops, int nz, double idz,
@@ -552,75 +554,67 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
   const float zlastf = __ldg(&pops.zt[CLR_NA - 1].x);
   const float idzf = (float)idz;
   constexpr int npop = NPOP;          // compile-time population count: dead per-population code folds away
-  // a warp owns 256-cell segments of a row (lane <-> float2 number lane + 32*q: 256 contiguous bytes per
-  // load instruction); a CTA walks a contiguous range of segments
   const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const unsigned spr = ((unsigned)d.n + 255u) >> 8;
-  const unsigned n_seg = (unsigned)d.nz_here * (unsigned)d.n * spr;      // < 2^32 up to n = 4096
-  const unsigned per_cta = (n_seg + gridDim.x - 1) / gridDim.x;
-  const unsigned seg_end = min(n_seg, (blockIdx.x + 1) * per_cta);
-  // one set of partial sums per float2 slot q: slot (lane, q) sees the same x in successive rows, so its
-  // redshift bin (~100 cells wide) rarely changes and flushes to the shared histogram are rare
-  constexpr int NQ = kRun / 2;
-  int curbin[NQ], cnt[NQ];
-  float zs[NQ], bs[NQ][kFastPop];
+  const int nstrips = (d.n + 63) >> 6;
+  const int groups = (nstrips + wpc - 1) / wpc;                        // CTAs side by side along x
+  const int n_ranges = max(1, (int)gridDim.x / groups);
+  const int strip = (int)(blockIdx.x % groups) * wpc + wip;
+  const int range = (int)(blockIdx.x / groups);
+  const unsigned n_rows = (unsigned)d.nz_here * (unsigned)d.n;
+  const unsigned per = (n_rows + n_ranges - 1) / n_ranges;
+  const unsigned row0 = range * per, row1 = min(n_rows, row0 + per);
+  const int xq = strip * 32 + lane;                                   // float2 index inside the row
+  const bool ok = strip < nstrips && 2 * xq < d.n && range < n_ranges;
+  int curbin = -1, cnt = 0;
+  float zs = 0.f, bs[kFastPop];
 #pragma unroll
-  for (int q = 0; q < NQ; q++) {
-    curbin[q] = -1; cnt[q] = 0; zs[q] = 0.f;
+  for (int ip = 0; ip < kFastPop; ip++) bs[ip] = 0.f;
+  auto flush = [&]() {
+    if (curbin >= 0 && cnt > 0) {
+      atomicAdd(&s_n[curbin], (unsigned)cnt);
+      add_fixed(0, curbin, zs);
 #pragma unroll
-    for (int ip = 0; ip < kFastPop; ip++) bs[q][ip] = 0.f;
-  }
-  auto flush = [&](int q) {
-    if (curbin[q] >= 0 && cnt[q] > 0) {
-      atomicAdd(&s_n[curbin[q]], (unsigned)cnt[q]);
-      add_fixed(0, curbin[q], zs[q]);
-#pragma unroll
-      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) add_fixed(1 + ip, curbin[q], bs[q][ip]);
+      for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) add_fixed(1 + ip, curbin, bs[ip]);
     }
-    cnt[q] = 0; zs[q] = 0.f;
+    cnt = 0; zs = 0.f;
 #pragma unroll
-    for (int ip = 0; ip < kFastPop; ip++) bs[q][ip] = 0.f;
+    for (int ip = 0; ip < kFastPop; ip++) bs[ip] = 0.f;
   };
-  for (unsigned seg = blockIdx.x * per_cta + wip; seg < seg_end; seg += wpc) {
-    const unsigned row = seg / spr;
-    const int sg = (int)(seg - row * spr);
-    const int iz = (int)(row / (unsigned)d.n), iy = (int)(row - (unsigned)iz * (unsigned)d.n);
-    const float y0 = __ldg(d.cf[1] + iy), z0 = __ldg(d.cf[2] + iz + d.iz0_here);
-    const float yy = __fmul_rn(y0, y0), zz = __fmul_rn(z0, z0);
-    const int xq0 = sg * 128 + lane;
-    const float2 *p = reinterpret_cast<const float2 *>(dens + (long long)row * d.pitch) + xq0;
-    const float2 *xc = reinterpret_cast<const float2 *>(d.cf[0]) + xq0;
-    float2 dv[NQ], xv[NQ];
-    bool ok[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      ok[q] = 2 * (xq0 + 32 * q) < d.n;
-      if (ok[q]) { dv[q] = p[32 * q]; xv[q] = __ldg(xc + 32 * q); }
-    }
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      if (!ok[q]) continue;
-      // phase A, branch free: bin, z and bias_model of the two cells of the slot
+  if (ok) {
+    const float2 xc = __ldg(reinterpret_cast<const float2 *>(d.cf[0]) + xq);
+    const float xx[2] = {__fmul_rn(xc.x, xc.x), __fmul_rn(xc.y, xc.y)};
+    int iz = (int)(row0 / (unsigned)d.n), iy = (int)(row0 - (unsigned)iz * (unsigned)d.n);
+    float zz = 0.f;
+    { const float z0 = __ldg(d.cf[2] + iz + d.iz0_here); zz = __fmul_rn(z0, z0); }
+    const float2 *p = reinterpret_cast<const float2 *>(dens + (long long)row0 * d.pitch) + xq;
+    const int pitch2 = d.pitch >> 1;
+    float2 dv = row0 < row1 ? *p : make_float2(0.f, 0.f);
+    for (unsigned row = row0; row < row1; row++) {
+      const float2 dcur = dv;
+      p += pitch2;
+      if (row + 1 < row1) dv = *p;                                     // next row's load flies under this row's math
+      const float y0 = __ldg(d.cf[1] + iy);
+      const float yy = __fmul_rn(y0, y0);
       int bin2[2];
       float zf2[2], bm2[2][kFastPop];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        float x0 = h ? xv[q].y : xv[q].x, dl = h ? dv[q].y : dv[q].x;
-        float r2 = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), yy), zz);   // same order as the reference
-        float rf = clr_sqrt_fast(r2);
-        float tr = fminf(rf * idrf, (float)(CLR_NA - 2) + 0.5f);
-        float mr = clr_floor_magic(tr);
-        int ir = clr_magic_int(mr);
-        float fr = tr - (mr - 8388608.f);
+        const float dl = h ? dcur.y : dcur.x;
+        const float r2 = __fadd_rn(__fadd_rn(xx[h], yy), zz);          // same order as the reference
+        const float rf = clr_sqrt_fast(r2);
+        const float tr = fminf(rf * idrf, (float)(CLR_NA - 2) + 0.5f);
+        const float mr = clr_floor_magic(tr);
+        const int ir = clr_magic_int(mr);
+        const float fr = tr - (mr - 8388608.f);
         // pops.zb: {z_i, z_i+1 - z_i, b_i, b_i+1 - b_i} of the first population: one 16-byte load per cell
-        float4 tz = __ldg(pops.zb + ir);
+        const float4 tz = __ldg(pops.zb + ir);
         const bool past = rf >= rtabf;
-        float zf = past ? zlastf : fmaf(tz.y, fr, tz.x);
-        float tb = zf * idzf;
-        float tbn = __fadd_rn(__fadd_rn(tb, 12582912.f), -12582912.f);   // nearest integer, conversion-free
-        int ind_z = clr_magic_int(clr_floor_magic(tb)) + 1;              // tb >= 0
-        if (fabsf(tb - tbn) < 1e-4f) {                                   // ~2e-4 of the cells: exact edge decision
-          double redshift = clr_bg_z(d, sqrt((double)r2));              // density.c:1166-1168 verbatim
+        const float zf = past ? zlastf : fmaf(tz.y, fr, tz.x);
+        const float tb = zf * idzf;
+        const float tbn = __fadd_rn(__fadd_rn(tb, 12582912.f), -12582912.f);   // nearest integer, conversion-free
+        int ind_z = clr_magic_int(clr_floor_magic(tb)) + 1;            // tb >= 0
+        if (fabsf(tb - tbn) < 1e-4f) {                                 // ~2e-4 of the cells: exact edge decision
+          double redshift = clr_bg_z(d, sqrt((double)r2));            // density.c:1166-1168 verbatim
           ind_z = (int)(redshift * idz) + 1;
         }
         bin2[h] = ((unsigned)ind_z < (unsigned)nz) ? ind_z : -1;
@@ -628,7 +622,7 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
 #pragma unroll
         for (int ip = 0; ip < kFastPop; ip++) {
           bm2[h][ip] = 0.f;
-          if (ip < npop && bin2[h] >= 0) {          // box corners beyond z(L/2): coherent skip
+          if (ip < npop) {
             float bi;
             if (ip == 0) bi = past ? 1.f : fmaf(tz.w, fr, tz.z);
             else { float2 t = __ldg(pops.bt[ip] + ir); bi = past ? 1.f : fmaf(t.y, fr, t.x); }
@@ -636,27 +630,29 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
           }
         }
       }
-      // phase B: both cells in the slot's current bin (the common case) -> plain register sums
-      if (bin2[0] == curbin[q] && bin2[1] == curbin[q]) {
-        cnt[q] += 2;
-        zs[q] += zf2[0] + zf2[1];
+      if (bin2[0] == curbin && bin2[1] == curbin) {                    // the common case: plain register sums
+        cnt += 2;
+        zs += zf2[0] + zf2[1];
 #pragma unroll
-        for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) bs[q][ip] += bm2[0][ip] + bm2[1][ip];
+        for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) bs[ip] += bm2[0][ip] + bm2[1][ip];
       } else {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          if (bin2[h] != curbin[q]) { flush(q); curbin[q] = bin2[h]; }
-          cnt[q]++;
-          zs[q] += zf2[h];
+          if (bin2[h] != curbin) { flush(); curbin = bin2[h]; }
+          cnt++;
+          zs += zf2[h];
 #pragma unroll
-          for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) bs[q][ip] += bm2[h][ip];
+          for (int ip = 0; ip < kFastPop; ip++) if (ip < npop) bs[ip] += bm2[h][ip];
         }
       }
-      if (cnt[q] >= 4096) flush(q);      // keep the fp32 partial sums short
+      if (cnt >= 4096) flush();          // keep the fp32 partial sums short
+      if (++iy == d.n) {
+        iy = 0; iz++;
+        if (row + 1 < row1) { const float z0 = __ldg(d.cf[2] + iz + d.iz0_here); zz = __fmul_rn(z0, z0); }
+      }
     }
+    flush();
   }
-#pragma unroll
-  for (int q = 0; q < NQ; q++) flush(q);
   __syncthreads();
   for (int i = threadIdx.x; i < nz; i += blockDim.x) {
     if (s_n[i]) {
@@ -844,7 +840,11 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
       float4 *tab4 = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(tab + (size_t)(kFastPop + 1) * CLR_NA) + 15) & ~(uintptr_t)15);
       lerp_table2_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, npop ? d_bz[0] : nullptr, tab4, CLR_NA);
       pf.zb = tab4;
-      int grid = grid_for(c, n_cells / kRun, 8);   // 8 cells per thread and iteration
+      // CTAs side by side along x (8 strips of 64 cells each) x row ranges; 8 resident CTAs per SM
+      const int groups = ((c->dev.n + 63) / 64 + 7) / 8;
+      long long n_rows = (long long)c->dev.nz_here * c->dev.n;
+      long long ranges = std::min<long long>(n_rows, std::max<long long>(1, (long long)c->sm_count * 8 / groups));
+      int grid = (int)(ranges * groups);
       switch (npop) {
         case 0: norm_hist_fast_kernel<0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
         case 1: norm_hist_fast_kernel<1><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
