@@ -190,7 +190,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-grid", type=int, default=1024)
-    ap.add_argument("--ref-n-grid", type=int, default=256, help="bounded sample size of the CPU baseline")
+    ap.add_argument("--ref-n-grid", type=int, default=512, help="bounded sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -11,7 +11,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kCellsPerThread = 4;
 constexpr int kChunk = kThreads * kCellsPerThread;   // cells per CTA chunk (flat, x fastest)
-constexpr int kSub = 8;                              // chunks a Poisson CTA screens before it runs the exact path
+constexpr int kSub = 8; // chunks a Poisson CTA screens before it runs the exact path
 
 // ---- gsl_ran_poisson (GSL randist/poisson.c) and its helpers, restated for the device ---------
 __device__ __noinline__ double dev_gamma_large(ClrStream &s, double a)
