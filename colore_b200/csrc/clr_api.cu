@@ -16,6 +16,28 @@ void clr_set_error(const char *fmt, ...)
   va_end(ap);
 }
 
+namespace {
+__global__ void copy_small_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int n_words)
+{
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+int clr_read_small(clr_ctx *c, void *host_dst, const void *dev_src, size_t bytes)
+{
+  CLR_CHECK(bytes % 4 == 0, "clr_read_small: %zu bytes", bytes);
+  for (size_t off = 0; off < bytes; off += CLR_SMALL_BYTES) {
+    size_t nb = bytes - off < CLR_SMALL_BYTES ? bytes - off : CLR_SMALL_BYTES;
+    copy_small_kernel<<<1, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(static_cast<const char *>(dev_src) + off),
+                                                 static_cast<uint32_t *>(c->d_small), (int)(nb / 4));
+    CLR_CUDA(cudaGetLastError());
+    c->launches++;
+    CLR_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(static_cast<char *>(host_dst) + off, c->h_small, nb);
+  }
+  return 0;
+}
+
 extern "C" {
 
 int clr_version(void) { return 100; }
@@ -50,6 +72,9 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   CLR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CLR_CUDA(cudaEventCreateWithFlags(&c->ev_srcs_ready, cudaEventDisableTiming));
   CLR_CUDA(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
+  for (int b = 0; b < 2; b++) CLR_CUDA(cudaEventCreateWithFlags(&c->ev_buf_free[b], cudaEventDisableTiming));
+  CLR_CUDA(cudaHostAlloc(&c->h_small, CLR_SMALL_BYTES, cudaHostAllocMapped));
+  CLR_CUDA(cudaHostGetDevicePointer(&c->d_small, c->h_small, 0));
   CLR_CUDA(cudaEventCreate(&c->evp0)); CLR_CUDA(cudaEventCreate(&c->evp1));
   // host copies of the tables
   copy_tab(c->h_logk, p->logkarr, p->numk); copy_tab(c->h_pk, p->pkarr, p->numk);
@@ -137,7 +162,7 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
 static void free_pop(clr_ctx::Pop &P)
 {
   cudaFree(P.d_a); cudaFree(P.d_b); cudaFree(P.d_norm); cudaFree(P.d_counts); cudaFree(P.d_bound);
-  cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs);
+  cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs); cudaFree(P.d_srcs_alt);
 }
 
 int clr_destroy(clr_ctx *c)
@@ -154,8 +179,10 @@ int clr_destroy(clr_ctx *c)
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_srcs_ready); cudaEventDestroy(c->ev_copy_done);
+  for (int b = 0; b < 2; b++) cudaEventDestroy(c->ev_buf_free[b]);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
+  if (c->h_small) cudaFreeHost(c->h_small);
   delete c;
   return 0;
 }
@@ -165,6 +192,7 @@ int clr_synchronize(clr_ctx *c)
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->copy_stream));
   c->copy_pending = false;
+  c->buf_busy[0] = c->buf_busy[1] = false;
   return 0;
 }
 long long clr_launch_count(clr_ctx *c) { return c->launches; }
@@ -261,8 +289,7 @@ int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *o
   if (clr_halo_update(c)) return 1;
   if (clr_comm_allreduce_f64(c, c->d_scratch, 2)) return 1;            // fourier.c:69-70
   double mom[2];
-  CLR_CUDA(cudaMemcpyAsync(mom, c->d_scratch, sizeof(mom), cudaMemcpyDeviceToHost, c->stream));
-  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  if (clr_read_small(c, mom, c->d_scratch, sizeof(mom))) return 1;
   finish_moments(c, mom, out2);
   return 0;
 }
@@ -437,6 +464,8 @@ int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
     CLR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_srcs_ready, 0));
     CLR_CUDA(cudaMemcpyAsync(srcs9, P.d_srcs, (size_t)P.nsrc * 9 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
     CLR_CUDA(cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    CLR_CUDA(cudaEventRecord(c->ev_buf_free[P.srcs_buf], c->copy_stream));
+    c->buf_busy[P.srcs_buf] = true;
     c->copy_pending = true;
     return 0;
   }

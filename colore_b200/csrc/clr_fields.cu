@@ -6,6 +6,7 @@
 // reference's scalar C code (no fused multiply-add contraction).
 #include "clr_internal.cuh"
 #include <algorithm>
+#include <string.h>
 
 namespace {
 
@@ -787,8 +788,7 @@ int clr_fields_scale_moments(clr_ctx *c, double *out2)
     CLR_CUDA(cudaGetLastError());
   }
   if (clr_comm_allreduce_f64(c, c->d_scratch, 2)) return 1;
-  CLR_CUDA(cudaMemcpyAsync(out2, c->d_scratch, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  if (clr_read_small(c, out2, c->d_scratch, 2 * sizeof(double))) return 1;
   return 0;
 }
 
@@ -859,10 +859,14 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
   // density.c:1262-1269: histograms summed over the slabs
   if (clr_comm_allreduce_u64(c, g_n, nz)) return 1;
   if (clr_comm_allreduce_f64(c, g_z, (size_t)nz * (1 + npop))) return 1;
-  CLR_CUDA(cudaMemcpyAsync(h_n, g_n, nz * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CLR_CUDA(cudaMemcpyAsync(h_z, g_z, nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (npop) CLR_CUDA(cudaMemcpyAsync(h_b, g_b, (size_t)npop * nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  {
+    // g_n, g_z, g_b are contiguous in the scratch buffer: one small read-back
+    std::vector<double> tmp(nd);
+    if (clr_read_small(c, tmp.data(), c->d_scratch, nd * sizeof(double))) return 1;
+    memcpy(h_n, tmp.data(), nz * sizeof(unsigned long long));
+    memcpy(h_z, tmp.data() + nz, nz * sizeof(double));
+    if (npop) memcpy(h_b, tmp.data() + 2 * nz, (size_t)npop * nz * sizeof(double));
+  }
   return 0;
 }
 

@@ -76,6 +76,9 @@ struct clr_ctx {
     float *d_bound = nullptr;       // fp32 screening table of the Poisson pass (4 floats per r-bin)
     long long nsrc = 0;
     float *d_pos = nullptr; int32_t *d_ipix = nullptr; float *d_srcs = nullptr;
+    // async_results: second Src buffer, so that the read-back of run s may take the whole of run s+1
+    float *d_srcs_alt = nullptr;
+    int srcs_buf = 0;               // which of the two buffers d_srcs currently is
     size_t cap_src = 0;
   } srcs[CLR_NPOP_MAX], imap[CLR_NPOP_MAX];
   double z0_norm = 0, zf_norm = 0;
@@ -103,6 +106,11 @@ struct clr_ctx {
   // option async_results: catalogue read-back on its own stream, overlapping the next run
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_srcs_ready = nullptr, ev_copy_done = nullptr;
+  // small results (moments, histograms, counters) reach the host through MAPPED pinned memory written by a tiny
+  // kernel: a cudaMemcpy D2H on the main stream would queue behind the catalogue read-back on the copy engine
+  void *h_small = nullptr, *d_small = nullptr;
+  cudaEvent_t ev_buf_free[2] = {nullptr, nullptr};   // last read-back of Src buffer 0 / 1 has finished
+  bool buf_busy[2] = {false, false};
   int async_results = 0;
   bool copy_pending = false;
   struct Pending { std::string name; int slot; int nl; };
@@ -177,6 +185,9 @@ int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n);
 int clr_comm_allreduce_i32(clr_ctx *c, int *dbuf, size_t n);
 int clr_comm_halo(clr_ctx *c);
 int clr_ensure_scratch(clr_ctx *c, size_t bytes);
+#define CLR_SMALL_BYTES 65536
+// host_dst <- dev_src (bytes a multiple of 4; meant for a few KB), ordered after the work queued on c->stream; blocks
+int clr_read_small(clr_ctx *c, void *host_dst, const void *dev_src, size_t bytes);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -5,6 +5,7 @@
 // Compiled with -fmad=false: counts and pixel indices must be bit-exact against the CPU oracle
 // for identical uniform draws, so double arithmetic must round like scalar C code.
 #include "clr_internal.cuh"
+#include <utility>
 
 namespace {
 
@@ -611,24 +612,33 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
     CLR_CUDA(cudaGetLastError());
   }
   long long total = 0;
-  CLR_CUDA(cudaMemcpyAsync(&total, d_offs + n_chunks, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  if (clr_read_small(c, &total, d_offs + n_chunks, sizeof(long long))) return 1;
   P.nsrc = total;
-  if (c->copy_pending) {   // an asynchronous catalogue read-back may still be reading d_srcs
-    if ((size_t)total > P.cap_src) CLR_CUDA(cudaStreamSynchronize(c->copy_stream));
-    else CLR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
-    c->copy_pending = false;
-  }
   if ((size_t)total > P.cap_src) {
+    if (c->copy_pending) CLR_CUDA(cudaStreamSynchronize(c->copy_stream));   // a read-back may still use the old buffers
+    c->copy_pending = false; c->buf_busy[0] = c->buf_busy[1] = false;
     if (P.d_pos) cudaFree(P.d_pos);
     if (P.d_ipix) cudaFree(P.d_ipix);
     if (P.d_srcs) cudaFree(P.d_srcs);
-    P.d_pos = nullptr; P.d_ipix = nullptr; P.d_srcs = nullptr;
+    if (P.d_srcs_alt) cudaFree(P.d_srcs_alt);
+    P.d_pos = nullptr; P.d_ipix = nullptr; P.d_srcs = nullptr; P.d_srcs_alt = nullptr;
     size_t cap = (size_t)total + (size_t)total / 16 + 1024;
     CLR_CUDA(cudaMalloc(&P.d_pos, cap * 4 * sizeof(float)));
     CLR_CUDA(cudaMalloc(&P.d_ipix, cap * sizeof(int32_t)));
     CLR_CUDA(cudaMalloc(&P.d_srcs, cap * 9 * sizeof(float)));
     P.cap_src = cap;
+  }
+  if (c->async_results) {
+    // two Src buffers: this run fills the one the LAST read-back did not use, so that copy may take the whole
+    // of this run; only the read-back of two runs ago (same buffer) has to be finished, checked on the device
+    if (!P.d_srcs_alt) CLR_CUDA(cudaMalloc(&P.d_srcs_alt, P.cap_src * 9 * sizeof(float)));
+    std::swap(P.d_srcs, P.d_srcs_alt);
+    P.srcs_buf ^= 1;
+    if (c->buf_busy[P.srcs_buf]) CLR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_buf_free[P.srcs_buf], 0));
+    c->buf_busy[P.srcs_buf] = false;
+  } else if (c->copy_pending) {
+    CLR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+    c->copy_pending = false;
   }
   if (total > 0) {
     // the 9-float Src buffer is not written until clr_srcs_local: borrow it for the source references
