@@ -303,6 +303,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "keep_particles")) { c->keep_particles = value; return 0; }
   if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
+  if (!strcmp(name, "p2p_tiled")) { c->p2p_tiled = value; return 0; }
   clr_set_error("unknown option %s", name);
   return 1;
 }

@@ -297,6 +297,8 @@ __device__ __forceinline__ void fft_lines(float2 (&v)[FftPlan<M>::E], float2 *s,
 struct LineAddr {
   long long outer_stride, hi_stride, lo_stride;
   int lo_bits;
+  // tile-major staging layout of the distributed c2r (see c2r_3d_dist): [source][z-pass tile][z_local][T]
+  int tiled = 0, tile_rows = 0;
   __device__ __forceinline__ long long off(int e) const
   { return (long long)(e >> lo_bits) * hi_stride + (long long)(e & ((1 << lo_bits) - 1)) * lo_stride; }
 };
@@ -323,6 +325,19 @@ struct StridedTile {
     long long io, oo;
     if (!locate(tile, io, oo)) return;
     const int mask = (1 << aout.lo_bits) - 1;
+    if (aout.tiled) {
+      // tile-major: the T lines of this tile at plane z_local sit next to those at z_local+1, so the two (or four)
+      // consecutive points a warp stores per instruction form one 256-byte run on the destination GPU, and a
+      // whole (tile, destination) block is contiguous -- NVLink writes of 64/128-byte pieces are what limits
+      // the natural layout
+      const long long tbase = (tile - (tile / tiles_per_outer) * tiles_per_outer) * (long long)(mask + 1) * T + l;
+#pragma unroll
+      for (int i = 0; i < P::E; i++) {
+        const int e = j + i * P::TPL;
+        peers.p[e >> aout.lo_bits][tbase + (long long)(e & mask) * T] = v[i];
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < P::E; i++) {
       const int e = j + i * P::TPL;
@@ -343,6 +358,21 @@ struct StridedTile {
     long long io, oo;
     bool ok = locate(tile, io, oo);
     const float2 *bin = ok ? gin + io : gin;
+    if (ain.tiled) {
+      // y pass of the distributed c2r reading the tile-major staging buffer: element e = ky lives in source block
+      // e >> lo_bits, at z-pass position inner = ky_local * nc + kx, i.e. tile inner / T, row z_local, slot inner % T
+      const long long outer = tile / tiles_per_outer;                   // z_local
+      const int kx = (int)(tile - outer * tiles_per_outer) * T + l;
+      const int mask = (1 << ain.lo_bits) - 1;
+#pragma unroll
+      for (int i = 0; i < P::E; i++) {
+        const int e = j + i * P::TPL;
+        const long long inner = (long long)(e & mask) * ain.lo_stride + kx;
+        const long long a = (long long)(e >> ain.lo_bits) * ain.hi_stride + ((inner / T) * ain.tile_rows + outer) * T + (inner % T);
+        cp_async8(s + sidx<M, true, T>(e, l), gin + (ok ? a : 0), ok);
+      }
+      return;
+    }
     if (ain.lo_bits == 31) {             // single-level stride: step a pointer instead of 64-bit multiplies
       const float2 *p = bin + (ok ? (long long)j * ain.lo_stride : 0);
       const long long step = ok ? (long long)P::TPL * ain.lo_stride : 0;
@@ -630,10 +660,35 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
   const long long nc = N / 2 + 1;
   const int P = c->nranks, nzl = N / P, nyl = N / P;
   float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
-  if (c->p2p && c->p2p_enabled) {
+  // tile-major staging pays when the remote runs of the natural layout are short (T = 8 lines = 64 bytes at
+  // n_grid = 2048: 346 -> 496 GB/s per direction on 8 GPUs, step 46.2 -> 42.5 ms) and most of the output leaves the
+  // GPU; with 128-byte runs (n_grid = 1024) or 2 GPUs the gather it forces on the y pass costs more than it saves
+  const bool tiled = c->p2p_tiled < 0 ? (c->nranks >= 4 && Cfg<N>::T_STRIDED <= 8) : c->p2p_tiled != 0;
+  if (c->p2p && c->p2p_enabled && tiled) {
     // z pass with the slab transpose fused into its stores: plane z of the result belongs to rank z / nzl and is
     // written straight into that rank's staging buffer over NVLink (block = source rank), tile by tile while
     // the next tile is being transformed. Barriers: nobody still reads its staging buffer / everything arrived.
+    constexpr int TT = Cfg<N>::T_STRIDED;
+    const long long blk_t = (long long)nzl * TT * ((nyl * nc + TT - 1) / TT);     // tile-major block of one source
+    { StageScope sc(c, "fft_z", 1);
+      if (clr_comm_barrier(c)) return 1;
+      PeerPtrs pp = peer_blocks(c, (size_t)blk_t);
+      LineAddr ain{0, 0, (long long)nyl * nc, 31};
+      LineAddr aout{0, 0, (long long)nyl * nc, ilog2_host(nzl)};
+      aout.tiled = 1;
+      if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
+      if (clr_comm_barrier(c)) return 1;
+      c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1); }
+    { StageScope sc2(c, "fft_y", 1);
+      LineAddr yin{0, blk_t, nc, ilog2_host(nyl)};
+      yin.tiled = 1; yin.tile_rows = nzl;
+      LineAddr yout{(long long)N * nc, 0, nc, 31};
+      if (run_strided2<N, +1>(c, stage, g, yin, yout, nzl, (int)nc)) return 1; }
+    StageScope sc3(c, "fft_x", 1);
+    if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)nzl * N, (int)nc, norm, mom);
+    return run_c2r_x<N / 2, false>(c, g, (long long)nzl * N, (int)nc, norm, nullptr);
+  } else if (c->p2p && c->p2p_enabled) {
+    // same fusion, natural staging layout [source][z_local][ky_in_source][kx]
     StageScope sc(c, "fft_z", 1);
     if (clr_comm_barrier(c)) return 1;
     PeerPtrs pp = peer_blocks(c, (size_t)nzl * nyl * nc);

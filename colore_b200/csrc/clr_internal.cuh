@@ -91,6 +91,7 @@ struct clr_ctx {
   float *peer_stage[CLR_MAX_PEERS] = {nullptr};
   bool p2p = false;
   int p2p_enabled = 1;              // option "p2p_fused"
+  int p2p_tiled = -1;               // option "p2p_tiled": tile-major staging layout of the fused c2r (-1: auto)
   int *d_barrier = nullptr;
   double a2a_bytes = 0;             // bytes this rank has sent through the FFT all-to-all
   // bookkeeping

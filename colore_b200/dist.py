@@ -41,6 +41,8 @@ def init_comm(par, rank: int, nranks: int):
     import os
     if os.environ.get("COLORE_B200_P2P", "1") == "0":      # force the NCCL all-to-all (comparison runs)
         par.set_option("p2p_fused", 0)
+    if os.environ.get("COLORE_B200_P2P_TILED"):            # 0 / 1: force the staging layout (comparison runs)
+        par.set_option("p2p_tiled", int(os.environ["COLORE_B200_P2P_TILED"]))
 
 
 def transpose_mode(par) -> str:
