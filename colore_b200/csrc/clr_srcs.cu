@@ -416,13 +416,19 @@ expand_kernel(const int32_t *__restrict__ counts, const long long *__restrict__ 
     for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
-    int woff = 0;
-    for (int k = 0; k < w; k++) woff += wsum[k];
+    // exclusive prefix of the 8 warp sums: every warp scans them redundantly with three shuffles
+    int ws = lane < kThreads / 32 ? wsum[lane] : 0, wincl = ws;
+#pragma unroll
+    for (int o = 1; o < kThreads / 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, wincl, o); if (lane >= o) wincl += v; }
+    const int woff = __shfl_sync(0xffffffffu, wincl - ws, w);
     long long off = base + woff + incl - tsum;
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kCellsPerThread; q++)
-      for (int ip = 0; ip < c[q]; ip++) src_ref[off++] = ((unsigned long long)(i0 + q) << 24) | (unsigned)ip;
+    // one loop over the thread's sources (usually 0 or 1) instead of one data-dependent loop per cell
+    for (int k = 0; k < tsum; k++) {
+      int q = 0, ip = k;
+      if (ip >= c[0]) { ip -= c[0]; q = 1; if (ip >= c[1]) { ip -= c[1]; q = 2; if (ip >= c[2]) { ip -= c[2]; q = 3; } } }
+      src_ref[off + k] = ((unsigned long long)(i0 + q) << 24) | (unsigned)ip;
+    }
   }
 }
 

@@ -60,13 +60,35 @@ def kspace_slab(ck_full: np.ndarray, rank: int, nranks: int) -> np.ndarray:
     return np.ascontiguousarray(ck_full[:, rank * nyl:(rank + 1) * nyl, :])
 
 
-def c2r_dist_numpy(kslab: np.ndarray, rank: int, nranks: int, alltoall) -> np.ndarray:
-    """Distributed unnormalised c2r. ``alltoall(list_of_P_blocks) -> list_of_P_blocks``."""
+def tiled_stage_index(inner, z_local, nzl: int, tile: int):
+    """Position of z-pass line ``inner`` (= ky_local*nc + kx) at plane ``z_local`` inside one source block of the
+    TILE-MAJOR staging layout of the fused c2r transpose (clr_fft.cu: store_peer / prefetch, ``tiled``):
+    [z-pass tile][z_local][T], so that the T lines of a tile at consecutive planes are contiguous."""
+    return ((inner // tile) * nzl + z_local) * tile + inner % tile
+
+
+def c2r_dist_numpy(kslab: np.ndarray, rank: int, nranks: int, alltoall, tile: int = 0) -> np.ndarray:
+    """Distributed unnormalised c2r. ``alltoall(list_of_P_blocks) -> list_of_P_blocks``.
+    ``tile`` > 0: the blocks travel in the tile-major staging layout (``tiled_stage_index``)."""
     n, nyl, nc = kslab.shape
     nzl = n // nranks
     a = np.fft.ifft(kslab, axis=0) * n                       # z pass on [kz][ky_local][kx]
     send = [np.ascontiguousarray(a[h * nzl:(h + 1) * nzl]) for h in range(nranks)]   # contiguous z ranges
-    recv = alltoall(send)                                     # staging [source][z_local][ky_in_source][kx]
+    if tile:
+        n_inner = nyl * nc
+        blk = nzl * tile * ((n_inner + tile - 1) // tile)
+        zz, ii = np.meshgrid(np.arange(nzl), np.arange(n_inner), indexing="ij")
+        pos = tiled_stage_index(ii, zz, nzl, tile)
+        packed = []
+        for b in send:                                        # what the z pass stores on the destination
+            t = np.zeros(blk, b.dtype)
+            t[pos.ravel()] = b.reshape(nzl, n_inner).ravel()
+            packed.append(t)
+        got = alltoall(packed)
+        # what the y pass gathers: element (z_local, ky = src*nyl + ky_l, kx) from block src
+        recv = [g[pos.ravel()].reshape(nzl, nyl, nc) for g in got]
+    else:
+        recv = alltoall(send)                                 # staging [source][z_local][ky_in_source][kx]
     stage = np.stack(recv, axis=0)
     # y pass: element e of the line = stage[e // nyl, z_local, e % nyl, kx]  (two-level stride)
     lines = stage.transpose(1, 0, 2, 3).reshape(nzl, n, nc)
@@ -85,3 +107,34 @@ def r2c_dist_numpy(rslab: np.ndarray, rank: int, nranks: int, alltoall) -> np.nd
     recv = alltoall(send)                                     # block h = z planes of rank h, my ky
     full_z = np.concatenate(recv, axis=0)                     # [kz][ky_local][kx]
     return np.fft.fft(full_z, axis=0)
+
+
+# ---- numpy restatement of the LPT particle routing (test support) ----------------------------------
+
+def lpt_planes_numpy(z: np.ndarray, interp: int, n: int, l_box: float) -> np.ndarray:
+    """Global z planes touched by the NGP / CIC / TSC deposit of particles at height ``z`` (float32), as
+    clr_lpt.cu:lpt_planes computes them (density.c:37-188): array [len(z), 1|2|3], wrapped into [0, n)."""
+    z = np.asarray(z, np.float32)
+    i_agrid = np.float32(n) / np.float32(l_box)
+    if interp == 0:
+        i0 = (z * i_agrid).astype(np.float64) + 0.5
+        pl = np.floor(i0).astype(np.int64)[:, None]
+    elif interp == 1:
+        i0 = np.floor(z * i_agrid).astype(np.int64)
+        pl = np.stack([i0, i0 + 1], axis=1)
+    else:
+        c0 = np.floor(((z * i_agrid).astype(np.float64) + 0.5).astype(np.float32)).astype(np.int64)
+        pl = np.stack([c0 - 1, c0, c0 + 1], axis=1)
+    return np.mod(pl, n)
+
+
+def lpt_destinations_numpy(z: np.ndarray, interp: int, n: int, l_box: float, nranks: int, me: int) -> np.ndarray:
+    """Boolean [len(z), nranks]: rank h needs the particle (share_particles, density.c:191-374, restated as in
+    clr_lpt.cu:lpt_route_kernel): h owns one of the touched planes and h != me (own particles are deposited in place)."""
+    nzl = n // nranks
+    owner = lpt_planes_numpy(z, interp, n, l_box) // nzl
+    need = np.zeros((len(z), nranks), bool)
+    for k in range(owner.shape[1]):
+        need[np.arange(len(z)), owner[:, k]] = True
+    need[:, me] = False
+    return need

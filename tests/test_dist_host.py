@@ -52,6 +52,9 @@ def _worker(rank, world, port, n, errs):
         got = c2r_dist_numpy(kspace_slab(ck, rank, world), rank, world, _alltoall)
         ref = np.fft.irfftn(ck, s=(n, n, n), axes=(0, 1, 2)) * n ** 3
         e1 = np.abs(got - ref[iz0:iz0 + nzl]).max() / np.abs(ref).max()
+        # the same exchange through the tile-major staging layout of the fused transpose (ragged last tile: nc odd)
+        got_t = c2r_dist_numpy(kspace_slab(ck, rank, world), rank, world, _alltoall, tile=8)
+        e1 = max(e1, np.abs(got_t - got).max() / np.abs(ref).max())
         # r2c: real z slab -> y slab of the spectrum
         x = rng.standard_normal((n, n, n))
         gotk = r2c_dist_numpy(x[iz0:iz0 + nzl], rank, world, _alltoall)
@@ -75,6 +78,46 @@ def test_distributed_fft_bookkeeping_gloo(n):
         mp.spawn(_worker, args=(world, _free_port(), n, errs), nprocs=world, join=True)
         assert len(errs) == world
         assert max(errs.values()) < 1e-12
+
+
+def test_tiled_stage_index_is_a_bijection():
+    """tile-major staging layout (clr_fft.cu store_peer / prefetch): every (line, plane) gets its own slot, the T
+    lines of a tile at consecutive planes are contiguous, and a whole (tile, destination) block is one run."""
+    from colore_b200.dist import tiled_stage_index
+    nzl, nyl, nc, tile = 4, 8, 17, 8
+    n_inner = nyl * nc
+    zz, ii = np.meshgrid(np.arange(nzl), np.arange(n_inner), indexing="ij")
+    pos = tiled_stage_index(ii, zz, nzl, tile)
+    assert len(np.unique(pos)) == pos.size and pos.max() < nzl * tile * ((n_inner + tile - 1) // tile)
+    assert np.all(np.diff(pos[0, :tile]) == 1)                       # lines of one tile are adjacent
+    assert tiled_stage_index(0, 1, nzl, tile) - tiled_stage_index(0, 0, nzl, tile) == tile   # next plane follows
+    assert tiled_stage_index(tile, 0, nzl, tile) == nzl * tile       # next tile starts after all planes
+
+
+@pytest.mark.parametrize("interp", [0, 1, 2])
+def test_lpt_routing_covers_every_plane_once(interp):
+    """Particle exchange bookkeeping of the multi-GPU LPT: with every rank depositing its own particles plus the
+    ones routed to it (each only into planes it owns), every (particle, plane) pair is deposited exactly once."""
+    from colore_b200.dist import lpt_destinations_numpy, lpt_planes_numpy
+    n, l_box, P = 32, 100.0, 4
+    rng = np.random.default_rng(5)
+    nzl = n // P
+    total = np.zeros(n)
+    ref = np.zeros(n)
+    for me in range(P):
+        # particles born in slab `me`, displaced by up to ~1.5 slabs (periodic wrap like density.c:875-876)
+        z = (rng.uniform(me * nzl, (me + 1) * nzl, 500) + rng.normal(0, 0.6 * nzl, 500)) * l_box / n
+        z = np.mod(z, l_box).astype(np.float32)
+        z[z >= np.float32(l_box)] = 0
+        planes = lpt_planes_numpy(z, interp, n, l_box)
+        np.add.at(ref, planes.ravel(), 1)
+        need = lpt_destinations_numpy(z, interp, n, l_box, P, me)
+        for h in range(P):
+            sel = np.ones(len(z), bool) if h == me else need[:, h]      # own particles stay, routed ones arrive
+            pl = planes[sel]
+            mine = (pl // nzl) == h                                     # the deposit's slab check
+            np.add.at(total, pl[mine], 1)
+    assert np.array_equal(total, ref)
 
 
 def test_slab_bounds():
