@@ -85,8 +85,7 @@ extern "C" int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128
   d.ky0 = rank * d.nyl;
   // staging buffer of the FFT all-to-all: one slab
   // (+ padding: the tile-major layout of the fused c2r transpose rounds every source block up to whole tiles)
-  // every k-space row is rounded up to whole tiles of <= 64 lines: at most 63 extra complex per (row, plane)
-  size_t bytes = (size_t)d.pitch * d.n * d.nz_here * sizeof(float) + (size_t)d.n * d.nz_here * 64 * sizeof(float2);
+  size_t bytes = (size_t)d.pitch * d.n * d.nz_here * sizeof(float) + (size_t)nranks * d.nz_here * 64 * sizeof(float2);
   CLR_CUDA(cudaMalloc(&c->d_stage, bytes));
   CLR_CUDA(cudaMalloc(&c->d_barrier, sizeof(int)));
   CLR_CUDA(cudaMemset(c->d_barrier, 0, sizeof(int)));

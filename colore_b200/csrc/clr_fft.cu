@@ -329,8 +329,8 @@ struct StridedTile {
       // tile-major: the T lines of this tile at plane z_local sit next to those at z_local+1, so the two (or four)
       // consecutive points a warp stores per instruction form one 256-byte run on the destination GPU, and a
       // whole (tile, destination) block is contiguous -- NVLink writes of 64/128-byte pieces are what limits
-      // the natural layout. Tiles are numbered (ky_local, kx tile): the z pass runs row by row (n_outer = rows).
-      const long long tbase = tile * (long long)(mask + 1) * T + l;
+      // the natural layout
+      const long long tbase = (tile - (tile / tiles_per_outer) * tiles_per_outer) * (long long)(mask + 1) * T + l;
 #pragma unroll
       for (int i = 0; i < P::E; i++) {
         const int e = j + i * P::TPL;
@@ -360,16 +360,15 @@ struct StridedTile {
     const float2 *bin = ok ? gin + io : gin;
     if (ain.tiled) {
       // y pass of the distributed c2r reading the tile-major staging buffer: element e = ky lives in source block
-      // e >> lo_bits, z-pass tile (ky_local, this kx tile), row z_local, slot l -- the T lanes of a point read one
-      // contiguous piece because the z pass tiles every k-space row separately (same kx tiles as here)
+      // e >> lo_bits, at z-pass position inner = ky_local * nc + kx, i.e. tile inner / T, row z_local, slot inner % T
       const long long outer = tile / tiles_per_outer;                   // z_local
-      const long long tx = tile - outer * tiles_per_outer;              // kx tile
+      const int kx = (int)(tile - outer * tiles_per_outer) * T + l;
       const int mask = (1 << ain.lo_bits) - 1;
 #pragma unroll
       for (int i = 0; i < P::E; i++) {
         const int e = j + i * P::TPL;
-        const long long a = (long long)(e >> ain.lo_bits) * ain.hi_stride +
-                            (((long long)(e & mask) * tiles_per_outer + tx) * ain.tile_rows + outer) * T + l;
+        const long long inner = (long long)(e & mask) * ain.lo_stride + kx;
+        const long long a = (long long)(e >> ain.lo_bits) * ain.hi_stride + ((inner / T) * ain.tile_rows + outer) * T + (inner % T);
         cp_async8(s + sidx<M, true, T>(e, l), gin + (ok ? a : 0), ok);
       }
       return;
@@ -670,16 +669,14 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
     // written straight into that rank's staging buffer over NVLink (block = source rank), tile by tile while
     // the next tile is being transformed. Barriers: nobody still reads its staging buffer / everything arrived.
     constexpr int TT = Cfg<N>::T_STRIDED;
-    const long long tpr = (nc + TT - 1) / TT;                                      // kx tiles per k-space row
-    const long long blk_t = (long long)nzl * TT * nyl * tpr;                       // tile-major block of one source
+    const long long blk_t = (long long)nzl * TT * ((nyl * nc + TT - 1) / TT);     // tile-major block of one source
     { StageScope sc(c, "fft_z", 1);
       if (clr_comm_barrier(c)) return 1;
       PeerPtrs pp = peer_blocks(c, (size_t)blk_t);
-      // row by row (outer = ky_local, inner = kx) so that the z-pass tiles coincide with the y pass's kx tiles
-      LineAddr ain{nc, 0, (long long)nyl * nc, 31};
-      LineAddr aout{0, 0, 0, ilog2_host(nzl)};
+      LineAddr ain{0, 0, (long long)nyl * nc, 31};
+      LineAddr aout{0, 0, (long long)nyl * nc, ilog2_host(nzl)};
       aout.tiled = 1;
-      if (run_strided2<N, +1>(c, g, nullptr, ain, aout, nyl, (int)nc, &pp)) return 1;
+      if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
       if (clr_comm_barrier(c)) return 1;
       c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1); }
     { StageScope sc2(c, "fft_y", 1);

@@ -60,13 +60,11 @@ def kspace_slab(ck_full: np.ndarray, rank: int, nranks: int) -> np.ndarray:
     return np.ascontiguousarray(ck_full[:, rank * nyl:(rank + 1) * nyl, :])
 
 
-def tiled_stage_index(ky_l, kx, z_local, nzl: int, nc: int, tile: int):
-    """Position of k-space line (ky_local, kx) at plane ``z_local`` inside one source block of the TILE-MAJOR
-    staging layout of the fused c2r transpose (clr_fft.cu: store_peer / prefetch, ``tiled``):
-    [ky_local][kx tile][z_local][T] -- every k-space row is cut into its own tiles of T lines (the same kx tiles the
-    y pass works on), and the T lines of a tile at consecutive planes are contiguous."""
-    tpr = (nc + tile - 1) // tile
-    return ((ky_l * tpr + kx // tile) * nzl + z_local) * tile + kx % tile
+def tiled_stage_index(inner, z_local, nzl: int, tile: int):
+    """Position of z-pass line ``inner`` (= ky_local*nc + kx) at plane ``z_local`` inside one source block of the
+    TILE-MAJOR staging layout of the fused c2r transpose (clr_fft.cu: store_peer / prefetch, ``tiled``):
+    [z-pass tile][z_local][T], so that the T lines of a tile at consecutive planes are contiguous."""
+    return ((inner // tile) * nzl + z_local) * tile + inner % tile
 
 
 def c2r_dist_numpy(kslab: np.ndarray, rank: int, nranks: int, alltoall, tile: int = 0) -> np.ndarray:
@@ -77,17 +75,18 @@ def c2r_dist_numpy(kslab: np.ndarray, rank: int, nranks: int, alltoall, tile: in
     a = np.fft.ifft(kslab, axis=0) * n                       # z pass on [kz][ky_local][kx]
     send = [np.ascontiguousarray(a[h * nzl:(h + 1) * nzl]) for h in range(nranks)]   # contiguous z ranges
     if tile:
-        blk = nzl * tile * nyl * ((nc + tile - 1) // tile)
-        zz, yy, xx = np.meshgrid(np.arange(nzl), np.arange(nyl), np.arange(nc), indexing="ij")
-        pos = tiled_stage_index(yy, xx, zz, nzl, nc, tile).ravel()
+        n_inner = nyl * nc
+        blk = nzl * tile * ((n_inner + tile - 1) // tile)
+        zz, ii = np.meshgrid(np.arange(nzl), np.arange(n_inner), indexing="ij")
+        pos = tiled_stage_index(ii, zz, nzl, tile)
         packed = []
         for b in send:                                        # what the z pass stores on the destination
             t = np.zeros(blk, b.dtype)
-            t[pos] = b.ravel()
+            t[pos.ravel()] = b.reshape(nzl, n_inner).ravel()
             packed.append(t)
         got = alltoall(packed)
         # what the y pass gathers: element (z_local, ky = src*nyl + ky_l, kx) from block src
-        recv = [g[pos].reshape(nzl, nyl, nc) for g in got]
+        recv = [g[pos.ravel()].reshape(nzl, nyl, nc) for g in got]
     else:
         recv = alltoall(send)                                 # staging [source][z_local][ky_in_source][kx]
     stage = np.stack(recv, axis=0)

@@ -85,14 +85,13 @@ def test_tiled_stage_index_is_a_bijection():
     lines of a tile at consecutive planes are contiguous, and a whole (tile, destination) block is one run."""
     from colore_b200.dist import tiled_stage_index
     nzl, nyl, nc, tile = 4, 8, 17, 8
-    tpr = (nc + tile - 1) // tile
-    zz, yy, xx = np.meshgrid(np.arange(nzl), np.arange(nyl), np.arange(nc), indexing="ij")
-    pos = tiled_stage_index(yy, xx, zz, nzl, nc, tile)
-    assert len(np.unique(pos)) == pos.size and pos.max() < nzl * tile * nyl * tpr
-    assert np.all(np.diff(pos[0, 0, :tile]) == 1)                    # lines of one tile are adjacent
-    assert tiled_stage_index(0, 0, 1, nzl, nc, tile) - tiled_stage_index(0, 0, 0, nzl, nc, tile) == tile   # next plane follows
-    assert tiled_stage_index(0, tile, 0, nzl, nc, tile) == nzl * tile          # next kx tile starts after all planes
-    assert tiled_stage_index(1, 0, 0, nzl, nc, tile) == tpr * nzl * tile       # rows are tiled separately
+    n_inner = nyl * nc
+    zz, ii = np.meshgrid(np.arange(nzl), np.arange(n_inner), indexing="ij")
+    pos = tiled_stage_index(ii, zz, nzl, tile)
+    assert len(np.unique(pos)) == pos.size and pos.max() < nzl * tile * ((n_inner + tile - 1) // tile)
+    assert np.all(np.diff(pos[0, :tile]) == 1)                       # lines of one tile are adjacent
+    assert tiled_stage_index(0, 1, nzl, tile) - tiled_stage_index(0, 0, nzl, tile) == tile   # next plane follows
+    assert tiled_stage_index(tile, 0, nzl, tile) == nzl * tile       # next tile starts after all planes
 
 
 @pytest.mark.parametrize("interp", [0, 1, 2])
