@@ -840,6 +840,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
       float4 *tab4 = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(tab + (size_t)(kFastPop + 1) * CLR_NA) + 15) & ~(uintptr_t)15);
       lerp_table2_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, npop ? d_bz[0] : nullptr, tab4, CLR_NA);
       pf.zb = tab4;
+      c->launches += 2 + npop;                     // the lerp-table kernels above
       // CTAs side by side along x (8 strips of 64 cells each) x row ranges; 8 resident CTAs per SM
       const int groups = ((c->dev.n + 63) / 64 + 7) / 8;
       long long n_rows = (long long)c->dev.nz_here * c->dev.n;
