@@ -184,6 +184,6 @@ def choose_nside_base(nnodes: int) -> int:
         if npix % nnodes == 0:
             return nside_base
         pernode = npix // nnodes
-        if (pernode + 1.) / pernode < 1.2:
+        if pernode > 0 and (pernode + 1.) / pernode < 1.2:       # C: (0+1.)/0 = inf -> not balanced yet
             return nside_base
         nside_base *= 2
