@@ -1,6 +1,8 @@
+"""Per-call wall times of the end-to-end loop (synchronous vs asynchronous catalogue read-back): shows which host
+call waits when a device-to-host copy queues behind the catalogue copy. python tools/e2e_trace.py"""
 import os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import colore_b200 as cb
 from bench import build_tables, make_config
