@@ -230,6 +230,16 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
         float4 xf4 = __ldg(reinterpret_cast<const float4 *>(d.cf[0] + ix));
         float xf[4] = {xf4.x, xf4.y, xf4.z, xf4.w};
         float yz2 = yf * yf + zf * zf;
+        // box corners (48 % of the cells lie outside the sampled sphere, srcs.c:169): all four cells beyond the
+        // cut -> no random numbers, no screening; neighbouring threads agree, so the branch is coherent
+        {
+          const float r2min = fminf(fminf(xf[0] * xf[0], xf[1] * xf[1]), fminf(xf[2] * xf[2], xf[3] * xf[3])) + yz2;
+          const float rc = sk.rcutf + 0.05f;
+          if (r2min > rc * rc * 1.000001f) {
+            *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
+            continue;
+          }
+        }
         unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
         uint32_t w[4];
         clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
