@@ -501,12 +501,10 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
   }
 }
 
-// Fast variant of the same histogram (default path): every thread walks a run of 8 consecutive cells
-// along x and keeps the sums of its current bin in registers (bins are thick shells, a run almost
-// never crosses an edge); the run totals are merged per warp with one round of shuffles and one
-// shared-memory atomic per (warp, bin). fp32 evaluation of z(r), b(r) and bias_model; the bin index
-// falls back to the exact double expression within 1e-4 bins of an edge, so counts stay exact.
-constexpr int kRun = 8;
+// Fast variant of the same histogram (default path; kernel further down): fp32 evaluation of z(r), b(r) and
+// bias_model with per-lane register sums; the bin index falls back to the exact double expression within
+// 1e-4 bins of an edge, so the counts stay exact. Needs an even row length (float2 loads).
+constexpr int kRun = 2;
 constexpr int kFastPop = 4;
 // lerp tables {f[i], f[i+1]-f[i]} in fp32: entry 0 = z(r), entries 1.. = b(r) per population
 struct NormPopsF { const float2 *zt; const float4 *zb; const float2 *bt[kFastPop]; int npop; };
