@@ -5,6 +5,7 @@
 // Compiled with -fmad=false: counts and pixel indices must be bit-exact against the CPU oracle
 // for identical uniform draws, so double arithmetic must round like scalar C code.
 #include "clr_internal.cuh"
+#include <math.h>
 #include <utility>
 
 namespace {
@@ -164,14 +165,40 @@ __device__ __forceinline__ bool screen_cell(const ScreenK &k, const float4 *__re
   return outside || (inside && u0_hi <= e_lo);               // NaN tables: comparison false -> exact path
 }
 
+// Group screen: ONE bound for the four neighbouring cells a thread owns (they share a Philox block). With
+// dmax = largest delta, [rmin, rmax] = their radii and umax = the largest of their first uniforms, all four are
+// surely empty if umax <= exp(-lambda_hi(dmax)): bias_model is increasing in delta for b >= 0, and for delta < 0 the
+// smallest b gives the largest value, for delta >= 0 the largest b. ~88 % of the groups inside the sphere pass; the
+// rest is re-screened cell by cell on dense warps (phase 1b). Needs b >= 0 over the window, else no proof.
+__device__ __forceinline__ bool screen_group(const ScreenK &k, const float4 *__restrict__ bound_grp, float r2min,
+                                             float r2max, float dmax, uint32_t umax)
+{
+  const float rmin = clr_sqrt_fast(r2min), rmax = clr_sqrt_fast(r2max);
+  const bool inside = rmax < k.rcutf - 0.05f && rmin > 0.05f && rmax < k.rtabf - 1.f;
+  const float4 e = __ldg(bound_grp + clr_magic_int(clr_floor_magic(fminf(rmin * k.idrf, (float)(CLR_NA - 1)))));
+  float bm;
+  if (k.bias_model == 2) {
+    const float ex = clr_ex2_fast(1.4426951f * e.y * dmax * clr_rcp_fast(fmaxf(1.f + dmax, 1e-30f)));
+    bm = dmax < 0.f ? ex : fmaf(e.z, dmax, 1.f);
+  } else if (k.bias_model == 3) bm = fmaxf(dmax < 0.f ? fmaf(e.y, dmax, 1.f) : fmaf(e.z, dmax, 1.f), 0.f);
+  else return false;
+  bm = dmax <= -1.f ? 0.f : bm;
+  const float lam_hi = e.x * bm * 1.001f;
+  const float e_lo = clr_ex2_fast(-1.4426951f * lam_hi) * (1.f - 1e-5f);
+  const float u_hi = (__uint_as_float(0x4B000000u | (umax >> 9)) - 8388607.f) * 1.1920928955078125e-07f;
+  return inside && e.y >= 0.f && u_hi <= e_lo;               // NaN anywhere: comparison false -> not proven
+}
+
 // one entry per r-bin of the NA grid; window [ir-1, ir+2] covers an off-by-one fp32 bin index
-__global__ void poisson_bound_kernel(const ClrDev d, ClrPop pop, float vol, float4 *__restrict__ bound)
+// `up`: how many bins above ir the window reaches (2 for one cell; wider for the 4-cell group table, whose
+// entry is looked up at the SMALLEST radius of the group and must cover the largest one)
+__global__ void poisson_bound_kernel(const ClrDev d, ClrPop pop, float vol, float4 *__restrict__ bound, int up)
 {
   int ir = blockIdx.x * blockDim.x + threadIdx.x;
   if (ir >= CLR_NA) return;
   double a = 0, nm = fmax(fabs(pop.norm_0), fabs(pop.norm_f)), blo = 1e300, bhi = -1e300;
   bool bad = false;
-  for (int k = ir - 1; k <= ir + 2; k++) {
+  for (int k = ir - 1; k <= ir + up; k++) {
     int kk = k < 0 ? 0 : (k > CLR_NA - 1 ? CLR_NA - 1 : k);
     double n = pop.nz[kk], m = pop.norm[kk], b = pop.bz[kk];
     if (!(n == n) || !(m == m) || !(b == b)) bad = true;
@@ -189,7 +216,8 @@ __global__ void poisson_bound_kernel(const ClrDev d, ClrPop pop, float vol, floa
 // (oracle/shim/gsl_shim.c:shim_philox_seek_cell), so one thread screens 4 neighbouring cells per block.
 __global__ void __launch_bounds__(kThreads, 4)
 poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const float4 *__restrict__ bound,
-               uint32_t seed, int ipop, int32_t *__restrict__ counts, int32_t *__restrict__ chunk_tot, long long n_cells)
+               const float4 *__restrict__ bound_grp, uint32_t seed, int ipop, int32_t *__restrict__ counts,
+               int32_t *__restrict__ chunk_tot, long long n_cells)
 {
   const double dx = (double)(d.l_box / d.n);       // float division, as in the reference (srcs.c:147)
   const double cell_vol = dx * dx * dx;
@@ -204,10 +232,11 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
   // need the exact path; phase 2 then runs over a queue long enough to fill every lane of the CTA.
   __shared__ int sub_tot[kSub];
   __shared__ unsigned short q_cell[kSub * kChunk];
-  __shared__ int q_len;
+  __shared__ unsigned short q_grp[kSub * kChunk / 4];
+  __shared__ int q_len, g_len;
   const long long n_chunks = (n_cells + kChunk - 1) / kChunk;
   const long long n_super = (n_chunks + kSub - 1) / kSub;
-  if (threadIdx.x == 0) q_len = 0;
+  if (threadIdx.x == 0) { q_len = 0; g_len = 0; }
   if (threadIdx.x < kSub) sub_tot[threadIdx.x] = 0;
   __syncthreads();
   for (long long sup = blockIdx.x; sup < n_super; sup += gridDim.x) {
@@ -232,8 +261,8 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
         float yz2 = yf * yf + zf * zf;
         // box corners (48 % of the cells lie outside the sampled sphere, srcs.c:169): all four cells beyond the
         // cut -> no random numbers, no screening; neighbouring threads agree, so the branch is coherent
+        const float r2min = fminf(fminf(xf[0] * xf[0], xf[1] * xf[1]), fminf(xf[2] * xf[2], xf[3] * xf[3])) + yz2;
         {
-          const float r2min = fminf(fminf(xf[0] * xf[0], xf[1] * xf[1]), fminf(xf[2] * xf[2], xf[3] * xf[3])) + yz2;
           const float rc = sk.rcutf + 0.05f;
           if (r2min > rc * rc * 1.000001f) {
             *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
@@ -243,17 +272,12 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
         unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
         uint32_t w[4];
         clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
-        unsigned pend = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (!screen_cell(sk, bound, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
         *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
-        if (pend) {
-          int base = atomicAdd(&q_len, __popc(pend));
-#pragma unroll
-          for (int q = 0; q < 4; q++)
-            if (pend >> q & 1) q_cell[base++] = (unsigned short)(lc0 + q);
-        }
+        const float r2max = fmaxf(fmaxf(xf[0] * xf[0], xf[1] * xf[1]), fmaxf(xf[2] * xf[2], xf[3] * xf[3])) + yz2;
+        const float dmax = fmaxf(fmaxf(dl[0], dl[1]), fmaxf(dl[2], dl[3]));
+        const uint32_t umax = max(max(w[0], w[1]), max(w[2], w[3]));
+        if (!screen_group(sk, bound_grp, r2min, r2max, dmax, umax))
+          q_grp[atomicAdd(&g_len, 1)] = (unsigned short)(lc0 >> 2);       // phase 1b looks at the cells one by one
       } else {
         for (int q = 0; q < kCellsPerThread; q++) {
           long long i = i0 + q;
@@ -268,6 +292,36 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
           if (screen_cell(sk, bound, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
           else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)(lc0 + q);
         }
+      }
+    }
+    __syncthreads();
+    // ---- phase 1b (groups the group screen could not clear, ~12 %): the per-cell fp32 screen on dense warps
+    const int ng = g_len;
+    for (int k = threadIdx.x; k < ng; k += kThreads) {
+      const int lc0 = (int)q_grp[k] << 2;
+      const long long i0 = cell0 + lc0;
+      int ix, iy, iz;
+      clr_cell(d, i0, ix, iy, iz);
+      const float *drow = dens + ((long long)iz * d.n + iy) * d.pitch + ix;
+      float2 da = __ldg(reinterpret_cast<const float2 *>(drow));
+      float2 db = __ldg(reinterpret_cast<const float2 *>(drow) + 1);
+      float dl[4] = {da.x, da.y, db.x, db.y};
+      float yf = __ldg(d.cf[1] + iy), zf = __ldg(d.cf[2] + iz + d.iz0_here);
+      float4 xf4 = __ldg(reinterpret_cast<const float4 *>(d.cf[0] + ix));
+      float xf[4] = {xf4.x, xf4.y, xf4.z, xf4.w};
+      float yz2 = yf * yf + zf * zf;
+      unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
+      uint32_t w[4];
+      clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
+      unsigned pend = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (!screen_cell(sk, bound, xf[q] * xf[q] + yz2, dl[q], w[q])) pend |= 1u << q;
+      if (pend) {
+        int base = atomicAdd(&q_len, __popc(pend));
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (pend >> q & 1) q_cell[base++] = (unsigned short)(lc0 + q);
       }
     }
     __syncthreads();
@@ -308,7 +362,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
       if (chunk < n_chunks) chunk_tot[chunk] = sub_tot[threadIdx.x];
       sub_tot[threadIdx.x] = 0;
     }
-    if (threadIdx.x == 0) q_len = 0;
+    if (threadIdx.x == 0) { q_len = 0; g_len = 0; }
     __syncthreads();
   }
 }
@@ -606,18 +660,24 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
   long long *d_offs = reinterpret_cast<long long *>(c->d_scratch);
   int32_t *d_tot = reinterpret_cast<int32_t *>(d_offs + n_chunks + 1);
   ClrPop pop{P.d_a, P.d_b, P.d_norm, P.norm_0, P.norm_f};
-  if (!P.d_bound) CLR_CUDA(cudaMalloc(&P.d_bound, (size_t)CLR_NA * 4 * sizeof(float)));
+  if (!P.d_bound) CLR_CUDA(cudaMalloc(&P.d_bound, (size_t)2 * CLR_NA * 4 * sizeof(float)));   // per-cell + group table
   {
     StageScope sc(c, "srcs_bound", 1);
     const double dx = (double)(c->dev.l_box / c->dev.n);
     poisson_bound_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev, pop, (float)(dx * dx * dx) * 1.0001f,
-                                                                      reinterpret_cast<float4 *>(P.d_bound));
+                                                                      reinterpret_cast<float4 *>(P.d_bound), 2);
+    // group table: looked up at the smallest radius of 4 cells in a row, must reach 3 cells further out
+    const int up = (int)ceil(3. * dx * c->p.glob_idr) + 3;
+    poisson_bound_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev, pop, (float)(dx * dx * dx) * 1.0001f,
+                                                                      reinterpret_cast<float4 *>(P.d_bound) + CLR_NA, up);
+    c->launches++;
     CLR_CUDA(cudaGetLastError());
   }
   {
     StageScope sc(c, "srcs_poisson", 1);
     poisson_kernel<<<grid_for(c, (n_chunks + kSub - 1) / kSub, 8), kThreads, 0, c->stream>>>(
-        c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound), seed, ipop, P.d_counts, d_tot, n_cells);
+        c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound),
+        reinterpret_cast<const float4 *>(P.d_bound) + CLR_NA, seed, ipop, P.d_counts, d_tot, n_cells);
     CLR_CUDA(cudaGetLastError());
   }
   {
