@@ -290,7 +290,6 @@ lognormal_kernel(const ClrDev d, float *__restrict__ dens, double sigma2, int cl
 {
   const int halfn = d.n / 2;                       // float2 per row holding real cells
   const long long n2 = (long long)d.nz_here * d.n * halfn;
-  const float dx = d.l_box / d.n;
   const float idr = (float)d.glob_idr, rtab = (float)d.r_tab_max, dlast = __ldg(d.d1_f + CLR_NA - 1);
   const float hs2 = (float)(0.5 * sigma2);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
@@ -408,7 +407,6 @@ norm_hist_kernel(const ClrDev d, const float *__restrict__ dens, NormPops pops, 
   for (int i = threadIdx.x; i < nz; i += blockDim.x) s_n[i] = 0;
   __syncthreads();
   const long long n_cells = (long long)d.nz_here * d.n * d.n;
-  const float dx = d.l_box / d.n;
   const long long n_iter = (n_cells + (long long)gridDim.x * blockDim.x - 1) / ((long long)gridDim.x * blockDim.x);
   for (long long it = 0; it < n_iter; it++) {
     long long i = (it * gridDim.x + blockIdx.x) * (long long)blockDim.x + threadIdx.x;
