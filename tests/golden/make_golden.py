@@ -32,13 +32,21 @@ CASES = {
     # no smoothing of the potential, different grid size
     "ref_n48_nosmooth": RunConfig(n_grid=48, dens_type=0, nz_amplitude=30.0, smooth_potential=False,
                                   r_smooth=-1.0, seed=5),
+    # the other compile-time bias models of common.h:414-431 (drivers built by `make -C oracle refbm`):
+    # model 1 = pow(1+d,b) (no flag), model 3 = max(1+b d, 0) (-D_BIAS_MODEL_3)
+    "ref_n32_bias1": RunConfig(n_grid=32, dens_type=0, nz_amplitude=60.0, imap_nside=8, imap_nchannels=4, seed=21),
+    "ref_n32_bias3": RunConfig(n_grid=32, dens_type=0, nz_amplitude=60.0, imap_nside=8, imap_nchannels=4, seed=23),
 }
+DRIVER = {"ref_n32_bias1": "ref_driver_bm1", "ref_n32_bias3": "ref_driver_bm3"}
 
 
 def main():
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
-    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "refbm"])
+    only = set(sys.argv[1:])                                   # optional: fixture names to (re)generate
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
+        drv = os.path.join(ROOT, "oracle", "_ref", DRIVER.get(name, "ref_driver"))
         tmp = tempfile.mkdtemp(prefix="golden_")
         try:
             paths = write_inputs(os.path.join(tmp, "in"), cfg)

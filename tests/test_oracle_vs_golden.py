@@ -13,14 +13,19 @@ import pytest
 
 from oracle.oracle import NA, RNG_MT, Oracle, tables_from_dump
 
-CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth", "ref_n32_1lpt_cic", "ref_n32_2lpt_tsc", "ref_n32_2lpt_ngp"]
+CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth", "ref_n32_1lpt_cic", "ref_n32_2lpt_tsc", "ref_n32_2lpt_ngp",
+         "ref_n32_bias1", "ref_n32_bias3"]       # the reference compiled with the other bias models (common.h:414-431)
+
+
+def _bias_model(name):
+    return 1 if "bias1" in name else (3 if "bias3" in name else 2)
 
 
 @pytest.fixture(scope="module", params=CASES)
 def case(request, golden_dir):
     g = dict(np.load(os.path.join(golden_dir, request.param + ".npz")))
     t = tables_from_dump(g)
-    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]), bias_model=_bias_model(request.param))
     return g, t, o
 
 
