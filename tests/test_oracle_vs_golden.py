@@ -127,3 +127,21 @@ def test_table_lookup_edges(case):
     hi = o.pk_linear0(t["logkmax"] + 1.0)
     assert np.isclose(hi, t["pk_pk"][-1] * 1e-3)
     assert len(t["z"]) == NA
+
+
+def test_shim_poisson_moments():
+    """gsl_ran_poisson is third-party arithmetic the repo has to restate (oracle/shim/gsl_shim.c):
+    Knuth's product for mu <= 10, the gamma / binomial (BTPE) reduction above. No reference vectors exist for it,
+    so its distribution is checked: mean and variance of 4000 draws at each mu within 5 sigma of mu."""
+    import ctypes as C
+    from oracle.oracle import RNG_PHILOX, build
+    lib = C.CDLL(build())
+    lib.orc_poisson_from_stream.restype = C.c_int
+    lib.orc_poisson_from_stream.argtypes = [C.c_int, C.c_ulong, C.c_uint, C.c_ulonglong, C.c_double]
+    n = 4000
+    for mu in (0.03, 0.7, 9.5, 10.5, 37.0, 400.0, 12345.0):
+        k = np.array([lib.orc_poisson_from_stream(RNG_PHILOX, 77, 3, i, mu) for i in range(n)], np.float64)
+        assert k.min() >= 0
+        assert abs(k.mean() - mu) < 5 * np.sqrt(mu / n), (mu, k.mean())
+        # var of the sample variance of a Poisson: (mu + 2 mu^2 (n/(n-1))) / n  ~  (mu + 2 mu^2) / n
+        assert abs(k.var(ddof=1) - mu) < 5 * np.sqrt((mu + 2 * mu * mu) / n), (mu, k.var(ddof=1))
