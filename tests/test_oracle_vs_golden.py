@@ -145,3 +145,66 @@ def test_shim_poisson_moments():
         assert abs(k.mean() - mu) < 5 * np.sqrt(mu / n), (mu, k.mean())
         # var of the sample variance of a Poisson: (mu + 2 mu^2 (n/(n-1))) / n  ~  (mu + 2 mu^2) / n
         assert abs(k.var(ddof=1) - mu) < 5 * np.sqrt((mu + 2 * mu * mu) / n), (mu, k.var(ddof=1))
+
+
+@pytest.mark.parametrize("n", [16, 48])
+def test_shim_fft_matches_numpy(golden_dir, n):
+    """The reference's FFT is FFTW, which this image does not have: oracle/shim/fftw_shim.c restates the c2r / r2c
+    definition (unnormalised, complex passes over z and y, half-complex x pass last). Checked against an
+    independent implementation (numpy / pocketfft), including a NON-Hermitian spectrum like the one
+    create_grids_fourier fills (fourier.c:325-345): the imaginary parts of the x-DC / x-Nyquist lines are dropped."""
+    g = dict(np.load(os.path.join(golden_dir, "ref_n32_lognormal.npz")))
+    t = tables_from_dump(g)
+    o = Oracle(t, n)
+    rng = np.random.default_rng(n)
+    nc = n // 2 + 1
+    ck = (rng.standard_normal((n, n, nc)) + 1j * rng.standard_normal((n, n, nc))).astype(np.complex64)
+    got = o.c2r(ck.copy())[:, :, :n].astype(np.float64)
+    ref = np.fft.irfftn(ck.astype(np.complex128), s=(n, n, n), axes=(0, 1, 2)) * float(n) ** 3
+    assert np.abs(got - ref).max() < 2e-6 * np.abs(ref).max()
+    x = rng.standard_normal((n, n, n)).astype(np.float32)
+    pad = np.zeros((n, n, 2 * nc), np.float32)
+    pad[:, :, :n] = x
+    gotk = o.r2c(pad).view(np.complex64).reshape(n, n, nc).astype(np.complex128)
+    refk = np.fft.rfftn(x.astype(np.float64), axes=(0, 1, 2))
+    assert np.abs(gotk - refk).max() < 2e-6 * np.abs(refk).max()
+
+
+def test_shim_mt19937_known_answers():
+    """gsl_rng_mt19937 restated in oracle/shim/gsl_shim.c: init_genrand seeding (seed 0 -> 4357), uniform = 32-bit
+    output / 2^32. Known answers: the published MT19937 reference stream (seed 5489 -> 3499211612, 581869302,
+    3890346734, ...; 10000th output 4123659995) and numpy's independent implementation for the run seed."""
+    import ctypes as C
+    from oracle.oracle import build
+    lib = C.CDLL(build())
+    lib.orc_mt19937_fill.argtypes = [C.c_ulong, C.c_long, C.c_void_p]
+
+    def stream(seed, n):
+        out = np.empty(n)
+        lib.orc_mt19937_fill(seed, n, out.ctypes.data_as(C.c_void_p))
+        return (out * 4294967296.0).astype(np.uint64)
+
+    s = stream(5489, 10000)
+    assert list(s[:3]) == [3499211612, 581869302, 3890346734] and s[9999] == 4123659995
+    mt = np.random.MT19937()
+    mt._legacy_seeding(1003)
+    assert np.array_equal(stream(1003, 1000), mt.random_raw(1000))
+    assert np.array_equal(stream(0, 5), stream(4357, 5))            # gsl_rng_set: seed 0 means 4357
+
+
+def test_shim_philox_known_answers():
+    """Philox4x32-10 (Salmon et al. 2011), the counter-based generator of the GPU path: the Random123 known-answer
+    vectors. The CUDA implementation (clr_internal.cuh:clr_philox) is compared with this one in the GPU suite."""
+    import ctypes as C
+    from oracle.oracle import build
+    lib = C.CDLL(build())
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        c = (C.c_uint * 4)(*ctr)
+        k = (C.c_uint * 2)(*key)
+        out = (C.c_uint * 4)()
+        lib.orc_philox(c, k, out)
+        assert tuple(out) == want, [hex(v) for v in out]
