@@ -349,7 +349,7 @@ def main():
 
     # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline and rank == 0:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:      # N=1 only (the other ranks would just wait)
         threads = os.cpu_count() or 1
         try:
             v, st = run_reference_sample(args.ref_n_grid, threads)
