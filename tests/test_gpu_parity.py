@@ -16,7 +16,17 @@ pytestmark = pytest.mark.gpu
 import colore_b200 as cb  # noqa: E402
 from oracle.oracle import RNG_MT, RNG_PHILOX, Oracle, tables_from_dump  # noqa: E402
 
-GOLDEN = ["ref_n32_lognormal", "ref_n32_clip"]
+# The last two fixtures come from the reference compiled with the other bias models (common.h:414-431, see
+# tests/golden/make_golden.py). They were added after the GPU budget of round 1 was spent: the oracle side is pinned
+# bit-exactly on the CPU (tests/test_oracle_vs_golden.py), the CUDA side of bias models 1 and 3 has not run on
+# hardware yet, hence the non-strict xfail (remove it once seen green).
+_UNSEEN = pytest.mark.xfail(reason="bias models 1/3: fixtures added after the round-1 GPU budget was spent", strict=False)
+GOLDEN = ["ref_n32_lognormal", "ref_n32_clip", pytest.param("ref_n32_bias1", marks=_UNSEEN),
+          pytest.param("ref_n32_bias3", marks=_UNSEEN)]
+
+
+def _bias_model(name):
+    return 1 if "bias1" in name else (3 if "bias3" in name else 2)
 
 
 def _load(golden_dir, name):
@@ -33,8 +43,9 @@ def _par(t, **kw):
 @pytest.fixture(scope="module", params=GOLDEN)
 def case(request, golden_dir):
     g, t = _load(golden_dir, request.param)
-    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
-    par = _par(t)
+    bm = _bias_model(request.param)
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]), bias_model=bm)
+    par = _par(t, bias_model=bm)
     yield g, t, o, par
     par.free()
 
