@@ -141,6 +141,21 @@ def run_reference_sample(n_grid: int, threads: int):
     return n_grid ** 3 / (path_ms * 1e-3) / 1e6, stages
 
 
+def scipy_fft_ms(n_grid: int, threads: int):
+    """Two single-precision c2r transforms of the sample size with scipy's pocketfft on all threads: a sanity figure
+    next to the reference's FFT stage, which here runs the oracle shim FFT instead of FFTW."""
+    try:
+        import scipy.fft as sf
+        a = (np.random.default_rng(0).standard_normal((n_grid, n_grid, n_grid // 2 + 1)) + 0j).astype(np.complex64)
+        sf.irfftn(a, s=(n_grid,) * 3, workers=threads)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            sf.irfftn(a, s=(n_grid,) * 3, workers=threads)
+        return (time.perf_counter() - t0) * 1e3
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,7 +184,7 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": cfg_name, "sample_n_grid": n_s},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
-                         "stages_ms": stages},
+                         "stages_ms": stages, "scipy_irfftn_2x_ms": scipy_fft_ms(n_s, threads)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -356,7 +371,7 @@ def main():
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": f"unmodified reference (oracle/_ref/CoLoRe_ref; shim FFT instead of FFTW) at "
                              f"n_grid={args.ref_n_grid}, {threads} OpenMP threads, field->sources stages",
-                   "stages_ms": st}
+                   "stages_ms": st, "scipy_irfftn_2x_ms": scipy_fft_ms(args.ref_n_grid, threads)}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"failed: {e}"[:200]}
 
