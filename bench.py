@@ -277,7 +277,7 @@ def main():
     launches = par.launch_count - l0
     ms_step = ms_total / args.steps
     value = n ** 3 / (ms_step * 1e-3) / 1e6
-    stage_names = ["fill_modes", "fft_z", "fft_a2a", "fft_y", "fft_x", "halo", "lognormal", "norm_hist", "srcs_poisson",
+    stage_names = ["fill_modes", "fill_fft_z", "fft_z", "fft_a2a", "fft_y", "fft_x", "fft_yx", "halo", "lognormal", "norm_hist", "srcs_poisson",
                    "srcs_scan", "srcs_expand", "srcs_place", "srcs_local"]
     stages = {}
     for nm in stage_names:
@@ -294,6 +294,9 @@ def main():
     alg_bytes = {                           # algorithmic bytes per LAUNCH
         "fill_modes": 2 * grid_bytes,                      # two complex grids written (8 B/cell)
         "fft_z": 2 * grid_bytes, "fft_y": 2 * grid_bytes, "fft_x": 2 * grid_bytes,   # 8 B/cell per pass
+        # fused kernels, counted as the stages they replace: fill (8 B/cell) + the z pass of both fields (2 x 8 B/cell);
+        # y pass + x pass of one field (2 x 8 B/cell)
+        "fill_fft_z": 6 * grid_bytes, "fft_yx": 4 * grid_bytes,
         "lognormal": 8.0 * cells, "norm_hist": 4.0 * cells, "srcs_poisson": 8.0 * cells,
         "srcs_expand": 4.0 * cells + 8.0 * nsrc, "srcs_place": 36.0 * nsrc,
     }
@@ -309,8 +312,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes[dom], "ms_per_launch": per_launch_ms}
-    fft_ms = sum(stages[k]["ms_per_step"] for k in ("fft_z", "fft_y", "fft_x") if k in stages)
-    fft_gbs = 2 * 24.0 * cells / (fft_ms * 1e-3) / 1e9 if fft_ms else None        # per GPU
+    # mode fill + both 3-D c2r transforms: 8 + 2 x 24 B/cell (the fill is fused into the z pass on one GPU)
+    fft_ms = sum(stages[k]["ms_per_step"] for k in ("fill_modes", "fill_fft_z", "fft_z", "fft_y", "fft_x", "fft_yx") if k in stages)
+    fft_gbs = (8.0 + 2 * 24.0) * cells / (fft_ms * 1e-3) / 1e9 if fft_ms else None        # per GPU
     nvlink = None
     if world > 1 and cb.dist.transpose_mode(par) == "p2p-fused":
         # the transpose is fused into the z pass: its stores go straight to the destination GPU over NVLink,

@@ -52,16 +52,31 @@ int clr_device_count(void)
 
 static void copy_tab(std::vector<double> &dst, const double *src, size_t n) { dst.assign(src, src + n); }
 
+static int create_impl(clr_ctx *c, const clr_params *p, int device);
+
 int clr_create(const clr_params *p, int device, clr_ctx **out)
 {
   CLR_CHECK(p && out, "clr_create: null argument");
+  *out = nullptr;
   CLR_CHECK(clr_device_count() > device, "clr_create: CUDA device %d not available (no CPU fallback exists)", device);
-  CLR_CHECK(p->n_grid >= 16 && p->n_grid % 4 == 0, "n_grid=%d unsupported (multiple of 4, >=16)", p->n_grid);
+  // the FFT (clr_fft.cu) is a power-of-two Stockham transform: fail here, not at the first transform
+  CLR_CHECK(p->n_grid >= 16 && p->n_grid <= 4096 && (p->n_grid & (p->n_grid - 1)) == 0,
+            "n_grid=%d unsupported: the GPU FFT takes powers of two in [16,4096]", p->n_grid);
   CLR_CHECK(p->nz_here > 0 && p->iz0_here >= 0 && p->iz0_here + p->nz_here <= p->n_grid, "bad slab bounds");
   CLR_CHECK(p->r_arr_r2z && p->z_arr_r2z && p->growth_d_arr && p->growth_v_arr && p->pkarr && p->logkarr,
             "clr_create: missing tables");
   CLR_CUDA(cudaSetDevice(device));
   clr_ctx *c = new clr_ctx();
+  if (create_impl(c, p, device)) {
+    clr_destroy(c);                 // frees whatever the failed construction had allocated
+    return 1;
+  }
+  *out = c;
+  return 0;
+}
+
+static int create_impl(clr_ctx *c, const clr_params *p, int device)
+{
   c->device = device;
   c->p = *p;
   cudaDeviceProp prop;
@@ -108,7 +123,8 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   // grids: allocate_fftw (fourier.c:211-238): dens slab, npot slab + 2 halo planes
   ClrDev &d = c->dev;
   d.n = p->n_grid; d.nc = p->n_grid / 2 + 1; d.nz_here = p->nz_here; d.iz0_here = p->iz0_here;
-  d.pitch = 2 * d.nc;
+  d.ncp = (d.nc + 7) & ~7;
+  d.pitch = 2 * d.ncp;
   d.nyl = d.n; d.ky0 = 0;
   d.log2n = -1;
   for (int b = 0; b < 31; b++) if ((1 << b) == d.n) d.log2n = b;
@@ -152,10 +168,16 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   }
   size_t plane = (size_t)d.pitch * d.n;
   CLR_CUDA(cudaMalloc(&c->d_dens, plane * d.nz_here * sizeof(float)));
-  CLR_CUDA(cudaMalloc(&c->d_npot, plane * (d.nz_here + 2) * sizeof(float)));
+  // potential: slab + 4 halo planes stored behind it: [nz] = plane iz0-1, [nz+1] = plane iz0+nz (slice_left / slice_right,
+  // fourier.c:401-414), [nz+2] = plane iz0-2, [nz+3] = plane iz0+nz+1 (second ring, needed by the CIC velocity stencil of
+  // sources that sit in the first / last plane of a slab, srcs.c:486-504)
+  CLR_CUDA(cudaMalloc(&c->d_npot, plane * (d.nz_here + 4) * sizeof(float)));
+  // the padding columns are never written by the kernels: keep them finite
+  CLR_CUDA(cudaMemsetAsync(c->d_dens, 0, plane * d.nz_here * sizeof(float), c->stream));
+  CLR_CUDA(cudaMemsetAsync(c->d_npot, 0, plane * (d.nz_here + 4) * sizeof(float), c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
   d.slice_left = c->d_npot + plane * d.nz_here;
   d.slice_right = c->d_npot + plane * (d.nz_here + 1);
-  *out = c;
   return 0;
 }
 
@@ -173,7 +195,7 @@ int clr_destroy(clr_ctx *c)
   clr_comm_destroy(c);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
-  cudaFree(c->d_coord_f); cudaFree(c->d_coord_d);
+  cudaFree(c->d_coord_f); cudaFree(c->d_coord_d); cudaFree(c->d_fft_tmp); cudaFree(c->d_fft_sync);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch); cudaFree(c->d_pkt); cudaFree(c->d_sincos);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
@@ -238,21 +260,29 @@ int clr_set_imap(clr_ctx *c, int ipop, const double *tz_arr, const double *bz_ar
 
 static float *grid_ptr(clr_ctx *c, int which) { return which == CLR_GRID_DENS ? c->d_dens : c->d_npot; }
 
+// host side = the reference layout, rows of 2*(n/2+1) floats (fourier.c:46-51); device side = rows of dev.pitch floats
 int clr_grid_put(clr_ctx *c, int which, const float *host)
 {
-  size_t bytes = (size_t)c->dev.pitch * c->dev.n * c->dev.nz_here * sizeof(float);
-  CLR_CUDA(cudaMemcpyAsync(grid_ptr(c, which), host, bytes, cudaMemcpyHostToDevice, c->stream));
+  const size_t hrow = (size_t)2 * c->dev.nc * sizeof(float), drow = (size_t)c->dev.pitch * sizeof(float);
+  CLR_CUDA(cudaMemcpy2DAsync(grid_ptr(c, which), drow, host, hrow, hrow, (size_t)c->dev.n * c->dev.nz_here,
+                             cudaMemcpyHostToDevice, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 int clr_grid_get(clr_ctx *c, int which, float *host)
 {
-  size_t bytes = (size_t)c->dev.pitch * c->dev.n * c->dev.nz_here * sizeof(float);
-  CLR_CUDA(cudaMemcpyAsync(host, grid_ptr(c, which), bytes, cudaMemcpyDeviceToHost, c->stream));
+  const size_t hrow = (size_t)2 * c->dev.nc * sizeof(float), drow = (size_t)c->dev.pitch * sizeof(float);
+  CLR_CUDA(cudaMemcpy2DAsync(host, hrow, grid_ptr(c, which), drow, hrow, (size_t)c->dev.n * c->dev.nz_here,
+                             cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 int clr_grid_device_ptr(clr_ctx *c, int which, void **dptr) { *dptr = grid_ptr(c, which); return 0; }
+int clr_grid_pitch(clr_ctx *c, long long *pitch_floats)
+{
+  *pitch_floats = c->dev.pitch;
+  return 0;
+}
 
 int clr_fill_modes(clr_ctx *c, uint32_t seed) { return clr_fields_fill(c, seed); }
 int clr_fft_c2r(clr_ctx *c, int which) { return clr_fft_c2r_impl(c, grid_ptr(c, which), 1.0, nullptr); }
@@ -280,12 +310,17 @@ int clr_normalize_fields(clr_ctx *c, double *out2)
 
 int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *out2)
 {
-  if (!inject && clr_fields_fill(c, seed)) return 1;
   if (clr_ensure_scratch(c, 4096)) return 1;
   CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
   double norm = pow(sqrt(2 * M_PI) / c->p.l_box, 3);      // fourier.c:389
-  if (clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch)) return 1;   // scaling + moments fused in the x pass
-  if (clr_fft_c2r_impl(c, c->d_npot, norm, nullptr)) return 1;
+  bool ran = false;
+  // own stream on one GPU: mode fill fused into the z pass of both transforms (clr_fft.cu)
+  if (!inject && clr_fft_fill_c2r(c, seed, norm, c->d_scratch, &ran)) return 1;
+  if (!ran) {
+    if (!inject && clr_fields_fill(c, seed)) return 1;
+    if (clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch)) return 1;   // scaling + moments fused in the x pass
+    if (clr_fft_c2r_impl(c, c->d_npot, norm, nullptr)) return 1;
+  }
   if (clr_halo_update(c)) return 1;
   if (clr_comm_allreduce_f64(c, c->d_scratch, 2)) return 1;            // fourier.c:69-70
   double mom[2];
@@ -302,6 +337,8 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "lpt_interp_type")) { c->lpt_interp_type = value; return 0; }
   if (!strcmp(name, "keep_particles")) { c->keep_particles = value; return 0; }
   if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
+  if (!strcmp(name, "fft_fused")) { c->fft_fused = value; return 0; }
+  if (!strcmp(name, "fill_fused")) { c->fill_fused = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
   if (!strcmp(name, "p2p_tiled")) { c->p2p_tiled = value; return 0; }
   clr_set_error("unknown option %s", name);
@@ -436,11 +473,12 @@ int clr_srcs_get_counts(clr_ctx *c, int ipop, int32_t *nsources_padded)
   CLR_CHECK(P.d_counts, "no counts for population %d", ipop);
   // device layout is unpadded [nz][n][n]; the reference array has the padded pitch (srcs.c:125)
   const ClrDev &d = c->dev;
-  CLR_CUDA(cudaMemcpy2DAsync(nsources_padded, (size_t)d.pitch * sizeof(int32_t), P.d_counts, (size_t)d.n * sizeof(int32_t),
+  const int hpitch = 2 * d.nc;
+  CLR_CUDA(cudaMemcpy2DAsync(nsources_padded, (size_t)hpitch * sizeof(int32_t), P.d_counts, (size_t)d.n * sizeof(int32_t),
                              (size_t)d.n * sizeof(int32_t), (size_t)d.n * d.nz_here, cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   for (long long row = 0; row < (long long)d.n * d.nz_here; row++)
-    for (int x = d.n; x < d.pitch; x++) nsources_padded[row * d.pitch + x] = 0;
+    for (int x = d.n; x < hpitch; x++) nsources_padded[row * hpitch + x] = 0;
   return 0;
 }
 

@@ -23,6 +23,9 @@
 //  * The last pass of the c2r optionally fuses the (sqrt(2 pi)/L)^3 scaling and the sum / sum of
 //    squares needed by compute_sigma_dens (fourier.c:24-79, 394-397).
 #include "clr_internal.cuh"
+#include "clr_fill.cuh"
+#include <algorithm>
+#include <utility>
 
 namespace {
 
@@ -150,9 +153,13 @@ __host__ __device__ constexpr int ilog2c(int v) { return v <= 1 ? 0 : 1 + ilog2c
 // Stage plan of a length-M transform: radices (descending) R0*R1*R2 = M, every thread owns E = R0
 // points of a line, so a 1024-point line is two radix-32 stages with ONE exchange through shared
 // memory (the exchange traffic, not the flops, is what bounds a Stockham pass on this machine).
-template <int M> struct FftPlan {
+// kWide flags an alternative plan of the same length (FftPlan<2048 | kWide> = 32 x 8 x 8: 32 points per thread, half as
+// many threads per line), used where the thread count of a tile must match another transform's (yx_fused_kernel)
+constexpr int kWide = 1 << 20;
+template <int MM> struct FftPlan {
+  static constexpr int M = MM & (kWide - 1);
   static constexpr int NST = M <= 32 ? 1 : (M <= 1024 ? 2 : 3);
-  static constexpr bool WIDE3 = (CLR_FFT_VARIANT == 1 || CLR_FFT_VARIANT == 2) && M == 2048;   // 32 x 8 x 8
+  static constexpr bool WIDE3 = ((MM & kWide) != 0 || CLR_FFT_VARIANT == 1 || CLR_FFT_VARIANT == 2) && M == 2048;   // 32 x 8 x 8
   static constexpr int R0 = M <= 32 ? M : (M == 64 ? 8 : (M == 128 || M == 256 ? 16 : (M <= 1024 || WIDE3 ? 32 : 16)));
   static constexpr int R1 = NST < 2 ? 1 : (M <= 128 ? 8 : (M <= 512 ? 16 : (M == 1024 ? 32 : (WIDE3 ? 8 : 16))));
   static constexpr int R2 = NST < 3 ? 1 : M / (R0 * R1);
@@ -299,6 +306,9 @@ struct LineAddr {
   int lo_bits;
   // tile-major staging layout of the distributed c2r (see c2r_3d_dist): [source][z-pass tile][z_local][T]
   int tiled = 0, tile_rows = 0;
+  // kx-tile layout of the single-GPU c2r (see yx_fused_kernel): the z pass stores point z of line (ky, kx) at
+  // [z / G][kx / 8][ky][z % G][kx % 8], so that the G*8 lines a y tile needs are ONE contiguous block of n*G*64 bytes
+  int tile8 = 0, t8_g_log2 = 0, t8_nkt = 0, t8_n = 0;
   __device__ __forceinline__ long long off(int e) const
   { return (long long)(e >> lo_bits) * hi_stride + (long long)(e & ((1 << lo_bits) - 1)) * lo_stride; }
 };
@@ -388,6 +398,20 @@ struct StridedTile {
   {
     long long io, oo;
     if (!locate(tile, io, oo)) return;
+    if (aout.tile8) {
+      // z pass of the single-GPU c2r: inner = ky * ncp + kx (ncp a multiple of 8, so an 8-block never straddles a row)
+      const int inner = (int)(tile - (tile / tiles_per_outer) * tiles_per_outer) * T + l;
+      const int b = inner >> 3, ky = b / aout.t8_nkt, kxt = b - ky * aout.t8_nkt;
+      const int gl = aout.t8_g_log2;
+      float2 *bo = gout + (((long long)kxt * aout.t8_n + ky) << (gl + 3)) + (inner & 7);
+      const long long zstep = ((long long)aout.t8_nkt * aout.t8_n) << (gl + 3);      // one group of G planes
+#pragma unroll
+      for (int i = 0; i < P::E; i++) {
+        const int e = j + i * P::TPL;
+        bo[(long long)(e >> gl) * zstep + ((e & ((1 << gl) - 1)) << 3)] = v[i];
+      }
+      return;
+    }
     float2 *bout = gout + oo;
     if (aout.lo_bits == 31) {
       float2 *p = bout + (long long)j * aout.lo_stride;
@@ -583,6 +607,350 @@ fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
 }
 
 // ------------------------------------------------------------------------------------------
+// y pass + x pass of the c2r in ONE persistent kernel (single GPU / local slab).
+//
+// Why: a plane of the half-spectrum (4.3 MB at n = 1024, 17 MB at 2048) fits the 126 MB L2 many times over, so the
+// y pass of plane z can hand its output to the x pass of the same plane THROUGH L2: DRAM sees one read of the z-pass
+// output and one write of the real field (8 B/cell) instead of two reads and two writes (measured with copy kernels
+// of the same shape, tools/membench.cu: 1.76 ms against 3.50 ms for a 1024^3 field).
+//
+// Input `src`: z-pass output in the kx-tile layout [z / G][kx / 8][ky][z % G][kx % 8] (LineAddr::tile8), so a y tile
+// (G*8 lines x n points) is one contiguous block of n*G*64 bytes, fetched by the TMA engine with bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx) straight into the padded Stockham layout. Output `dst`: the real field in
+// the usual layout [z][y][pitch].
+//
+// Work order: one global ticket counter. Per step s the tickets are: the NKT y tiles of plane group s, then the x tiles
+// of group s - LAG. An x tile waits (acquire load) until all y tiles of its group have signalled (release). Every
+// y ticket is handed out before the x tickets that depend on it and y tiles never wait, so with all CTAs co-resident
+// the wait cannot deadlock; LAG covers the y tiles still in flight so that it is hardly ever entered.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy on the TMA engine (UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int N, int G> struct YxCfg {
+  static constexpr int NY = N == 2048 ? (N | kWide) : N;         // 32 points per thread in both transforms
+  using PY = FftPlan<NY>;
+  using PX = FftPlan<N / 2>;
+  static constexpr int TY = 8 * G;                               // lines per y tile
+  static constexpr int THREADS = TY * PY::TPL;
+  static constexpr int XR = THREADS / PX::TPL;                   // rows per x tile
+  static_assert(THREADS % PX::TPL == 0 && XR >= 1 && N % XR == 0, "x tile shape");
+  static_assert(PY::NST >= 2 && PX::NST >= 2, "fused y+x pass needs n >= 128");
+  static constexpr int BUF = (PY::LSTRIDE * TY > PX::LSTRIDE * XR) ? PY::LSTRIDE * TY : PX::LSTRIDE * XR;   // float2
+  static constexpr int G_LOG2 = ilog2c(G);
+  static constexpr size_t SMEM = 128 + ((size_t)BUF + PY::NTW + PX::NTW + N / 2) * sizeof(float2);
+  // registers: <= 128 per thread whenever the tile is small enough for several CTAs per SM
+  static constexpr int MIN_CTAS = SMEM > 110 * 1024 ? 1 : (THREADS >= 512 ? 1 : (512 / THREADS > 8 ? 8 : 512 / THREADS));
+};
+
+struct YxArgs {
+  const float2 *src; float2 *dst;
+  const float2 *W; int wn;
+  int nz, ncp, nkt, lag;            // planes of this slab, complex pitch, kx tiles per row, lag in plane groups
+  float norm;
+  double *mom;
+  unsigned *ticket, *done;          // done[group] counts finished y tiles
+};
+
+template <int N, int G, bool MOM>
+__global__ void __launch_bounds__(YxCfg<N, G>::THREADS, YxCfg<N, G>::MIN_CTAS)
+yx_fused_kernel(const YxArgs a)
+{
+  using C = YxCfg<N, G>;
+  using PY = typename C::PY;
+  using PX = typename C::PX;
+  constexpr int M = N / 2, NY = C::NY;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  // s_tk[0..1]: ticket of the current / next tile (double buffered), s_tk[2..3]: its loads have been issued
+  volatile unsigned *s_tk = reinterpret_cast<volatile unsigned *>(smem_raw + 16);
+  float2 *s = reinterpret_cast<float2 *>(smem_raw + 128);
+  float2 *tw_y = s + C::BUF;
+  float2 *tw_x = tw_y + PY::NTW;
+  float2 *wx = tw_x + PX::NTW;                                    // exp(+2*pi*i*k/n), k < M
+  const int tid = threadIdx.x;
+  const int jy = tid / C::TY, ly = tid % C::TY;                   // y tile: lane <-> line
+  const int jx = tid % PX::TPL, lx = tid / PX::TPL;               // x tile: lane <-> point
+  const int np = a.nz >> C::G_LOG2;                               // plane groups
+  const int nxt = N / C::XR;                                      // x tiles per plane
+  const unsigned per = (unsigned)a.nkt + (unsigned)(G * nxt);
+  const unsigned total = (unsigned)(np + a.lag) * per;
+  // bytes of one row of the half-spectrum, rounded up to the 16 bytes a bulk copy moves (the pitch has room)
+  constexpr uint32_t ROW_BYTES = ((uint32_t)(M + 1) * 8u + 15u) & ~15u;
+  constexpr uint32_t YCHUNK_ROWS = 1u << PY::PADSH, YCHUNK_BYTES = YCHUNK_ROWS * C::TY * 8u, YCHUNKS = N / YCHUNK_ROWS;
+
+  // warp 0 only: start the loads of the tile of ticket t. An x tile needs every y tile of its plane group to have
+  // signalled; when `blocking` is false and they have not, nothing is issued and false is returned (the caller retries
+  // with blocking = true once this CTA has no unsignalled y tile of its own left, else it could wait for itself).
+  auto try_issue = [&](unsigned t, bool blocking) -> bool {
+    if (t >= total) return true;
+    const int st = (int)(t / per), r = (int)(t - (unsigned)st * per);
+    if (r < a.nkt) {
+      if (st >= np) return true;
+      const float2 *blk = a.src + ((long long)st * a.nkt + r) * ((long long)N * C::TY);
+      if (tid == 0) { fence_proxy_async(); mbar_expect_tx(bar, (uint32_t)N * C::TY * 8u); }
+      __syncwarp();
+      for (unsigned c = tid; c < YCHUNKS; c += 32)
+        bulk_g2s(s + (size_t)(c * YCHUNK_ROWS + c) * C::TY, blk + (size_t)c * YCHUNK_ROWS * C::TY, YCHUNK_BYTES, bar);
+      return true;
+    }
+    const int p = st - a.lag;
+    if (p < 0) return true;
+    unsigned ready = 0;
+    if (tid == 0) {
+      for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.done + p) : "memory");
+        ready = v >= (unsigned)a.nkt;
+        if (ready || !blocking) break;
+        __nanosleep(100);
+      }
+      if (ready) {
+        fence_proxy_async();             // the rows were written through the generic proxy, the copy reads them asynchronously
+        mbar_expect_tx(bar, ROW_BYTES * C::XR);
+      }
+    }
+    ready = __shfl_sync(0xffffffffu, ready, 0);
+    if (!ready) return false;
+    const int xb = r - a.nkt, z = (p << C::G_LOG2) + xb / nxt, row0 = (xb % nxt) * C::XR;
+    const float2 *rows = a.dst + ((long long)z * N + row0) * a.ncp;
+    for (int rr = tid; rr < C::XR; rr += 32)
+      bulk_g2s(s + (size_t)rr * PX::LSTRIDE, rows + (long long)rr * a.ncp, ROW_BYTES, bar);
+    return true;
+  };
+  // warp 0 only: take the next ticket, publish it in s_tk[slot], prefetch its tile if that is possible right now
+  auto issue_next = [&](int slot) {
+    unsigned t = 0;
+    if (tid == 0) t = atomicAdd(a.ticket, 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const bool issued = try_issue(t, false);
+    if (tid == 0) { s_tk[slot] = t; s_tk[2 + slot] = issued ? 1u : 0u; }
+  };
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  load_twiddles<NY, +1>(tw_y, a.W, a.wn);
+  load_twiddles<M, +1>(tw_x, a.W, a.wn);
+  for (int k = tid; k < M; k += blockDim.x) wx[k] = a.W[k * (a.wn / (2 * M))];
+  __syncthreads();
+  if (tid < 32) issue_next(0);
+  __syncthreads();
+  double acc1 = 0, acc2 = 0;
+  uint32_t phase = 0;
+  int slot = 0;
+  for (unsigned t = s_tk[0]; t < total; t = s_tk[slot]) {
+    const int st = (int)(t / per), r = (int)(t - (unsigned)st * per);
+    const bool is_y = r < a.nkt;
+    const int p = is_y ? st : st - a.lag;
+    const bool valid = is_y ? st < np : p >= 0;
+    const bool issued = s_tk[2 + slot] != 0;
+    slot ^= 1;
+    if (!valid) {                                            // head / tail of the ticket sequence: nothing to do
+      if (tid < 32) issue_next(slot);
+      __syncthreads();
+      continue;
+    }
+    if (!issued && tid < 32) try_issue(t, true);             // x tile whose y tiles were still in flight at prefetch time
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    if (is_y) {
+      float2 v[PY::E];
+      stage_load<NY, true, C::TY>(v, s, jy, ly);
+      stage_math<NY, +1, 0>(v, tw_y, jy);
+      __syncthreads();
+      stage_store<NY, true, C::TY, 0>(v, s, jy, ly);
+      __syncthreads();
+      stage_load<NY, true, C::TY>(v, s, jy, ly);
+      if constexpr (PY::NST >= 3) {
+        stage_math<NY, +1, 1>(v, tw_y, jy);
+        __syncthreads();
+        stage_store<NY, true, C::TY, 1>(v, s, jy, ly);
+        __syncthreads();
+        stage_load<NY, true, C::TY>(v, s, jy, ly);
+      }
+      __syncthreads();                                       // last exchange read back: the buffer is free
+      if (tid < 32) issue_next(slot);
+      stage_math<NY, +1, PY::NST - 1>(v, tw_y, jy);
+      // line ly = (z % G, kx % 8) of plane group p, kx tile r; point e = ky
+      const int z = (p << C::G_LOG2) + (ly >> 3);
+      float2 *o = a.dst + (long long)z * N * a.ncp + (r << 3) + (ly & 7);
+#pragma unroll
+      for (int i = 0; i < PY::E; i++) o[(long long)(jy + i * PY::TPL) * a.ncp] = v[i];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(a.done + p, 1u);               // ordered after every thread's stores by the fence + barrier
+    } else {
+      const int xb = r - a.nkt, z = (p << C::G_LOG2) + xb / nxt, row0 = (xb % nxt) * C::XR;
+      float2 *X = a.dst + ((long long)z * N + row0 + lx) * a.ncp;
+      float2 v[PX::E];
+      const float2 *raw = s + lx * PX::LSTRIDE;
+#pragma unroll
+      for (int i = 0; i < PX::E; i++) {
+        const int k = jx + i * PX::TPL;
+        float2 x0 = raw[k], x1 = raw[M - k];
+        if (k == 0) { x0.y = 0.f; x1.y = 0.f; }             // x-DC and x-Nyquist are taken as real (FFTW c2r)
+        const float2 e = make_float2(x0.x + x1.x, x0.y - x1.y);
+        const float2 d = cmul(make_float2(x0.x - x1.x, x0.y + x1.y), wx[k]);
+        v[i] = make_float2(e.x - d.y, e.y + d.x);
+      }
+      __syncthreads();                                       // everybody has its inputs: s is the exchange buffer now
+      stage_math<M, +1, 0>(v, tw_x, jx);
+      stage_store<M, false, C::XR, 0>(v, s, jx, lx);
+      __syncthreads();
+      stage_load<M, false, C::XR>(v, s, jx, lx);
+      if constexpr (PX::NST >= 3) {
+        stage_math<M, +1, 1>(v, tw_x, jx);
+        __syncthreads();
+        stage_store<M, false, C::XR, 1>(v, s, jx, lx);
+        __syncthreads();
+        stage_load<M, false, C::XR>(v, s, jx, lx);
+      }
+      __syncthreads();
+      if (tid < 32) issue_next(slot);
+      stage_math<M, +1, PX::NST - 1>(v, tw_x, jx);
+      float s1 = 0, s2 = 0;
+#pragma unroll
+      for (int i = 0; i < PX::E; i++) {
+        float2 o = v[i];
+        o.x *= a.norm; o.y *= a.norm;
+        if (MOM) { s1 += o.x + o.y; s2 += o.x * o.x + o.y * o.y; }
+        __stcs(X + jx + i * PX::TPL, o);                     // final result: streams out, keep L2 for the planes in flight
+      }
+      if (MOM) { acc1 += s1; acc2 += s2; }
+      __syncthreads();                                       // s_tk[slot] is visible
+    }
+  }
+  if (MOM) {
+    acc1 = clr_warp_sum(acc1);
+    acc2 = clr_warp_sum(acc2);
+    __shared__ double red[2][32];
+    const int w = tid >> 5, ln = tid & 31;
+    if (ln == 0) { red[0][w] = acc1; red[1][w] = acc2; }
+    __syncthreads();
+    if (w == 0) {
+      const int nw = (blockDim.x + 31) >> 5;
+      double x = ln < nw ? red[0][ln] : 0, y = ln < nw ? red[1][ln] : 0;
+      x = clr_warp_sum(x); y = clr_warp_sum(y);
+      if (ln == 0) { atomicAdd(a.mom, x); atomicAdd(a.mom + 1, y); }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gaussian mode fill FUSED into the z pass of the c2r, for delta_k and phi_k at once (create_grids_fourier,
+// fourier.c:285-359, + the first axis of fftw_wrap_c2r). The modes are never written to memory: a CTA generates the
+// 8 kx x n kz modes of its tile for both fields into two shared-memory buffers (one Philox block per mode pair, the
+// arithmetic of clr_fill.cuh), two thread groups transform one buffer each along z, and only the z-pass OUTPUT goes
+// to HBM, in the kx-tile layout the fused y+x pass reads. Saves the 8 B/cell write of the stand-alone fill and the
+// 8 B/cell read of two z passes; the kernel is bound by instruction issue (Philox + transcendentals + butterflies).
+template <int N> struct FzCfg {
+  using P = FftPlan<N>;
+  static constexpr int W = 8;                                   // lines (kx) per tile and field
+  static constexpr int GT = W * P::TPL;                         // threads of one field group
+  static constexpr int THREADS = 2 * GT;
+  static constexpr int BUF = P::LSTRIDE * W;                    // float2 per field
+  static constexpr size_t SMEM = ((size_t)2 * BUF + P::NTW) * sizeof(float2);
+  static constexpr int MIN_CTAS = THREADS >= 512 ? 1 : (512 / THREADS > 4 ? 4 : 512 / THREADS);
+  static_assert(P::NST >= 2, "fused fill + z pass needs n >= 64");
+};
+
+struct FzArgs {
+  float2 *out_d, *out_p;            // z-pass output of delta / phi, kx-tile layout [z][kx/8][ky_local][kx%8]
+  const float2 *W; int wn;
+  const float2 *pkt, *sct;
+  uint32_t seed;
+  int n, nc, nyl, ky0, nkt;         // grid side, n/2+1, ky slab of this rank, kx tiles per row
+  FillFastK k;
+};
+
+template <int N>
+__global__ void __launch_bounds__(FzCfg<N>::THREADS, FzCfg<N>::MIN_CTAS)
+fill_z_kernel(const __grid_constant__ FzArgs a)
+{
+  using C = FzCfg<N>;
+  using P = typename C::P;
+  constexpr int W = C::W;
+  extern __shared__ float2 smem[];
+  float2 *tw = smem + 2 * C::BUF;
+  const int tid = threadIdx.x;
+  const int grp = tid / C::GT, tg = tid - grp * C::GT;           // field of this thread's transform
+  const int j = tg / W, l = tg % W;
+  float2 *sg = smem + grp * C::BUF;
+  float2 *outg = grp ? a.out_p : a.out_d;
+  load_twiddles<N, +1>(tw, a.W, a.wn);
+  const int npair_row = (a.nc + 1) / 2;
+  const long long n_tiles = (long long)a.nkt * a.nyl;
+  const long long zstep = (long long)a.nkt * a.nyl * 8;          // one z plane of the kx-tile layout
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // consecutive tiles = consecutive ky of the same kx tile: their 64-byte output runs are neighbours in memory
+    const int kxt = (int)(tile / a.nyl), kyl = (int)(tile - (long long)kxt * a.nyl);
+    const int jj = a.ky0 + kyl;
+    const int mj = (2 * jj <= N ? jj : N - jj);
+    // ---- fill: W/2 mode pairs per kz
+    for (int q = tid; q < N * (W / 2); q += C::THREADS) {
+      const int kz = q / (W / 2), pr = q - kz * (W / 2);
+      const int mi = (2 * kz <= N ? kz : N - kz);
+      const int m_row = mj * mj + mi * mi;
+      const int kk0 = kxt * 8 + 2 * pr;
+      const unsigned long long gidx = (unsigned long long)(kk0 >> 1) + (unsigned long long)npair_row * ((unsigned long long)jj + (unsigned long long)N * kz);
+      float2 dk2[2], pk2[2];
+      dk2[0] = dk2[1] = pk2[0] = pk2[1] = make_float2(0.f, 0.f);
+      if (kk0 < a.nc) {                                          // beyond the Nyquist column: padding lines, zero
+        uint32_t w[4];
+        clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, a.seed, 0u, w);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int kk = kk0 + h, m = kk * kk + m_row;
+          if (kk < a.nc && m > 0) clr_fill_mode(a.k, a.pkt, a.sct, m, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
+        }
+      }
+      const int si = sidx<N, true, W>(kz, 2 * pr);
+      *reinterpret_cast<float4 *>(smem + si) = make_float4(dk2[0].x, dk2[0].y, dk2[1].x, dk2[1].y);
+      *reinterpret_cast<float4 *>(smem + C::BUF + si) = make_float4(pk2[0].x, pk2[0].y, pk2[1].x, pk2[1].y);
+    }
+    __syncthreads();
+    // ---- transform along z: group 0 = delta_k, group 1 = phi_k
+    float2 v[P::E];
+    stage_load<N, true, W>(v, sg, j, l);
+    stage_math<N, +1, 0>(v, tw, j);
+    __syncthreads();
+    stage_store<N, true, W, 0>(v, sg, j, l);
+    __syncthreads();
+    stage_load<N, true, W>(v, sg, j, l);
+    if constexpr (P::NST >= 3) {
+      stage_math<N, +1, 1>(v, tw, j);
+      __syncthreads();
+      stage_store<N, true, W, 1>(v, sg, j, l);
+      __syncthreads();
+      stage_load<N, true, W>(v, sg, j, l);
+    }
+    __syncthreads();                                             // buffers free: the next fill may overwrite them
+    stage_math<N, +1, P::NST - 1>(v, tw, j);
+    float2 *o = outg + ((long long)kxt * a.nyl + kyl) * 8 + l;
+#pragma unroll
+    for (int i = 0; i < P::E; i++) o[(long long)(j + i * P::TPL) * zstep] = v[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side dispatch
 template <int M> struct Cfg {   // lines per CTA tile, per transform length
   static constexpr int TPL = FftPlan<M>::TPL;
@@ -595,12 +963,21 @@ template <int M> struct Cfg {   // lines per CTA tile, per transform length
   static constexpr int T_X = M >= 2048 ? 4 : (256 / TPL > 64 ? 64 : 256 / TPL);
 };
 
+// grid of a persistent kernel = resident CTAs per SM x SMs (capped by the tile count). The attribute call and the
+// occupancy query cost ~10 us each: done once per (kernel, block size, shared memory), not per launch.
 template <typename K> int launch_cfg(clr_ctx *c, K kernel, int threads, size_t smem, long long n_tiles, int *grid)
 {
+  static std::map<std::pair<const void *, std::pair<int, size_t>>, int> cache;
+  const auto key = std::make_pair(reinterpret_cast<const void *>(kernel), std::make_pair(threads, smem));
+  auto it = cache.find(key);
   int per_sm = 0;
-  CLR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-  CLR_CHECK(per_sm > 0, "FFT kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
+  if (it != cache.end()) per_sm = it->second;
+  else {
+    CLR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    CLR_CHECK(per_sm > 0, "FFT kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
+    cache[key] = per_sm;
+  }
   long long g = (long long)per_sm * c->sm_count;
   if (g > n_tiles) g = n_tiles;
   *grid = (int)g;
@@ -657,7 +1034,7 @@ template <int M> int run_r2c_x(clr_ctx *c, float2 *g, long long n_rows, int pitc
 template <int N>
 int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
 {
-  const long long nc = N / 2 + 1;
+  const long long nc = c->dev.ncp;     // complex PITCH of a row (>= N/2+1, multiple of 8)
   const int P = c->nranks, nzl = N / P, nyl = N / P;
   float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
   // tile-major staging pays when the remote runs of the natural layout are short (T = 8 lines = 64 bytes at
@@ -683,7 +1060,7 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
       LineAddr yin{0, blk_t, nc, ilog2_host(nyl)};
       yin.tiled = 1; yin.tile_rows = nzl;
       LineAddr yout{(long long)N * nc, 0, nc, 31};
-      if (run_strided2<N, +1>(c, stage, g, yin, yout, nzl, (int)nc)) return 1; }
+      if (run_strided2<N, +1>(c, stage, g, yin, yout, nzl, N / 2 + 1)) return 1; }
     StageScope sc3(c, "fft_x", 1);
     if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)nzl * N, (int)nc, norm, mom);
     return run_c2r_x<N / 2, false>(c, g, (long long)nzl * N, (int)nc, norm, nullptr);
@@ -706,7 +1083,7 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
   { StageScope sc(c, "fft_y", 1);
     LineAddr ain{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};
     LineAddr aout{(long long)N * nc, 0, nc, 31};
-    if (run_strided2<N, +1>(c, stage, g, ain, aout, nzl, (int)nc)) return 1; }
+    if (run_strided2<N, +1>(c, stage, g, ain, aout, nzl, N / 2 + 1)) return 1; }
   StageScope sc(c, "fft_x", 1);
   if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)nzl * N, (int)nc, norm, mom);
   return run_c2r_x<N / 2, false>(c, g, (long long)nzl * N, (int)nc, norm, nullptr);
@@ -715,7 +1092,7 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
 template <int N>
 int r2c_3d_dist(clr_ctx *c, float2 *g)
 {
-  const long long nc = N / 2 + 1;
+  const long long nc = c->dev.ncp;     // complex PITCH of a row (>= N/2+1, multiple of 8)
   const int P = c->nranks, nzl = N / P, nyl = N / P;
   float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
   { StageScope sc(c, "fft_x", 1); if (run_r2c_x<N / 2>(c, g, (long long)nzl * N, (int)nc)) return 1; }
@@ -726,7 +1103,7 @@ int r2c_3d_dist(clr_ctx *c, float2 *g)
       PeerPtrs pp = peer_blocks(c, (size_t)nzl * nyl * nc);
       LineAddr ain{(long long)N * nc, 0, nc, 31};
       LineAddr aout{(long long)nyl * nc, 0, nc, ilog2_host(nyl)};
-      if (run_strided2<N, -1>(c, g, nullptr, ain, aout, nzl, (int)nc, &pp)) return 1;
+      if (run_strided2<N, -1>(c, g, nullptr, ain, aout, nzl, N / 2 + 1, &pp)) return 1;
       if (clr_comm_barrier(c)) return 1;
       c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1); }
     StageScope sc(c, "fft_z", 1);
@@ -736,7 +1113,7 @@ int r2c_3d_dist(clr_ctx *c, float2 *g)
   { StageScope sc(c, "fft_y", 1);
     LineAddr ain{(long long)N * nc, 0, nc, 31};
     LineAddr aout{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};
-    if (run_strided2<N, -1>(c, g, stage, ain, aout, nzl, (int)nc)) return 1; }
+    if (run_strided2<N, -1>(c, g, stage, ain, aout, nzl, N / 2 + 1)) return 1; }
   { StageScope sc(c, "fft_a2a", 0);
     if (clr_comm_alltoall(c, stage, g, (size_t)nzl * nyl * nc * 2)) return 1; }
   StageScope sc(c, "fft_z", 1);
@@ -773,14 +1150,70 @@ int run_r2c_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c)
   return 0;
 }
 
+// scratch of the single-GPU c2r: the z-pass output in the kx-tile layout (one slab) + ticket / done counters
+int ensure_fft_tmp(clr_ctx *c)
+{
+  const size_t bytes = (size_t)c->dev.nz_here * c->dev.n * c->dev.ncp * sizeof(float2);
+  if (c->d_fft_tmp && c->fft_tmp_bytes >= bytes) return 0;
+  if (c->d_fft_tmp) cudaFree(c->d_fft_tmp);
+  c->d_fft_tmp = nullptr; c->fft_tmp_bytes = 0;
+  CLR_CUDA(cudaMalloc(&c->d_fft_tmp, bytes));
+  c->fft_tmp_bytes = bytes;
+  if (!c->d_fft_sync) CLR_CUDA(cudaMalloc(&c->d_fft_sync, (size_t)(c->dev.n + 8) * sizeof(unsigned)));
+  return 0;
+}
+
+template <int N, int G, bool MOM>
+int run_yx_fused(clr_ctx *c, const float2 *src, float2 *dst, float norm, double *mom)
+{
+  using C = YxCfg<N, G>;
+  auto k = yx_fused_kernel<N, G, MOM>;
+  int grid;
+  if (launch_cfg(c, k, C::THREADS, C::SMEM, 1LL << 30, &grid)) return 1;
+  const int nz = c->dev.nz_here, np = nz / G;
+  CLR_CHECK(nz % G == 0, "fused y+x pass: %d planes are not a multiple of the group size %d", nz, G);
+  YxArgs a;
+  a.src = src; a.dst = dst; a.W = c->d_twiddle; a.wn = c->dev.n;
+  a.nz = nz; a.ncp = c->dev.ncp; a.nkt = c->dev.ncp / 8;
+  // tickets of (grid / tickets-per-group) plane groups are in flight at any time: the x tiles trail by one more
+  const int per = a.nkt + G * (N / C::XR);
+  a.lag = std::min(np, grid / per + 2);
+  a.norm = norm; a.mom = mom;
+  a.ticket = c->d_fft_sync; a.done = c->d_fft_sync + 1;
+  CLR_CUDA(cudaMemsetAsync(c->d_fft_sync, 0, (size_t)(np + 1) * sizeof(unsigned), c->stream));
+  k<<<grid, C::THREADS, C::SMEM, c->stream>>>(a);
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// does the fused path exist for this size? (n >= 128: both transforms need a shared-memory exchange; n = 4096: a y tile
+// of 8 lines no longer fits shared memory)
+template <int N> constexpr bool kHasYx = N >= 128 && N <= 2048;
+
 template <int N>
 int c2r_3d(clr_ctx *c, float2 *g, float norm, double *mom)
 {
-  const long long nc = N / 2 + 1;
+  const long long nc = c->dev.ncp;     // complex PITCH of a row (>= N/2+1, multiple of 8)
+  if constexpr (kHasYx<N>) {
+    if (c->fft_fused) {
+      if (ensure_fft_tmp(c)) return 1;
+      float2 *tmp = reinterpret_cast<float2 *>(c->d_fft_tmp);
+      // z pass: lines along z, contiguous index = flattened (ky,kx) of a plane; output in the kx-tile layout
+      { StageScope sc(c, "fft_z", 1);
+        LineAddr ain{0, 0, (long long)N * nc, 31};
+        LineAddr aout = ain;
+        aout.tile8 = 1; aout.t8_g_log2 = 0; aout.t8_nkt = (int)(nc / 8); aout.t8_n = N;
+        if (run_strided2<N, +1, Cfg<N>::T_Z>(c, g, tmp, ain, aout, 1, (int)(N * nc))) return 1; }
+      // y + x passes, plane by plane through L2
+      StageScope sc(c, "fft_yx", 1);
+      if (mom) return run_yx_fused<N, 1, true>(c, tmp, g, norm, mom);
+      return run_yx_fused<N, 1, false>(c, tmp, g, norm, nullptr);
+    }
+  }
   // z pass: lines along z, contiguous index = flattened (ky,kx) of a plane
   { StageScope sc(c, "fft_z", 1); if (run_strided<N, +1, Cfg<N>::T_Z>(c, g, 1, 0, (long long)N * nc, (int)(N * nc))) return 1; }
   // y pass: per z plane, lines along y, contiguous index = kx
-  { StageScope sc(c, "fft_y", 1); if (run_strided<N, +1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1; }
+  { StageScope sc(c, "fft_y", 1); if (run_strided<N, +1>(c, g, N, (long long)N * nc, nc, N / 2 + 1)) return 1; }
   // x pass: half-complex -> real
   StageScope sc(c, "fft_x", 1);
   if (mom) return run_c2r_x<N / 2, true>(c, g, (long long)N * N, (int)nc, norm, mom);
@@ -790,14 +1223,57 @@ int c2r_3d(clr_ctx *c, float2 *g, float norm, double *mom)
 template <int N>
 int r2c_3d(clr_ctx *c, float2 *g)
 {
-  const long long nc = N / 2 + 1;
+  const long long nc = c->dev.ncp;     // complex PITCH of a row (>= N/2+1, multiple of 8)
   { StageScope sc(c, "fft_x", 1); if (run_r2c_x<N / 2>(c, g, (long long)N * N, (int)nc)) return 1; }
-  { StageScope sc(c, "fft_y", 1); if (run_strided<N, -1>(c, g, N, (long long)N * nc, nc, (int)nc)) return 1; }
+  { StageScope sc(c, "fft_y", 1); if (run_strided<N, -1>(c, g, N, (long long)N * nc, nc, N / 2 + 1)) return 1; }
   StageScope sc(c, "fft_z", 1);
   return run_strided<N, -1, Cfg<N>::T_Z>(c, g, 1, 0, (long long)N * nc, (int)(N * nc));
 }
 
+template <int N>
+int run_fill_c2r(clr_ctx *c, uint32_t seed, float norm, double *mom)
+{
+  using C = FzCfg<N>;
+  if (ensure_fft_tmp(c)) return 1;
+  FzArgs a;
+  if (clr_fill_fast_setup(c, &a.k)) return 1;
+  // z-pass output of delta -> scratch, of phi -> the (still unused) density grid; then phi: density grid -> potential
+  // grid, delta: scratch -> density grid
+  float2 *tmp = reinterpret_cast<float2 *>(c->d_fft_tmp), *dens = reinterpret_cast<float2 *>(c->d_dens),
+         *npot = reinterpret_cast<float2 *>(c->d_npot);
+  a.out_d = tmp; a.out_p = dens;
+  a.W = c->d_twiddle; a.wn = c->dev.n; a.pkt = c->d_pkt; a.sct = c->d_sincos; a.seed = seed;
+  a.n = N; a.nc = c->dev.nc; a.nyl = c->dev.nyl; a.ky0 = c->dev.ky0; a.nkt = c->dev.ncp / 8;
+  { StageScope sc(c, "fill_fft_z", 1);
+    auto k = fill_z_kernel<N>;
+    int grid;
+    if (launch_cfg(c, k, C::THREADS, C::SMEM, (long long)a.nkt * a.nyl, &grid)) return 1;
+    k<<<grid, C::THREADS, C::SMEM, c->stream>>>(a);
+    CLR_CUDA(cudaGetLastError()); }
+  StageScope sc(c, "fft_yx", 2);
+  if (run_yx_fused<N, 1, false>(c, dens, npot, norm, nullptr)) return 1;
+  if (mom) return run_yx_fused<N, 1, true>(c, tmp, dens, norm, mom);
+  return run_yx_fused<N, 1, false>(c, tmp, dens, norm, nullptr);
+}
+
 }  // namespace
+
+// create_grids_fourier + both fftw_wrap_c2r of create_cartesian_fields (fourier.c:285-359, 81-102, 394-397) with the
+// mode fill fused into the z pass. *ran = false when this path does not apply (multi-GPU slab, exact_math, sizes outside
+// [128,1024]): the caller then runs the stand-alone fill and two transforms.
+int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, bool *ran)
+{
+  *ran = false;
+  if (c->nranks > 1 || !c->fft_fused || !c->fill_fused || !clr_fill_fast_ok(c)) return 0;
+  *ran = true;
+  switch (c->dev.n) {
+    case 128: return run_fill_c2r<128>(c, seed, (float)norm, d_moments);
+    case 256: return run_fill_c2r<256>(c, seed, (float)norm, d_moments);
+    case 512: return run_fill_c2r<512>(c, seed, (float)norm, d_moments);
+    case 1024: return run_fill_c2r<1024>(c, seed, (float)norm, d_moments);
+    default: *ran = false; return 0;
+  }
+}
 
 // norm multiplies the output (1.0 = plain fftw_wrap_c2r); d_moments != NULL accumulates
 // {sum, sum of squares} of the scaled output over the unpadded cells.

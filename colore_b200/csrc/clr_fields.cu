@@ -5,6 +5,7 @@
 // Compiled with -fmad=false so that double-precision table lookups round exactly like the
 // reference's scalar C code (no fused multiply-add contraction).
 #include "clr_internal.cuh"
+#include "clr_fill.cuh"
 #include <algorithm>
 #include <string.h>
 
@@ -15,8 +16,8 @@ constexpr int kThreads = 256;
 // ---------------------------------------------------------------------------------------------
 // create_grids_fourier (fourier.c:285-359) + rng_delta_gauss (common.c:191-201) + pk_linear0
 // (cosmo.c:291-308). One thread per mode (kz_local, ky, kx<=n/2). RNG: substream
-// (seed, stream 0, global mode-pair index): the modes kk and kk+32 of a 64-mode chunk of a row share one
-// Philox block, words 0,1 -> phase, modulus of the lower mode, words 2,3 -> the upper mode (phase first, as
+// (seed, stream 0, global mode-pair index): the neighbouring modes 2p, 2p+1 of a row share one
+// Philox block, words 0,1 -> phase, modulus of the even mode, words 2,3 -> the odd mode (phase first, as
 // the reference draws them). Arithmetic in double like the reference; the two complex64 stores per
 // mode are the only HBM traffic (8 B per real-space cell).
 template <bool EXACT>
@@ -49,7 +50,7 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
     if (row >= n_rows || my_r >= rows_par) continue;
     int ii_true = (int)(row / (unsigned)d.nyl);
     int jj = d.ky0 + (int)(row - (unsigned)ii_true * (unsigned)d.nyl);
-    long long idx = (long long)row * d.nc + kk;
+    long long idx = (long long)row * d.ncp + kk;
     double kz = (2 * ii_true <= d.n) ? ii_true * dk : -(d.n - ii_true) * dk;
     double ky = (2 * jj <= d.n) ? jj * dk : -(d.n - jj) * dk;
     double kx = (2 * kk <= d.n) ? kk * dk : -(d.n - kk) * dk;
@@ -76,10 +77,10 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
       } else pk = __ldg(pkarr + numk - 1) * (double)exp10f((float)(-3 * (lgk - logkmax)));
       float sigma2 = (float)(pk * idk3);
       uint32_t w[4];
-      // modes kk and kk+32 of a 64-mode chunk share one Philox block: (kk>>6)*32 + (kk&31) + npair*(jj + n*ii)
-      unsigned long long gidx = (unsigned long long)((kk >> 6) * 32 + (kk & 31)) + 32ULL * (unsigned long long)((d.nc + 63) / 64) * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
+      // the neighbouring modes 2p, 2p+1 share one Philox block: p + npair*(jj + n*ii), npair = ceil(nc/2)
+      unsigned long long gidx = (unsigned long long)(kk >> 1) + (unsigned long long)((d.nc + 1) / 2) * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
       clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
-      if (kk & 32) { w[0] = w[2]; w[1] = w[3]; }
+      if (kk & 1) { w[0] = w[2]; w[1] = w[3]; }
       // ln(1-u2) without a branch: T = 2^32 - w is 1-u2 in units of 2^-32 (exact integer). logf of the
       // float-rounded T plus the first-order term of the (exact) rounding residue keeps full relative
       // accuracy both for u2 -> 0 (T -> 2^32, result -> 0) and u2 -> 1.
@@ -115,10 +116,10 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
       } else pk = __ldg(pkarr + numk - 1) * pow(10., -3 * (lgk - logkmax));
       double sigma2 = pk * idk3;
       uint32_t w[4];
-      // modes kk and kk+32 of a 64-mode chunk share one Philox block: (kk>>6)*32 + (kk&31) + npair*(jj + n*ii)
-      unsigned long long gidx = (unsigned long long)((kk >> 6) * 32 + (kk & 31)) + 32ULL * (unsigned long long)((d.nc + 63) / 64) * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
+      // the neighbouring modes 2p, 2p+1 share one Philox block: p + npair*(jj + n*ii), npair = ceil(nc/2)
+      unsigned long long gidx = (unsigned long long)(kk >> 1) + (unsigned long long)((d.nc + 1) / 2) * ((unsigned long long)jj + (unsigned long long)d.n * ii_true);
       clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
-      if (kk & 32) { w[0] = w[2]; w[1] = w[3]; }
+      if (kk & 1) { w[0] = w[2]; w[1] = w[3]; }
       double u1 = w[0] * (1.0 / 4294967296.0), u2 = w[1] * (1.0 / 4294967296.0);
       double delta_mod = sqrt(-sigma2 * log(1 - u2));
       double sn, cs;
@@ -141,39 +142,8 @@ fill_modes_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 mode fill (default; exact_math=0). Same draws, same formulae, but:
-//  * k^2/dk^2 = m is an integer: the P(k) table position of k = dk*sqrt(m) is
-//    t = T[e] + c1*log2(f), m = f*2^e, with T[e] tabulated in double on the host and split into an
-//    integer and a fraction, so the fp32 sum only ever carries the position INSIDE a few table bins;
-//  * P(k)/dk^3 comes from an fp32 lerp table {p_i, p_{i+1}-p_i};
-//  * the phase 2*pi*u1 (25 bits) = coarse angle from a 4096-entry table x a small-angle rotation;
-//  * row invariants are hoisted: no per-mode 64-bit or double arithmetic is left.
-struct FillFastK {
-  int e_int[26];
-  float e_frac[26];
-  float c1, nscal_c, m3_c, tmax, p_first, p_last, neg_prefac_idk2, smooth_c, smooth_c2;
-  int numk, do_smoothing, smooth_potential;
-};
-
-// ln(1 - w*2^-32) for a 32-bit uniform word, relative error <~ 1.3e-6 (3e-7 typical), no branches:
-//  * u < 1/8: the series -u(1 + u/2 + ... + u^7/8) (truncation 6e-8 relative);
-//  * otherwise T = 2^32 - w is normalised to [0.5,1) (exact shift), ln = ln2*(lg2(T') - shift): lg2.approx carries
-//    an absolute error of 1.6e-7, which is < 1.3e-6 relative once |ln| >= ln(8/7).
-__device__ __forceinline__ float clr_log_one_minus_u(uint32_t w)
-{
-  const float u = __uint2float_rn(w) * 2.3283064365386963e-10f;
-  float sr = fmaf(u, 0.125f, 0.14285715f);
-  sr = fmaf(sr, u, 0.16666667f); sr = fmaf(sr, u, 0.2f); sr = fmaf(sr, u, 0.25f);
-  sr = fmaf(sr, u, 0.33333334f); sr = fmaf(sr, u, 0.5f); sr = fmaf(sr, u, 1.f);
-  const uint32_t T = 0u - w;
-  const int cz = __clz(T);                      // w = 0 -> T = 0 -> cz = 32: the series branch is taken anyway
-  const float Tf = __uint2float_rn(T << (cz & 31)) * 2.3283064365386963e-10f;
-  float lg;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(Tf));
-  const float ll = 0.69314718f * (lg - (__int_as_float(0x4B000000 | cz) - 8388608.f));
-  return w < 0x20000000u ? -u * sr : ll;
-}
-
+// fp32 mode fill (default; exact_math=0): arithmetic in clr_fill.cuh. One thread per mode PAIR (2p, 2p+1) of a row:
+// one Philox block and one 16-byte store per grid (rows are 64-byte aligned, the pair never straddles the pitch).
 __global__ void __launch_bounds__(kThreads)
 fill_modes_fast_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__restrict__ npot_f, uint32_t seed,
                        const float2 *__restrict__ pkt, const float2 *__restrict__ sct, const FillFastK k, int kxs_log2)
@@ -181,67 +151,28 @@ fill_modes_fast_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__re
   const unsigned n_rows = (unsigned)d.n * (unsigned)d.nyl;          // rows (kz, ky_local) of nc modes
   const unsigned kxs = 1u << kxs_log2, rows_par = blockDim.x >> kxs_log2;
   const unsigned my_r = threadIdx.x >> kxs_log2, my_k = threadIdx.x & (kxs - 1);
-  const int npair_row = 32 * ((d.nc + 63) / 64);                     // pair slots per row
+  const int npair_row = (d.nc + 1) / 2;                              // pairs per row
   for (unsigned row = blockIdx.x * rows_par + my_r; row < n_rows; row += gridDim.x * rows_par) {
     const int ii = (int)(row / (unsigned)d.nyl);
     const int jj = d.ky0 + (int)(row - (unsigned)ii * (unsigned)d.nyl);
     const int mi = (2 * ii <= d.n ? ii : d.n - ii), mj = (2 * jj <= d.n ? jj : d.n - jj);
     const int m_row = mj * mj + mi * mi;
-    const long long idx0 = (long long)row * d.nc;
+    const long long idx0 = (long long)row * d.ncp;
     const unsigned long long g0 = (unsigned long long)npair_row * ((unsigned long long)jj + (unsigned long long)d.n * ii);
-    // a thread takes the modes kk and kk + 32 of a 64-mode chunk: one Philox block for both, and each of the
-    // two store instructions of the warp covers 256 contiguous bytes
     for (int kp = (int)my_k; kp < npair_row; kp += (int)kxs) {
       const unsigned long long gidx = g0 + (unsigned)kp;
       uint32_t w[4];
       clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, seed, 0u, w);
+      float2 dk2[2], pk2[2];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int kk = (kp >> 5) * 64 + (kp & 31) + 32 * h;
-        if (kk >= d.nc) break;
-        float2 dk_out = make_float2(0.f, 0.f), pk_out = make_float2(0.f, 0.f);
+        const int kk = 2 * kp + h;
+        dk2[h] = make_float2(0.f, 0.f); pk2[h] = make_float2(0.f, 0.f);
         const int m = kk * kk + m_row;
-        if (m > 0) {
-          const int e2 = 31 - __clz(m);
-          const float mf = __int2float_rn(m);
-          const float fm = mf * __int_as_float((127 - e2) << 23);            // m * 2^-e2 in [1,2)
-          float lgm;
-          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lgm) : "f"(fm));
-          const float par = k.e_frac[e2] + k.c1 * lgm;                       // >= 0
-          const float pm = clr_floor_magic(par);
-          const float fl = pm - 8388608.f;
-          const int ik = k.e_int[e2] + clr_magic_int(pm);
-          float sigma2;
-          if (ik >= 0 && ik < k.numk) {
-            float2 t = __ldg(pkt + ik);
-            sigma2 = fmaf(par - fl, t.y, t.x);
-          } else {
-            float tf = (float)k.e_int[e2] + par;
-            sigma2 = ik < 0 ? k.p_first * exp10f(k.nscal_c * tf) : k.p_last * exp10f(k.m3_c * (tf - k.tmax));
-          }
-          const float delta_mod = clr_sqrt_fast(-sigma2 * clr_log_one_minus_u(w[2 * h + 1]));
-          // phase = 2*pi*q/2^25, q = hi*2^13 + lo
-          const uint32_t q = w[2 * h] >> 7;
-          const float2 cs_h = __ldg(sct + (q >> 13));
-          const float a = (__int_as_float(0x4B000000 | (q & 8191u)) - 8388608.f) * 1.872535141e-07f;   // 2*pi/2^25
-          const float a2 = a * a;
-          const float sa = a - a * a2 * 0.16666667f, ca1 = 0.5f * a2;       // sin a, 1 - cos a
-          const float cs = cs_h.x - (cs_h.x * ca1 + cs_h.y * sa);
-          const float sn = cs_h.y - (cs_h.y * ca1 - cs_h.x * sa);
-          float dre = delta_mod * cs, dim = delta_mod * sn;
-          const float pk2 = k.neg_prefac_idk2 * clr_rcp_fast(mf);
-          float pre = pk2 * dre, pim = pk2 * dim;
-          if (k.do_smoothing) {
-            const float sm = clr_ex2_fast(k.smooth_c2 * mf);
-            dre *= sm; dim *= sm;
-            if (k.smooth_potential) { pre *= sm; pim *= sm; }
-          }
-          dk_out = make_float2(dre, dim);
-          pk_out = make_float2(pre, pim);
-        }
-        dens_f[idx0 + kk] = dk_out;
-        npot_f[idx0 + kk] = pk_out;
+        if (kk < d.nc && m > 0) clr_fill_mode(k, pkt, sct, m, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
       }
+      *reinterpret_cast<float4 *>(dens_f + idx0 + 2 * kp) = make_float4(dk2[0].x, dk2[0].y, dk2[1].x, dk2[1].y);
+      *reinterpret_cast<float4 *>(npot_f + idx0 + 2 * kp) = make_float4(pk2[0].x, pk2[0].y, pk2[1].x, pk2[1].y);
     }
   }
 }
@@ -709,7 +640,7 @@ int clr_ensure_scratch(clr_ctx *c, size_t bytes)
   return 0;
 }
 
-int clr_fields_fill_fast(clr_ctx *c, uint32_t seed)
+int clr_fill_fast_setup(clr_ctx *c, FillFastK *kp)
 {
   const double dk = 2 * M_PI / c->p.l_box, idk3 = 1. / (dk * dk * dk), lgdk = log10(dk);
   const int numk = c->p.numk;
@@ -726,7 +657,7 @@ int clr_fields_fill_fast(clr_ctx *c, uint32_t seed)
     CLR_CUDA(cudaMalloc(&c->d_sincos, 4096 * sizeof(float2)));
     CLR_CUDA(cudaMemcpy(c->d_sincos, sc.data(), 4096 * sizeof(float2), cudaMemcpyHostToDevice));
   }
-  FillFastK k;
+  FillFastK &k = *kp;
   for (int e = 0; e < 26; e++) {
     double v = (lgdk + 0.15051499783199060 * e - c->p.logkmin) * c->p.idlogk;
     double fl = floor(v);
@@ -743,8 +674,18 @@ int clr_fields_fill_fast(clr_ctx *c, uint32_t seed)
   k.smooth_c = (float)(-0.5 * c->p.r2_smooth * dk * dk);
   k.smooth_c2 = (float)(-0.5 * c->p.r2_smooth * dk * dk * 1.4426950408889634);   // for ex2
   k.numk = numk; k.do_smoothing = c->p.do_smoothing; k.smooth_potential = c->p.smooth_potential;
+  return 0;
+}
+
+// the fp32 fill needs k^2/dk^2 < 2^24 (exact integer in a float): n_grid <= 4096
+bool clr_fill_fast_ok(const clr_ctx *c) { return !c->exact_math && 3LL * (c->dev.n / 2) * (c->dev.n / 2) < (1LL << 24); }
+
+int clr_fields_fill_fast(clr_ctx *c, uint32_t seed)
+{
+  FillFastK k;
+  if (clr_fill_fast_setup(c, &k)) return 1;
   int kxs_log2 = 5;      // lanes per row: one lane per mode PAIR, whole warps
-  while ((1 << kxs_log2) < 32 * ((c->dev.nc + 63) / 64) && (1 << kxs_log2) < kThreads) kxs_log2++;
+  while ((1 << kxs_log2) < (c->dev.nc + 1) / 2 && (1 << kxs_log2) < kThreads) kxs_log2++;
   const int rows_par = kThreads >> kxs_log2;
   long long n_rows = (long long)c->dev.n * c->dev.nyl;
   fill_modes_fast_kernel<<<grid_for(c, (n_rows + rows_par - 1) / rows_par * kThreads, 8), kThreads, 0, c->stream>>>(
@@ -757,7 +698,7 @@ int clr_fields_fill_fast(clr_ctx *c, uint32_t seed)
 int clr_fields_fill(clr_ctx *c, uint32_t seed)
 {
   StageScope sc(c, "fill_modes", 1);
-  if (!c->exact_math && 3LL * (c->dev.n / 2) * (c->dev.n / 2) < (1LL << 24)) return clr_fields_fill_fast(c, seed);
+  if (clr_fill_fast_ok(c)) return clr_fields_fill_fast(c, seed);
   long long n_modes = (long long)c->dev.nz_here * c->dev.n * c->dev.nc;
   double lgdk = log10(2 * M_PI / c->p.l_box);
   auto k = c->exact_math ? fill_modes_kernel<true> : fill_modes_kernel<false>;

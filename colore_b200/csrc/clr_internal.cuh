@@ -16,7 +16,11 @@
 // device-visible parameter block (passed by value as __grid_constant__ where needed)
 struct ClrDev {
   int n, nc, nz_here, iz0_here;     // grid side, n/2+1, slab
-  int pitch;                        // floats per real row = 2*nc (reference layout)
+  // INTERNAL row pitch: ncp = nc rounded up to a multiple of 8 complex numbers, pitch = 2*ncp floats, so every row
+  // starts on a 64-byte boundary (float4 streaming accesses, 16-byte cp.async, bulk-copy / TMA alignment, whole
+  // 32-byte sectors per 8-mode tile). The reference layout of the host side (2*nc floats per row, fourier.c:46-51)
+  // is converted in clr_grid_put / clr_grid_get.
+  int ncp, pitch;
   int log2n;                        // log2(n) when n is a power of two, else -1 (index arithmetic)
   int nyl, ky0;                     // k-space slab of this rank: ky in [ky0, ky0+nyl), layout [kz][ky_local][kx]
   int bias_model, nside_base;
@@ -59,6 +63,11 @@ struct clr_ctx {
   float2 *d_twiddle = nullptr;                       // exp(+2*pi*i*k/n), k<n
   float2 *d_pkt = nullptr, *d_sincos = nullptr;      // fp32 tables of the fast mode fill (clr_fields.cu)
   double *d_scratch = nullptr;                       // reductions / histograms
+  // single-GPU c2r (clr_fft.cu): z-pass output in the kx-tile layout, ticket + per-plane-group counters of the fused y+x pass
+  void *d_fft_tmp = nullptr; size_t fft_tmp_bytes = 0;
+  unsigned *d_fft_sync = nullptr;
+  int fft_fused = 1;                                 // option "fft_fused": 0 = three separate axis passes
+  int fill_fused = 1;                                // option "fill_fused": 0 = stand-alone mode fill + z pass
   size_t scratch_bytes = 0;
   double sigma2_gauss = 0, mean_gauss = 0;
   // populations
@@ -161,6 +170,7 @@ struct StageScope {
 // kernels implemented in the other translation units
 int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments);
 int clr_fft_r2c_impl(clr_ctx *c, float *grid);
+int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, bool *ran);
 int clr_fields_fill(clr_ctx *c, uint32_t seed);
 int clr_fields_scale_moments(clr_ctx *c, double *out2);
 int clr_fields_lognormal(clr_ctx *c, int clip);

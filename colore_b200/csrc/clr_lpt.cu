@@ -37,7 +37,7 @@ lpt_kspace1_kernel(const ClrDev d, const float2 *dens_f, LptFields f, int order)
       if (row >= n_rows) continue;
       int ii_true = (int)(row / (unsigned)d.nyl);
       int jj = d.ky0 + (int)(row - (unsigned)ii_true * (unsigned)d.nyl);
-      long long idx = (long long)row * d.nc + kk;
+      long long idx = (long long)row * d.ncp + kk;
       double kv[3];
       kv[2] = (2 * ii_true <= d.n) ? ii_true * dk : -(d.n - ii_true) * dk;
       kv[1] = (2 * jj <= d.n) ? jj * dk : -(d.n - jj) * dk;
@@ -86,7 +86,7 @@ lpt_kspace2_kernel(const ClrDev d, LptFields f)
       if (row >= n_rows) continue;
       int ii_true = (int)(row / (unsigned)d.nyl);
       int jj = d.ky0 + (int)(row - (unsigned)ii_true * (unsigned)d.nyl);
-      long long idx = (long long)row * d.nc + kk;
+      long long idx = (long long)row * d.ncp + kk;
       double kv[3];
       kv[2] = (2 * ii_true <= d.n) ? ii_true * dk : -(d.n - ii_true) * dk;
       kv[1] = (2 * jj <= d.n) ? jj * dk : -(d.n - jj) * dk;

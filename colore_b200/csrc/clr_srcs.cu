@@ -162,7 +162,9 @@ __device__ __forceinline__ bool screen_cell(const ScreenK &k, const float4 *__re
   const float e_lo = clr_ex2_fast(-1.4426951f * lam_hi) * (1.f - 1e-5f);
   // upper bound of the first uniform from its top 23 bits, conversion free: ((word >> 9) + 1) * 2^-23 >= u0
   const float u0_hi = (__uint_as_float(0x4B000000u | (word >> 9)) - 8388607.f) * 1.1920928955078125e-07f;
-  return outside || (inside && u0_hi <= e_lo);               // NaN tables: comparison false -> exact path
+  // gsl_ran_poisson returns 0 iff u0 <= exp(-mu) only in its mu <= 10 branch (Knuth's product); above it the gamma /
+  // binomial reduction consumes the draws differently, so such cells always take the exact path
+  return outside || (inside && lam_hi < 9.99f && u0_hi <= e_lo);   // NaN tables: comparison false -> exact path
 }
 
 // Group screen: ONE bound for the four neighbouring cells a thread owns (they share a Philox block). With
@@ -186,7 +188,7 @@ __device__ __forceinline__ bool screen_group(const ScreenK &k, const float4 *__r
   const float lam_hi = e.x * bm * 1.001f;
   const float e_lo = clr_ex2_fast(-1.4426951f * lam_hi) * (1.f - 1e-5f);
   const float u_hi = (__uint_as_float(0x4B000000u | (umax >> 9)) - 8388607.f) * 1.1920928955078125e-07f;
-  return inside && e.y >= 0.f && u_hi <= e_lo;               // NaN anywhere: comparison false -> not proven
+  return inside && e.y >= 0.f && lam_hi < 9.99f && u_hi <= e_lo;   // NaN anywhere: comparison false -> not proven
 }
 
 // one entry per r-bin of the NA grid; window [ir-1, ir+2] covers an off-by-one fp32 bin index

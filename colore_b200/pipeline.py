@@ -104,7 +104,19 @@ class ParamCoLoRe:
         return int(self.lib.clr_launch_count(self.ctx))
 
     def grid_shape(self):
+        """Host-side (reference) layout of a grid: rows of 2*(n/2+1) floats (fourier.c:46-51)."""
         return (self.nz_here, self.n_grid, 2 * self.nc)
+
+    def grid_pitch(self) -> int:
+        """Floats per row of the DEVICE grids (rows are padded to 64 bytes; see clr_grid_pitch)."""
+        v = C.c_longlong()
+        check(self.lib.clr_grid_pitch(self.ctx, C.byref(v)))
+        return int(v.value)
+
+    def grid_device_ptr(self, which: int) -> int:
+        p = C.c_void_p()
+        check(self.lib.clr_grid_device_ptr(self.ctx, C.c_int(which), C.byref(p)))
+        return int(p.value)
 
     # -- populations ------------------------------------------------------------------------
     def set_srcs(self, ipop: int, nz_arr, bz_arr):

@@ -97,6 +97,9 @@ int clr_grid_put(clr_ctx *ctx, int which, const float *host_padded);  /* real or
 int clr_grid_get(clr_ctx *ctx, int which, float *host_padded);
 /* device pointer of a grid (for zero-copy callers that already live on the GPU) */
 int clr_grid_device_ptr(clr_ctx *ctx, int which, void **dptr);
+/* floats per row of the DEVICE grids: 2*ceil8(n_grid/2+1), rows 64-byte aligned (the host side of clr_grid_put / get is
+ * the reference layout, 2*(n_grid/2+1) floats per row, fourier.c:46-51) */
+int clr_grid_pitch(clr_ctx *ctx, long long *pitch_floats);
 
 /* ---- Gaussian field (fourier.c) ---------------------------------------------------------- */
 /* create_grids_fourier (fourier.c:285-359) with the counter-based RNG stream */

@@ -16,13 +16,9 @@ pytestmark = pytest.mark.gpu
 import colore_b200 as cb  # noqa: E402
 from oracle.oracle import RNG_MT, RNG_PHILOX, Oracle, tables_from_dump  # noqa: E402
 
-# The last two fixtures come from the reference compiled with the other bias models (common.h:414-431, see
-# tests/golden/make_golden.py). They were added after the GPU budget of round 1 was spent: the oracle side is pinned
-# bit-exactly on the CPU (tests/test_oracle_vs_golden.py), the CUDA side of bias models 1 and 3 has not run on
-# hardware yet, hence the non-strict xfail (remove it once seen green).
-_UNSEEN = pytest.mark.xfail(reason="bias models 1/3: fixtures added after the round-1 GPU budget was spent", strict=False)
-GOLDEN = ["ref_n32_lognormal", "ref_n32_clip", pytest.param("ref_n32_bias1", marks=_UNSEEN),
-          pytest.param("ref_n32_bias3", marks=_UNSEEN)]
+# ref_n32_bias1 / ref_n32_bias3: the reference compiled with the other bias models (common.h:414-431);
+# ref_n32_nosmooth: do_smoothing = 0, smooth_potential = false on a power-of-two grid (fourier.c:347-351 skipped)
+GOLDEN = ["ref_n32_lognormal", "ref_n32_clip", "ref_n32_bias1", "ref_n32_bias3", "ref_n32_nosmooth"]
 
 
 def _bias_model(name):
@@ -99,6 +95,129 @@ def test_fft_drops_imag_of_xdc_and_nyquist(golden_dir):
     # numpy's irfftn follows the same convention (complex axes first, real axis last)
     ref = np.fft.irfftn(ck.astype(np.complex128), s=(n, n, n), axes=(0, 1, 2)) * n ** 3
     assert np.abs(a - ref).max() / ref.std() < 2e-5
+    par.free()
+
+
+class _DevArray:
+    """Raw device pointer -> torch, through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def _dev_view(par, which):
+    import torch
+    pitch = par.grid_pitch()
+    t = torch.as_tensor(_DevArray(par.grid_device_ptr(which), par.nz_here * par.n_grid * pitch), device="cuda:0")
+    return t.view(par.nz_here, par.n_grid, pitch)
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("n", [512, 1024, 2048])
+def test_fft_large_vs_cufft(golden_dir, n, fused):
+    """The transforms the bench times (FftPlan<512/1024/2048>, the fused y+x pass and the three separate passes) against
+    an INDEPENDENT implementation: cuFFT through torch.fft, test-only, applied axis by axis in
+    chunks (complex passes over z and y, then half-complex -> real over x with Im of the x-DC / x-Nyquist lines
+    dropped = FFTW's c2r on a non-Hermitian spectrum). Tolerance: 2e-5 of the rms of the result, L-infinity."""
+    import torch
+    if n == 2048 and torch.cuda.mem_get_info()[1] < 150e9:
+        pytest.skip("needs ~125 GB of device memory")
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    par = cb.ParamCoLoRe(t, n)
+    par.set_option("fft_fused", fused)
+    nc = n // 2 + 1
+    gd = _dev_view(par, cb.GRID_DENS)
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    # ---- c2r: random non-Hermitian half spectrum, written straight into the device grid
+    for z0 in range(0, n, 64):
+        gd[z0:z0 + 64].normal_(generator=gen)
+    ref = torch.empty((n, n, nc), dtype=torch.complex64, device="cuda")
+    for z0 in range(0, n, 64):
+        ref[z0:z0 + 64] = torch.view_as_complex(gd[z0:z0 + 64, :, :2 * nc].reshape(-1, n, nc, 2).contiguous())
+    cb.fftw_wrap_c2r(par, cb.GRID_DENS)
+    par.synchronize()
+    cy = max(1, (1 << 27) // (n * n))                      # lines per chunk: ~1 GB temporaries
+    for x0 in range(0, nc, cy):
+        ref[:, :, x0:x0 + cy] = torch.fft.ifft(ref[:, :, x0:x0 + cy], dim=0, norm="forward")
+    for z0 in range(0, n, cy):
+        ref[z0:z0 + cy] = torch.fft.ifft(ref[z0:z0 + cy], dim=1, norm="forward")
+    ref[:, :, 0].imag.zero_()
+    ref[:, :, nc - 1].imag.zero_()
+    err, s2 = 0.0, 0.0
+    for z0 in range(0, n, cy):
+        r = torch.fft.irfft(ref[z0:z0 + cy], n=n, dim=2, norm="forward")
+        err = max(err, float((gd[z0:z0 + cy, :, :n] - r).abs().max()))
+        s2 += float((r.double() ** 2).sum())
+    rms = (s2 / float(n) ** 3) ** 0.5
+    assert err < 2e-5 * rms, f"c2r n={n} fused={fused}: max error {err / rms:.2e} of rms (fp32 tolerance 2e-5)"
+    # ---- r2c of a real field against rfft / fft / fft
+    for z0 in range(0, n, 64):
+        gd[z0:z0 + 64].normal_(generator=gen)
+    for z0 in range(0, n, cy):
+        ref[z0:z0 + cy] = torch.fft.rfft(gd[z0:z0 + cy, :, :n], dim=2)
+    cb.fftw_wrap_r2c(par, cb.GRID_DENS)
+    par.synchronize()
+    for z0 in range(0, n, cy):
+        ref[z0:z0 + cy] = torch.fft.fft(ref[z0:z0 + cy], dim=1)
+    err, s2 = 0.0, 0.0
+    for x0 in range(0, nc, cy):
+        r = torch.fft.fft(ref[:, :, x0:x0 + cy], dim=0)
+        got = torch.view_as_complex(gd[:, :, 2 * x0:2 * min(nc, x0 + cy)].reshape(n, n, -1, 2).contiguous())
+        err = max(err, float((got - r).abs().max()))
+        s2 += float((r.abs().double() ** 2).sum())
+    rms = (s2 / (float(n) ** 2 * nc)) ** 0.5
+    assert err < 2e-5 * rms, f"r2c n={n}: max error {err / rms:.2e} of rms"
+    del ref
+    torch.cuda.empty_cache()
+    par.free()
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_fused_fields_vs_oracle(golden_dir, n):
+    """n >= 128 on one GPU: the mode fill is fused into the z pass and the y + x passes run as one kernel through L2
+    (clr_fft.cu: fill_z_kernel, yx_fused_kernel). Same Philox stream in the oracle -> fields to 2e-5 sigma."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    t = dict(t)
+    t["l_box"] = float(np.float32(2 * t["r_max"] * (1 + 2. / n)))
+    t["pos_obs"] = 0.5 * t["l_box"]
+    o = Oracle(t, n)
+    par = cb.ParamCoLoRe(t, n, seed=77)
+    dk, pk = o.fill_modes(RNG_PHILOX, 77)
+    dens, npot = o.c2r(dk), o.c2r(pk)
+    o.normalize_fields(dens, npot)
+    _, s2_ref = o.sigma_dens(dens)
+    mean, s2 = cb.create_cartesian_fields(par)
+    got_d, got_p = par.grid_get(cb.GRID_DENS), par.grid_get(cb.GRID_NPOT)
+    assert np.abs(_real(got_d, n) - _real(dens, n)).max() < 2e-5 * np.sqrt(s2_ref)
+    assert np.abs(_real(got_p, n) - _real(npot, n)).max() < 2e-5 * _real(npot, n).std()
+    assert abs(s2 / s2_ref - 1) < 1e-5 and abs(mean) < 1e-5 * np.sqrt(s2_ref)
+    par.free()
+
+
+@pytest.mark.parametrize("n", [128, 512, 1024])
+def test_fused_fields_match_separate_passes(golden_dir, n):
+    """Full-size consistency of the two code paths of create_cartesian_fields: fused (fill + z pass, y + x pass) against
+    stand-alone fill + three separate axis passes, same seed. Both evaluate the same butterflies in fp32."""
+    import torch
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    t = dict(t)
+    t["l_box"] = float(np.float32(2 * t["r_max"] * (1 + 2. / n)))
+    t["pos_obs"] = 0.5 * t["l_box"]
+    par = cb.ParamCoLoRe(t, n, seed=5)
+    mean1, s2_1 = cb.create_cartesian_fields(par)
+    a_d = _dev_view(par, cb.GRID_DENS)[:, :, :n].clone()
+    a_p = _dev_view(par, cb.GRID_NPOT)[:, :, :n].clone()
+    par.set_option("fft_fused", 0)
+    par.set_option("fill_fused", 0)
+    mean2, s2_2 = cb.create_cartesian_fields(par)
+    par.synchronize()
+    b_d, b_p = _dev_view(par, cb.GRID_DENS)[:, :, :n], _dev_view(par, cb.GRID_NPOT)[:, :, :n]
+    assert float((a_d - b_d).abs().max()) < 5e-6 * np.sqrt(s2_2)
+    assert float((a_p - b_p).abs().max()) < 5e-6 * float(b_p.std())
+    assert abs(s2_1 / s2_2 - 1) < 1e-6
+    # halo planes of the potential (fourier.c:401-414) are refreshed by both paths: first / last plane copies
+    del a_d, a_p, b_d, b_p
+    torch.cuda.empty_cache()
     par.free()
 
 
@@ -236,6 +355,35 @@ def test_sources_bit_exact_vs_oracle(case):
         # statistical sanity against the reference's own MT19937 catalogue: same expected number
         n_ref = g[f"s4_srcs_ipix_{ipop}"].size
         assert abs(tot - n_ref) < 6 * np.sqrt(n_ref)
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.15, 0.04])
+def test_poisson_dense_bit_exact(golden_dir, scale):
+    """gsl_ran_poisson's mu > 10 branch (gamma / binomial reduction, common.c:187; dev_gamma_int, dev_gamma_large,
+    dev_binomial in clr_srcs.cu) against the oracle, bit for bit. ref_n32_dense holds ~120 sources per cell; the scale
+    factors put the bulk of the occupied cells at lambda ~ 80-1000, ~12-150 and ~3-40 (the switch at mu = 10, where the
+    fp32 screen must hand over to the exact path)."""
+    g, t = _load(golden_dir, "ref_n32_dense")
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    par = _par(t)
+    nz = t["srcs_nz_0"] * scale
+    par.grid_put(cb.GRID_DENS, g["s2_dens"])
+    par.grid_put(cb.GRID_NPOT, g["s1_npot"])
+    par.update_halo()
+    par.set_srcs(0, nz, t["srcs_bz_0"])
+    ends = g["s3_srcs_norm_ends_0"]
+    cb.set_norm(par, 0, 0, g["s3_srcs_norm_0"], ends)
+    seed = int(t["seed"])
+    nsrc = cb.srcs_set_cartesian(par)[0]
+    ns, tot = o.srcs_poisson(g["s2_dens"], nz, t["srcs_bz_0"], g["s3_srcs_norm_0"], ends[0], ends[1], RNG_PHILOX, seed, 0)
+    got = cb.srcs_get_counts(par, 0)
+    assert (ns > 10).mean() > 0.1 and (scale > 0.1 or ((ns > 0) & (ns <= 10)).mean() > 0.02)
+    assert nsrc == tot and np.array_equal(got, ns), f"{(got != ns).sum()} cells differ"
+    o.set_halo(g["s1_npot"])
+    pos_ref, ipix_ref = o.srcs_place(g["s1_npot"], ns, RNG_PHILOX, seed, 0)
+    pos, ipix = cb.srcs_get_cartesian(par, 0)
+    assert np.array_equal(ipix, ipix_ref) and np.array_equal(pos[:, :3], pos_ref[:, :3])
+    par.free()
 
 
 def test_async_results_match_sync(case):

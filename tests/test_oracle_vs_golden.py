@@ -14,7 +14,23 @@ import pytest
 from oracle.oracle import NA, RNG_MT, Oracle, tables_from_dump
 
 CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth", "ref_n32_1lpt_cic", "ref_n32_2lpt_tsc", "ref_n32_2lpt_ngp",
-         "ref_n32_bias1", "ref_n32_bias3"]       # the reference compiled with the other bias models (common.h:414-431)
+         "ref_n32_bias1", "ref_n32_bias3",       # the reference compiled with the other bias models (common.h:414-431)
+         "ref_n32_nosmooth",                     # power-of-two grid without smoothing (runs on the GPU too)
+         "ref_n32_dense"]                        # ~120 sources per cell: gsl_ran_poisson's mu > 10 branch (common.c:187)
+
+
+def _same(arr, g, key):
+    """arr == g[key] bit for bit; large catalogues are stored as digests (make_golden.py:compact)."""
+    if key in g:
+        return np.array_equal(np.asarray(arr).ravel(), g[key].ravel())
+    import hashlib
+    a = np.ascontiguousarray(arr)
+    return (a.size == int(g[key + "__size"][0]) and np.array_equal(a.ravel()[:4096], g[key + "__head"])
+            and hashlib.sha256(a.tobytes()).digest() == g[key + "__sha256"].tobytes())
+
+
+def _size(g, key):
+    return g[key].size if key in g else int(g[key + "__size"][0])
 
 
 def _bias_model(name):
@@ -81,14 +97,20 @@ def test_sources_bit_exact(case):
         ends = g[f"s3_srcs_norm_ends_{ipop}"]
         ns, tot = o.srcs_poisson(dens, t[f"srcs_nz_{ipop}"], t[f"srcs_bz_{ipop}"], g[f"s3_srcs_norm_{ipop}"],
                                  ends[0], ends[1], RNG_MT, int(t["seed"]), ipop)
-        assert tot == g[f"s4_srcs_ipix_{ipop}"].size
+        assert tot == _size(g, f"s4_srcs_ipix_{ipop}")
         assert ns[:, :, o.n:].sum() == 0          # padding columns never hold sources
         pos, ipix = o.srcs_place(npot, ns, RNG_MT, int(t["seed"]), ipop)
-        assert np.array_equal(pos.ravel(), g[f"s4_srcs_pos_{ipop}"])
-        assert np.array_equal(ipix, g[f"s4_srcs_ipix_{ipop}"])
+        assert _same(pos, g, f"s4_srcs_pos_{ipop}")
+        assert _same(ipix, g, f"s4_srcs_ipix_{ipop}")
         srcs = o.srcs_local_properties(pos)
-        ref = g[f"s5_srcs_cat_{ipop}"].reshape(-1, 9)
-        assert np.array_equal(srcs[:, :6], ref[:, :6])
+        if f"s5_srcs_cat_{ipop}" in g:
+            ref = g[f"s5_srcs_cat_{ipop}"].reshape(-1, 9)
+            assert np.array_equal(srcs[:, :6], ref[:, :6])
+        else:
+            # compact fixture: columns 6-8 (kappa, dra, ddec) are zero in a run without lensing
+            full = np.zeros((srcs.shape[0], 9), np.float32)
+            full[:, :6] = srcs[:, :6]
+            assert _same(full, g, f"s5_srcs_cat_{ipop}")
         if f"s6_srcs_cat_{ipop}" in g:
             o.srcs_beam_rsd(npot, pos, srcs)
             assert np.array_equal(srcs[:, :6], g[f"s6_srcs_cat_{ipop}"].reshape(-1, 9)[:, :6])

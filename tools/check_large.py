@@ -79,12 +79,11 @@ def main():
     par.set_srcs(0, t["srcs_nz_0"], t["srcs_bz_0"])
     out = {"n_grid": n, "n_gpus": world, "dens_type": args.dens_type,
            "transpose": cb.dist.transpose_mode(par) if world > 1 else "none"}
-    nfl = nzl * n * 2 * par.nc
+    pitch = par.grid_pitch()
+    nfl = nzl * n * pitch
 
     def dev_view(which):
-        p = C.c_void_p()
-        cb._lib.check(par.lib.clr_grid_device_ptr(par.ctx, C.c_int(which), C.byref(p)))
-        return torch.as_tensor(_DevArray(p.value, nfl), device=f"cuda:{local}").view(nzl, n, 2 * par.nc)
+        return torch.as_tensor(_DevArray(par.grid_device_ptr(which), nfl), device=f"cuda:{local}").view(nzl, n, pitch)
 
     # ---- property checks -----------------------------------------------------------------
     mean, s2 = cb.create_cartesian_fields(par)
