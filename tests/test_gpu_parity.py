@@ -134,6 +134,7 @@ def test_fft_large_vs_cufft(golden_dir, n, fused):
     ref = torch.empty((n, n, nc), dtype=torch.complex64, device="cuda")
     for z0 in range(0, n, 64):
         ref[z0:z0 + 64] = torch.view_as_complex(gd[z0:z0 + 64, :, :2 * nc].reshape(-1, n, nc, 2).contiguous())
+    torch.cuda.synchronize()         # the library runs on its own (non-blocking) stream: torch's writes must have landed
     cb.fftw_wrap_c2r(par, cb.GRID_DENS)
     par.synchronize()
     cy = max(1, (1 << 27) // (n * n))                      # lines per chunk: ~1 GB temporaries
@@ -155,6 +156,7 @@ def test_fft_large_vs_cufft(golden_dir, n, fused):
         gd[z0:z0 + 64].normal_(generator=gen)
     for z0 in range(0, n, cy):
         ref[z0:z0 + cy] = torch.fft.rfft(gd[z0:z0 + cy, :, :n], dim=2)
+    torch.cuda.synchronize()
     cb.fftw_wrap_r2c(par, cb.GRID_DENS)
     par.synchronize()
     for z0 in range(0, n, cy):
@@ -205,8 +207,10 @@ def test_fused_fields_match_separate_passes(golden_dir, n):
     t["pos_obs"] = 0.5 * t["l_box"]
     par = cb.ParamCoLoRe(t, n, seed=5)
     mean1, s2_1 = cb.create_cartesian_fields(par)
+    par.synchronize()
     a_d = _dev_view(par, cb.GRID_DENS)[:, :, :n].clone()
     a_p = _dev_view(par, cb.GRID_NPOT)[:, :, :n].clone()
+    torch.cuda.synchronize()         # the library runs on its own (non-blocking) stream
     par.set_option("fft_fused", 0)
     par.set_option("fill_fused", 0)
     mean2, s2_2 = cb.create_cartesian_fields(par)

@@ -92,6 +92,7 @@ def main():
     if not args.skip_roundtrip:
         g = dev_view(cb.GRID_NPOT)
         ref = g[:, :, :n].clone()
+        torch.cuda.synchronize()               # the library runs on its own non-blocking stream
         cb.fftw_wrap_r2c(par, cb.GRID_NPOT)
         cb.fftw_wrap_c2r(par, cb.GRID_NPOT)
         par.synchronize()
