@@ -794,9 +794,10 @@ yx_fused_kernel(const YxArgs a)
       float2 *o = a.dst + (long long)z * N * a.ncp + (r << 3) + (ly & 7);
 #pragma unroll
       for (int i = 0; i < PY::E; i++) o[(long long)(jy + i * PY::TPL) * a.ncp] = v[i];
-      __threadfence();
       __syncthreads();
-      if (tid == 0) atomicAdd(a.done + p, 1u);               // ordered after every thread's stores by the fence + barrier
+      // one RELEASE by one thread publishes the stores of the whole CTA (they happen before it through the barrier;
+      // release is cumulative), instead of a device-wide fence in every thread
+      if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.done + p), "r"(1u) : "memory");
     } else {
       const int xb = r - a.nkt, z = (p << C::G_LOG2) + xb / nxt, row0 = (xb % nxt) * C::XR;
       float2 *X = a.dst + ((long long)z * N + row0 + lx) * a.ncp;
@@ -905,6 +906,7 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
     const int jj = a.ky0 + kyl;
     const int mj = (2 * jj <= N ? jj : N - jj);
     // ---- fill: W/2 mode pairs per kz
+#pragma unroll 2
     for (int q = tid; q < N * (W / 2); q += C::THREADS) {
       const int kz = q / (W / 2), pr = q - kz * (W / 2);
       const int mi = (2 * kz <= N ? kz : N - kz);
@@ -912,15 +914,12 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
       const int kk0 = kxt * 8 + 2 * pr;
       const unsigned long long gidx = (unsigned long long)(kk0 >> 1) + (unsigned long long)npair_row * ((unsigned long long)jj + (unsigned long long)N * kz);
       float2 dk2[2], pk2[2];
-      dk2[0] = dk2[1] = pk2[0] = pk2[1] = make_float2(0.f, 0.f);
-      if (kk0 < a.nc) {                                          // beyond the Nyquist column: padding lines, zero
-        uint32_t w[4];
-        clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, a.seed, 0u, w);
+      uint32_t w[4];
+      clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, a.seed, 0u, w);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int kk = kk0 + h, m = kk * kk + m_row;
-          if (kk < a.nc && m > 0) clr_fill_mode(a.k, a.pkt, a.sct, m, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
-        }
+      for (int h = 0; h < 2; h++) {
+        const int kk = kk0 + h, m = kk * kk + m_row;            // beyond the Nyquist column: padding lines, zero
+        clr_fill_mode(a.k, a.pkt, a.sct, m, kk < a.nc && m > 0, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
       }
       const int si = sidx<N, true, W>(kz, 2 * pr);
       *reinterpret_cast<float4 *>(smem + si) = make_float4(dk2[0].x, dk2[0].y, dk2[1].x, dk2[1].y);

@@ -167,9 +167,8 @@ fill_modes_fast_kernel(const ClrDev d, float2 *__restrict__ dens_f, float2 *__re
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int kk = 2 * kp + h;
-        dk2[h] = make_float2(0.f, 0.f); pk2[h] = make_float2(0.f, 0.f);
         const int m = kk * kk + m_row;
-        if (kk < d.nc && m > 0) clr_fill_mode(k, pkt, sct, m, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
+        clr_fill_mode(k, pkt, sct, m, kk < d.nc && m > 0, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
       }
       *reinterpret_cast<float4 *>(dens_f + idx0 + 2 * kp) = make_float4(dk2[0].x, dk2[0].y, dk2[1].x, dk2[1].y);
       *reinterpret_cast<float4 *>(npot_f + idx0 + 2 * kp) = make_float4(pk2[0].x, pk2[0].y, pk2[1].x, pk2[1].y);

@@ -41,39 +41,40 @@ __device__ __forceinline__ float clr_log_one_minus_u(uint32_t w)
   return w < 0x20000000u ? -u * sr : ll;
 }
 
-// One mode: m = kx^2 + ky^2 + kz^2 in units of dk^2 (> 0), draws {phase word, modulus word}.
-// Every product is written with explicit intrinsics so that the result does not depend on the FMA-contraction
-// setting of the translation unit (clr_fields.cu is built with -fmad=false, clr_fft.cu is not).
+// One mode: m = kx^2 + ky^2 + kz^2 in units of dk^2, draws {phase word, modulus word}; `live` = false (k = 0 or a
+// padding column) gives zeros. Branch free apart from the (never taken at usual sizes) power-law ends of the P(k) table.
+// Every multiply-add is an explicit fmaf / __fmul_rn, so the result does not depend on the FMA-contraction setting of the
+// translation unit (clr_fields.cu is built with -fmad=false, clr_fft.cu is not).
 __device__ __forceinline__ void clr_fill_mode(const FillFastK &k, const float2 *__restrict__ pkt, const float2 *__restrict__ sct,
-                                              int m, uint32_t w_phase, uint32_t w_mod, float2 &dk_out, float2 &pk_out)
+                                              int m, bool live, uint32_t w_phase, uint32_t w_mod, float2 &dk_out, float2 &pk_out)
 {
+  m = max(m, 1);
   const int e2 = 31 - __clz(m);
   const float mf = __int2float_rn(m);
   const float fm = __fmul_rn(mf, __int_as_float((127 - e2) << 23));     // m * 2^-e2 in [1,2)
   float lgm;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lgm) : "f"(fm));
-  const float par = __fadd_rn(k.e_frac[e2], __fmul_rn(k.c1, lgm));      // >= 0
+  const float par = fmaf(k.c1, lgm, k.e_frac[e2]);                       // >= 0
   const float pm = clr_floor_magic(par);
   const float fl = pm - 8388608.f;
   const int ik = k.e_int[e2] + clr_magic_int(pm);
-  float sigma2;
-  if (ik >= 0 && ik < k.numk) {
-    float2 t = __ldg(pkt + ik);
-    sigma2 = fmaf(par - fl, t.y, t.x);
-  } else {
-    float tf = (float)k.e_int[e2] + par;
+  const float2 t = __ldg(pkt + min(max(ik, 0), k.numk - 1));
+  float sigma2 = fmaf(par - fl, t.y, t.x);
+  if (ik < 0 || ik >= k.numk) {                                           // cosmo.c:295-304: k^ns below, k^-3 above the table
+    const float tf = (float)k.e_int[e2] + par;
     sigma2 = ik < 0 ? k.p_first * exp10f(k.nscal_c * tf) : k.p_last * exp10f(k.m3_c * (tf - k.tmax));
   }
   const float delta_mod = clr_sqrt_fast(__fmul_rn(-sigma2, clr_log_one_minus_u(w_mod)));
-  // phase = 2*pi*q/2^25, q = hi*2^13 + lo
+  // phase = 2*pi*q/2^25, q = hi*2^13 + lo: table entry of the coarse angle, rotated by the small angle a < 1.6e-3
+  // (sin a = a and cos a = 1 - a^2/2 to 7e-10 and 3e-13)
   const uint32_t q = w_phase >> 7;
   const float2 cs_h = __ldg(sct + (q >> 13));
   const float a = __fmul_rn(__int_as_float(0x4B000000 | (q & 8191u)) - 8388608.f, 1.872535141e-07f);   // 2*pi/2^25
-  const float a2 = __fmul_rn(a, a);
-  const float sa = __fsub_rn(a, __fmul_rn(__fmul_rn(a, a2), 0.16666667f)), ca1 = __fmul_rn(0.5f, a2);   // sin a, 1 - cos a
-  const float cs = __fsub_rn(cs_h.x, __fadd_rn(__fmul_rn(cs_h.x, ca1), __fmul_rn(cs_h.y, sa)));
-  const float sn = __fsub_rn(cs_h.y, __fsub_rn(__fmul_rn(cs_h.y, ca1), __fmul_rn(cs_h.x, sa)));
-  float dre = __fmul_rn(delta_mod, cs), dim = __fmul_rn(delta_mod, sn);
+  const float ca1 = __fmul_rn(__fmul_rn(0.5f, a), a);
+  const float cs = fmaf(-cs_h.y, a, fmaf(-cs_h.x, ca1, cs_h.x));
+  const float sn = fmaf(cs_h.x, a, fmaf(-cs_h.y, ca1, cs_h.y));
+  const float amp = live ? delta_mod : 0.f;
+  float dre = __fmul_rn(amp, cs), dim = __fmul_rn(amp, sn);
   const float pk2 = __fmul_rn(k.neg_prefac_idk2, clr_rcp_fast(mf));
   float pre = __fmul_rn(pk2, dre), pim = __fmul_rn(pk2, dim);
   if (k.do_smoothing) {
