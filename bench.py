@@ -156,33 +156,50 @@ def scipy_fft_ms(n_grid: int, threads: int):
         return None
 
 
+def workload_config(n: int):
+    """`config` of both arms (identical keys and values, so that the driver can tell the two lines describe one workload)."""
+    return {"workload": f"n_grid={n} lognormal + 1 galaxy population + RSD (field->sources)", "n_grid": n,
+            "mean_sources_per_cell": MEAN_SRC_PER_CELL,
+            "l2_policy": f"inputs ({8.0 * n * n * (n // 2 + 1) * 2 / 1e9:.1f} GB of grids) exceed the 126 MB L2",
+            "seed_per_step": "varies"}
+
+
 def reference_arm(args):
+    """The unmodified reference on the host cores, SAME n_grid as the GPU arm (a step = one whole run of the binary;
+    ~35 s at n_grid=1024 on 16 cores). Steps are capped by a wall-clock budget so that the arm always ends."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_s = args.ref_n_grid
-    cfg_name = f"n_grid={args.n_grid} lognormal + 1 galaxy population + RSD (field->sources)"
+    n_s = args.ref_n_grid or args.n_grid
+    budget_s = float(os.environ.get("CLR_REF_BUDGET_S", "1200"))
     try:
-        for _ in range(args.warmup if args.warmup < 2 else 1):
+        t_start = time.time()
+        vals, stages, done = [], {}, 0
+        for w in range(1 if args.warmup > 0 else 0):
             run_reference_sample(n_s, threads)
-        vals = []
         t0 = time.time()
         for _ in range(args.steps):
             v, stages = run_reference_sample(n_s, threads)
             vals.append(v)
-        ms = (time.time() - t0) * 1e3 / args.steps
+            done += 1
+            per = (time.time() - t0) / done
+            if time.time() - t_start + per > budget_s:
+                break
+        ms = (time.time() - t0) * 1e3 / done
         val = float(np.mean(vals))
     except Exception as e:  # noqa: BLE001
         print(json.dumps({"impl": "reference", "unavailable": str(e).splitlines()[0][:200]}))
         return
     sample = (f"unmodified reference (oracle/_ref/CoLoRe_ref, gcc -O3 -fopenmp, FFTW replaced by the oracle shim FFT) "
               f"at n_grid={n_s}, same cosmology/tables recipe, {threads} OpenMP threads; stage timers of common.c:114-168 "
-              f"summed from mode fill to source redistribution")
+              f"summed from mode fill to source redistribution; {done} whole runs of the binary"
+              + ("" if done == args.steps else f" (of {args.steps}: {budget_s:.0f} s wall-clock budget)"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": cfg_name, "sample_n_grid": n_s},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.n_grid), "steps_run": done,
+        "sample_n_grid": n_s,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
                          "stages_ms": stages, "scipy_irfftn_2x_ms": scipy_fft_ms(n_s, threads)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,6 +215,152 @@ def run_step(cb, par, seed, tabs):
     return cb.srcs_set_cartesian(par)[0]
 
 
+class _DevArray:
+    """Raw device pointer -> torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+def grid_view(torch, par, which, local):
+    pitch = par.grid_pitch()
+    t = torch.as_tensor(_DevArray(par.grid_device_ptr(which), par.nz_here * par.n_grid * pitch), device=f"cuda:{local}")
+    return t.view(par.nz_here, par.n_grid, pitch)
+
+
+PARITY_SEED = 4242
+# catalogue length of the PARITY_SEED realisation of the bench workload at n_grid=1024 on ONE GPU (measured, round 2):
+# the Poisson stream is keyed by the global cell index, so every slab decomposition must reproduce it
+PARITY_NSRC_1024 = 31129449
+
+
+def parity_checks(cb, torch, par, tabs, n, local, allsum, allmax):
+    """Correctness bits carried by every bench line (size-independent properties, cheap): distributed r2c(c2r(.))
+    round trip of the potential, sum of the per-cell counts == catalogue length, total number of sources of a fixed seed
+    (identical for every number of GPUs), moments of the Gaussian field equal on every rank."""
+    out = {}
+    par.seed = PARITY_SEED
+    mean, s2 = cb.create_cartesian_fields(par)
+    par.synchronize()
+    out["sigma2_gauss"] = s2
+    out["sigma2_same_on_all_ranks"] = bool(allmax(s2) == s2 and -allmax(-s2) == s2)
+    g = grid_view(torch, par, cb.GRID_NPOT, local)
+    ref = g[:, :, :n].clone()
+    torch.cuda.synchronize()
+    cb.fftw_wrap_r2c(par, cb.GRID_NPOT)
+    cb.fftw_wrap_c2r(par, cb.GRID_NPOT)
+    par.synchronize()
+    err = float((g[:, :, :n] * (1.0 / float(n) ** 3) - ref).abs().max())
+    s1 = allsum(float(ref.double().sum()))
+    s2r = allsum(float((ref.double() ** 2).sum()))
+    sig = (s2r / float(n) ** 3 - (s1 / float(n) ** 3) ** 2) ** 0.5
+    out["fft_roundtrip_err_over_sigma"] = allmax(err) / sig
+    g[:, :, :n].copy_(ref)
+    del ref
+    torch.cuda.synchronize()
+    par.update_halo()
+    cb.compute_physical_density_field(par)
+    cb.compute_density_normalization(par)
+    nsrc = cb.srcs_set_cartesian(par)[0]
+    counts = cb.srcs_get_counts(par, 0)
+    out["sum_counts_equals_catalogue"] = bool(allsum(float(int(counts.sum()) == nsrc)) == allsum(1.0))
+    tot = int(allsum(nsrc))
+    out["sources_total_parity_seed"] = tot
+    if n == 1024 and PARITY_NSRC_1024 is not None:
+        out["sources_total_equals_1gpu_value"] = bool(tot == PARITY_NSRC_1024)
+    out["ok"] = bool(out["fft_roundtrip_err_over_sigma"] < 5e-5 and out["sum_counts_equals_catalogue"]
+                     and out["sigma2_same_on_all_ranks"] and out.get("sources_total_equals_1gpu_value", True))
+    return out
+
+
+def ncu_traffic_table():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the newest committed `ncu --set full` summaries of THIS
+    workload (n_grid=1024, one GPU) under profiles/ (written by tools/ncu_summary.py)."""
+    import csv
+    import glob
+    stage_of = {"fill_z_kernel": "fill_fft_z", "yx_fused_kernel": "fft_yx", "fill_modes_fast_kernel": "fill_modes",
+                "lognormal_hist_kernel": "lognormal", "lognormal_fast_kernel": "lognormal", "norm_hist_fast_kernel": "norm_hist",
+                "poisson_kernel": "srcs_poisson", "expand_kernel": "srcs_expand", "place_src_kernel": "srcs_place"}
+    tab, src = {}, {}
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*_full.csv"))):      # later rounds override earlier ones
+        try:
+            for row in csv.DictReader(open(f)):
+                name = row.get("kernel", "")
+                for key, st in stage_of.items():
+                    if key in name and "dram__bytes_read.sum" in row:
+                        def gb(x):
+                            v, u = x.split()[:2]
+                            return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+                        tab[st] = gb(row["dram__bytes_read.sum"]) + gb(row["dram__bytes_write.sum"])
+                        src[st] = os.path.basename(f)
+        except Exception:  # noqa: BLE001
+            continue
+    return tab, src
+
+
+def north_star_run(cb, torch, dist, rank, world, local, allsum, allmax, barrier, steps=3):
+    """BASELINE.json north star: 2048^3 lognormal + sources + kappa (nside 1024) on 8 GPUs, with its property checks and
+    the HBM fractions of the FFT / lognormal stages. Appended to the --gpus 8 line under "north_star"."""
+    n = 2048
+    cfg = make_config(n)
+    tabs = build_tables(cfg)
+    nzl, iz0 = cb.dist.slab_bounds(n, world, rank)
+    par = cb.ParamCoLoRe(tabs, n, dens_type=0, seed=cfg.seed, device=local, nz_here=nzl, iz0_here=iz0)
+    cb.dist.init_comm(par, rank, world)
+    par.set_srcs(0, tabs["srcs_nz_0"], tabs["srcs_bz_0"])
+    out = {"workload": "n_grid=2048 lognormal + 1 galaxy population + RSD + kappa/ISW nside 1024", "n_gpus": world,
+           "transpose": cb.dist.transpose_mode(par)}
+    out["checks"] = parity_checks(cb, torch, par, tabs, n, local, allsum, allmax)
+    run_step(cb, par, 7, tabs)
+    par.synchronize()
+    barrier()
+    par.set_profiling(True)
+    par.timer_start()
+    nsrc = 0
+    for s in range(steps):
+        nsrc = run_step(cb, par, 100 + s, tabs)
+    ms = allmax(par.timer_stop_ms()) / steps
+    st = {}
+    for nm in STAGES:
+        m, nl = par.stage_ms(nm)
+        if m or nl:
+            st[nm] = {"ms_per_step_max": allmax(m) / steps, "ms_per_step_min": -allmax(-m) / steps}
+    par.set_profiling(False)
+    peak, _ = measured_hbm_peak()
+    cells = float(n) ** 3 / world
+    fft_ms = sum(st[k]["ms_per_step_max"] for k in ("fill_modes", "fill_fft_z", "fft_z", "fft_y", "fft_x", "fft_yx") if k in st)
+    out.update({"ms_per_step": ms, "Mcells_per_s": float(n) ** 3 / ms / 1e3, "sources_per_step": int(allsum(nsrc)), "stages": st,
+                "fill_plus_fft_hbm_gbs_per_gpu": 56.0 * cells / (fft_ms * 1e-3) / 1e9,
+                "fill_plus_fft_frac_of_hbm_peak": 56.0 * cells / (fft_ms * 1e-3) / 1e9 / peak})
+    if "lognormal" in st:
+        lb = 12.0 if "norm_hist" not in st else 8.0       # lognormal alone: 8 B/cell; with the fused histogram: + 4
+        out["lognormal_frac_of_hbm_peak"] = lb * cells / (st["lognormal"]["ms_per_step_max"] * 1e-3) / 1e9 / peak
+    if out["transpose"] == "p2p-fused":
+        zname = "fill_fft_z" if "fill_fft_z" in st else "fft_z"
+        sent = 2 * 8.0 * n * n * (n // 2 + 1) / world * (world - 1) / world
+        out["nvlink_gbs_per_direction_during_fused_pass"] = sent / (st[zname]["ms_per_step_max"] * 1e-3) / 1e9
+    # kappa + ISW maps at nside 1024 on two planes
+    rf = np.interp([0.2, 0.4], tabs["z"], tabs["r"]).astype(np.float32)
+    _, pos = cb.healpix.hp_shell_pixels(1024, 2)
+    for name, fn in (("kappa_los", cb.kappa_get_beam_properties), ("isw_los", cb.isw_get_beam_properties)):
+        fn(par, pos[:1024], rf)
+        barrier()
+        par.set_profiling(True)
+        t0 = time.perf_counter()
+        m = fn(par, pos, rf)
+        wall = allmax(time.perf_counter() - t0)
+        kms, _ = par.stage_ms(name)
+        par.set_profiling(False)
+        out[name] = {"nside": 1024, "kernel_ms_max": allmax(kms), "api_wall_ms": wall * 1e3,
+                     "finite": bool(np.isfinite(m).all()), "map_rms": float(m.astype(np.float64).std())}
+    par.free()
+    return out
+
+
+STAGES = ["fill_modes", "fill_fft_z", "fft_z", "fft_a2a", "fft_y", "fft_x", "fft_yx", "halo", "lognormal", "norm_hist",
+          "srcs_bound", "srcs_poisson", "srcs_scan", "srcs_expand", "srcs_place", "srcs_local"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,7 +368,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-grid", type=int, default=1024)
-    ap.add_argument("--ref-n-grid", type=int, default=512, help="bounded sample size of the CPU baseline")
+    ap.add_argument("--ref-n-grid", type=int, default=0,
+                    help="n_grid of the CPU runs: --impl reference defaults to --n-grid (same config); the cpu_baseline leg "
+                         "of the GPU arm defaults to 512 (a bounded sample)")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the 2048^3 run that --gpus 8 appends")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -277,13 +443,13 @@ def main():
     launches = par.launch_count - l0
     ms_step = ms_total / args.steps
     value = n ** 3 / (ms_step * 1e-3) / 1e6
-    stage_names = ["fill_modes", "fill_fft_z", "fft_z", "fft_a2a", "fft_y", "fft_x", "fft_yx", "halo", "lognormal", "norm_hist", "srcs_poisson",
-                   "srcs_scan", "srcs_expand", "srcs_place", "srcs_local"]
     stages = {}
-    for nm in stage_names:
+    for nm in STAGES:
         ms, nl = par.stage_ms(nm)
         if nl or ms:
-            stages[nm] = {"ms_per_step": ms / args.steps, "launches_per_step": nl / args.steps}
+            # this rank's value (rank 0 prints) + min / max over the ranks: edge slabs hold fewer sources than middle ones
+            stages[nm] = {"ms_per_step": ms / args.steps, "launches_per_step": nl / args.steps,
+                          "ms_per_step_max": allmax(ms) / args.steps, "ms_per_step_min": -allmax(-ms) / args.steps}
     par.set_profiling(False)
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
@@ -301,16 +467,14 @@ def main():
         "srcs_expand": 4.0 * cells + 8.0 * nsrc, "srcs_place": 36.0 * nsrc,
     }
     dom = max((k for k in stages if k in alg_bytes and stages[k]["launches_per_step"] > 0),
-              key=lambda k: stages[k]["ms_per_step"])
+              key=lambda k: stages[k]["ms_per_step"] / stages[k]["launches_per_step"])
     per_launch_ms = stages[dom]["ms_per_step"] / stages[dom]["launches_per_step"]
     achieved = alg_bytes[dom] / (per_launch_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of THIS
-    # workload (n_grid=1024, one GPU): profiles/r1_ncu_top_kernels_v8_full.csv (Poisson: ..._v4_full.csv)
-    ncu_traffic = {"fill_modes": 9.33e9, "fft_z": 8.55e9, "fft_y": 8.55e9, "fft_x": 8.56e9, "lognormal": 8.58e9,
-                   "norm_hist": 4.33e9, "srcs_poisson": 9.32e9, "srcs_expand": 3.72e9, "srcs_place": 5.81e9}
+    ncu_traffic, ncu_src = ncu_traffic_table()
     traffic = ncu_traffic.get(dom) if (n == 1024 and world == 1) else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": ncu_src.get(dom) if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes[dom], "ms_per_launch": per_launch_ms}
     # mode fill + both 3-D c2r transforms: 8 + 2 x 24 B/cell (the fill is fused into the z pass on one GPU)
     fft_ms = sum(stages[k]["ms_per_step"] for k in ("fill_modes", "fill_fft_z", "fft_z", "fft_y", "fft_x", "fft_yx") if k in stages)
@@ -371,28 +535,41 @@ def main():
     if not args.no_cpu_baseline and rank == 0 and world == 1:      # N=1 only (the other ranks would just wait)
         threads = os.cpu_count() or 1
         try:
-            v, st = run_reference_sample(args.ref_n_grid, threads)
+            n_cpu = args.ref_n_grid or 512
+            v, st = run_reference_sample(n_cpu, threads)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                    "sample": f"unmodified reference (oracle/_ref/CoLoRe_ref; shim FFT instead of FFTW) at "
-                             f"n_grid={args.ref_n_grid}, {threads} OpenMP threads, field->sources stages",
-                   "stages_ms": st, "scipy_irfftn_2x_ms": scipy_fft_ms(args.ref_n_grid, threads)}
+                             f"n_grid={n_cpu} (bounded sample; `--impl reference` runs the full n_grid), {threads} OpenMP "
+                             f"threads, field->sources stages",
+                   "stages_ms": st, "scipy_irfftn_2x_ms": scipy_fft_ms(n_cpu, threads)}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"failed: {e}"[:200]}
 
+    # ---- correctness bits of this very configuration (after the timed regions) ------------------
+    parity = parity_checks(cb, torch, par, tabs, n, local, allsum, allmax)
+    transpose = cb.dist.transpose_mode(par) if world > 1 else "none"
+    par.free()
+    par = None
+    north = None
+    if world == 8 and not args.no_north_star:
+        try:
+            north = north_star_run(cb, torch, dist, rank, world, local, allsum, allmax, barrier)
+        except Exception as e:  # noqa: BLE001
+            north = {"failed": str(e)[:300]}
+
     if rank == 0:
+        cfgd = workload_config(n)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"n_grid={n} lognormal + 1 galaxy population + RSD (field->sources)",
-                       "n_grid": n, "sources_per_step": nsrc_total,
-                       "parallelism": f"{world} z-slab(s), one process per GPU, FFT slab transpose: "
-                                      + (cb.dist.transpose_mode(par) if world > 1 else "none"),
-                       "l2_policy": "inputs (8.6 GB of grids at 1024^3) exceed the 126 MB L2", "seed_per_step": "varies"},
+            "data": "synthetic", "config": cfgd, "sources_per_step": nsrc_total,
+            "parallelism": f"{world} z-slab(s), one process per GPU, FFT slab transpose: {transpose}",
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "fft_hbm_gbs": fft_gbs, "nvlink": nvlink, "stages": stages, "cpu_baseline": cpu,
+            "roofline": roofline, "fft_hbm_gbs": fft_gbs, "nvlink": nvlink, "stages": stages, "parity": parity,
+            "north_star": north, "cpu_baseline": cpu,
         }))
-    par.free()
+    if par is not None:
+        par.free()
     if dist is not None:
         dist.destroy_process_group()
 

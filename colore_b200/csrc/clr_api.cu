@@ -195,7 +195,7 @@ int clr_destroy(clr_ctx *c)
   clr_comm_destroy(c);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
-  cudaFree(c->d_coord_f); cudaFree(c->d_coord_d); cudaFree(c->d_fft_tmp); cudaFree(c->d_fft_sync);
+  cudaFree(c->d_coord_f); cudaFree(c->d_coord_d); cudaFree(c->d_fft_tmp); cudaFree(c->d_fft_sync); cudaFree(c->d_hist);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch); cudaFree(c->d_pkt); cudaFree(c->d_sincos);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1);
@@ -232,6 +232,7 @@ static int set_pop(clr_ctx *c, clr_ctx::Pop &P, const double *a, const double *b
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   P.set = true;
   P.have_norm = false;
+  c->hist_valid = false;
   return 0;
 }
 
@@ -263,6 +264,7 @@ static float *grid_ptr(clr_ctx *c, int which) { return which == CLR_GRID_DENS ? 
 // host side = the reference layout, rows of 2*(n/2+1) floats (fourier.c:46-51); device side = rows of dev.pitch floats
 int clr_grid_put(clr_ctx *c, int which, const float *host)
 {
+  if (which == CLR_GRID_DENS) c->hist_valid = false;
   const size_t hrow = (size_t)2 * c->dev.nc * sizeof(float), drow = (size_t)c->dev.pitch * sizeof(float);
   CLR_CUDA(cudaMemcpy2DAsync(grid_ptr(c, which), drow, host, hrow, hrow, (size_t)c->dev.n * c->dev.nz_here,
                              cudaMemcpyHostToDevice, c->stream));
@@ -277,7 +279,12 @@ int clr_grid_get(clr_ctx *c, int which, float *host)
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
-int clr_grid_device_ptr(clr_ctx *c, int which, void **dptr) { *dptr = grid_ptr(c, which); return 0; }
+int clr_grid_device_ptr(clr_ctx *c, int which, void **dptr)
+{
+  c->hist_valid = false;            // the caller may write the grid behind our back
+  *dptr = grid_ptr(c, which);
+  return 0;
+}
 int clr_grid_pitch(clr_ctx *c, long long *pitch_floats)
 {
   *pitch_floats = c->dev.pitch;
@@ -285,8 +292,8 @@ int clr_grid_pitch(clr_ctx *c, long long *pitch_floats)
 }
 
 int clr_fill_modes(clr_ctx *c, uint32_t seed) { return clr_fields_fill(c, seed); }
-int clr_fft_c2r(clr_ctx *c, int which) { return clr_fft_c2r_impl(c, grid_ptr(c, which), 1.0, nullptr); }
-int clr_fft_r2c(clr_ctx *c, int which) { return clr_fft_r2c_impl(c, grid_ptr(c, which)); }
+int clr_fft_c2r(clr_ctx *c, int which) { c->hist_valid = false; return clr_fft_c2r_impl(c, grid_ptr(c, which), 1.0, nullptr); }
+int clr_fft_r2c(clr_ctx *c, int which) { c->hist_valid = false; return clr_fft_r2c_impl(c, grid_ptr(c, which)); }
 int clr_update_halo(clr_ctx *c) { return clr_halo_update(c); }
 
 static void finish_moments(clr_ctx *c, const double mom[2], double *out2)
@@ -310,6 +317,7 @@ int clr_normalize_fields(clr_ctx *c, double *out2)
 
 int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *out2)
 {
+  c->hist_valid = false;
   if (clr_ensure_scratch(c, 4096)) return 1;
   CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
   double norm = pow(sqrt(2 * M_PI) / c->p.l_box, 3);      // fourier.c:389
@@ -333,7 +341,8 @@ int clr_set_sigma2_gauss(clr_ctx *c, double s2) { c->sigma2_gauss = s2; return 0
 
 int clr_set_option(clr_ctx *c, const char *name, int value)
 {
-  if (!strcmp(name, "exact_math")) { c->exact_math = value; return 0; }
+  if (!strcmp(name, "exact_math")) { c->exact_math = value; c->hist_valid = false; return 0; }
+  if (!strcmp(name, "hist_fused")) { c->hist_fused = value; c->hist_valid = false; return 0; }
   if (!strcmp(name, "lpt_interp_type")) { c->lpt_interp_type = value; return 0; }
   if (!strcmp(name, "keep_particles")) { c->keep_particles = value; return 0; }
   if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
@@ -347,6 +356,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
 
 int clr_compute_physical_density_field(clr_ctx *c)
 {
+  c->hist_valid = false;
   if (c->p.dens_type == CLR_DENS_TYPE_LGNR) return clr_fields_lognormal(c, 0);
   if (c->p.dens_type == CLR_DENS_TYPE_CLIP) return clr_fields_lognormal(c, 1);
   if (c->p.dens_type == CLR_DENS_TYPE_1LPT) return clr_lpt_run(c, 1);

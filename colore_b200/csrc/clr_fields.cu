@@ -436,6 +436,8 @@ constexpr int kRun = 2;
 constexpr int kFastPop = 4;
 // lerp tables {f[i], f[i+1]-f[i]} in fp32: entry 0 = z(r), entries 1.. = b(r) per population
 struct NormPopsF { const float2 *zt; const float4 *zb; const float2 *bt[kFastPop]; int npop; };
+// lognormal / clip transform fused into the histogram walk (XFORM): growth table, 0.5*sigma^2, dens_type 3
+struct XformArgs { const float2 *d1_t; float hs2, dlast; int clip; };
 
 __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
 {
@@ -455,10 +457,14 @@ __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
 // thick shell) changes every ~60 steps: the lane keeps {count, sum z, sum bias_model} of its current bin in
 // registers and touches the shared-memory histogram only when the bin changes. The 8 warps of a CTA take 8
 // neighbouring strips of the same rows (2 KB contiguous per row step).
-template <int NPOP>
+// XFORM: the walk first applies lognormalize / densclip (density.c:1034-1103, the arithmetic of lognormal_fast_kernel) to
+// the Gaussian cell, stores it, and bins the transformed value: one read of the field for both stages, radius and table
+// position computed once.
+template <int NPOP, bool XFORM>
 __global__ void __launch_bounds__(kThreads)
-norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF pops, int nz, double idz,
-                      unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b)
+norm_hist_fast_kernel(const ClrDev d, float *__restrict__ dens, NormPopsF pops, int nz, double idz,
+                      unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b,
+                      const XformArgs xf)
 {
   // CTA histogram in shared memory, updated with 32-bit integer atomics only (the float / double / 64-bit
   // shared atomics of sm_100 are CAS spin loops): counts as u32, sums as 64-bit fixed point (2^-20) held
@@ -513,11 +519,13 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
     int iz = (int)(row0 / (unsigned)d.n), iy = (int)(row0 - (unsigned)iz * (unsigned)d.n);
     float zz = 0.f;
     { const float z0 = __ldg(d.cf[2] + iz + d.iz0_here); zz = __fmul_rn(z0, z0); }
-    const float2 *p = reinterpret_cast<const float2 *>(dens + (long long)row0 * d.pitch) + xq;
+    float2 *p = reinterpret_cast<float2 *>(dens + (long long)row0 * d.pitch) + xq;
     const int pitch2 = d.pitch >> 1;
     float2 dv = row0 < row1 ? *p : make_float2(0.f, 0.f);
     for (unsigned row = row0; row < row1; row++) {
       const float2 dcur = dv;
+      float2 *pcur = p;
+      float xo[2];
       p += pitch2;
       if (row + 1 < row1) dv = *p;                                     // next row's load flies under this row's math
       const float y0 = __ldg(d.cf[1] + iy);
@@ -526,7 +534,7 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
       float zf2[2], bm2[2][kFastPop];
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const float dl = h ? dcur.y : dcur.x;
+        float dl = h ? dcur.y : dcur.x;
         const float r2 = __fadd_rn(__fadd_rn(xx[h], yy), zz);          // same order as the reference
         const float rf = clr_sqrt_fast(r2);
         const float tr = fminf(rf * idrf, (float)(CLR_NA - 2) + 0.5f);
@@ -536,6 +544,12 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
         // pops.zb: {z_i, z_i+1 - z_i, b_i, b_i+1 - b_i} of the first population: one 16-byte load per cell
         const float4 tz = __ldg(pops.zb + ir);
         const bool past = rf >= rtabf;
+        if (XFORM) {
+          const float2 e = __ldg(xf.d1_t + ir);
+          const float dg = past ? xf.dlast : fmaf(e.y, fr, e.x);
+          dl = xf.clip ? fmaxf(fmaf(dg, dl, 1.f), 0.f) - 1.f : clr_ex2_fast(1.4426950408889634f * dg * fmaf(-xf.hs2, dg, dl)) - 1.f;
+          xo[h] = dl;
+        }
         const float zf = past ? zlastf : fmaf(tz.y, fr, tz.x);
         const float tb = zf * idzf;
         const float tbn = __fadd_rn(__fadd_rn(tb, 12582912.f), -12582912.f);   // nearest integer, conversion-free
@@ -557,6 +571,7 @@ norm_hist_fast_kernel(const ClrDev d, const float *__restrict__ dens, NormPopsF 
           }
         }
       }
+      if (XFORM) *pcur = make_float2(xo[0], xo[1]);
       if (bin2[0] == curbin && bin2[1] == curbin) {                    // the common case: plain register sums
         cnt += 2;
         zs += zf2[0] + zf2[1];
@@ -728,10 +743,105 @@ int clr_fields_scale_moments(clr_ctx *c, double *out2)
   return 0;
 }
 
+// bins of compute_density_normalization (density.c:1233-1245): nz = (int)(z(L/2)/0.05)+2, idz = (nz-2)/z(L/2)
+static void norm_bins(const clr_ctx *c, int *nz, double *idz)
+{
+  const double r = (double)(c->p.l_box * 0.5);
+  double zmax;
+  if (r <= 0) zmax = 0;
+  else if (r >= c->h_r[CLR_NA - 1]) zmax = c->h_z[CLR_NA - 1];
+  else {
+    int ir = (int)(r * c->p.glob_idr);
+    zmax = c->h_z[ir] + (c->h_z[ir + 1] - c->h_z[ir]) * (r - c->h_r[ir]) * c->p.glob_idr;
+  }
+  *nz = (int)(zmax / 0.05) + 2;
+  *idz = (*nz - 2) / zmax;
+}
+
+// every population that enters the normalisation, in the order of density.c:1246-1260 (sources, then intensity maps)
+static int norm_pops(clr_ctx *c, const double **d_bz)
+{
+  int npop = 0;
+  for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->srcs[i].set) { if (d_bz) d_bz[npop] = c->srcs[i].d_b; npop++; }
+  for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->imap[i].set) { if (d_bz) d_bz[npop] = c->imap[i].d_b; npop++; }
+  return npop;
+}
+
+// Launch the fp32 histogram walk into c->d_hist ({counts[nz], sum z[nz], sum bias_model[npop][nz]}), optionally with
+// the lognormal / clip transform fused in (xf != nullptr).
+static int launch_hist_walk(clr_ctx *c, int npop, const double *const *d_bz, int nz, double idz, const XformArgs *xf)
+{
+  const size_t nd = (size_t)nz * (2 + npop);
+  const size_t tab_bytes = (size_t)(kFastPop + 3) * CLR_NA * sizeof(float2) + 64;
+  if (!c->d_hist || c->hist_bytes < nd * sizeof(double) + tab_bytes) {
+    if (c->d_hist) cudaFree(c->d_hist);
+    c->d_hist = nullptr;
+    c->hist_bytes = nd * sizeof(double) + tab_bytes;
+    CLR_CUDA(cudaMalloc(&c->d_hist, c->hist_bytes));
+  }
+  CLR_CUDA(cudaMemsetAsync(c->d_hist, 0, nd * sizeof(double), c->stream));
+  unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_hist);
+  double *g_z = c->d_hist + nz;
+  double *g_b = c->d_hist + 2 * nz;
+  // fp32 lerp tables of z(r) and the b(r) live behind the histograms
+  NormPopsF pf;
+  pf.npop = npop;
+  float2 *tab = reinterpret_cast<float2 *>(c->d_hist + nd);
+  lerp_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, tab, CLR_NA);
+  pf.zt = tab;
+  for (int i = 0; i < npop; i++) {
+    lerp_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(d_bz[i], tab + (size_t)(i + 1) * CLR_NA, CLR_NA);
+    pf.bt[i] = tab + (size_t)(i + 1) * CLR_NA;
+  }
+  for (int i = npop; i < kFastPop; i++) pf.bt[i] = tab;
+  float4 *tab4 = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(tab + (size_t)(kFastPop + 1) * CLR_NA) + 15) & ~(uintptr_t)15);
+  lerp_table2_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, npop ? d_bz[0] : nullptr, tab4, CLR_NA);
+  pf.zb = tab4;
+  c->launches += 2 + npop;                     // the lerp-table kernels above
+  // CTAs side by side along x (8 strips of 64 cells each) x row ranges; 8 resident CTAs per SM
+  const int groups = ((c->dev.n + 63) / 64 + 7) / 8;
+  long long n_rows = (long long)c->dev.nz_here * c->dev.n;
+  long long ranges = std::min<long long>(n_rows, std::max<long long>(1, (long long)c->sm_count * 8 / groups));
+  int grid = (int)(ranges * groups);
+  const size_t smem = nd * sizeof(double);
+  XformArgs x0{nullptr, 0.f, 0.f, 0};
+#define CLR_HIST(NP)                                                                                                              \
+  if (xf) norm_hist_fast_kernel<NP, true><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf); \
+  else norm_hist_fast_kernel<NP, false><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, x0)
+  switch (npop) {
+    case 0: CLR_HIST(0); break;
+    case 1: CLR_HIST(1); break;
+    case 2: CLR_HIST(2); break;
+    case 3: CLR_HIST(3); break;
+    default: CLR_HIST(4); break;
+  }
+#undef CLR_HIST
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int clr_fields_lognormal(clr_ctx *c, int clip)
 {
-  StageScope sc(c, "lognormal", 1);
+  c->hist_valid = false;
   long long n2 = (long long)c->dev.nz_here * c->dev.n * (c->dev.n / 2);
+  // populations already known (the usual run flow: read_run_params before the fields): do the normalisation histogram
+  // of compute_density_normalization in the same pass over the field and keep it for that call
+  const double *d_bz[CLR_MAX_NORM_POP];
+  const int npop = norm_pops(c, nullptr);
+  if (!c->exact_math && c->hist_fused && npop >= 1 && npop <= kFastPop && c->dev.n % kRun == 0) {
+    int nz; double idz;
+    norm_bins(c, &nz, &idz);
+    if (nz <= CLR_MAX_NZ) {
+      norm_pops(c, d_bz);
+      StageScope sc(c, "lognormal", 1);
+      XformArgs xf{c->dev.d1_t, (float)(0.5 * c->sigma2_gauss), (float)c->h_d1[CLR_NA - 1], clip};
+      if (launch_hist_walk(c, npop, d_bz, nz, idz, &xf)) return 1;
+      c->hist_valid = true; c->hist_npop = npop; c->hist_nz = nz;
+      for (int i = 0; i < npop; i++) c->hist_bz[i] = d_bz[i];
+      return 0;
+    }
+  }
+  StageScope sc(c, "lognormal", 1);
   if (c->exact_math)
     lognormal_kernel<true><<<grid_for(c, n2, 8), kThreads, 0, c->stream>>>(c->dev, c->d_dens, c->sigma2_gauss, clip);
   else if (c->dev.n % 8 == 0)
@@ -747,59 +857,39 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
 {
   CLR_CHECK(npop <= CLR_MAX_NORM_POP && nz <= CLR_MAX_NZ, "normalisation: npop=%d nz=%d too large", npop, nz);
   size_t nd = (size_t)nz * (2 + npop);
-  if (clr_ensure_scratch(c, nd * sizeof(double) + (size_t)(kFastPop + 3) * CLR_NA * sizeof(float2) + 64)) return 1;
-  CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
-  unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_scratch);
-  double *g_z = c->d_scratch + nz;
-  double *g_b = c->d_scratch + 2 * nz;
-  NormPops pops;
-  pops.npop = npop;
-  for (int i = 0; i < npop; i++) pops.bz[i] = d_bz[i];
-  {
+  double *d_res = nullptr;
+  bool cached = c->hist_valid && c->hist_npop == npop && c->hist_nz == nz && !c->exact_math;
+  for (int i = 0; i < npop && cached; i++) cached = c->hist_bz[i] == d_bz[i];
+  c->hist_valid = false;                         // one use: the all-reduce below runs in place
+  if (cached) d_res = c->d_hist;                 // filled by the fused lognormal + histogram pass on this very field
+  else if (!c->exact_math && npop <= kFastPop && c->dev.n % kRun == 0) {
+    StageScope sc(c, "norm_hist", 1);
+    if (launch_hist_walk(c, npop, d_bz, nz, idz, nullptr)) return 1;
+    d_res = c->d_hist;
+  } else {
+    if (clr_ensure_scratch(c, nd * sizeof(double) + 64)) return 1;
+    CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, nd * sizeof(double), c->stream));
+    NormPops pops;
+    pops.npop = npop;
+    for (int i = 0; i < npop; i++) pops.bz[i] = d_bz[i];
     StageScope sc(c, "norm_hist", 1);
     long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
     size_t smem = nd * sizeof(double);
+    unsigned long long *g_n = reinterpret_cast<unsigned long long *>(c->d_scratch);
     if (c->exact_math)
-      norm_hist_kernel<true><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
-    else if (npop <= kFastPop && c->dev.n % kRun == 0) {
-      // fp32 lerp tables of z(r) and the b(r) live behind the histograms in the scratch buffer
-      NormPopsF pf;
-      pf.npop = npop;
-      float2 *tab = reinterpret_cast<float2 *>(c->d_scratch + nd);
-      lerp_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, tab, CLR_NA);
-      pf.zt = tab;
-      for (int i = 0; i < npop; i++) {
-        lerp_table_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(d_bz[i], tab + (size_t)(i + 1) * CLR_NA, CLR_NA);
-        pf.bt[i] = tab + (size_t)(i + 1) * CLR_NA;
-      }
-      for (int i = npop; i < kFastPop; i++) pf.bt[i] = tab;
-      float4 *tab4 = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(tab + (size_t)(kFastPop + 1) * CLR_NA) + 15) & ~(uintptr_t)15);
-      lerp_table2_kernel<<<(CLR_NA + 255) / 256, 256, 0, c->stream>>>(c->dev.z_arr, npop ? d_bz[0] : nullptr, tab4, CLR_NA);
-      pf.zb = tab4;
-      c->launches += 2 + npop;                     // the lerp-table kernels above
-      // CTAs side by side along x (8 strips of 64 cells each) x row ranges; 8 resident CTAs per SM
-      const int groups = ((c->dev.n + 63) / 64 + 7) / 8;
-      long long n_rows = (long long)c->dev.nz_here * c->dev.n;
-      long long ranges = std::min<long long>(n_rows, std::max<long long>(1, (long long)c->sm_count * 8 / groups));
-      int grid = (int)(ranges * groups);
-      switch (npop) {
-        case 0: norm_hist_fast_kernel<0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
-        case 1: norm_hist_fast_kernel<1><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
-        case 2: norm_hist_fast_kernel<2><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
-        case 3: norm_hist_fast_kernel<3><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
-        default: norm_hist_fast_kernel<4><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b); break;
-      }
-    } else
-      norm_hist_kernel<false><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, g_z, g_b);
+      norm_hist_kernel<true><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, c->d_scratch + nz, c->d_scratch + 2 * nz);
+    else
+      norm_hist_kernel<false><<<grid_for(c, n_cells, 8), kThreads, smem, c->stream>>>(c->dev, c->d_dens, pops, nz, idz, g_n, c->d_scratch + nz, c->d_scratch + 2 * nz);
     CLR_CUDA(cudaGetLastError());
+    d_res = c->d_scratch;
   }
   // density.c:1262-1269: histograms summed over the slabs
-  if (clr_comm_allreduce_u64(c, g_n, nz)) return 1;
-  if (clr_comm_allreduce_f64(c, g_z, (size_t)nz * (1 + npop))) return 1;
+  if (clr_comm_allreduce_u64(c, reinterpret_cast<unsigned long long *>(d_res), nz)) return 1;
+  if (clr_comm_allreduce_f64(c, d_res + nz, (size_t)nz * (1 + npop))) return 1;
   {
-    // g_n, g_z, g_b are contiguous in the scratch buffer: one small read-back
+    // counts, z sums, bias sums are contiguous: one small read-back
     std::vector<double> tmp(nd);
-    if (clr_read_small(c, tmp.data(), c->d_scratch, nd * sizeof(double))) return 1;
+    if (clr_read_small(c, tmp.data(), d_res, nd * sizeof(double))) return 1;
     memcpy(h_n, tmp.data(), nz * sizeof(unsigned long long));
     memcpy(h_z, tmp.data() + nz, nz * sizeof(double));
     if (npop) memcpy(h_b, tmp.data() + 2 * nz, (size_t)npop * nz * sizeof(double));

@@ -70,6 +70,11 @@ struct clr_ctx {
   int fill_fused = 1;                                // option "fill_fused": 0 = stand-alone mode fill + z pass
   size_t scratch_bytes = 0;
   double sigma2_gauss = 0, mean_gauss = 0;
+  // normalisation histogram produced by the fused lognormal + histogram pass (clr_fields.cu), valid for ONE later
+  // clr_compute_density_normalization on the same field with the same populations
+  double *d_hist = nullptr; size_t hist_bytes = 0;
+  bool hist_valid = false; int hist_npop = 0, hist_nz = 0; const double *hist_bz[CLR_NPOP_MAX * 2] = {nullptr};
+  int hist_fused = 1;                                // option "hist_fused": 0 = separate lognormal and histogram passes
   // populations
   struct Pop {
     bool set = false;

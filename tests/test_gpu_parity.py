@@ -323,6 +323,32 @@ def test_density_normalization_vs_reference(case, exact):
         np.testing.assert_allclose(norm, g["s3_imap_norm_0"], rtol=rtol)
 
 
+def test_fused_lognormal_histogram(case):
+    """Default flow with the populations known before the density transform: lognormalize / densclip and the
+    normalisation histogram run as ONE pass (clr_fields.cu: norm_hist_fast_kernel<.., XFORM>). Both the field and the
+    normalisation tables must match the reference (fp32 tolerances) and the separate passes."""
+    g, t, o, par = case
+    n = o.n
+    npop = sum(1 for k in t if k.startswith("srcs_bz_"))
+    for i in range(npop):
+        par.set_srcs(i, t[f"srcs_nz_{i}"], t[f"srcs_bz_{i}"])
+    res = {}
+    for fused in (1, 0):
+        par.set_option("hist_fused", fused)
+        par.grid_put(cb.GRID_DENS, g["s1_dens_gauss"])
+        par.set_sigma2_gauss(g["s1_sigma2_gauss"][0])
+        cb.compute_physical_density_field(par)
+        cb.compute_density_normalization(par)
+        res[fused] = (_real(par.grid_get(cb.GRID_DENS), n).astype(np.float64), [cb.get_norm(par, 0, i)[0] for i in range(npop)])
+    par.set_option("hist_fused", 1)
+    ref = _real(g["s2_dens"], n).astype(np.float64)
+    assert (np.abs(res[1][0] - ref) / (1 + np.abs(ref))).max() < 1e-6
+    assert (np.abs(res[1][0] - res[0][0]) / (1 + np.abs(ref))).max() < 5e-7
+    for i in range(npop):
+        np.testing.assert_allclose(res[1][1][i], g[f"s3_srcs_norm_{i}"], rtol=1e-6)
+        np.testing.assert_allclose(res[1][1][i], res[0][1][i], rtol=1e-6)
+
+
 # ------------------------------------------------------------------------------------ sources
 def _setup_sources(g, t, par):
     par.grid_put(cb.GRID_DENS, g["s2_dens"])
