@@ -38,6 +38,16 @@ int clr_read_small(clr_ctx *c, void *host_dst, const void *dev_src, size_t bytes
   return 0;
 }
 
+// The potential may still be in flight on the second stream (clr_create_cartesian_fields, multi-GPU): make the main
+// stream wait for it and exchange its z halo (fourier.c:401-414). Called by everything that reads or writes the grid.
+int clr_npot_ready(clr_ctx *c)
+{
+  if (!c->npot_pending) return 0;
+  c->npot_pending = false;
+  CLR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_npot, 0));
+  return clr_halo_update(c);
+}
+
 extern "C" {
 
 int clr_version(void) { return 100; }
@@ -191,7 +201,8 @@ int clr_destroy(clr_ctx *c)
 {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   clr_comm_destroy(c);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
@@ -211,6 +222,7 @@ int clr_destroy(clr_ctx *c)
 
 int clr_synchronize(clr_ctx *c)
 {
+  if (clr_npot_ready(c)) return 1;
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->copy_stream));
   c->copy_pending = false;
@@ -265,6 +277,7 @@ static float *grid_ptr(clr_ctx *c, int which) { return which == CLR_GRID_DENS ? 
 int clr_grid_put(clr_ctx *c, int which, const float *host)
 {
   if (which == CLR_GRID_DENS) c->hist_valid = false;
+  if (which == CLR_GRID_NPOT && clr_npot_ready(c)) return 1;
   const size_t hrow = (size_t)2 * c->dev.nc * sizeof(float), drow = (size_t)c->dev.pitch * sizeof(float);
   CLR_CUDA(cudaMemcpy2DAsync(grid_ptr(c, which), drow, host, hrow, hrow, (size_t)c->dev.n * c->dev.nz_here,
                              cudaMemcpyHostToDevice, c->stream));
@@ -273,6 +286,7 @@ int clr_grid_put(clr_ctx *c, int which, const float *host)
 }
 int clr_grid_get(clr_ctx *c, int which, float *host)
 {
+  if (which == CLR_GRID_NPOT && clr_npot_ready(c)) return 1;
   const size_t hrow = (size_t)2 * c->dev.nc * sizeof(float), drow = (size_t)c->dev.pitch * sizeof(float);
   CLR_CUDA(cudaMemcpy2DAsync(host, hrow, grid_ptr(c, which), drow, hrow, (size_t)c->dev.n * c->dev.nz_here,
                              cudaMemcpyDeviceToHost, c->stream));
@@ -282,6 +296,7 @@ int clr_grid_get(clr_ctx *c, int which, float *host)
 int clr_grid_device_ptr(clr_ctx *c, int which, void **dptr)
 {
   c->hist_valid = false;            // the caller may write the grid behind our back
+  if (which == CLR_GRID_NPOT && clr_npot_ready(c)) return 1;
   *dptr = grid_ptr(c, which);
   return 0;
 }
@@ -291,10 +306,20 @@ int clr_grid_pitch(clr_ctx *c, long long *pitch_floats)
   return 0;
 }
 
-int clr_fill_modes(clr_ctx *c, uint32_t seed) { return clr_fields_fill(c, seed); }
-int clr_fft_c2r(clr_ctx *c, int which) { c->hist_valid = false; return clr_fft_c2r_impl(c, grid_ptr(c, which), 1.0, nullptr); }
-int clr_fft_r2c(clr_ctx *c, int which) { c->hist_valid = false; return clr_fft_r2c_impl(c, grid_ptr(c, which)); }
-int clr_update_halo(clr_ctx *c) { return clr_halo_update(c); }
+int clr_fill_modes(clr_ctx *c, uint32_t seed) { if (clr_npot_ready(c)) return 1; return clr_fields_fill(c, seed); }
+int clr_fft_c2r(clr_ctx *c, int which)
+{
+  c->hist_valid = false;
+  if (clr_npot_ready(c)) return 1;
+  return clr_fft_c2r_impl(c, grid_ptr(c, which), 1.0, nullptr);
+}
+int clr_fft_r2c(clr_ctx *c, int which)
+{
+  c->hist_valid = false;
+  if (clr_npot_ready(c)) return 1;
+  return clr_fft_r2c_impl(c, grid_ptr(c, which));
+}
+int clr_update_halo(clr_ctx *c) { if (clr_npot_ready(c)) return 1; return clr_halo_update(c); }
 
 static void finish_moments(clr_ctx *c, const double mom[2], double *out2)
 {
@@ -308,6 +333,8 @@ static void finish_moments(clr_ctx *c, const double mom[2], double *out2)
 
 int clr_normalize_fields(clr_ctx *c, double *out2)
 {
+  c->hist_valid = false;
+  if (clr_npot_ready(c)) return 1;
   double mom[2];
   if (clr_fields_scale_moments(c, mom)) return 1;
   if (clr_halo_update(c)) return 1;
@@ -318,6 +345,7 @@ int clr_normalize_fields(clr_ctx *c, double *out2)
 int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *out2)
 {
   c->hist_valid = false;
+  if (clr_npot_ready(c)) return 1;
   if (clr_ensure_scratch(c, 4096)) return 1;
   CLR_CUDA(cudaMemsetAsync(c->d_scratch, 0, 2 * sizeof(double), c->stream));
   double norm = pow(sqrt(2 * M_PI) / c->p.l_box, 3);      // fourier.c:389
@@ -326,10 +354,31 @@ int clr_create_cartesian_fields(clr_ctx *c, uint32_t seed, int inject, double *o
   if (!inject && clr_fft_fill_c2r(c, seed, norm, c->d_scratch, &ran)) return 1;
   if (!ran) {
     if (!inject && clr_fields_fill(c, seed)) return 1;
-    if (clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch)) return 1;   // scaling + moments fused in the x pass
-    if (clr_fft_c2r_impl(c, c->d_npot, norm, nullptr)) return 1;
+    if (c->nranks > 1 && c->stream2 && c->p2p && c->p2p_enabled && c->fft_overlap) {
+      // Two pipelines: the density is transformed on the main stream; once its z pass has been exchanged (NVLink is
+      // free again) the potential follows on the second stream with its own staging buffer, under the y / x passes of
+      // the density and whatever the caller queues next (lognormal, normalisation, Poisson). The z halo of the
+      // potential is exchanged by clr_npot_ready when the first consumer shows up.
+      c->ev_after_z = c->ev_z_done;
+      int bad = clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch);
+      c->ev_after_z = nullptr;
+      if (bad) return 1;
+      cudaStream_t main_stream = c->stream;
+      CLR_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_z_done, 0));
+      c->stream = c->stream2;
+      clr_use_set(c, 1);
+      bad = clr_fft_c2r_impl(c, c->d_npot, norm, nullptr);
+      if (!bad && cudaEventRecord(c->ev_npot, c->stream) != cudaSuccess) bad = 1;
+      c->stream = main_stream;
+      clr_use_set(c, 0);
+      if (bad) return 1;
+      c->npot_pending = true;
+    } else {
+      if (clr_fft_c2r_impl(c, c->d_dens, norm, c->d_scratch)) return 1;   // scaling + moments fused in the x pass
+      if (clr_fft_c2r_impl(c, c->d_npot, norm, nullptr)) return 1;
+    }
   }
-  if (clr_halo_update(c)) return 1;
+  if (!c->npot_pending && clr_halo_update(c)) return 1;
   if (clr_comm_allreduce_f64(c, c->d_scratch, 2)) return 1;            // fourier.c:69-70
   double mom[2];
   if (clr_read_small(c, mom, c->d_scratch, sizeof(mom))) return 1;
@@ -349,6 +398,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "fft_fused")) { c->fft_fused = value; return 0; }
   if (!strcmp(name, "fill_fused")) { c->fill_fused = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
+  if (!strcmp(name, "fft_overlap")) { if (clr_npot_ready(c)) return 1; c->fft_overlap = value; return 0; }
   if (!strcmp(name, "p2p_tiled")) { c->p2p_tiled = value; return 0; }
   clr_set_error("unknown option %s", name);
   return 1;
@@ -359,6 +409,7 @@ int clr_compute_physical_density_field(clr_ctx *c)
   c->hist_valid = false;
   if (c->p.dens_type == CLR_DENS_TYPE_LGNR) return clr_fields_lognormal(c, 0);
   if (c->p.dens_type == CLR_DENS_TYPE_CLIP) return clr_fields_lognormal(c, 1);
+  if (clr_npot_ready(c)) return 1;          // LPT borrows the transform machinery and staging buffer
   if (c->p.dens_type == CLR_DENS_TYPE_1LPT) return clr_lpt_run(c, 1);
   if (c->p.dens_type == CLR_DENS_TYPE_2LPT) return clr_lpt_run(c, 2);
   clr_set_error("Density type %d not supported\n", c->p.dens_type);     // density.c:1119
@@ -523,7 +574,7 @@ int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
   return 0;
 }
 
-int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { return clr_srcs_beam(c, ipop); }
+int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { if (clr_npot_ready(c)) return 1; return clr_srcs_beam(c, ipop); }
 int clr_lpt_get_particles(clr_ctx *c, float *x, float *y, float *z) { return clr_lpt_particles(c, x, y, z); }
 int clr_lpt_exchange_counts(clr_ctx *c, long long *sent, long long *received)
 {
@@ -532,11 +583,12 @@ int clr_lpt_exchange_counts(clr_ctx *c, long long *sent, long long *received)
   return 0;
 }
 
-int clr_imap_set_cartesian(clr_ctx *c, int ipop, float *data, int32_t *nadd) { return clr_maps_imap(c, ipop, data, nadd); }
+int clr_imap_set_cartesian(clr_ctx *c, int ipop, float *data, int32_t *nadd)
+{ if (clr_npot_ready(c)) return 1; return clr_maps_imap(c, ipop, data, nadd); }
 int clr_kappa_get_beam_properties(clr_ctx *c, long long num_pix, const double *pos3, int nplanes, const float *rf, float *data)
-{ return clr_maps_los(c, 0, num_pix, pos3, nplanes, rf, data); }
+{ if (clr_npot_ready(c)) return 1; return clr_maps_los(c, 0, num_pix, pos3, nplanes, rf, data); }
 int clr_isw_get_beam_properties(clr_ctx *c, long long num_pix, const double *pos3, int nplanes, const float *rf, float *data)
-{ return clr_maps_los(c, 1, num_pix, pos3, nplanes, rf, data); }
+{ if (clr_npot_ready(c)) return 1; return clr_maps_los(c, 1, num_pix, pos3, nplanes, rf, data); }
 
 int clr_timer_start(clr_ctx *c) { CLR_CUDA(cudaEventRecord(c->ev0, c->stream)); return 0; }
 int clr_timer_stop_ms(clr_ctx *c, float *ms)
@@ -550,6 +602,7 @@ static int resolve_stage_events(clr_ctx *c)
 {
   if (c->ev_pending.empty()) return 0;
   CLR_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->stream2) CLR_CUDA(cudaStreamSynchronize(c->stream2));
   for (auto &pe : c->ev_pending) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev_pool[pe.slot], c->ev_pool[pe.slot + 1]);

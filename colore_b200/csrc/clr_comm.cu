@@ -83,62 +83,148 @@ extern "C" int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128
   c->nccl_comm = comm;
   d.nyl = d.n / nranks;
   d.ky0 = rank * d.nyl;
-  // staging buffer of the FFT all-to-all: one slab
-  // (+ padding: the tile-major layout of the fused c2r transpose rounds every source block up to whole tiles)
-  size_t bytes = (size_t)d.pitch * d.n * d.nz_here * sizeof(float) + (size_t)nranks * d.nz_here * 64 * sizeof(float2);
+  // staging buffers of the FFT slab transpose: one slab each (+ padding: the tile-major layout of the fused c2r transpose
+  // rounds every source block up to whole tiles), followed by the flag words of the peer-memory barriers. The second
+  // buffer belongs to the potential's pipeline (fft_overlap); it is skipped when memory is short (4096^3 on 8 GPUs).
+  size_t floats = (size_t)d.pitch * d.n * d.nz_here + (size_t)nranks * d.nz_here * 64 * 2;
+  floats = (floats + 63) & ~(size_t)63;
+  c->stage_floats = floats;
+  const size_t bytes = floats * sizeof(float) + 4096;
   CLR_CUDA(cudaMalloc(&c->d_stage, bytes));
+  CLR_CUDA(cudaMemset(reinterpret_cast<char *>(c->d_stage) + floats * sizeof(float), 0, 4096));
+  c->sets[0].stage = c->d_stage;
+  {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t slab = (size_t)d.pitch * d.n * d.nz_here * sizeof(float);
+    if (c->fft_overlap && free_b > bytes + 2 * slab + (8ULL << 30)) {       // leave room for counts + catalogue
+      CLR_CUDA(cudaMalloc(&c->sets[1].stage, bytes));
+      CLR_CUDA(cudaMemset(reinterpret_cast<char *>(c->sets[1].stage) + floats * sizeof(float), 0, 4096));
+    }
+  }
   CLR_CUDA(cudaMalloc(&c->d_barrier, sizeof(int)));
   CLR_CUDA(cudaMemset(c->d_barrier, 0, sizeof(int)));
   // Peer mapping of the staging buffers (CUDA IPC; the GPUs of one node see each other over NVLink / NVSwitch).
   // Handles travel through an ncclAllGather. If any rank cannot map a peer, every rank falls back to the NCCL
   // all-to-all (the decision is all-reduced so that the ranks never disagree).
   int ok = nranks <= CLR_MAX_PEERS ? 1 : 0;
-  cudaIpcMemHandle_t mine;
-  if (ok && cudaIpcGetMemHandle(&mine, c->d_stage) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-  unsigned char *d_h = nullptr;
-  CLR_CUDA(cudaMalloc(&d_h, (size_t)nranks * sizeof(cudaIpcMemHandle_t)));
-  CLR_CUDA(cudaMemset(d_h, 0, (size_t)nranks * sizeof(cudaIpcMemHandle_t)));
-  if (ok) CLR_CUDA(cudaMemcpy(d_h + (size_t)rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
-  CLR_NCCL(g_nccl.AllGather(d_h + (size_t)rank * sizeof(mine), d_h, sizeof(mine), ncclChar, comm, c->stream));
-  CLR_CUDA(cudaStreamSynchronize(c->stream));
-  std::vector<cudaIpcMemHandle_t> all(nranks);
-  CLR_CUDA(cudaMemcpy(all.data(), d_h, (size_t)nranks * sizeof(mine), cudaMemcpyDeviceToHost));
-  cudaFree(d_h);
-  for (int h = 0; h < nranks && ok; h++) {
-    if (h == rank) { c->peer_stage[h] = c->d_stage; continue; }
-    void *ptr = nullptr;
-    if (cudaIpcOpenMemHandle(&ptr, all[h], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-    c->peer_stage[h] = static_cast<float *>(ptr);
+  int have2 = c->sets[1].stage ? 1 : 0;
+  for (int b = 0; b < 2; b++) {
+    if (!c->sets[b].stage) continue;
+    cudaIpcMemHandle_t mine;
+    if (ok && cudaIpcGetMemHandle(&mine, c->sets[b].stage) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    unsigned char *d_h = nullptr;
+    CLR_CUDA(cudaMalloc(&d_h, (size_t)nranks * sizeof(cudaIpcMemHandle_t)));
+    CLR_CUDA(cudaMemset(d_h, 0, (size_t)nranks * sizeof(cudaIpcMemHandle_t)));
+    if (ok) CLR_CUDA(cudaMemcpy(d_h + (size_t)rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    CLR_NCCL(g_nccl.AllGather(d_h + (size_t)rank * sizeof(mine), d_h, sizeof(mine), ncclChar, comm, c->stream));
+    CLR_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<cudaIpcMemHandle_t> all(nranks);
+    CLR_CUDA(cudaMemcpy(all.data(), d_h, (size_t)nranks * sizeof(mine), cudaMemcpyDeviceToHost));
+    cudaFree(d_h);
+    for (int h = 0; h < nranks && ok; h++) {
+      if (h == rank) { c->sets[b].peer[h] = c->sets[b].stage; }
+      else {
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[h], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        c->sets[b].peer[h] = static_cast<float *>(ptr);
+      }
+      c->sets[b].flag_peer[h] = reinterpret_cast<unsigned *>(c->sets[b].peer[h] + floats);
+    }
   }
+  for (int h = 0; h < nranks; h++) c->peer_stage[h] = c->sets[0].peer[h];
+  // every rank must have the second pipeline, or none uses it
+  CLR_CUDA(cudaMemcpy(c->d_barrier, &have2, sizeof(int), cudaMemcpyHostToDevice));
+  CLR_NCCL(g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMin, comm, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  CLR_CUDA(cudaMemcpy(&have2, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost));
   CLR_CUDA(cudaMemcpy(c->d_barrier, &ok, sizeof(int), cudaMemcpyHostToDevice));
   CLR_NCCL(g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMin, comm, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
   CLR_CUDA(cudaMemcpy(&ok, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost));
   c->p2p = ok != 0;
+  c->flag_barrier = c->p2p && have2;                 // only the two-pipeline mode needs barriers that are not NCCL calls
+  if (!(c->p2p && have2)) {                          // no second pipeline: everything runs on the main stream
+    if (c->sets[1].stage) {
+      for (int h = 0; h < nranks; h++)
+        if (c->sets[1].peer[h] && c->sets[1].peer[h] != c->sets[1].stage) cudaIpcCloseMemHandle(c->sets[1].peer[h]);
+      cudaFree(c->sets[1].stage);
+    }
+    c->sets[1] = clr_ctx::StageSet();
+  } else {
+    CLR_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CLR_CUDA(cudaEventCreateWithFlags(&c->ev_z_done, cudaEventDisableTiming));
+    CLR_CUDA(cudaEventCreateWithFlags(&c->ev_npot, cudaEventDisableTiming));
+  }
   return 0;
 }
 
+// select the staging buffer + barrier flags (clr_fft.cu works on c->d_stage / c->peer_stage)
+void clr_use_set(clr_ctx *c, int set)
+{
+  c->cur_set = set;
+  c->d_stage = c->sets[set].stage;
+  for (int h = 0; h < CLR_MAX_PEERS; h++) c->peer_stage[h] = c->sets[set].peer[h];
+}
+
+namespace {
+// Barrier over all ranks, ordered in the stream: thread h tells rank h "I have reached epoch e" with a release store into
+// h's flag array (peer memory), then waits until rank h has told me the same. Everything queued before the barrier on
+// the peers' streams (their stores into my staging buffer) has completed when it returns.
+struct FlagPtrs { unsigned *p[CLR_MAX_PEERS]; };
+__global__ void flag_barrier_kernel(FlagPtrs f, int rank, int nranks, unsigned epoch)
+{
+  const int h = threadIdx.x;
+  if (h >= nranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[h] + rank), "r"(epoch) : "memory");
+  unsigned v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.p[rank] + h) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    __nanosleep(200);
+  }
+}
+}  // namespace
+
+
 extern "C" int clr_comm_p2p(clr_ctx *c) { return c->p2p && c->p2p_enabled ? 1 : 0; }
 
-// all ranks have finished everything queued on their streams so far (tiny all-reduce, stream ordered)
+// all ranks have finished everything queued on their streams (of the current pipeline) so far
 int clr_comm_barrier(clr_ctx *c)
 {
   if (c->nranks == 1) return 0;
+  if (c->flag_barrier) {
+    clr_ctx::StageSet &S = c->sets[c->cur_set];
+    FlagPtrs f;
+    for (int h = 0; h < CLR_MAX_PEERS; h++) f.p[h] = S.flag_peer[h];
+    flag_barrier_kernel<<<1, 32, 0, c->stream>>>(f, c->rank, c->nranks, ++S.epoch);
+    CLR_CUDA(cudaGetLastError());
+    return 0;
+  }
+  CLR_CHECK(c->cur_set == 0, "the potential pipeline needs peer-memory barriers");
   CLR_NCCL(g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMax, (ncclComm_t)c->nccl_comm, c->stream));
   return 0;
 }
 
 int clr_comm_destroy(clr_ctx *c)
 {
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
   c->nccl_comm = nullptr;
-  for (int h = 0; h < CLR_MAX_PEERS; h++) {
-    if (c->peer_stage[h] && c->peer_stage[h] != c->d_stage) cudaIpcCloseMemHandle(c->peer_stage[h]);
-    c->peer_stage[h] = nullptr;
+  for (int b = 0; b < 2; b++) {
+    for (int h = 0; h < CLR_MAX_PEERS; h++)
+      if (c->sets[b].peer[h] && c->sets[b].peer[h] != c->sets[b].stage) cudaIpcCloseMemHandle(c->sets[b].peer[h]);
+    if (c->sets[b].stage) cudaFree(c->sets[b].stage);
+    c->sets[b] = clr_ctx::StageSet();
   }
-  c->p2p = false;
-  if (c->d_stage) cudaFree(c->d_stage);
+  for (int h = 0; h < CLR_MAX_PEERS; h++) c->peer_stage[h] = nullptr;
   c->d_stage = nullptr;
+  c->p2p = false;
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_z_done) cudaEventDestroy(c->ev_z_done);
+  if (c->ev_npot) cudaEventDestroy(c->ev_npot);
+  c->stream2 = nullptr; c->ev_z_done = nullptr; c->ev_npot = nullptr;
   if (c->d_barrier) cudaFree(c->d_barrier);
   c->d_barrier = nullptr;
   return 0;
@@ -207,8 +293,10 @@ int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n)
   return 0;
 }
 
-// z-halo of the potential (fourier.c:401-414): my last plane -> right neighbour's slice_left,
-// my first plane -> left neighbour's slice_right
+// z-halo of the potential (fourier.c:401-414): my last plane -> right neighbour's slice_left, my first plane -> left
+// neighbour's slice_right; plus the SECOND ring (my second-to-last / second plane), stored behind the first one, which
+// the CIC velocity stencil of sources in the first / last plane of a slab reaches (srcs.c:486-504 gets them through the
+// slab rotation of beaming.c:325-352)
 int clr_comm_halo(clr_ctx *c)
 {
   const ClrDev &d = c->dev;
@@ -216,11 +304,19 @@ int clr_comm_halo(clr_ctx *c)
   size_t plane = (size_t)d.pitch * d.n;
   int right = (c->rank + 1) % c->nranks, left = (c->rank - 1 + c->nranks) % c->nranks;
   float *slice_left = c->d_npot + plane * d.nz_here, *slice_right = slice_left + plane;
+  float *left2 = slice_right + plane, *right2 = left2 + plane;
+  const bool two = d.nz_here >= 2;
   CLR_NCCL(g_nccl.GroupStart());
   CLR_NCCL(g_nccl.Send(c->d_npot + plane * (d.nz_here - 1), plane, ncclFloat, right, comm, c->stream));
   CLR_NCCL(g_nccl.Recv(slice_left, plane, ncclFloat, left, comm, c->stream));
   CLR_NCCL(g_nccl.Send(c->d_npot, plane, ncclFloat, left, comm, c->stream));
   CLR_NCCL(g_nccl.Recv(slice_right, plane, ncclFloat, right, comm, c->stream));
+  if (two) {
+    CLR_NCCL(g_nccl.Send(c->d_npot + plane * (d.nz_here - 2), plane, ncclFloat, right, comm, c->stream));
+    CLR_NCCL(g_nccl.Recv(left2, plane, ncclFloat, left, comm, c->stream));
+    CLR_NCCL(g_nccl.Send(c->d_npot + plane, plane, ncclFloat, left, comm, c->stream));
+    CLR_NCCL(g_nccl.Recv(right2, plane, ncclFloat, right, comm, c->stream));
+  }
   CLR_NCCL(g_nccl.GroupEnd());
   return 0;
 }

@@ -1054,6 +1054,7 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
       aout.tiled = 1;
       if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
       if (clr_comm_barrier(c)) return 1;
+      if (c->ev_after_z) CLR_CUDA(cudaEventRecord(c->ev_after_z, c->stream));
       c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1); }
     { StageScope sc2(c, "fft_y", 1);
       LineAddr yin{0, blk_t, nc, ilog2_host(nyl)};
@@ -1072,12 +1073,14 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
     LineAddr aout{0, 0, (long long)nyl * nc, ilog2_host(nzl)};
     if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
     if (clr_comm_barrier(c)) return 1;
+    if (c->ev_after_z) CLR_CUDA(cudaEventRecord(c->ev_after_z, c->stream));
     c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1);
   } else {
     { StageScope sc(c, "fft_z", 1);
       if (run_strided<N, +1>(c, g, 1, 0, (long long)nyl * nc, (int)(nyl * nc))) return 1; }
     { StageScope sc(c, "fft_a2a", 0);
       if (clr_comm_alltoall(c, g, stage, (size_t)nzl * nyl * nc * 2)) return 1; }
+    if (c->ev_after_z) CLR_CUDA(cudaEventRecord(c->ev_after_z, c->stream));
   }
   { StageScope sc(c, "fft_y", 1);
     LineAddr ain{(long long)nyl * nc, (long long)nzl * nyl * nc, nc, ilog2_host(nyl)};

@@ -105,6 +105,24 @@ struct clr_ctx {
   float *peer_stage[CLR_MAX_PEERS] = {nullptr};
   bool p2p = false;
   int p2p_enabled = 1;              // option "p2p_fused"
+  // Second transform pipeline (option "fft_overlap"): the c2r of the potential runs on its own stream with its own
+  // staging buffer and flag barriers, so its NVLink-bound z pass overlaps the HBM-bound y / x passes, the lognormal
+  // transform and the Poisson pass of the density on the main stream. Consumers of the potential call clr_npot_ready.
+  struct StageSet { float *stage = nullptr; float *peer[CLR_MAX_PEERS] = {nullptr}; unsigned *flag_peer[CLR_MAX_PEERS] = {nullptr}; unsigned epoch = 0; } sets[2];
+  int cur_set = 0;
+  size_t stage_floats = 0;          // floats of one staging buffer (the flag words of the barriers sit behind them)
+  bool flag_barrier = false;        // stream-ordered barriers through peer-memory flags instead of a 1-int all-reduce
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_z_done = nullptr, ev_npot = nullptr;
+  cudaEvent_t ev_after_z = nullptr; // when set, the distributed c2r records it once its z pass has been exchanged
+  bool npot_pending = false;        // the potential is still being transformed on stream2 (halo not exchanged yet)
+  // Default OFF. Measured on 2 GPUs at 1024^3 (profiles/r2_bench_2gpu_overlap_experiment.json): step 14.56 ms against
+  // 14.72 ms, end to end 46.9 ms against 17.2 ms. The passes are persistent kernels whose CTAs hold 132 KB of shared
+  // memory and all 64K registers of an SM, so a z pass on the second stream and a y / x pass on the main stream never
+  // share an SM: whichever starts first owns the GPU and the two pipelines serialise; the system-scope flag barriers
+  // also stall behind the catalogue read-back of the end-to-end loop. A real overlap needs an SM partition between
+  // the two pipelines (about 40 SMs saturate NVLink at 8 GPUs).
+  int fft_overlap = 0;
   int p2p_tiled = -1;               // option "p2p_tiled": tile-major staging layout of the fused c2r (-1: auto)
   int *d_barrier = nullptr;
   double a2a_bytes = 0;             // bytes this rank has sent through the FFT all-to-all
@@ -188,6 +206,8 @@ int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
 int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,
                  float *h_data);
 int clr_halo_update(clr_ctx *c);
+int clr_npot_ready(clr_ctx *c);     // main stream waits for the potential pipeline, then exchanges the z halo
+void clr_use_set(clr_ctx *c, int set);   // select the staging buffer / barrier flags (and stream) of pipeline 0 / 1
 int clr_lpt_run(clr_ctx *c, int order);
 int clr_lpt_particles(clr_ctx *c, float *x, float *y, float *z);
 int clr_comm_destroy(clr_ctx *c);

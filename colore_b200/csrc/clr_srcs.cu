@@ -562,15 +562,32 @@ local_props_kernel(const ClrDev d, const float4 *__restrict__ pos, float *__rest
 
 // ---- RSD under beaming: CIC-interpolated potential gradient along the line of sight -----------
 // beaming.c:31-117 (get_element, RETURN_VEL) + beaming.c:183-265 (trilinear branch)
-__device__ __forceinline__ void dev_vel_element(const ClrDev &d, const float *__restrict__ npot, int ix, int iy, int iz, float v[3])
+// Plane index of LOCAL plane iz in [-2, nz_here+1]: the slab, then the halo planes stored behind it (clr_api.cu:
+// [nz] = -1, [nz+1] = nz, [nz+2] = -2, [nz+3] = nz+1). On a single slab iz is periodic and always inside.
+__device__ __forceinline__ long long dev_plane_index(const ClrDev &d, int iz)
+{
+  if (iz >= 0 && iz < d.nz_here) return iz;
+  if (iz == -1) return d.nz_here;
+  if (iz == d.nz_here) return d.nz_here + 1;
+  if (iz == -2) return d.nz_here + 2;
+  return d.nz_here + 3;
+}
+__device__ __forceinline__ void dev_vel_element(const ClrDev &d, const float *__restrict__ npot, int ix, int iy, int iz, bool whole_box,
+                                                float v[3])
 {
   const long long ngx = d.pitch, plane = ngx * d.n;
   int ix_hi = ix + 1 == d.n ? 0 : ix + 1, ix_lo = ix == 0 ? d.n - 1 : ix - 1;
   int iy_hi = iy + 1 == d.n ? 0 : iy + 1, iy_lo = iy == 0 ? d.n - 1 : iy - 1;
-  long long pz_hi = (iz == d.nz_here - 1) ? (long long)(d.nz_here + 1) : iz + 1;
-  long long pz_lo = (iz == 0) ? (long long)d.nz_here : iz - 1;
-  v[0] = npot[ix_hi + iy * ngx + iz * plane] - npot[ix_lo + iy * ngx + iz * plane];
-  v[1] = npot[ix + iy_hi * ngx + iz * plane] - npot[ix + iy_lo * ngx + iz * plane];
+  long long pz, pz_hi, pz_lo;
+  if (whole_box) {                               // one slab = the periodic box
+    pz = iz;
+    pz_hi = iz + 1 == d.n ? 0 : iz + 1;
+    pz_lo = iz == 0 ? d.n - 1 : iz - 1;
+  } else {
+    pz = dev_plane_index(d, iz); pz_hi = dev_plane_index(d, iz + 1); pz_lo = dev_plane_index(d, iz - 1);
+  }
+  v[0] = npot[ix_hi + iy * ngx + pz * plane] - npot[ix_lo + iy * ngx + pz * plane];
+  v[1] = npot[ix + iy_hi * ngx + pz * plane] - npot[ix + iy_lo * ngx + pz * plane];
   v[2] = npot[ix + iy * ngx + pz_hi * plane] - npot[ix + iy * ngx + pz_lo * plane];
 }
 
@@ -580,6 +597,7 @@ beam_rsd_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__
 {
   const double idx = (double)(d.n / d.l_box);
   const double factor_vel = -d.fgrowth_0 / (1.5 * d.hubble_0 * d.OmegaM);
+  const bool whole_box = d.nz_here == d.n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nsrc; i += (long long)gridDim.x * blockDim.x) {
     float4 p = pos[i];
     float *o = srcs + 9 * i;
@@ -602,12 +620,20 @@ beam_rsd_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__
       if (ix0[ax] >= d.n) ix0[ax] -= d.n; else if (ix0[ax] < 0) ix0[ax] += d.n;
       if (ix1[ax] >= d.n) ix1[ax] -= d.n; else if (ix1[ax] < 0) ix1[ax] += d.n;
     }
-    ix0[2] -= d.iz0_here; ix1[2] -= d.iz0_here;
+    // local plane of the two CIC corner planes. A source of this slab sits within half a cell of one of its planes, so
+    // with several slabs the corners lie in [-1, nz_here] (periodic distance to the slab) and are served by the halo:
+    // the reference sums exactly these contributions while the slabs rotate (beaming.c:325-352).
+    long lz[2] = {ix0[2] - d.iz0_here, ix1[2] - d.iz0_here};
+    if (!whole_box)
+      for (int cz = 0; cz < 2; cz++) {
+        if (lz[cz] > d.nz_here) lz[cz] -= d.n;           // e.g. rank 0, global plane n-1 = local -1
+        else if (lz[cz] < -1) lz[cz] += d.n;             // last rank, global plane 0 = local nz_here
+      }
     float v[3] = {0.f, 0.f, 0.f};
     bool added = false;
     for (int cz = 0; cz < 2; cz++) {
-      long izc = cz ? ix1[2] : ix0[2];
-      if (izc >= 0 && izc < d.nz_here) {
+      long izc = lz[cz];
+      if (whole_box ? (izc >= 0 && izc < d.nz_here) : (izc >= -1 && izc <= d.nz_here)) {
         float w4[4], v4[4][3];
         if (cz == 0) {
           w4[0] = h1x[2] * h1x[1] * h1x[0]; w4[1] = (float)(h1x[2] * h1x[1] * h0x[0]);
@@ -617,10 +643,10 @@ beam_rsd_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__
           w4[2] = (float)(h0x[2] * h0x[1] * h1x[0]); w4[3] = (float)(h0x[2] * h0x[1] * h0x[0]);
         }
         added = true;
-        dev_vel_element(d, npot, (int)ix0[0], (int)ix0[1], (int)izc, v4[0]);
-        dev_vel_element(d, npot, (int)ix1[0], (int)ix0[1], (int)izc, v4[1]);
-        dev_vel_element(d, npot, (int)ix0[0], (int)ix1[1], (int)izc, v4[2]);
-        dev_vel_element(d, npot, (int)ix1[0], (int)ix1[1], (int)izc, v4[3]);
+        dev_vel_element(d, npot, (int)ix0[0], (int)ix0[1], (int)izc, whole_box, v4[0]);
+        dev_vel_element(d, npot, (int)ix1[0], (int)ix0[1], (int)izc, whole_box, v4[1]);
+        dev_vel_element(d, npot, (int)ix0[0], (int)ix1[1], (int)izc, whole_box, v4[2]);
+        dev_vel_element(d, npot, (int)ix1[0], (int)ix1[1], (int)izc, whole_box, v4[3]);
         for (int ax = 0; ax < 3; ax++)
           v[ax] += (v4[0][ax] * w4[0] + v4[1][ax] * w4[1] + v4[2][ax] * w4[2] + v4[3][ax] * w4[3]);
       }
@@ -718,6 +744,7 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
     CLR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
     c->copy_pending = false;
   }
+  if (clr_npot_ready(c)) return 1;               // placement reads the potential (RSD) and its z halo
   if (total > 0) {
     // the 9-float Src buffer is not written until clr_srcs_local: borrow it for the source references
     unsigned long long *d_ref = reinterpret_cast<unsigned long long *>(P.d_srcs);

@@ -37,8 +37,10 @@ def init_comm(par, rank: int, nranks: int):
     box = [bytes(ident)]
     dist.broadcast_object_list(box, src=0)
     buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
-    check(par.lib.clr_comm_init(par.ctx, C.c_int(rank), C.c_int(nranks), buf))
     import os
+    if os.environ.get("COLORE_B200_OVERLAP", "0") == "1":  # second transform pipeline for the potential (experiment, default off)
+        par.set_option("fft_overlap", 1)
+    check(par.lib.clr_comm_init(par.ctx, C.c_int(rank), C.c_int(nranks), buf))
     if os.environ.get("COLORE_B200_P2P", "1") == "0":      # force the NCCL all-to-all (comparison runs)
         par.set_option("p2p_fused", 0)
     if os.environ.get("COLORE_B200_P2P_TILED"):            # 0 / 1: force the staging layout (comparison runs)

@@ -88,6 +88,16 @@ def main():
     pos, ipix = cb.srcs_get_cartesian(par, 0)
     assert np.array_equal(ipix, ipix_ref) and np.array_equal(pos[:, :3], pos_ref[:, :3])
     np.testing.assert_allclose(pos[:, 3], pos_ref[:, 3], rtol=2e-6, atol=1e-12)
+    # RSD under beaming (srcs.c:425-443, 486-504, 656-662): CIC corners of sources in the first / last plane of a slab
+    # reach into the neighbour slabs (two halo rings here, the slab rotation in the reference) -> full-box oracle
+    before = cb.srcs_get_local_properties(par, 0)
+    cb.srcs_beams(par)
+    after = cb.srcs_get_local_properties(par, 0)
+    o.set_halo(full)
+    rsd_ref = o.srcs_beam_rsd(full, pos, before.copy())
+    np.testing.assert_allclose(after[:, 3], rsd_ref[:, 3], rtol=2e-5, atol=1e-9)
+    edge = np.abs((pos[:, 2] + 0.5 * par.l_box) * (n / par.l_box) - iz0) < 0.5      # sources of the slab's first plane
+    assert edge.sum() > 0 and np.abs(after[edge, 3]).max() > 0
     # maps: every GPU integrates the ray segments inside its slab, the partial maps are all-reduced
     _, pix = cb.healpix.hp_shell_pixels(8, 2)
     rf = np.sort(g["s6_kappa_rf"])
