@@ -292,7 +292,7 @@ __device__ __forceinline__ double clr_bias_model(int model, double dd, double b)
 
 // Philox4x32-10 (Salmon et al. 2011), counter {index_lo, index_hi, block, stream}, key {seed, 0}.
 // Word j of substream (seed, stream, index) = word j%4 of block j/4. Same definition as
-// oracle/shim/gsl_shim.c:shim_philox_seek.
+// third_party/shim/gsl_shim.c:shim_philox_seek.
 __device__ __forceinline__ void clr_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                            uint32_t k0, uint32_t k1, uint32_t out[4])
 {
@@ -314,7 +314,7 @@ struct ClrStream {   // sequential reader of one counter-based substream
   __device__ __forceinline__ ClrStream(uint32_t seed, uint32_t strm, unsigned long long index)
       : k0(seed), k1(0), i0((uint32_t)index), i1((uint32_t)(index >> 32)), stream(strm), pos(0), first(0),
         first_pending(false) {}
-  // oracle/shim/gsl_shim.c:shim_philox_seek_cell: draw 0 = `w0`, draws j>=1 = words j-1 of the substream
+  // third_party/shim/gsl_shim.c:shim_philox_seek_cell: draw 0 = `w0`, draws j>=1 = words j-1 of the substream
   __device__ __forceinline__ void set_first(uint32_t w0) { first = w0; first_pending = true; }
   // position the reader at word `p` of the substream
   __device__ __forceinline__ void seek(uint32_t p)

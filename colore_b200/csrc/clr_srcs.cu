@@ -215,7 +215,7 @@ __global__ void poisson_bound_kernel(const ClrDev d, ClrPop pop, float vol, floa
 
 // counts: int32 per cell, unpadded flat order ix + n*(iy + n*iz_local); chunk_tot[chunk] = sum.
 // RNG: the first uniform of cell g is word g&3 of the Philox block shared by cells 4(g>>2)..+3
-// (oracle/shim/gsl_shim.c:shim_philox_seek_cell), so one thread screens 4 neighbouring cells per block.
+// (third_party/shim/gsl_shim.c:shim_philox_seek_cell), so one thread screens 4 neighbouring cells per block.
 __global__ void __launch_bounds__(kThreads, 4)
 poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const float4 *__restrict__ bound,
                const float4 *__restrict__ bound_grp, uint32_t seed, int ipop, int32_t *__restrict__ counts,

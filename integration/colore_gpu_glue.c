@@ -7,8 +7,8 @@
  * linked UNCHANGED, so `./CoLoRe param.cfg` stays the entry point (main.c:24-154).
  *
  * It is compiled against the reference's own common.h (-I<reference>/src); it contains no code of
- * the reference. One process drives one GPU (NNodes = 1 at this boundary); the slab decomposition
- * over several GPUs lives below the C ABI (clr_comm_init) and is driven by bench.py / torchrun.
+ * the reference. One process drives one GPU; COLORE_B200_NGPUS=P makes the executable fork into P ranks (see
+ * launch_ranks below), the slab decomposition itself lives below the C ABI (clr_comm_init).
  *
  * Host memory contract: par->cats_c / par->cats / shell data and nadd are
  * host-malloc'ed with the reference's own allocators because io.c writes and frees them;
@@ -16,12 +16,96 @@
  */
 #include "common.h"
 #include "colore_b200.h"
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#ifndef _SPREC
+#error "colore_gpu_glue.c: the GPU grids are fp32 -- build the drop-in with -D_SPREC (flouble must be float)"
+#endif
 
 static clr_ctx *g_ctx = NULL;
+
+/* ------------------------------------------------------------------ several GPUs without MPI
+ * COLORE_B200_NGPUS=P ./CoLoRe_b200 param.cfg: the process forks into P ranks BEFORE main runs (nothing of CUDA is
+ * initialised yet); rank r drives GPU r and owns the z slab [r n/P, (r+1) n/P) (fourier.c:172-181). This replaces
+ * mpi_init (common.c:216-274): the unchanged host code sees NodeThis = r, NNodes = P from the first stage call on, so
+ * io.c writes one catalogue / density file per rank exactly like an MPI run, and rank 0 writes the maps, which the
+ * library returns already summed over the slabs. While read_run_params runs, NodeThis / NNodes still say (0, 1), so
+ * that every rank allocates FULL-sky shells (hp_shell_alloc, common.c:505-552): the GPUs integrate every pixel over
+ * their own slab and all-reduce, instead of the reference's pixel ownership + slab rotation (beaming.c:293-374).
+ * The 128-byte NCCL id travels from rank 0 to the others through a file. */
+static int g_rank = 0, g_nranks = 1;
+static pid_t g_children[64];
+static char g_idfile[256];
+
+static void wait_for_ranks(void)
+{
+  int r, status;
+  for (r = 1; r < g_nranks; r++)
+    if (g_children[r] > 0) waitpid(g_children[r], &status, 0);
+  unlink(g_idfile);
+}
+
+__attribute__((constructor)) static void launch_ranks(void)
+{
+  const char *s = getenv("COLORE_B200_NGPUS");
+  int r, P = s ? atoi(s) : 1;
+  if (P <= 1) return;
+  if (P > 16) P = 16;
+  g_nranks = P;
+  snprintf(g_idfile, sizeof(g_idfile), "/tmp/colore_b200_nccl_id_%ld", (long)getpid());
+  unlink(g_idfile);
+  fflush(NULL);
+  for (r = 1; r < P; r++) {
+    pid_t pid = fork();
+    if (pid == 0) {                       /* rank r: quiet stdout (print_info only gates on NodeThis later) */
+      g_rank = r;
+      if (!freopen("/dev/null", "w", stdout)) exit(1);
+      return;
+    }
+    g_children[r] = pid;
+  }
+  atexit(wait_for_ranks);
+}
+
+static void exchange_nccl_id(unsigned char id[128])
+{
+  if (g_rank == 0) {
+    char tmpn[300];
+    FILE *f;
+    snprintf(tmpn, sizeof(tmpn), "%s.tmp", g_idfile);
+    f = fopen(tmpn, "wb");
+    if (!f || fwrite(id, 1, 128, f) != 128) report_error(1, "cannot write %s\n", tmpn);
+    fclose(f);
+    if (rename(tmpn, g_idfile)) report_error(1, "cannot publish %s\n", g_idfile);
+  } else {
+    int tries;
+    for (tries = 0; tries < 6000; tries++) {          /* up to 60 s */
+      FILE *f = fopen(g_idfile, "rb");
+      if (f) {
+        size_t got = fread(id, 1, 128, f);
+        fclose(f);
+        if (got == 128) return;
+      }
+      usleep(10000);
+    }
+    report_error(1, "rank %d: no NCCL id from rank 0 (%s)\n", g_rank, g_idfile);
+  }
+}
 
 static void chk(int status)
 {
   if (status) report_error(1, "colore_b200: %s\n", clr_last_error());
+}
+
+/* first stage call after read_run_params: from here on the host code sees the rank layout */
+static void adopt_rank_layout(void)
+{
+  if (g_nranks == 1 || NNodes == g_nranks) return;
+  NodeThis = g_rank; NNodes = g_nranks;
+  NodeLeft = (g_rank + g_nranks - 1) % g_nranks;
+  NodeRight = (g_rank + 1) % g_nranks;
 }
 
 static size_t slab_floats(ParamCoLoRe *par)
@@ -31,18 +115,27 @@ static size_t slab_floats(ParamCoLoRe *par)
 
 /* ------------------------------------------------------------------ fourier.c */
 void init_fftw(ParamCoLoRe *par)
-{ /* fourier.c:127-209, single-rank branch: the whole box is one slab */
-  par->nz_all = my_calloc(NNodes, sizeof(int));
-  par->iz0_all = my_calloc(NNodes, sizeof(int));
-  par->nz_here = par->n_grid;
-  par->iz0_here = 0;
+{ /* fourier.c:127-209: one z slab per rank (fourier.c:172-181); one rank = the whole box */
+  int r;
+  if (par->n_grid % g_nranks) report_error(1, "n_grid=%d is not divisible by %d GPUs\n", par->n_grid, g_nranks);
+  par->nz_all = my_calloc(g_nranks, sizeof(int));
+  par->iz0_all = my_calloc(g_nranks, sizeof(int));
+  for (r = 0; r < g_nranks; r++) {
+    par->nz_all[r] = par->n_grid / g_nranks;
+    par->iz0_all[r] = r * (par->n_grid / g_nranks);
+  }
+  par->nz_here = par->nz_all[g_rank];
+  par->iz0_here = par->iz0_all[g_rank];
   par->nz_max = par->nz_here;
-  par->nz_all[0] = par->nz_here;
-  par->iz0_all[0] = par->iz0_here;
+  if (g_rank > 0) par->do_pred = 0;       /* the theory predictions are rank 0's job (main.c:58-59) */
 }
 
+static int g_ngrid = 0;
+static int g_ctx_ngrid(void) { return g_ngrid; }
+
 void allocate_fftw(ParamCoLoRe *par)
-{ /* fourier.c:211-238: grids live on the device; tables are uploaded once */
+{
+  g_ngrid = par->n_grid; /* fourier.c:211-238: grids live on the device; tables are uploaded once */
   clr_params p;
   int i;
   memset(&p, 0, sizeof(p));
@@ -68,7 +161,17 @@ void allocate_fftw(ParamCoLoRe *par)
   p.growth_d2_arr = par->growth_d2_arr; p.growth_v_arr = par->growth_v_arr;
   p.growth_pd_arr = par->growth_pd_arr; p.ihub_arr = par->ihub_arr;
   p.a_arr_a2r = par->a_arr_a2r; p.r_arr_a2r = par->r_arr_a2r;
-  chk(clr_create(&p, 0, &g_ctx));
+  {
+    int ndev = clr_device_count();
+    if (ndev < 1) report_error(1, "colore_b200: no CUDA device (there is no CPU fallback)\n");
+    chk(clr_create(&p, g_rank % ndev, &g_ctx));
+  }
+  if (g_nranks > 1) {
+    unsigned char id[128];
+    if (g_rank == 0) chk(clr_comm_unique_id(id));
+    exchange_nccl_id(id);
+    chk(clr_comm_init(g_ctx, g_rank, g_nranks, id));
+  }
   chk(clr_set_option(g_ctx, "lpt_interp_type", par->lpt_interp_type));
   chk(clr_set_option(g_ctx, "keep_particles", par->output_lpt));
   for (i = 0; i < par->n_srcs; i++) chk(clr_set_srcs(g_ctx, i, par->srcs_nz_arr[i], par->srcs_bz_arr[i]));
@@ -88,17 +191,20 @@ void end_fftw(ParamCoLoRe *par)
   g_ctx = NULL;
 }
 
-/* fourier.c:81-125 on HOST arrays (kept for API completeness; the GPU path never round-trips) */
+/* fourier.c:81-125 on HOST arrays. Nothing of the host code that stays linked calls these (the transforms of the run
+ * flow happen inside clr_create_cartesian_fields / the LPT kernels); a host round trip would have to borrow a device
+ * grid and destroy the resident field, so they refuse instead of doing that silently. */
+static int g_fields_resident = 0;
 void fftw_wrap_c2r(int ng, dftw_complex *pin, flouble *pout)
 {
-  (void)ng;
+  if (g_fields_resident || ng != g_ctx_ngrid()) report_error(1, "fftw_wrap_c2r on host arrays would overwrite the resident GPU fields\n");
   chk(clr_grid_put(g_ctx, CLR_GRID_DENS, (const float *)pin));
   chk(clr_fft_c2r(g_ctx, CLR_GRID_DENS));
   chk(clr_grid_get(g_ctx, CLR_GRID_DENS, (float *)pout));
 }
 void fftw_wrap_r2c(int ng, flouble *pin, dftw_complex *pout)
 {
-  (void)ng;
+  if (g_fields_resident || ng != g_ctx_ngrid()) report_error(1, "fftw_wrap_r2c on host arrays would overwrite the resident GPU fields\n");
   chk(clr_grid_put(g_ctx, CLR_GRID_DENS, (const float *)pin));
   chk(clr_fft_r2c(g_ctx, CLR_GRID_DENS));
   chk(clr_grid_get(g_ctx, CLR_GRID_DENS, (float *)pout));
@@ -107,9 +213,11 @@ void fftw_wrap_r2c(int ng, flouble *pin, dftw_complex *pout)
 void create_cartesian_fields(ParamCoLoRe *par)
 { /* fourier.c:361-423 */
   double out[2];
+  adopt_rank_layout();
   print_info("*** Creating Gaussian density field (GPU)\n");
   if (NodeThis == 0) timer(0);
   chk(clr_create_cartesian_fields(g_ctx, par->seed_rng, 0, out));
+  g_fields_resident = 1;
   par->sigma2_gauss = out[1];
   if (NodeThis == 0) timer(2);
   print_info(" <d>=%.3lE, <d^2>=%.3lE\n", out[0], sqrt(par->sigma2_gauss));
@@ -204,7 +312,7 @@ void srcs_set_cartesian(ParamCoLoRe *par)
 }
 
 void srcs_distribute(ParamCoLoRe *par)
-{ /* srcs.c:375-384 with NNodes = 1: every source stays */
+{ /* srcs.c:375-384: every rank keeps (and writes) the sources of its own z slab */
   int ipop;
   for (ipop = 0; ipop < par->n_srcs; ipop++) par->nsources_this[ipop] = par->nsources_c_this[ipop];
 }
@@ -299,7 +407,7 @@ int interpolate_from_grid(ParamCoLoRe *par, double *x, flouble *d, flouble v[3],
 }
 
 void get_beam_properties(ParamCoLoRe *par)
-{ /* beaming.c:293-374 with one slab: no ring rotation, one pass over every tracer */
+{ /* beaming.c:293-374 without the ring rotation: every GPU integrates inside its own slab (+ halo), maps are summed */
   print_info("*** Getting LOS information (GPU)\n");
   if (!par->need_beaming) { print_info("  No need!\n\n"); return; }
   if (par->do_kappa) kappa_beams_preproc(par);

@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY.
  *
  * Driver that runs the UNMODIFIED reference translation units (compiled from
- * /root/reference/src against oracle/shim) in the order of main.c:50-147 and dumps the
+ * /root/reference/src against third_party/shim) in the order of main.c:50-147 and dumps the
  * state after every stage as .npy files. It is linked INSTEAD of the reference's main.c and
  * contains no reference code: it only calls the public functions declared in the reference's
  * common.h and reads fields of ParamCoLoRe.

@@ -1,7 +1,7 @@
 """Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
 
 Runs oracle/_ref/ref_driver (the reference's own translation units compiled against
-oracle/shim, see oracle/Makefile) with OMP_NUM_THREADS=1 on small synthetic configurations and
+third_party/shim, see oracle/Makefile) with OMP_NUM_THREADS=1 on small synthetic configurations and
 packs the per-stage dumps into compressed .npz files. Only runnable where /root/reference
 exists (this container); the fixtures are what travels.
 

@@ -152,7 +152,7 @@ def test_table_lookup_edges(case):
 
 
 def test_shim_poisson_moments():
-    """gsl_ran_poisson is third-party arithmetic the repo has to restate (oracle/shim/gsl_shim.c):
+    """gsl_ran_poisson is third-party arithmetic the repo has to restate (third_party/shim/gsl_shim.c):
     Knuth's product for mu <= 10, the gamma / binomial (BTPE) reduction above. No reference vectors exist for it,
     so its distribution is checked: mean and variance of 4000 draws at each mu within 5 sigma of mu."""
     import ctypes as C
@@ -171,7 +171,7 @@ def test_shim_poisson_moments():
 
 @pytest.mark.parametrize("n", [16, 48])
 def test_shim_fft_matches_numpy(golden_dir, n):
-    """The reference's FFT is FFTW, which this image does not have: oracle/shim/fftw_shim.c restates the c2r / r2c
+    """The reference's FFT is FFTW, which this image does not have: third_party/shim/fftw_shim.c restates the c2r / r2c
     definition (unnormalised, complex passes over z and y, half-complex x pass last). Checked against an
     independent implementation (numpy / pocketfft), including a NON-Hermitian spectrum like the one
     create_grids_fourier fills (fourier.c:325-345): the imaginary parts of the x-DC / x-Nyquist lines are dropped."""
@@ -193,7 +193,7 @@ def test_shim_fft_matches_numpy(golden_dir, n):
 
 
 def test_shim_mt19937_known_answers():
-    """gsl_rng_mt19937 restated in oracle/shim/gsl_shim.c: init_genrand seeding (seed 0 -> 4357), uniform = 32-bit
+    """gsl_rng_mt19937 restated in third_party/shim/gsl_shim.c: init_genrand seeding (seed 0 -> 4357), uniform = 32-bit
     output / 2^32. Known answers: the published MT19937 reference stream (seed 5489 -> 3499211612, 581869302,
     3890346734, ...; 10000th output 4123659995) and numpy's independent implementation for the run seed."""
     import ctypes as C
