@@ -574,6 +574,11 @@ int clr_srcs_get_local_properties(clr_ctx *c, int ipop, float *srcs9)
   return 0;
 }
 
+int clr_srcs_distribute(clr_ctx *c, int ipop, int beam_first, long long *nsrc_out)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX && c->srcs[ipop].set, "population index %d out of range", ipop);
+  return clr_srcs_distribute_impl(c, ipop, beam_first, nsrc_out);
+}
 int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { if (clr_npot_ready(c)) return 1; return clr_srcs_beam(c, ipop); }
 int clr_lpt_get_particles(clr_ctx *c, float *x, float *y, float *z) { return clr_lpt_particles(c, x, y, z); }
 int clr_lpt_exchange_counts(clr_ctx *c, long long *sent, long long *received)

@@ -202,6 +202,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
 int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed);
 int clr_srcs_local(clr_ctx *c, int ipop);
 int clr_srcs_beam(clr_ctx *c, int ipop);
+int clr_srcs_distribute_impl(clr_ctx *c, int ipop, int beam_first, long long *nsrc_out);
 int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
 int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,
                  float *h_data);

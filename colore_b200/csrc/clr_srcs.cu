@@ -7,6 +7,7 @@
 #include "clr_internal.cuh"
 #include <math.h>
 #include <utility>
+#include <vector>
 
 namespace {
 
@@ -666,6 +667,53 @@ beam_rsd_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__
   }
 }
 
+// ---- srcs_distribute_single (srcs.c:296-373): route every source to rank ipix % NNodes, order preserved ----------
+// Stable multi-split on the device: chunks of 256 sources, per-chunk counts per destination, offsets from a host
+// scan of the (small) count table, then every source computes its slot from warp ballots.
+constexpr int kDistThreads = 256;
+__global__ void __launch_bounds__(kDistThreads)
+dist_count_kernel(const int32_t *__restrict__ ipix, long long n, int nranks, int *__restrict__ cnt)
+{
+  __shared__ int h[CLR_MAX_PEERS];
+  if (threadIdx.x < CLR_MAX_PEERS) h[threadIdx.x] = 0;
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * kDistThreads + threadIdx.x;
+  const int d = i < n ? ipix[i] % nranks : -1;
+  for (int k = 0; k < nranks; k++) {
+    const unsigned m = __ballot_sync(0xffffffffu, d == k);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&h[k], __popc(m));
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks) cnt[(long long)blockIdx.x * nranks + threadIdx.x] = h[threadIdx.x];
+}
+__global__ void __launch_bounds__(kDistThreads)
+dist_scatter_kernel(const float4 *__restrict__ pos, const int32_t *__restrict__ ipix, long long n, int nranks,
+                    const long long *__restrict__ off, float4 *__restrict__ spos, int32_t *__restrict__ sipix)
+{
+  __shared__ int wcnt[kDistThreads / 32][CLR_MAX_PEERS];
+  const long long i = (long long)blockIdx.x * kDistThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int d = i < n ? ipix[i] % nranks : -1;
+  int before = 0;
+  for (int k = 0; k < nranks; k++) {
+    const unsigned m = __ballot_sync(0xffffffffu, d == k);
+    if (d == k) before = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[w][k] = __popc(m);
+  }
+  __syncthreads();
+  if (d < 0) return;
+  long long slot = off[(long long)blockIdx.x * nranks + d] + before;
+  for (int ww = 0; ww < w; ww++) slot += wcnt[ww][d];
+  spos[slot] = pos[i];
+  sipix[slot] = ipix[i];
+}
+// dz_rsd of the Src records (after the beam estimator) back into the Cartesian catalogue, which is what travels
+__global__ void rsd_to_pos_kernel(const float *__restrict__ srcs, float4 *__restrict__ pos, long long n)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    pos[i].w = srcs[9 * i + 3];
+}
+
 int grid_for(clr_ctx *c, long long blocks, int per_sm)
 {
   long long cap = (long long)c->sm_count * per_sm;
@@ -781,4 +829,106 @@ int clr_srcs_beam(clr_ctx *c, int ipop)
       c->dev, c->d_npot, reinterpret_cast<const float4 *>(P.d_pos), P.d_srcs, P.nsrc, 1, 1);
   CLR_CUDA(cudaGetLastError());
   return 0;
+}
+
+// srcs_distribute_single (srcs.c:296-373). After the call this rank holds the sources whose base pixel satisfies
+// ipix % nranks == rank, in the reference's order: blocks from rank-1, rank-2, ... (mod nranks), own sources last,
+// the order inside a block = the sender's catalogue order. beam_first: evaluate the RSD-under-beaming estimator
+// (srcs.c:486-504) on the slab that still holds the potential around each source and carry it in pos[3].
+int clr_srcs_distribute_impl(clr_ctx *c, int ipop, int beam_first, long long *nsrc_out)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  const int R = c->nranks;
+  if (beam_first) {
+    if (clr_npot_ready(c)) return 1;
+    if (clr_srcs_local(c, ipop)) return 1;
+    if (clr_srcs_beam(c, ipop)) return 1;
+    if (P.nsrc > 0) {
+      rsd_to_pos_kernel<<<grid_for(c, (P.nsrc + kThreads - 1) / kThreads, 8), kThreads, 0, c->stream>>>(
+          P.d_srcs, reinterpret_cast<float4 *>(P.d_pos), P.nsrc);
+      CLR_CUDA(cudaGetLastError());
+      c->launches++;
+    }
+  }
+  if (R == 1) { if (nsrc_out) *nsrc_out = P.nsrc; return 0; }
+  StageScope sc(c, "srcs_distribute", 2);
+  const long long n = P.nsrc;
+  const long long n_chunks = (n + kDistThreads - 1) / kDistThreads;
+  std::vector<int> h_cnt((size_t)n_chunks * R);
+  std::vector<long long> h_off((size_t)n_chunks * R);
+  int *d_cnt = nullptr; long long *d_off = nullptr;
+  float4 *d_spos = nullptr; int32_t *d_sipix = nullptr;
+  int rc = 1;
+  std::vector<unsigned long long> mat((size_t)R * R, 0ULL);
+  do {
+    if (n > 0) {
+      if (cudaMalloc(&d_cnt, h_cnt.size() * sizeof(int)) != cudaSuccess) { clr_set_error("srcs_distribute: out of device memory"); break; }
+      if (cudaMalloc(&d_off, h_off.size() * sizeof(long long)) != cudaSuccess) { clr_set_error("srcs_distribute: out of device memory"); break; }
+      if (cudaMalloc(&d_spos, (size_t)n * sizeof(float4)) != cudaSuccess) { clr_set_error("srcs_distribute: out of device memory"); break; }
+      if (cudaMalloc(&d_sipix, (size_t)n * sizeof(int32_t)) != cudaSuccess) { clr_set_error("srcs_distribute: out of device memory"); break; }
+      dist_count_kernel<<<(unsigned)n_chunks, kDistThreads, 0, c->stream>>>(P.d_ipix, n, R, d_cnt);
+      if (cudaMemcpyAsync(h_cnt.data(), d_cnt, h_cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) break;
+    }
+    // destination-major offsets: start of destination d + sources of earlier chunks going to d
+    std::vector<long long> tot(R, 0), start(R, 0);
+    for (long long ch = 0; ch < n_chunks; ch++)
+      for (int d = 0; d < R; d++) tot[d] += h_cnt[(size_t)ch * R + d];
+    for (int d = 1; d < R; d++) start[d] = start[d - 1] + tot[d - 1];
+    {
+      std::vector<long long> run(start);
+      for (long long ch = 0; ch < n_chunks; ch++)
+        for (int d = 0; d < R; d++) { h_off[(size_t)ch * R + d] = run[d]; run[d] += h_cnt[(size_t)ch * R + d]; }
+    }
+    if (n > 0) {
+      if (cudaMemcpyAsync(d_off, h_off.data(), h_off.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+      dist_scatter_kernel<<<(unsigned)n_chunks, kDistThreads, 0, c->stream>>>(reinterpret_cast<const float4 *>(P.d_pos), P.d_ipix, n, R,
+                                                                              d_off, d_spos, d_sipix);
+      if (cudaGetLastError() != cudaSuccess) break;
+    }
+    // transfer matrix (MPI_Allgather of ns_to_nodes, srcs.c:311-316): row = sender
+    if (clr_ensure_scratch(c, mat.size() * sizeof(unsigned long long))) break;
+    for (int d = 0; d < R; d++) mat[(size_t)c->rank * R + d] = (unsigned long long)tot[d];
+    if (cudaMemcpyAsync(c->d_scratch, mat.data(), mat.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+    if (clr_comm_allreduce_u64(c, reinterpret_cast<unsigned long long *>(c->d_scratch), mat.size())) break;
+    if (clr_read_small(c, mat.data(), c->d_scratch, mat.size() * sizeof(unsigned long long))) break;
+    // receive layout: blocks from rank-1, rank-2, ..., rank (srcs.c:347-352)
+    long long n_new = 0;
+    std::vector<size_t> roff(R), rn(R), soff(R), sn(R);
+    for (int ii = 0; ii < R; ii++) {
+      const int from = ((c->rank - 1 - ii) % R + R) % R;
+      roff[from] = (size_t)n_new;
+      rn[from] = (size_t)mat[(size_t)from * R + c->rank];
+      n_new += (long long)rn[from];
+    }
+    for (int d = 0; d < R; d++) { soff[d] = (size_t)start[d]; sn[d] = (size_t)tot[d]; }
+    // new catalogue buffers
+    float *n_pos = nullptr; int32_t *n_ipix = nullptr; float *n_srcs = nullptr;
+    const size_t cap = (size_t)n_new + (size_t)n_new / 16 + 1024;
+    if (cudaMalloc(&n_pos, cap * 4 * sizeof(float)) != cudaSuccess || cudaMalloc(&n_ipix, cap * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&n_srcs, cap * 9 * sizeof(float)) != cudaSuccess) { clr_set_error("srcs_distribute: out of device memory"); break; }
+    // own block: device copy; the rest: exact-size exchange (4 floats per position, 1 word per pixel index)
+    if (sn[c->rank]) {
+      cudaMemcpyAsync(n_pos + roff[c->rank] * 4, d_spos + soff[c->rank], sn[c->rank] * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream);
+      cudaMemcpyAsync(n_ipix + roff[c->rank], d_sipix + soff[c->rank], sn[c->rank] * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream);
+    }
+    std::vector<size_t> so4(R), sn4(R), ro4(R), rn4(R);
+    for (int d = 0; d < R; d++) { so4[d] = soff[d] * 4; sn4[d] = sn[d] * 4; ro4[d] = roff[d] * 4; rn4[d] = rn[d] * 4; }
+    if (clr_comm_alltoallv(c, reinterpret_cast<const float *>(d_spos), so4.data(), sn4.data(), n_pos, ro4.data(), rn4.data())) break;
+    if (clr_comm_alltoallv(c, reinterpret_cast<const float *>(d_sipix), soff.data(), sn.data(), reinterpret_cast<float *>(n_ipix),
+                           roff.data(), rn.data())) break;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) break;
+    if (c->copy_pending) cudaStreamSynchronize(c->copy_stream);
+    c->copy_pending = false; c->buf_busy[0] = c->buf_busy[1] = false;
+    cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs); cudaFree(P.d_srcs_alt);
+    P.d_pos = n_pos; P.d_ipix = n_ipix; P.d_srcs = n_srcs; P.d_srcs_alt = nullptr;
+    P.cap_src = cap; P.nsrc = n_new;
+    rc = 0;
+  } while (0);
+  cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_spos); cudaFree(d_sipix);
+  if (rc == 0) {
+    if (clr_srcs_local(c, ipop)) return 1;           // Src records of the new catalogue (dz_rsd = pos[3])
+    if (nsrc_out) *nsrc_out = P.nsrc;
+  }
+  return rc;
 }

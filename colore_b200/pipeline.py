@@ -258,9 +258,16 @@ def srcs_set_cartesian(par: ParamCoLoRe, seed: int | None = None):
     return dict(par.nsources)
 
 
-def srcs_distribute(par: ParamCoLoRe):
-    """srcs.c:296-384: one process per GPU keeps its slab's sources (NNodes=1 at the boundary)."""
-    return None
+def srcs_distribute(par: ParamCoLoRe, by_pixel: bool = False, beam_first: bool = False):
+    """srcs.c:296-384. Default: every GPU keeps (and writes) the sources of its own z slab. ``by_pixel``: the
+    reference's routing, source -> rank ipix % NNodes with the order preserved (clr_srcs_distribute)."""
+    if not by_pixel:
+        return dict(par.nsources)
+    for ipop in range(par.n_srcs):
+        n = C.c_longlong()
+        check(par.lib.clr_srcs_distribute(par.ctx, C.c_int(ipop), C.c_int(int(beam_first)), C.byref(n)))
+        par.nsources[ipop] = int(n.value)
+    return dict(par.nsources)
 
 
 def srcs_get_counts(par: ParamCoLoRe, ipop: int = 0) -> np.ndarray:

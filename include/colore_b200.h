@@ -156,6 +156,11 @@ int clr_srcs_get_counts(clr_ctx *ctx, int ipop, int32_t *nsources_padded);
 int clr_srcs_get_cartesian(clr_ctx *ctx, int ipop, float *pos4, int32_t *ipix);
 /* srcs_get_local_properties_single (srcs.c:386-416): Src records, 9 floats each (common.h:169-179) */
 int clr_srcs_get_local_properties(clr_ctx *ctx, int ipop, float *srcs9);
+/* srcs_distribute_single (srcs.c:296-373), several GPUs: route every source to rank ipix % nranks, order preserved
+ * (blocks received from rank-1, rank-2, ..., own sources last). beam_first != 0: evaluate the RSD-under-beaming
+ * estimator (srcs.c:486-504) first, on the slab that holds the potential around each source, and carry it along.
+ * Afterwards clr_srcs_get_cartesian / clr_srcs_get_local_properties return the redistributed catalogue. One GPU: no-op. */
+int clr_srcs_distribute(clr_ctx *ctx, int ipop, int beam_first, long long *nsrc_out);
 /* RSD under beaming: srcs_beams_preproc/get_beam_properties(lines 486-504)/postproc(656-662).
  * Updates dz_rsd (and e1=e2=0) of the resident catalogue; fetch with clr_srcs_get_local_properties */
 int clr_srcs_beam_rsd(clr_ctx *ctx, int ipop);

@@ -311,10 +311,28 @@ void srcs_set_cartesian(ParamCoLoRe *par)
   print_info("\n");
 }
 
+static int g_by_pixel = 0;   /* COLORE_B200_DISTRIBUTE=pixel: the reference's routing, source -> rank ipix % NNodes */
 void srcs_distribute(ParamCoLoRe *par)
-{ /* srcs.c:375-384: every rank keeps (and writes) the sources of its own z slab */
+{ /* srcs.c:375-384. Default: every rank keeps (and writes) the sources of its own z slab -- the union of the per-rank
+   * files is the same catalogue. With COLORE_B200_DISTRIBUTE=pixel the sources are routed like srcs.c:296-373 (on the
+   * device, clr_srcs_distribute); the RSD under beaming is then evaluated BEFORE they leave the slab that holds the
+   * potential around them. */
   int ipop;
-  for (ipop = 0; ipop < par->n_srcs; ipop++) par->nsources_this[ipop] = par->nsources_c_this[ipop];
+  const char *mode = getenv("COLORE_B200_DISTRIBUTE");
+  g_by_pixel = (NNodes > 1 && mode && !strcmp(mode, "pixel"));
+  for (ipop = 0; ipop < par->n_srcs; ipop++) {
+    if (g_by_pixel) {
+      long long n = 0;
+      if (NodeThis == 0) timer(0);
+      chk(clr_srcs_distribute(g_ctx, ipop, par->need_beaming, &n));
+      catalog_cartesian_free(par->cats_c[ipop]);
+      par->cats_c[ipop] = catalog_cartesian_alloc((int)n);
+      if (n > 0) chk(clr_srcs_get_cartesian(g_ctx, ipop, par->cats_c[ipop]->pos, par->cats_c[ipop]->ipix));
+      par->nsources_c_this[ipop] = (long)n;
+      if (NodeThis == 0) timer(2);
+    }
+    par->nsources_this[ipop] = par->nsources_c_this[ipop];
+  }
 }
 
 void srcs_get_local_properties(ParamCoLoRe *par)
@@ -333,7 +351,7 @@ void srcs_get_beam_properties(ParamCoLoRe *par)
 { /* srcs.c:452-632, RSD part: dz_rsd from the CIC-interpolated potential gradient */
   int ipop;
   for (ipop = 0; ipop < par->n_srcs; ipop++) {
-    chk(clr_srcs_beam_rsd(g_ctx, ipop));
+    if (!g_by_pixel) chk(clr_srcs_beam_rsd(g_ctx, ipop));      /* routed by pixel: already done before the exchange */
     if (par->cats[ipop]->nsrc > 0)
       chk(clr_srcs_get_local_properties(g_ctx, ipop, (float *)par->cats[ipop]->srcs));
   }

@@ -98,6 +98,28 @@ def main():
     np.testing.assert_allclose(after[:, 3], rsd_ref[:, 3], rtol=2e-5, atol=1e-9)
     edge = np.abs((pos[:, 2] + 0.5 * par.l_box) * (n / par.l_box) - iz0) < 0.5      # sources of the slab's first plane
     assert edge.sum() > 0 and np.abs(after[edge, 3]).max() > 0
+    # srcs_distribute (srcs.c:296-373): rank ipix % NNodes gets the source; blocks arrive from rank-1, rank-2, ..., own
+    # sources last, order inside a block = the sender's catalogue order. Checked against that rule applied to the
+    # gathered per-slab catalogues (bit for bit). (The maps below only read the potential.)
+    allc = [None] * world
+    dist.all_gather_object(allc, (pos.copy(), ipix.copy()))
+    want_p, want_i = [], []
+    for ii in range(world):
+        frm = (rank - 1 - ii) % world
+        sel = allc[frm][1] % world == rank
+        want_p.append(allc[frm][0][sel]); want_i.append(allc[frm][1][sel])
+    want_p, want_i = np.concatenate(want_p), np.concatenate(want_i)
+    n_before = par.nsources[0]
+    cb.srcs_distribute(par, by_pixel=True)
+    pos_d, ipix_d = cb.srcs_get_cartesian(par, 0)
+    assert np.array_equal(ipix_d, want_i) and np.array_equal(pos_d, want_p), (rank, len(ipix_d), len(want_i))
+    assert np.all(ipix_d % world == rank)
+    tot_d = torch.tensor([len(ipix_d), n_before], device="cuda")
+    dist.all_reduce(tot_d)
+    assert tot_d[0].item() == tot_d[1].item()
+    srcs_d = cb.srcs_get_local_properties(par, 0)
+    np.testing.assert_allclose(srcs_d[:, :3], os_.srcs_local_properties(pos_d)[:, :3], rtol=3e-7, atol=3e-5)
+    assert np.array_equal(srcs_d[:, 3], pos_d[:, 3])
     # maps: every GPU integrates the ray segments inside its slab, the partial maps are all-reduced
     _, pix = cb.healpix.hp_shell_pixels(8, 2)
     rf = np.sort(g["s6_kappa_rf"])
