@@ -328,3 +328,12 @@ def isw_get_beam_properties(par: ParamCoLoRe, pos: np.ndarray, rf) -> np.ndarray
     check(par.lib.clr_isw_get_beam_properties(par.ctx, C.c_longlong(pos.shape[0]), _vp(pos), C.c_int(len(rf)),
                                               _vp(rf), _vp(data)))
     return data
+
+
+def write_catalog(par: ParamCoLoRe, ipop: int, fname: str, fmt: str = "ascii", n_threads: int = 0) -> float:
+    """write_catalog (io.c:1019-1236), ASCII or FITS without lensing / skewers, from the device-resident records
+    (clr_write_catalog: pinned chunked read-back + multi-threaded formatting). Returns the wall time in seconds."""
+    sec = C.c_double()
+    check(par.lib.clr_write_catalog(par.ctx, C.c_int(ipop), fname.encode(), C.c_int({"ascii": 0, "fits": 1}[fmt]),
+                                    C.c_int(ipop), C.c_int(n_threads), C.byref(sec)))
+    return sec.value

@@ -156,6 +156,14 @@ int clr_srcs_get_counts(clr_ctx *ctx, int ipop, int32_t *nsources_padded);
 int clr_srcs_get_cartesian(clr_ctx *ctx, int ipop, float *pos4, int32_t *ipix);
 /* srcs_get_local_properties_single (srcs.c:386-416): Src records, 9 floats each (common.h:169-179) */
 int clr_srcs_get_local_properties(clr_ctx *ctx, int ipop, float *srcs9);
+/* write_catalog (io.c:1019-1236) for the formats without lensing / skewers, straight from the device-resident Src
+ * records: chunked device -> pinned host copies overlapped with multi-threaded formatting, one ordered file write.
+ * format: CLR_FORMAT_ASCII ("%d %E %E %E %E \n" rows under io.c's header line) or CLR_FORMAT_FITS (BINTABLE TYPE 1J +
+ * RA, DEC, Z_COSMO, DZ_RSD 1E, big endian). type_id = the population index io.c writes in column 1. n_threads <= 0: all
+ * host cores. *seconds (may be NULL) receives the wall time. Same bytes as io.c for the same records. */
+#define CLR_FORMAT_ASCII 0
+#define CLR_FORMAT_FITS 1
+int clr_write_catalog(clr_ctx *ctx, int ipop, const char *fname, int format, int type_id, int n_threads, double *seconds);
 /* srcs_distribute_single (srcs.c:296-373), several GPUs: route every source to rank ipix % nranks, order preserved
  * (blocks received from rank-1, rank-2, ..., own sources last). beam_first != 0: evaluate the RSD-under-beaming
  * estimator (srcs.c:486-504) first, on the slab that holds the potential around each source, and carry it along.

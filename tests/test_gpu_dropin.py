@@ -139,3 +139,32 @@ def test_dropin_executable_on_two_gpus_equals_one_gpu():
             ma = _read_healpix_map(os.path.join(tmp, f"out_one_{name}.fits"))
             mb = _read_healpix_map(os.path.join(tmp, f"out_two_{name}.fits"))
             np.testing.assert_allclose(ma, mb, rtol=1e-4, atol=1e-5 * np.abs(ma).max())
+
+
+@pytest.mark.skipif(not os.path.exists(B200), reason="drop-in binary not built")
+def test_native_fits_writer_header_equals_io_c():
+    """The FITS catalogue header written by clr_write_catalog card for card against the one the unchanged io.c writes
+    through its FITS layer in the drop-in executable (only NAXIS2, the row count, may differ)."""
+    import colore_b200 as cb
+    from colore_b200.inputs import RunConfig
+    from oracle.oracle import tables_from_dump
+    cfg = RunConfig(n_grid=32, dens_type=0, nz_amplitude=400.0, seed=5, output_format="FITS")
+    with tempfile.TemporaryDirectory() as tmp:
+        _run(B200, tmp, "fits", cfg)
+        ref = open(os.path.join(tmp, "out_fits_srcs_s1_0.fits"), "rb").read()
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_n32_lognormal.npz")))
+        t = tables_from_dump(g)
+        par = cb.ParamCoLoRe(t, 32, seed=5)
+        cb.create_cartesian_fields(par)
+        cb.compute_physical_density_field(par)
+        par.set_srcs(0, t["srcs_nz_0"], t["srcs_bz_0"])
+        cb.compute_density_normalization(par)
+        cb.srcs_set_cartesian(par)
+        mine_f = os.path.join(tmp, "mine.fits")
+        cb.write_catalog(par, 0, mine_f, "fits")
+        mine = open(mine_f, "rb").read()
+        par.free()
+    cards = lambda raw: [raw[i:i + 80].decode() for i in range(0, 5760, 80)]  # noqa: E731
+    a, b = cards(ref), cards(mine)
+    diff = [(x, y) for x, y in zip(a, b) if x != y]
+    assert all(x.startswith("NAXIS2") and y.startswith("NAXIS2") for x, y in diff), diff

@@ -596,3 +596,32 @@ def test_full_size_properties(golden_dir):
     assert srcs[:, 0].min() >= 0 and srcs[:, 0].max() <= 360.0 and np.abs(srcs[:, 1]).max() <= 90.0
     assert srcs[:, 2].max() < 0.5
     par.free()
+
+
+# --------------------------------------------------------------------------------------- writer
+def test_write_catalog_matches_io_c_formats(case, tmp_path):
+    """clr_write_catalog (pinned chunked read-back + multi-threaded formatting) against the formats of write_catalog
+    (io.c:1019-1236): the ASCII rows are exactly what C's "%d %E %E %E %E \\n" gives for the Src records (Python's %E is
+    an independent correctly-rounded implementation), the FITS table holds the same floats bit for bit."""
+    g, t, o, par = case
+    _setup_sources(g, t, par)
+    n = cb.srcs_set_cartesian(par)[0]
+    srcs = cb.srcs_get_local_properties(par, 0)
+    fa, ff = str(tmp_path / "cat.txt"), str(tmp_path / "cat.fits")
+    for nt in (1, 5):
+        cb.write_catalog(par, 0, fa, "ascii", n_threads=nt)
+        lines = open(fa).read().split("\n")
+        assert lines[0] == "#[1]type [2]RA, [3]dec, [4]z0, [5]dz_RSD " and lines[-1] == "" and len(lines) == n + 2
+        want = ["0 %E %E %E %E " % tuple(float(v) for v in row[:4]) for row in srcs]
+        assert lines[1:-1] == want
+    cb.write_catalog(par, 0, ff, "fits")
+    raw = open(ff, "rb").read()
+    assert len(raw) % 2880 == 0
+    cards = [raw[2880 + i:2880 + i + 80].decode() for i in range(0, 2880, 80)]
+    keys = {c[:8].strip(): c[10:].split("/")[0].strip() for c in cards if c[8:10] == "= "}
+    assert keys["XTENSION"] == "'BINTABLE'" and int(keys["NAXIS1"]) == 20 and int(keys["NAXIS2"]) == n and int(keys["TFIELDS"]) == 5
+    assert [keys[f"TTYPE{i}"].strip("' ") for i in range(1, 6)] == ["TYPE", "RA", "DEC", "Z_COSMO", "DZ_RSD"]
+    assert [keys[f"TFORM{i}"].strip("' ") for i in range(1, 6)] == ["1J", "1E", "1E", "1E", "1E"]
+    rows = np.frombuffer(raw[5760:5760 + 20 * n], dtype=np.dtype([("t", ">i4"), ("f", ">f4", (4,))]))
+    assert np.all(rows["t"] == 0) and np.array_equal(rows["f"].astype(np.float32), srcs[:, :4])
+    assert raw[5760 + 20 * n:] == b"\0" * (len(raw) - 5760 - 20 * n)
