@@ -373,6 +373,9 @@ def main():
                          "of the GPU arm defaults to 512 (a bounded sample)")
     ap.add_argument("--no-north-star", action="store_true", help="skip the 2048^3 run that --gpus 8 appends")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--writer", action="store_true",
+                    help="also time clr_write_catalog (ASCII + FITS, all host threads) on the last catalogue; off by default "
+                         "because it writes ~2.4 GB into the temporary directory")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -545,6 +548,19 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"failed: {e}"[:200]}
 
+    # ---- (optional) the native catalogue writer on the last catalogue --------------------------------
+    writer = None
+    if args.writer and rank == 0:
+        wd = tempfile.mkdtemp(prefix="clr_bench_out_")
+        try:
+            writer = {"sources": int(par.nsources[0]), "threads": os.cpu_count()}
+            for fmt in ("fits", "ascii"):
+                fn = os.path.join(wd, "cat." + fmt)
+                sec = cb.write_catalog(par, 0, fn, fmt)
+                writer[fmt] = {"seconds": sec, "bytes": os.path.getsize(fn), "Msources_per_s": par.nsources[0] / sec / 1e6}
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+
     # ---- correctness bits of this very configuration (after the timed regions) ------------------
     parity = parity_checks(cb, torch, par, tabs, n, local, allsum, allmax)
     transpose = cb.dist.transpose_mode(par) if world > 1 else "none"
@@ -566,7 +582,7 @@ def main():
             "parallelism": f"{world} z-slab(s), one process per GPU, FFT slab transpose: {transpose}",
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "fft_hbm_gbs": fft_gbs, "nvlink": nvlink, "stages": stages, "parity": parity,
-            "north_star": north, "cpu_baseline": cpu,
+            "north_star": north, "writer": writer, "cpu_baseline": cpu,
         }))
     if par is not None:
         par.free()

@@ -194,7 +194,7 @@ static int create_impl(clr_ctx *c, const clr_params *p, int device)
 static void free_pop(clr_ctx::Pop &P)
 {
   cudaFree(P.d_a); cudaFree(P.d_b); cudaFree(P.d_norm); cudaFree(P.d_counts); cudaFree(P.d_bound);
-  cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs); cudaFree(P.d_srcs_alt);
+  cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs); cudaFree(P.d_srcs_alt); cudaFree(P.d_sup_entries);
 }
 
 int clr_destroy(clr_ctx *c)
@@ -395,6 +395,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "lpt_interp_type")) { c->lpt_interp_type = value; return 0; }
   if (!strcmp(name, "keep_particles")) { c->keep_particles = value; return 0; }
   if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
+  if (!strcmp(name, "srcs_compact")) { c->srcs_compact = value; return 0; }
   if (!strcmp(name, "fft_fused")) { c->fft_fused = value; return 0; }
   if (!strcmp(name, "fill_fused")) { c->fill_fused = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
@@ -535,9 +536,14 @@ int clr_srcs_get_counts(clr_ctx *c, int ipop, int32_t *nsources_padded)
   // device layout is unpadded [nz][n][n]; the reference array has the padded pitch (srcs.c:125)
   const ClrDev &d = c->dev;
   const int hpitch = 2 * d.nc;
-  CLR_CUDA(cudaMemcpy2DAsync(nsources_padded, (size_t)hpitch * sizeof(int32_t), P.d_counts, (size_t)d.n * sizeof(int32_t),
-                             (size_t)d.n * sizeof(int32_t), (size_t)d.n * d.nz_here, cudaMemcpyDeviceToHost, c->stream));
-  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  int32_t *dense = nullptr;
+  bool owned = false;
+  if (clr_srcs_dense_counts(c, ipop, &dense, &owned)) return 1;
+  cudaError_t e1 = cudaMemcpy2DAsync(nsources_padded, (size_t)hpitch * sizeof(int32_t), dense, (size_t)d.n * sizeof(int32_t),
+                                     (size_t)d.n * sizeof(int32_t), (size_t)d.n * d.nz_here, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  if (owned) cudaFree(dense);
+  CLR_CHECK(e1 == cudaSuccess && e2 == cudaSuccess, "clr_srcs_get_counts: copy failed");
   for (long long row = 0; row < (long long)d.n * d.nz_here; row++)
     for (int x = d.n; x < hpitch; x++) nsources_padded[row * hpitch + x] = 0;
   return 0;

@@ -66,6 +66,7 @@ struct clr_ctx {
   // single-GPU c2r (clr_fft.cu): z-pass output in the kx-tile layout, ticket + per-plane-group counters of the fused y+x pass
   void *d_fft_tmp = nullptr; size_t fft_tmp_bytes = 0;
   unsigned *d_fft_sync = nullptr;
+  int srcs_compact = 1;                              // option "srcs_compact": 0 = dense per-cell counts + full-array expansion
   int fft_fused = 1;                                 // option "fft_fused": 0 = three separate axis passes
   int fill_fused = 1;                                // option "fill_fused": 0 = stand-alone mode fill + z pass
   size_t scratch_bytes = 0;
@@ -86,7 +87,11 @@ struct clr_ctx {
     int nside = 0, nr = 0;
     std::vector<float> r0, rf;
     // sources catalogue (device)
+    // per-cell counts: dense int32 [nz][n][n], or (default) compact entries per 8192-cell super chunk stored in the
+    // super chunk's own slice of this buffer + the number of entries per super chunk (clr_srcs.cu: poisson_kernel)
     int32_t *d_counts = nullptr;
+    bool counts_compact = false, d_sup_entries_valid = false;
+    int32_t *d_sup_entries = nullptr; size_t sup_entries_cap = 0;
     float *d_bound = nullptr;       // fp32 screening table of the Poisson pass (4 floats per r-bin)
     long long nsrc = 0;
     float *d_pos = nullptr; int32_t *d_ipix = nullptr; float *d_srcs = nullptr;
@@ -202,6 +207,7 @@ int clr_fields_norm_hist(clr_ctx *c, int npop, const double *const *d_bz, int nz
 int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed);
 int clr_srcs_local(clr_ctx *c, int ipop);
 int clr_srcs_beam(clr_ctx *c, int ipop);
+int clr_srcs_dense_counts(clr_ctx *c, int ipop, int32_t **d_dense, bool *owned);
 int clr_srcs_distribute_impl(clr_ctx *c, int ipop, int beam_first, long long *nsrc_out);
 int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
 int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,

@@ -217,10 +217,18 @@ __global__ void poisson_bound_kernel(const ClrDev d, ClrPop pop, float vol, floa
 // counts: int32 per cell, unpadded flat order ix + n*(iy + n*iz_local); chunk_tot[chunk] = sum.
 // RNG: the first uniform of cell g is word g&3 of the Philox block shared by cells 4(g>>2)..+3
 // (third_party/shim/gsl_shim.c:shim_philox_seek_cell), so one thread screens 4 neighbouring cells per block.
+// Output (COMPACT = true, the default): no dense count array is written. A CTA keeps the counts of its 8192-cell super
+// chunk in shared memory and emits only the occupied cells, in cell order, as 32-bit entries (local cell << 16 | count)
+// into the super chunk's OWN slice of the count buffer (entries[sup * 8192 ...]: at most one entry per cell, so the slice
+// always suffices), plus {entries, sources} per super chunk. At <N> = 0.03 that is ~1 KB written per 32 KB slice
+// instead of the whole slice, and the expansion pass reads the entries instead of every count. Counts above 65535
+// raise *overflow (the host then re-runs with COMPACT = false: dense int32 counts as in the reference, srcs.c:125).
+template <bool COMPACT>
 __global__ void __launch_bounds__(kThreads, 4)
 poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const float4 *__restrict__ bound,
                const float4 *__restrict__ bound_grp, uint32_t seed, int ipop, int32_t *__restrict__ counts,
-               int32_t *__restrict__ chunk_tot, long long n_cells)
+               int32_t *__restrict__ chunk_tot, int32_t *__restrict__ sup_entries, int *__restrict__ overflow,
+               long long n_cells)
 {
   const double dx = (double)(d.l_box / d.n);       // float division, as in the reference (srcs.c:147)
   const double cell_vol = dx * dx * dx;
@@ -236,6 +244,11 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
   __shared__ int sub_tot[kSub];
   __shared__ unsigned short q_cell[kSub * kChunk];
   __shared__ unsigned short q_grp[kSub * kChunk / 4];
+  // COMPACT: counts of the occupied cells of the super chunk (valid where the bitmap has the cell's bit set)
+  __shared__ unsigned short cnt_s[COMPACT ? kSub * kChunk : 1];
+  __shared__ unsigned bm_s[COMPACT ? kSub * kChunk / 32 : 1];
+  __shared__ int wsum_e[kThreads / 32];
+  static_assert(kSub * kChunk / 32 == kThreads, "one bitmap word per thread");
   __shared__ int q_len, g_len;
   const long long n_chunks = (n_cells + kChunk - 1) / kChunk;
   const long long n_super = (n_chunks + kSub - 1) / kSub;
@@ -244,6 +257,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
   __syncthreads();
   for (long long sup = blockIdx.x; sup < n_super; sup += gridDim.x) {
     const long long cell0 = sup * kSub * kChunk;
+    if (COMPACT) bm_s[threadIdx.x] = 0u;            // (made visible by the barrier that ends phase 1)
     // ---- phase 1 (all cells, fp32). Everything that is not surely empty -- about 3% of the cells at
     // <N> = 0.03 -- is queued for the exact double-precision path.
 #pragma unroll 1
@@ -268,14 +282,14 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
         {
           const float rc = sk.rcutf + 0.05f;
           if (r2min > rc * rc * 1.000001f) {
-            *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
+            if (!COMPACT) *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
             continue;
           }
         }
         unsigned long long grp = ((unsigned long long)i0 + goff) >> 2;
         uint32_t w[4];
         clr_philox((uint32_t)grp, (uint32_t)(grp >> 32), 0u, strm | 0x80000000u, seed, 0u, w);
-        *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
+        if (!COMPACT) *reinterpret_cast<int4 *>(counts + i0) = make_int4(0, 0, 0, 0);
         const float r2max = fmaxf(fmaxf(xf[0] * xf[0], xf[1] * xf[1]), fmaxf(xf[2] * xf[2], xf[3] * xf[3])) + yz2;
         const float dmax = fmaxf(fmaxf(dl[0], dl[1]), fmaxf(dl[2], dl[3]));
         const uint32_t umax = max(max(w[0], w[1]), max(w[2], w[3]));
@@ -292,7 +306,7 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
           unsigned long long gcell = (unsigned long long)i + goff;
           uint32_t w[4];
           clr_philox((uint32_t)(gcell >> 2), (uint32_t)(gcell >> 34), 0u, strm | 0x80000000u, seed, 0u, w);
-          if (screen_cell(sk, bound, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) counts[i] = 0;
+          if (screen_cell(sk, bound, xf * xf + yf * yf + zf * zf, dl, w[gcell & 3])) { if (!COMPACT) counts[i] = 0; }
           else q_cell[atomicAdd(&q_len, 1)] = (unsigned short)(lc0 + q);
         }
       }
@@ -356,17 +370,100 @@ poisson_kernel(const ClrDev d, const float *__restrict__ dens, ClrPop pop, const
           npp = (int)dev_poisson(s, lambda);
         }
       }
-      counts[i] = npp;
-      if (npp) atomicAdd(&sub_tot[lc / kChunk], npp);
+      if (COMPACT) {
+        if (npp) {
+          cnt_s[lc] = (unsigned short)min(npp, 65535);
+          atomicOr(&bm_s[lc >> 5], 1u << (lc & 31));
+          atomicAdd(&sub_tot[0], npp);
+          if (npp > 65535) *overflow = 1;
+        }
+      } else {
+        counts[i] = npp;
+        if (npp) atomicAdd(&sub_tot[lc / kChunk], npp);
+      }
     }
     __syncthreads();
-    if (threadIdx.x < kSub) {
+    if (COMPACT) {
+      // ordered compaction: thread t owns bitmap word t = the cells [32 t, 32 t + 32) of the super chunk
+      unsigned word = bm_s[threadIdx.x];
+      const int occ = __popc(word);
+      int incl = occ;
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) wsum_e[w] = incl;
+      __syncthreads();
+      int woff = 0, tot_e = 0;
+#pragma unroll
+      for (int k = 0; k < kThreads / 32; k++) { const int t = wsum_e[k]; if (k < w) woff += t; tot_e += t; }
+      int32_t *o = counts + cell0 + woff + incl - occ;
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        const int lc = threadIdx.x * 32 + b;
+        *o++ = (int32_t)(((unsigned)lc << 16) | cnt_s[lc]);
+      }
+      if (threadIdx.x == 0) { chunk_tot[sup] = sub_tot[0]; sup_entries[sup] = tot_e; sub_tot[0] = 0; }
+    } else if (threadIdx.x < kSub) {
       long long chunk = sup * kSub + threadIdx.x;
       if (chunk < n_chunks) chunk_tot[chunk] = sub_tot[threadIdx.x];
       sub_tot[threadIdx.x] = 0;
     }
     if (threadIdx.x == 0) { q_len = 0; g_len = 0; }
     __syncthreads();
+  }
+}
+
+__global__ void zero_words_kernel(uint32_t *p, int n) { if ((int)threadIdx.x < n) p[threadIdx.x] = 0u; }
+
+// dense per-cell counts (the reference's nsources array, srcs.c:125) from the compact entries: for clr_srcs_get_counts
+__global__ void __launch_bounds__(kThreads)
+entries_to_counts_kernel(const int32_t *__restrict__ entries, const int32_t *__restrict__ sup_entries, int32_t *__restrict__ dense,
+                         long long n_super, long long n_cells)
+{
+  for (long long sup = blockIdx.x; sup < n_super; sup += gridDim.x) {
+    const long long cell0 = sup * kSub * kChunk;
+    for (int k = threadIdx.x; k < kSub * kChunk && cell0 + k < n_cells; k += kThreads) dense[cell0 + k] = 0;
+    __syncthreads();
+    const int ne = sup_entries[sup];
+    for (int k = threadIdx.x; k < ne; k += kThreads) {
+      const unsigned e = (unsigned)entries[cell0 + k];
+      dense[cell0 + (e >> 16)] = (int32_t)(e & 0xffffu);
+    }
+    __syncthreads();
+  }
+}
+
+// expansion from the compact entries: one CTA per super chunk, entry k -> `count` source references at the ordered slots
+__global__ void __launch_bounds__(kThreads)
+expand_entries_kernel(const int32_t *__restrict__ entries, const int32_t *__restrict__ sup_entries,
+                      const long long *__restrict__ sup_offs, unsigned long long *__restrict__ src_ref, long long n_super)
+{
+  __shared__ int wsum[kThreads / 32];
+  for (long long sup = blockIdx.x; sup < n_super; sup += gridDim.x) {
+    const int ne = sup_entries[sup];
+    if (ne == 0) continue;                                 // uniform per CTA
+    const long long cell0 = sup * kSub * kChunk;
+    long long run = sup_offs[sup];
+    for (int k0 = 0; k0 < ne; k0 += kThreads) {
+      const int k = k0 + threadIdx.x;
+      const unsigned e = k < ne ? (unsigned)entries[cell0 + k] : 0u;
+      const int cnt = (int)(e & 0xffffu);
+      int incl = cnt;
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      __syncthreads();
+      if (lane == 31) wsum[w] = incl;
+      __syncthreads();
+      int woff = 0, tot = 0;
+#pragma unroll
+      for (int q = 0; q < kThreads / 32; q++) { const int t = wsum[q]; if (q < w) woff += t; tot += t; }
+      const unsigned long long cell = (unsigned long long)(cell0 + (e >> 16));
+      unsigned long long *o = src_ref + run + woff + incl - cnt;
+      for (int ip = 0; ip < cnt; ip++) o[ip] = (cell << 24) | (unsigned)ip;
+      run += tot;
+    }
   }
 }
 
@@ -729,12 +826,9 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
   CLR_CHECK(P.have_norm, "srcs population %d has no normalisation (clr_compute_density_normalization)", ipop);
   const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
   const long long n_chunks = (n_cells + kChunk - 1) / kChunk;
-  if (!P.d_counts) CLR_CUDA(cudaMalloc(&P.d_counts, n_cells * sizeof(int32_t)));
-  size_t need = (size_t)(n_chunks + 2) / 2 * sizeof(long long) + (size_t)(n_chunks + 1) * sizeof(long long) +
-                (size_t)kScanBlocks * sizeof(long long) + 64;
-  if (clr_ensure_scratch(c, need)) return 1;
-  long long *d_offs = reinterpret_cast<long long *>(c->d_scratch);
-  int32_t *d_tot = reinterpret_cast<int32_t *>(d_offs + n_chunks + 1);
+  const long long n_super = (n_chunks + kSub - 1) / kSub;
+  // the count buffer holds whole super-chunk slices (compact entries live in the slice of their super chunk)
+  if (!P.d_counts) CLR_CUDA(cudaMalloc(&P.d_counts, (size_t)n_super * kSub * kChunk * sizeof(int32_t)));
   ClrPop pop{P.d_a, P.d_b, P.d_norm, P.norm_0, P.norm_f};
   if (!P.d_bound) CLR_CUDA(cudaMalloc(&P.d_bound, (size_t)2 * CLR_NA * 4 * sizeof(float)));   // per-cell + group table
   {
@@ -749,22 +843,57 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
     c->launches++;
     CLR_CUDA(cudaGetLastError());
   }
-  {
-    StageScope sc(c, "srcs_poisson", 1);
-    poisson_kernel<<<grid_for(c, (n_chunks + kSub - 1) / kSub, 8), kThreads, 0, c->stream>>>(
-        c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound),
-        reinterpret_cast<const float4 *>(P.d_bound) + CLR_NA, seed, ipop, P.d_counts, d_tot, n_cells);
-    CLR_CUDA(cudaGetLastError());
-  }
-  {
-    StageScope sc(c, "srcs_scan", 2);
-    long long *d_seg = d_offs + n_chunks + 1 + (n_chunks + 2) / 2;   // behind offs[] and tot[]
-    scan_sums_kernel<<<kScanBlocks, 256, 0, c->stream>>>(d_tot, d_seg, n_chunks);
-    scan_chunks_kernel<<<kScanBlocks, 256, 0, c->stream>>>(d_tot, d_seg, d_offs, n_chunks);
-    CLR_CUDA(cudaGetLastError());
-  }
   long long total = 0;
-  if (clr_read_small(c, &total, d_offs + n_chunks, sizeof(long long))) return 1;
+  long long *d_offs = nullptr;
+  bool compact = c->srcs_compact != 0;
+  // entries per super chunk: kept with the catalogue (expansion, clr_srcs_get_counts). Written by the kernel itself: a
+  // device-to-device cudaMemcpy on the main stream would queue behind the catalogue read-back on the copy engine.
+  if (compact && (!P.d_sup_entries || P.sup_entries_cap < (size_t)n_super)) {
+    if (P.d_sup_entries) cudaFree(P.d_sup_entries);
+    P.d_sup_entries = nullptr;
+    CLR_CUDA(cudaMalloc(&P.d_sup_entries, (size_t)n_super * sizeof(int32_t)));
+    P.sup_entries_cap = (size_t)n_super;
+  }
+  for (int attempt = 0; attempt < 2; attempt++) {
+    // scratch: offs[n_scan + 2] (exclusive scan, grand total, overflow flag) | tot[n_scan] | segment sums | entries per super chunk
+    const long long n_scan = compact ? n_super : n_chunks;
+    size_t need = (size_t)(n_scan + 2) * sizeof(long long) + (size_t)(n_scan + 2) / 2 * sizeof(long long) +
+                  (size_t)kScanBlocks * sizeof(long long) + (size_t)(n_super + 2) / 2 * sizeof(long long) + 64;
+    if (clr_ensure_scratch(c, need)) return 1;
+    d_offs = reinterpret_cast<long long *>(c->d_scratch);
+    int32_t *d_tot = reinterpret_cast<int32_t *>(d_offs + n_scan + 2);
+    long long *d_seg = d_offs + n_scan + 2 + (n_scan + 2) / 2;
+    int32_t *d_sup_entries = P.d_sup_entries;
+    zero_words_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<uint32_t *>(d_offs + n_scan + 1), 2);   // overflow flag
+    c->launches++;
+    {
+      StageScope sc(c, "srcs_poisson", 1);
+      const int grid = grid_for(c, n_super, 8);
+      if (compact)
+        poisson_kernel<true><<<grid, kThreads, 0, c->stream>>>(
+            c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound), reinterpret_cast<const float4 *>(P.d_bound) + CLR_NA,
+            seed, ipop, P.d_counts, d_tot, d_sup_entries, reinterpret_cast<int *>(d_offs + n_scan + 1), n_cells);
+      else
+        poisson_kernel<false><<<grid, kThreads, 0, c->stream>>>(
+            c->dev, c->d_dens, pop, reinterpret_cast<const float4 *>(P.d_bound), reinterpret_cast<const float4 *>(P.d_bound) + CLR_NA,
+            seed, ipop, P.d_counts, d_tot, d_sup_entries, reinterpret_cast<int *>(d_offs + n_scan + 1), n_cells);
+      CLR_CUDA(cudaGetLastError());
+    }
+    {
+      StageScope sc(c, "srcs_scan", 2);
+      scan_sums_kernel<<<kScanBlocks, 256, 0, c->stream>>>(d_tot, d_seg, n_scan);
+      scan_chunks_kernel<<<kScanBlocks, 256, 0, c->stream>>>(d_tot, d_seg, d_offs, n_scan);
+      CLR_CUDA(cudaGetLastError());
+    }
+    long long res[2] = {0, 0};
+    if (clr_read_small(c, res, d_offs + n_scan, sizeof(res))) return 1;
+    total = res[0];
+    P.counts_compact = compact;
+    P.d_sup_entries_valid = false;
+    if (compact && res[1] != 0) { compact = false; continue; }       // a cell holds more than 65535 sources: dense counts
+    if (compact) P.d_sup_entries_valid = true;
+    break;
+  }
   P.nsrc = total;
   if ((size_t)total > P.cap_src) {
     if (c->copy_pending) CLR_CUDA(cudaStreamSynchronize(c->copy_stream));   // a read-back may still use the old buffers
@@ -798,7 +927,10 @@ int clr_srcs_run(clr_ctx *c, int ipop, uint32_t seed)
     unsigned long long *d_ref = reinterpret_cast<unsigned long long *>(P.d_srcs);
     {
       StageScope sc(c, "srcs_expand", 1);
-      expand_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(P.d_counts, d_offs, d_ref, n_cells);
+      if (P.counts_compact)
+        expand_entries_kernel<<<grid_for(c, n_super, 8), kThreads, 0, c->stream>>>(P.d_counts, P.d_sup_entries, d_offs, d_ref, n_super);
+      else
+        expand_kernel<<<grid_for(c, n_chunks, 8), kThreads, 0, c->stream>>>(P.d_counts, d_offs, d_ref, n_cells);
       CLR_CUDA(cudaGetLastError());
     }
     StageScope sc(c, "srcs_place", 1);
@@ -931,4 +1063,23 @@ int clr_srcs_distribute_impl(clr_ctx *c, int ipop, int beam_first, long long *ns
     if (nsrc_out) *nsrc_out = P.nsrc;
   }
   return rc;
+}
+
+// dense per-cell counts on the device, unpadded [nz][n][n] (the reference's nsources array, srcs.c:125); *owned = the
+// caller frees the buffer
+int clr_srcs_dense_counts(clr_ctx *c, int ipop, int32_t **d_dense, bool *owned)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  *owned = false;
+  if (!P.counts_compact) { *d_dense = P.d_counts; return 0; }
+  CLR_CHECK(P.d_sup_entries_valid, "no counts for population %d", ipop);
+  const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
+  const long long n_super = ((n_cells + kChunk - 1) / kChunk + kSub - 1) / kSub;
+  int32_t *buf = nullptr;
+  CLR_CUDA(cudaMalloc(&buf, (size_t)n_super * kSub * kChunk * sizeof(int32_t)));
+  entries_to_counts_kernel<<<grid_for(c, n_super, 8), kThreads, 0, c->stream>>>(P.d_counts, P.d_sup_entries, buf, n_super, n_cells);
+  if (cudaGetLastError() != cudaSuccess) { cudaFree(buf); clr_set_error("entries_to_counts_kernel failed"); return 1; }
+  c->launches++;
+  *d_dense = buf; *owned = true;
+  return 0;
 }
