@@ -207,6 +207,22 @@ int clr_comm_barrier(clr_ctx *c)
   return 0;
 }
 
+// Agreement before a collective: returns 0 when EVERY rank passed ok != 0, else sets the error on all ranks and returns 1
+// (a rank that failed locally, e.g. out of memory, must not leave the others waiting in the next collective).
+int clr_comm_all_ok(clr_ctx *c, int ok, const char *what)
+{
+  if (c->nranks > 1) {
+    int v = ok ? 1 : 0;
+    CLR_CUDA(cudaMemcpyAsync(c->d_barrier, &v, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CLR_NCCL(g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, ncclInt32, ncclMin, (ncclComm_t)c->nccl_comm, c->stream));
+    CLR_CUDA(cudaMemcpyAsync(&v, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CLR_CUDA(cudaStreamSynchronize(c->stream));
+    if (ok && !v) clr_set_error("%s: another rank failed", what);
+    ok = v;
+  }
+  return ok ? 0 : 1;
+}
+
 int clr_comm_destroy(clr_ctx *c)
 {
   if (c->stream2) cudaStreamSynchronize(c->stream2);

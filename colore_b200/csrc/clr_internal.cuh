@@ -222,6 +222,7 @@ int clr_comm_alltoall(clr_ctx *c, const void *send, void *recv, size_t block_flo
 int clr_comm_alltoallv(clr_ctx *c, const float *send, const size_t *send_off, const size_t *send_n, float *recv,
                        const size_t *recv_off, const size_t *recv_n);
 int clr_comm_barrier(clr_ctx *c);
+int clr_comm_all_ok(clr_ctx *c, int ok, const char *what);
 int clr_comm_allreduce_f64(clr_ctx *c, double *dbuf, size_t n);
 int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n);
 int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n);

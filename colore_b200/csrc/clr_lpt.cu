@@ -407,10 +407,13 @@ int clr_lpt_run(clr_ctx *c, int order)
     if (c->nranks > 1) {
       // share_particles (density.c:191-374): ship the particles whose stencil reaches another slab
       const int P = c->nranks;
-      if (clr_ensure_scratch(c, (size_t)(P * P + 2 * P) * sizeof(unsigned long long))) break;
+      // rank-local failures (allocation, launch) are agreed on before every collective: nobody is left waiting
+      int ok = clr_ensure_scratch(c, (size_t)(P * P + 2 * P) * sizeof(unsigned long long)) == 0;
       unsigned long long *d_mat = reinterpret_cast<unsigned long long *>(c->d_scratch);   // P x P counts [src][dst]
       unsigned long long *d_off = d_mat + (size_t)P * P, *d_cur = d_off + P;
-      if (cudaMemsetAsync(d_mat, 0, (size_t)(P * P + 2 * P) * sizeof(unsigned long long), c->stream) != cudaSuccess) break;
+      if (ok) ok = cudaMemsetAsync(d_mat, 0, (size_t)(P * P + 2 * P) * sizeof(unsigned long long), c->stream) == cudaSuccess;
+      if (ok) ok = cudaGetLastError() == cudaSuccess;        // the deposit / position kernels above
+      if (clr_comm_all_ok(c, ok, "LPT particle routing")) break;
       { StageScope sc(c, "lpt_route", 1);
         lpt_route_kernel<false><<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, pos[0], pos[1], pos[2], n_cells, c->lpt_interp_type, c->rank, P,
                                                                                     d_mat + (size_t)c->rank * P, nullptr, nullptr, nullptr); }
@@ -424,10 +427,15 @@ int clr_lpt_run(clr_ctx *c, int order)
         r_off[h + 1] = r_off[h] + mat[(size_t)h * P + c->rank];
       }
       const unsigned long long n_send = s_off[P], n_recv = r_off[P];
+      ok = 1;
       if (cudaMalloc(&d_send, (size_t)(3 * n_send + 3) * sizeof(float)) != cudaSuccess ||
           cudaMalloc(&d_recv, (size_t)(3 * n_recv + 3) * sizeof(float)) != cudaSuccess) {
-        clr_set_error("LPT: out of device memory (particle exchange: %llu out, %llu in)", n_send, n_recv); break; }
-      if (cudaMemcpyAsync(d_off, s_off.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+        cudaGetLastError();
+        clr_set_error("LPT: out of device memory (particle exchange: %llu out, %llu in)", n_send, n_recv);
+        ok = 0;
+      }
+      if (ok) ok = cudaMemcpyAsync(d_off, s_off.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+      if (clr_comm_all_ok(c, ok, "LPT particle exchange")) break;
       { StageScope sc(c, "lpt_route", 1);
         lpt_route_kernel<true><<<grid_for(c, n_cells, 8), kThreads, 0, c->stream>>>(d, pos[0], pos[1], pos[2], n_cells, c->lpt_interp_type, c->rank, P,
                                                                                    nullptr, d_off, d_cur, d_send); }
