@@ -55,6 +55,10 @@ class RunConfig:
     kappa_nside: int = 0            # 0 -> no kappa maps
     isw_nside: int = 0
     z_out: tuple = (0.2, 0.4)
+    srcs_lensing: bool = False      # include_lensing of every srcs section (srcs.c:531-614)
+    srcs_skewers: bool = False      # store_skewers (srcs.c:507-529)
+    gaussian_skewers: bool = False  # srcsN.gaussian_skewers (beaming.c:55-66)
+    cstm_nside: int = 0             # 0 -> no custom projected map (cstm.c)
     cosmo: Cosmology = field(default_factory=Cosmology)
 
 
@@ -103,6 +107,13 @@ def write_inputs(dirname: str, cfg: RunConfig) -> dict:
         edges = np.linspace(nu_rest / (1 + zhi), nu_rest / (1 + zlo), cfg.imap_nchannels + 1)
         paths["nu"] = os.path.join(dirname, "nu.txt")
         np.savetxt(paths["nu"], np.column_stack([edges[:-1], edges[1:]]), fmt="%.10e")
+    if cfg.cstm_nside > 0:
+        # custom projected tracer: a smooth radial kernel K(z) and its own bias b(z) (io.c:357-362, cosmo.c:631-662)
+        paths["kz_cstm"] = os.path.join(dirname, "kz_cstm.txt")
+        paths["bz_cstm"] = os.path.join(dirname, "bz_cstm.txt")
+        kz = np.exp(-0.5 * ((z - 0.6 * cfg.z_max) / (0.2 * cfg.z_max)) ** 2)
+        np.savetxt(paths["kz_cstm"], np.column_stack([z, kz]), fmt="%.10e")
+        np.savetxt(paths["bz_cstm"], np.column_stack([z, 1.2 + 0.3 * z]), fmt="%.10e")
     return paths
 
 
@@ -132,7 +143,12 @@ def write_param_file(fname: str, cfg: RunConfig, paths: dict, prefix_out: str) -
         lines += [f"srcs{ipop + 1}:", "{",
                   f'  nz_filename= "{paths[f"nz{ipop}"]}"',
                   f'  bias_filename= "{paths[f"bz{ipop}"]}"',
-                  "  include_lensing= false", "  store_skewers= false", "}"]
+                  f"  include_lensing= {b(cfg.srcs_lensing)}", f"  store_skewers= {b(cfg.srcs_skewers)}",
+                  f"  gaussian_skewers= {b(cfg.gaussian_skewers)}", "}"]
+    if cfg.cstm_nside > 0:
+        lines += ["custom1:", "{",
+                  f'  kz_filename= "{paths["kz_cstm"]}"', f'  bias_filename= "{paths["bz_cstm"]}"',
+                  f"  nside= {cfg.cstm_nside}", "}"]
     if cfg.imap_nside > 0:
         lines += ["imap1:", "{",
                   f'  tbak_filename= "{paths["tz"]}"', f'  bias_filename= "{paths["bz_im"]}"',

@@ -210,6 +210,30 @@ class Oracle:
                                    C.c_int(int(pre)), C.c_int(int(post)))
         return srcs
 
+    def srcs_beam_full(self, dens, npot, pos, srcs, sigma2, lensing=False, skewers=False, gaussian=False,
+                       dg_skw=None, v_skw=None, pre=True, post=True):
+        """srcs.c:425-744 (RSD + skewers + per-source lensing). Returns (srcs, dg_skw, v_skw)."""
+        n = pos.shape[0]
+        nr = self.n // 2
+        self.par.sigma2_gauss = float(sigma2)
+        if skewers and dg_skw is None:
+            dg_skw = np.zeros((n, nr), np.float32)
+            v_skw = np.zeros((n, nr), np.float32)
+        self.lib.orc_srcs_get_beam_properties(self.pp, _fp(dens), _fp(npot), _fp(pos), C.c_long(n), _fp(srcs),
+                                              C.c_int(int(lensing)), C.c_int(int(skewers)), C.c_int(int(gaussian)),
+                                              _fp(dg_skw) if skewers else None, _fp(v_skw) if skewers else None,
+                                              C.c_int(int(pre)), C.c_int(int(post)))
+        return srcs, dg_skw, v_skw
+
+    def cstm(self, dens, kz_tab, bz_tab, norm_tab, norm_0, norm_f, pos, data=None):
+        """cstm.c:68-145: custom projected map for the unit vectors pos[npix][3]."""
+        npix = pos.shape[0]
+        if data is None:
+            data = np.zeros(npix, np.float32)
+        self.lib.orc_cstm_get_beam_properties(self.pp, _fp(dens), _dp(kz_tab), _dp(bz_tab), _dp(norm_tab),
+                                              C.c_double(norm_0), C.c_double(norm_f), C.c_long(npix), _dp(pos), _fp(data))
+        return data
+
     def imap(self, dens, npot, tz_tab, bz_tab, norm_tab, norm_0, norm_f, nside, r0, rf):
         nr = len(r0)
         npix = 12 * nside * nside
@@ -275,6 +299,6 @@ def tables_from_arrays(arrs) -> dict:
     for i, k in enumerate(names):
         t[k] = float(sc[i])
     for k in list(arrs.keys()):
-        if k.startswith("tab_srcs_") or k.startswith("tab_imap_"):
+        if k.startswith("tab_srcs_") or k.startswith("tab_imap_") or k.startswith("tab_cstm_"):
             t[k[4:]] = np.asarray(arrs[k])
     return t

@@ -87,6 +87,10 @@ int main(int argc, char **argv)
     sprintf(nm, "tab_imap_tz_%d", i); dump_f64(d, nm, par->imap_tz_arr[i], NA);
     sprintf(nm, "tab_imap_bz_%d", i); dump_f64(d, nm, par->imap_bz_arr[i], NA);
   }
+  for (i = 0; i < par->n_cstm; i++) {
+    sprintf(nm, "tab_cstm_kz_%d", i); dump_f64(d, nm, par->cstm_kz_arr[i], NA);
+    sprintf(nm, "tab_cstm_bz_%d", i); dump_f64(d, nm, par->cstm_bz_arr[i], NA);
+  }
   sc[0] = par->l_box;          sc[1] = par->pos_obs[0];   sc[2] = par->glob_idr;
   sc[3] = par->prefac_lensing; sc[4] = par->fgrowth_0;    sc[5] = par->hubble_0;
   sc[6] = par->OmegaM;         sc[7] = par->n_scal;       sc[8] = par->r2_smooth;
@@ -119,6 +123,11 @@ int main(int argc, char **argv)
     double e[2] = {par->norm_imap_0[i], par->norm_imap_f[i]};
     sprintf(nm, "s3_imap_norm_%d", i); dump_f64(d, nm, par->imap_norm_arr[i], NA);
     sprintf(nm, "s3_imap_norm_ends_%d", i); dump_f64(d, nm, e, 2);
+  }
+  for (i = 0; i < par->n_cstm; i++) {
+    double e[2] = {par->norm_cstm_0[i], par->norm_cstm_f[i]};
+    sprintf(nm, "s3_cstm_norm_%d", i); dump_f64(d, nm, par->cstm_norm_arr[i], NA);
+    sprintf(nm, "s3_cstm_norm_ends_%d", i); dump_f64(d, nm, e, 2);
   }
   { double e[2] = {par->z0_norm, par->zf_norm}; dump_f64(d, "s3_znorm_ends", e, 2); }
 
@@ -167,8 +176,23 @@ int main(int argc, char **argv)
     }
     if (par->do_srcs) {
       for (i = 0; i < par->n_srcs; i++) {
+        Catalog *c = par->cats[i];
+        double fl[3] = {c->has_lensing, c->has_skw, c->skw_gauss};
         sprintf(nm, "s6_srcs_cat_%d", i);
-        dump_f32(d, nm, (float *)par->cats[i]->srcs, 9 * (long)par->cats[i]->nsrc);
+        dump_f32(d, nm, (float *)c->srcs, 9 * (long)c->nsrc);
+        sprintf(nm, "s6_srcs_flags_%d", i); dump_f64(d, nm, fl, 3);
+        if (c->nsrc > 0 && c->has_skw) { /* skewers of srcs.c:507-529, 725-733 */
+          sprintf(nm, "s6_srcs_dgskw_%d", i); dump_f32(d, nm, c->skw_gauss ? c->g_skw : c->d_skw, (long)c->nsrc * c->nr);
+          sprintf(nm, "s6_srcs_vskw_%d", i); dump_f32(d, nm, c->v_skw, (long)c->nsrc * c->nr);
+        }
+      }
+    }
+    if (par->do_cstm) { /* cstm.c:68-145 */
+      for (i = 0; i < par->n_cstm; i++) {
+        HealpixShells *m = par->cstm[i];
+        sprintf(nm, "s6_cstm_data_%d", i); dump_f32(d, nm, m->data, m->num_pix);
+        sprintf(nm, "s6_cstm_pos_%d", i); dump_f64(d, nm, m->pos, 3 * m->num_pix);
+        sprintf(nm, "s6_cstm_listpix_%d", i); dump_i64(d, nm, m->listpix, m->num_pix);
       }
     }
   }

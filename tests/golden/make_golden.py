@@ -39,6 +39,14 @@ CASES = {
     # dense population: lambda up to several hundred per cell, i.e. gsl_ran_poisson's mu > 10 branch
     # (gamma / binomial reduction, common.c:187) in most occupied cells
     "ref_n32_dense": RunConfig(n_grid=32, dens_type=0, nz_amplitude=12000.0, seed=31),
+    # per-source lensing (srcs.c:531-614) + density skewers (srcs.c:507-529) + a custom projected map (cstm.c:68-145);
+    # the catalogue is kept above 128 KB so that the Src records come from fresh (zero) pages: the reference never
+    # initialises kappa / dra / ddec before accumulating into them
+    "ref_n32_lensing": RunConfig(n_grid=32, dens_type=0, nz_amplitude=25.0, srcs_lensing=True, srcs_skewers=True,
+                                 cstm_nside=8, seed=41),
+    # Gaussian skewers (beaming.c:55-66), no lensing
+    "ref_n32_gskw": RunConfig(n_grid=32, dens_type=0, nz_amplitude=15.0, srcs_skewers=True, gaussian_skewers=True,
+                              seed=43),
     # the other compile-time bias models of common.h:414-431 (drivers built by `make -C oracle refbm`):
     # model 1 = pow(1+d,b) (no flag), model 3 = max(1+b d, 0) (-D_BIAS_MODEL_3)
     "ref_n32_bias1": RunConfig(n_grid=32, dens_type=0, nz_amplitude=60.0, imap_nside=8, imap_nchannels=4, seed=21),

@@ -16,6 +16,8 @@ from oracle.oracle import NA, RNG_MT, Oracle, tables_from_dump
 CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth", "ref_n32_1lpt_cic", "ref_n32_2lpt_tsc", "ref_n32_2lpt_ngp",
          "ref_n32_bias1", "ref_n32_bias3",       # the reference compiled with the other bias models (common.h:414-431)
          "ref_n32_nosmooth",                     # power-of-two grid without smoothing (runs on the GPU too)
+         "ref_n32_lensing",                      # per-source lensing + density skewers + custom map (srcs.c:506-615, cstm.c)
+         "ref_n32_gskw",                         # Gaussian skewers (beaming.c:55-66)
          "ref_n32_dense"]                        # ~120 sources per cell: gsl_ran_poisson's mu > 10 branch (common.c:187)
 
 
@@ -78,12 +80,17 @@ def test_physical_density_and_normalisation(case):
     bz = [t[f"srcs_bz_{i}"] for i in range(npop)]
     if "imap_bz_0" in t:
         bz.append(t["imap_bz_0"])
+    if "cstm_bz_0" in t:                    # custom maps are normalised like one more population (density.c:1177-1178)
+        bz.append(t["cstm_bz_0"])
     nm = o.density_normalization(dens, bz)
     for i in range(npop):
         assert np.array_equal(nm["norm"][i], g[f"s3_srcs_norm_{i}"])
         assert np.array_equal(nm["ends"][i], g[f"s3_srcs_norm_ends_{i}"])
     if "imap_bz_0" in t:
         assert np.array_equal(nm["norm"][npop], g["s3_imap_norm_0"])
+    if "cstm_bz_0" in t:
+        assert np.array_equal(nm["norm"][-1], g["s3_cstm_norm_0"])
+        assert np.array_equal(nm["ends"][-1], g["s3_cstm_norm_ends_0"])
     assert np.array_equal(nm["zends"], g["s3_znorm_ends"])
     assert nm["hist_n"].sum() <= o.n ** 3
 
@@ -111,9 +118,31 @@ def test_sources_bit_exact(case):
             full = np.zeros((srcs.shape[0], 9), np.float32)
             full[:, :6] = srcs[:, :6]
             assert _same(full, g, f"s5_srcs_cat_{ipop}")
-        if f"s6_srcs_cat_{ipop}" in g:
+        flags = g.get(f"s6_srcs_flags_{ipop}", np.zeros(3)).astype(int)
+        if f"s6_srcs_cat_{ipop}" in g and not flags.any():
             o.srcs_beam_rsd(npot, pos, srcs)
             assert np.array_equal(srcs[:, :6], g[f"s6_srcs_cat_{ipop}"].reshape(-1, 9)[:, :6])
+        elif f"s6_srcs_cat_{ipop}" in g:
+            # srcs.c:452-744 with per-source lensing and / or skewers: all 9 columns and both skewer arrays
+            srcs[:, 6:] = 0
+            srcs, dg, vs = o.srcs_beam_full(dens, npot, pos, srcs, g["s1_sigma2_gauss"][0], lensing=flags[0],
+                                            skewers=flags[1], gaussian=flags[2])
+            ref = g[f"s6_srcs_cat_{ipop}"].reshape(-1, 9)
+            ncol = 9 if flags[0] else 6
+            assert np.array_equal(srcs[:, :ncol], ref[:, :ncol])
+            if flags[1]:
+                assert np.array_equal(dg.ravel(), g[f"s6_srcs_dgskw_{ipop}"])
+                assert np.array_equal(vs.ravel(), g[f"s6_srcs_vskw_{ipop}"])
+
+
+def test_custom_map_bit_exact(case):
+    g, t, o = case
+    if "s6_cstm_data_0" not in g:
+        pytest.skip("case has no custom map")
+    ends = g["s3_cstm_norm_ends_0"]
+    pos = g["s6_cstm_pos_0"].reshape(-1, 3)
+    data = o.cstm(g["s2_dens"], t["cstm_kz_0"], t["cstm_bz_0"], g["s3_cstm_norm_0"], ends[0], ends[1], pos)
+    assert np.array_equal(data, g["s6_cstm_data_0"])
 
 
 def test_maps_bit_exact(case):
