@@ -195,6 +195,7 @@ static void free_pop(clr_ctx::Pop &P)
 {
   cudaFree(P.d_a); cudaFree(P.d_b); cudaFree(P.d_norm); cudaFree(P.d_counts); cudaFree(P.d_bound);
   cudaFree(P.d_pos); cudaFree(P.d_ipix); cudaFree(P.d_srcs); cudaFree(P.d_srcs_alt); cudaFree(P.d_sup_entries);
+  cudaFree(P.d_skw_dg); cudaFree(P.d_skw_v);
 }
 
 int clr_destroy(clr_ctx *c)
@@ -204,7 +205,7 @@ int clr_destroy(clr_ctx *c)
   if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->stream) cudaStreamSynchronize(c->stream);
   clr_comm_destroy(c);
-  for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); }
+  for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); free_pop(c->cstm[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
   cudaFree(c->d_coord_f); cudaFree(c->d_coord_d); cudaFree(c->d_fft_tmp); cudaFree(c->d_fft_sync); cudaFree(c->d_hist);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
@@ -269,6 +270,12 @@ int clr_set_imap(clr_ctx *c, int ipop, const double *tz_arr, const double *bz_ar
   P.r0.resize(nr); P.rf.resize(nr);
   for (int i = 0; i < nr; i++) { P.r0[i] = r0[order[i]]; P.rf[i] = rf[order[i]]; }
   return 0;
+}
+
+int clr_set_cstm(clr_ctx *c, int ipop, const double *kz_arr, const double *bz_arr)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
+  return set_pop(c, c->cstm[ipop], kz_arr, bz_arr);
 }
 
 static float *grid_ptr(clr_ctx *c, int which) { return which == CLR_GRID_DENS ? c->d_dens : c->d_npot; }
@@ -449,6 +456,7 @@ int clr_compute_density_normalization(clr_ctx *c)
   std::vector<clr_ctx::Pop *> pops;
   for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->srcs[i].set) pops.push_back(&c->srcs[i]);
   for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->imap[i].set) pops.push_back(&c->imap[i]);
+  for (int i = 0; i < CLR_NPOP_MAX; i++) if (c->cstm[i].set) pops.push_back(&c->cstm[i]);     // density.c:1177-1178
   int npop = (int)pops.size();
   std::vector<const double *> d_bz(npop ? npop : 1);
   for (int i = 0; i < npop; i++) d_bz[i] = pops[i]->d_b;
@@ -495,7 +503,7 @@ int clr_compute_density_normalization(clr_ctx *c)
 static clr_ctx::Pop *pick_pop(clr_ctx *c, int kind, int ipop)
 {
   if (ipop < 0 || ipop >= CLR_NPOP_MAX) return nullptr;
-  return kind == 0 ? &c->srcs[ipop] : &c->imap[ipop];
+  return kind == 0 ? &c->srcs[ipop] : kind == 1 ? &c->imap[ipop] : &c->cstm[ipop];
 }
 
 int clr_get_norm(clr_ctx *c, int kind, int ipop, double *norm_arr, double *ends2, double *zends2)
@@ -586,6 +594,22 @@ int clr_srcs_distribute(clr_ctx *c, int ipop, int beam_first, long long *nsrc_ou
   return clr_srcs_distribute_impl(c, ipop, beam_first, nsrc_out);
 }
 int clr_srcs_beam_rsd(clr_ctx *c, int ipop) { if (clr_npot_ready(c)) return 1; return clr_srcs_beam(c, ipop); }
+int clr_srcs_get_beam_properties(clr_ctx *c, int ipop, int has_lensing, int has_skw, int skw_gauss, int rsd_done)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX && c->srcs[ipop].set, "population index %d out of range", ipop);
+  if (clr_npot_ready(c)) return 1;
+  return clr_beam_srcs(c, ipop, has_lensing, has_skw, skw_gauss, rsd_done);
+}
+int clr_srcs_get_skewers(clr_ctx *c, int ipop, float *dg_skw, float *v_skw)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
+  return clr_beam_get_skewers(c, ipop, dg_skw, v_skw);
+}
+int clr_cstm_get_beam_properties(clr_ctx *c, int ipop, long long num_pix, const double *pos3, float *data)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
+  return clr_beam_cstm(c, ipop, num_pix, pos3, data);
+}
 int clr_lpt_get_particles(clr_ctx *c, float *x, float *y, float *z) { return clr_lpt_particles(c, x, y, z); }
 int clr_lpt_exchange_counts(clr_ctx *c, long long *sent, long long *received)
 {

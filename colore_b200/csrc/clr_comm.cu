@@ -336,3 +336,22 @@ int clr_comm_halo(clr_ctx *c)
   CLR_NCCL(g_nccl.GroupEnd());
   return 0;
 }
+
+// One-plane halo of the DENSITY for the custom maps (clr_beam.cu): the CIC pair of a sample owned by this slab may
+// reach plane iz0 + nz, the first plane of the right neighbour (periodic).
+int clr_comm_dens_halo(clr_ctx *c, float *dst_plane)
+{
+  const ClrDev &d = c->dev;
+  size_t plane = (size_t)d.pitch * d.n;
+  if (c->nranks == 1) {
+    CLR_CUDA(cudaMemcpyAsync(dst_plane, c->d_dens, plane * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+  }
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  int right = (c->rank + 1) % c->nranks, left = (c->rank - 1 + c->nranks) % c->nranks;
+  CLR_NCCL(g_nccl.GroupStart());
+  CLR_NCCL(g_nccl.Send(c->d_dens, plane, ncclFloat, left, comm, c->stream));
+  CLR_NCCL(g_nccl.Recv(dst_plane, plane, ncclFloat, right, comm, c->stream));
+  CLR_NCCL(g_nccl.GroupEnd());
+  return 0;
+}

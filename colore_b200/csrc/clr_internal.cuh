@@ -99,7 +99,10 @@ struct clr_ctx {
     float *d_srcs_alt = nullptr;
     int srcs_buf = 0;               // which of the two buffers d_srcs currently is
     size_t cap_src = 0;
-  } srcs[CLR_NPOP_MAX], imap[CLR_NPOP_MAX];
+    // skewers of the last clr_srcs_get_beam_properties (clr_beam.cu): nsrc x skw_nr floats each
+    float *d_skw_dg = nullptr, *d_skw_v = nullptr;
+    long long skw_n = -1; int skw_nr = 0;
+  } srcs[CLR_NPOP_MAX], imap[CLR_NPOP_MAX], cstm[CLR_NPOP_MAX];   // cstm: h_a = K(z) table (cosmo.c:659-664)
   double z0_norm = 0, zf_norm = 0;
   // multi-GPU
   int rank = 0, nranks = 1;
@@ -212,6 +215,9 @@ int clr_srcs_distribute_impl(clr_ctx *c, int ipop, int beam_first, long long *ns
 int clr_maps_imap(clr_ctx *c, int ipop, float *h_data, int32_t *h_nadd);
 int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, int nplanes, const float *rf,
                  float *h_data);
+int clr_beam_cstm(clr_ctx *c, int ipop, long long num_pix, const double *h_pos, float *h_data);
+int clr_beam_srcs(clr_ctx *c, int ipop, int has_lensing, int has_skw, int skw_gauss, int rsd_done);
+int clr_beam_get_skewers(clr_ctx *c, int ipop, float *h_dg, float *h_v);
 int clr_halo_update(clr_ctx *c);
 int clr_npot_ready(clr_ctx *c);     // main stream waits for the potential pipeline, then exchanges the z halo
 void clr_use_set(clr_ctx *c, int set);   // select the staging buffer / barrier flags (and stream) of pipeline 0 / 1
@@ -228,6 +234,7 @@ int clr_comm_allreduce_u64(clr_ctx *c, unsigned long long *dbuf, size_t n);
 int clr_comm_allreduce_f32(clr_ctx *c, float *dbuf, size_t n);
 int clr_comm_allreduce_i32(clr_ctx *c, int *dbuf, size_t n);
 int clr_comm_halo(clr_ctx *c);
+int clr_comm_dens_halo(clr_ctx *c, float *dst_plane);   // dst <- first density plane of the right neighbour
 int clr_ensure_scratch(clr_ctx *c, size_t bytes);
 #define CLR_SMALL_BYTES 65536
 // host_dst <- dev_src (bytes a multiple of 4; meant for a few KB), ordered after the work queued on c->stream; blocks

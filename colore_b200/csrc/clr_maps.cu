@@ -9,6 +9,7 @@
 // and the maps are summed afterwards; the reference's ring rotation of whole slabs
 // (beaming.c:325-352) is not needed.
 #include "clr_internal.cuh"
+#include "clr_stencil.cuh"
 #include <math.h>
 
 namespace {
@@ -275,44 +276,6 @@ struct LosPlan {
   int restrict_z;
   double za, zb;
 };
-
-// beaming.c:85-116: Hessian stencil of the potential at cell (ix,iy,iz_local), unnormalised
-__device__ __forceinline__ void dev_tidal(const ClrDev &d, const float *__restrict__ g, int ix, int iy, int iz, float t[6])
-{
-  const long long ngx = d.pitch, plane = ngx * d.n;
-  long long x0 = ix, xh = ix + 1 == d.n ? 0 : ix + 1, xl = ix == 0 ? d.n - 1 : ix - 1;
-  long long y0 = (long long)iy * ngx, yh = (long long)(iy + 1 == d.n ? 0 : iy + 1) * ngx, yl = (long long)(iy == 0 ? d.n - 1 : iy - 1) * ngx;
-  long long z0 = iz * plane;
-  long long zh = ((iz == d.nz_here - 1) ? (long long)(d.nz_here + 1) : iz + 1) * plane;
-  long long zl = ((iz == 0) ? (long long)d.nz_here : iz - 1) * plane;
-  float c = g[x0 + y0 + z0];
-  t[0] = (g[xh + y0 + z0] + g[xl + y0 + z0] - 2 * c);
-  t[3] = (g[x0 + yh + z0] + g[x0 + yl + z0] - 2 * c);
-  t[1] = (float)(0.25 * (double)(g[xh + yh + z0] + g[xl + yl + z0] - g[xh + yl + z0] - g[xl + yh + z0]));
-  t[5] = (g[x0 + y0 + zh] + g[x0 + y0 + zl] - 2 * c);
-  // the reference pairs the terms differently at the slab edges (beaming.c:92-107): same operands,
-  // same left-to-right order hi,lo,-,- so one expression serves the three branches
-  if (iz == d.nz_here - 1 && d.nz_here > 1) {
-    t[2] = (float)(0.25 * (double)(g[xh + y0 + zh] + g[xl + y0 + zl] - g[xh + y0 + zl] - g[xl + y0 + zh]));
-    t[4] = (float)(0.25 * (double)(g[x0 + yh + zh] + g[x0 + yl + zl] - g[x0 + yh + zl] - g[x0 + yl + zh]));
-  } else {
-    t[2] = (float)(0.25 * (double)(g[xh + y0 + zh] + g[xl + y0 + zl] - g[xh + y0 + zl] - g[xl + y0 + zh]));
-    t[4] = (float)(0.25 * (double)(g[x0 + yh + zh] + g[x0 + yl + zl] - g[x0 + yh + zl] - g[x0 + yl + zh]));
-  }
-}
-
-// NGP cell of a sample (beaming.c:148-157); returns false when the plane is not in this slab
-__device__ __forceinline__ bool dev_ngp(const ClrDev &d, const double xn[3], int c[3])
-{
-#pragma unroll
-  for (int ax = 0; ax < 3; ax++) {
-    long v = (long)(xn[ax] + 0.5);
-    if (v >= d.n) v -= d.n; else if (v < 0) v += d.n;
-    c[ax] = (int)v;
-  }
-  c[2] -= d.iz0_here;
-  return c[2] >= 0 && c[2] < d.nz_here;
-}
 
 template <bool KAPPA>
 __global__ void __launch_bounds__(kThreads)

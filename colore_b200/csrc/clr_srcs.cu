@@ -5,6 +5,7 @@
 // Compiled with -fmad=false: counts and pixel indices must be bit-exact against the CPU oracle
 // for identical uniform draws, so double arithmetic must round like scalar C code.
 #include "clr_internal.cuh"
+#include "clr_stencil.cuh"
 #include <math.h>
 #include <utility>
 #include <vector>
@@ -660,35 +661,6 @@ local_props_kernel(const ClrDev d, const float4 *__restrict__ pos, float *__rest
 
 // ---- RSD under beaming: CIC-interpolated potential gradient along the line of sight -----------
 // beaming.c:31-117 (get_element, RETURN_VEL) + beaming.c:183-265 (trilinear branch)
-// Plane index of LOCAL plane iz in [-2, nz_here+1]: the slab, then the halo planes stored behind it (clr_api.cu:
-// [nz] = -1, [nz+1] = nz, [nz+2] = -2, [nz+3] = nz+1). On a single slab iz is periodic and always inside.
-__device__ __forceinline__ long long dev_plane_index(const ClrDev &d, int iz)
-{
-  if (iz >= 0 && iz < d.nz_here) return iz;
-  if (iz == -1) return d.nz_here;
-  if (iz == d.nz_here) return d.nz_here + 1;
-  if (iz == -2) return d.nz_here + 2;
-  return d.nz_here + 3;
-}
-__device__ __forceinline__ void dev_vel_element(const ClrDev &d, const float *__restrict__ npot, int ix, int iy, int iz, bool whole_box,
-                                                float v[3])
-{
-  const long long ngx = d.pitch, plane = ngx * d.n;
-  int ix_hi = ix + 1 == d.n ? 0 : ix + 1, ix_lo = ix == 0 ? d.n - 1 : ix - 1;
-  int iy_hi = iy + 1 == d.n ? 0 : iy + 1, iy_lo = iy == 0 ? d.n - 1 : iy - 1;
-  long long pz, pz_hi, pz_lo;
-  if (whole_box) {                               // one slab = the periodic box
-    pz = iz;
-    pz_hi = iz + 1 == d.n ? 0 : iz + 1;
-    pz_lo = iz == 0 ? d.n - 1 : iz - 1;
-  } else {
-    pz = dev_plane_index(d, iz); pz_hi = dev_plane_index(d, iz + 1); pz_lo = dev_plane_index(d, iz - 1);
-  }
-  v[0] = npot[ix_hi + iy * ngx + pz * plane] - npot[ix_lo + iy * ngx + pz * plane];
-  v[1] = npot[ix + iy_hi * ngx + pz * plane] - npot[ix + iy_lo * ngx + pz * plane];
-  v[2] = npot[ix + iy * ngx + pz_hi * plane] - npot[ix + iy * ngx + pz_lo * plane];
-}
-
 __global__ void __launch_bounds__(kThreads)
 beam_rsd_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__restrict__ pos, float *__restrict__ srcs,
                 long long nsrc, int do_pre, int do_post)

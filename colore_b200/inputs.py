@@ -50,6 +50,7 @@ class RunConfig:
     n_srcs: int = 1
     nz_amplitude: float = 3.0e3     # A in N(z) [deg^-2]; sets the mean number of sources per cell
     nz_z0: float = 0.25
+    nz_zcut: float = 0.0            # > 0: N(z) tapers to zero above this redshift (no sources near / beyond z_max)
     imap_nside: int = 0             # 0 -> no intensity mapping
     imap_nchannels: int = 8
     kappa_nside: int = 0            # 0 -> no kappa maps
@@ -91,6 +92,8 @@ def write_inputs(dirname: str, cfg: RunConfig) -> dict:
     for ipop in range(cfg.n_srcs):
         amp = cfg.nz_amplitude / (1 + ipop)
         nz = amp * z ** 2 * np.exp(-(z / cfg.nz_z0) ** 1.5)
+        if cfg.nz_zcut > 0:
+            nz = nz * 0.5 * (1.0 - np.tanh((z - cfg.nz_zcut) / 0.004))
         bz = 1.0 + z + 0.2 * ipop
         paths[f"nz{ipop}"] = os.path.join(dirname, f"nz{ipop}.txt")
         paths[f"bz{ipop}"] = os.path.join(dirname, f"bz{ipop}.txt")

@@ -133,6 +133,11 @@ class ParamCoLoRe:
         self.n_imap = max(self.n_imap, ipop + 1)
         self.imap_shells[ipop] = (nside, len(r0))
 
+    def set_cstm(self, ipop: int, kz_arr, bz_arr):
+        """Custom projected tracer (cstm.c): K(z) and b(z) tables (cosmo.c:631-717)."""
+        a, b = np.ascontiguousarray(kz_arr, np.float64), np.ascontiguousarray(bz_arr, np.float64)
+        check(self.lib.clr_set_cstm(self.ctx, C.c_int(ipop), _vp(a), _vp(b)))
+
     # -- grids ------------------------------------------------------------------------------
     def grid_put(self, which: int, host: np.ndarray):
         """Upload a grid in the reference layout: float32 [nz][n][2*nc] or complex64 [nz][n][nc]."""
@@ -298,6 +303,29 @@ def srcs_beams(par: ParamCoLoRe):
     """srcs_beams_preproc / get_beam_properties (RSD part) / postproc (srcs.c:425-443,486-504,656-662)."""
     for ipop in range(par.n_srcs):
         check(par.lib.clr_srcs_beam_rsd(par.ctx, C.c_int(ipop)))
+
+
+def srcs_get_beam_properties(par: ParamCoLoRe, ipop: int = 0, *, lensing: bool = False, skewers: bool = False,
+                             gaussian_skewers: bool = False, rsd_done: bool = False):
+    """srcs_beams_preproc + srcs_get_beam_properties + srcs_beams_postproc (srcs.c:425-744): RSD under beaming,
+    per-source lensing (e1, e2, kappa, dra, ddec) and skewers. Returns (srcs[n,9], dg_skw[n,nr] | None, v_skw | None)."""
+    check(par.lib.clr_srcs_get_beam_properties(par.ctx, C.c_int(ipop), C.c_int(int(lensing)), C.c_int(int(skewers)),
+                                               C.c_int(int(gaussian_skewers)), C.c_int(int(rsd_done))))
+    srcs = srcs_get_local_properties(par, ipop)
+    dg = vs = None
+    if skewers:
+        n, nr = par.nsources.get(ipop, 0), par.n_grid // 2
+        dg, vs = np.zeros((n, nr), np.float32), np.zeros((n, nr), np.float32)
+        check(par.lib.clr_srcs_get_skewers(par.ctx, C.c_int(ipop), _vp(dg), _vp(vs)))
+    return srcs, dg, vs
+
+
+def cstm_get_beam_properties(par: ParamCoLoRe, ipop: int, pos: np.ndarray) -> np.ndarray:
+    """cstm.c:38-145 for pixels with unit vectors ``pos`` [npix,3] -> data[npix] (nadd = 1 everywhere)."""
+    pos = np.ascontiguousarray(pos, np.float64)
+    data = np.empty(pos.shape[0], np.float32)
+    check(par.lib.clr_cstm_get_beam_properties(par.ctx, C.c_int(ipop), C.c_longlong(pos.shape[0]), _vp(pos), _vp(data)))
+    return data
 
 
 def imap_set_cartesian(par: ParamCoLoRe, ipop: int = 0):

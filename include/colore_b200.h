@@ -92,6 +92,10 @@ int clr_set_srcs(clr_ctx *ctx, int ipop, const double *nz_arr, const double *bz_
 int clr_set_imap(clr_ctx *ctx, int ipop, const double *tz_arr, const double *bz_arr,
                  int nside, int nr, const float *r0, const float *rf);
 
+/* custom projected tracer (cstm.c): K(z) and b(z) tables of cosmo.c:631-717; takes part in the normalisation
+ * (density.c:1177-1178) as kind 2 of clr_get_norm / clr_set_norm */
+int clr_set_cstm(clr_ctx *ctx, int ipop, const double *kz_arr, const double *bz_arr);
+
 /* ---- grids: host <-> device in the reference layout ------------------------------------- */
 int clr_grid_put(clr_ctx *ctx, int which, const float *host_padded);  /* real or complex view */
 int clr_grid_get(clr_ctx *ctx, int which, float *host_padded);
@@ -141,7 +145,7 @@ int clr_lpt_get_particles(clr_ctx *ctx, float *x, float *y, float *z);
 /* particles this rank shipped to / received from other slabs in the last LPT density (0 on one GPU) */
 int clr_lpt_exchange_counts(clr_ctx *ctx, long long *sent, long long *received);
 /* compute_density_normalization (density.c:1227-1393). Afterwards the norm tables are resident;
- * clr_get_norm returns srcs (kind 0) / imap (kind 1) tables: norm_arr[CLR_NA], ends[2] */
+ * clr_get_norm returns srcs (kind 0) / imap (kind 1) / custom (kind 2) tables: norm_arr[CLR_NA], ends[2] */
 int clr_compute_density_normalization(clr_ctx *ctx);
 int clr_get_norm(clr_ctx *ctx, int kind, int ipop, double *norm_arr, double *ends2, double *zends2);
 int clr_set_norm(clr_ctx *ctx, int kind, int ipop, const double *norm_arr, const double *ends2);
@@ -173,7 +177,21 @@ int clr_srcs_distribute(clr_ctx *ctx, int ipop, int beam_first, long long *nsrc_
  * Updates dz_rsd (and e1=e2=0) of the resident catalogue; fetch with clr_srcs_get_local_properties */
 int clr_srcs_beam_rsd(clr_ctx *ctx, int ipop);
 
-/* ---- maps (imap.c, kappa.c, isw.c, beaming.c) --------------------------------------------- */
+/* The whole of srcs_beams_preproc / srcs_get_beam_properties / srcs_beams_postproc (srcs.c:425-744, default build
+ * without _USE_FAST_LENSING): RSD under beaming as clr_srcs_beam_rsd, plus
+ *   has_lensing: e1, e2, kappa, dra, ddec of every source from the NGP velocity / tidal stencils along its ray
+ *                (srcs.c:531-614, 722-723); kappa / dra / ddec start from 0 (the reference accumulates into
+ *                uninitialised my_malloc memory, common.c:375);
+ *   has_skw:     density (skw_gauss = 0) or Gaussian-field (1, beaming.c:55-66) and radial-velocity skewers,
+ *                nsrc x n_grid/2 samples (srcs.c:507-529, 725-733 including its overrun into the next skewer).
+ * rsd_done != 0: dz_rsd already final (sources routed by clr_srcs_distribute with beam_first). Several GPUs: every
+ * rank integrates its slab's part of every ray, the partial results are summed on the rank that holds the source.
+ * Results: clr_srcs_get_local_properties (9-float Src records), clr_srcs_get_skewers. */
+int clr_srcs_get_beam_properties(clr_ctx *ctx, int ipop, int has_lensing, int has_skw, int skw_gauss, int rsd_done);
+/* Catalog.d_skw or g_skw, and v_skw (common.h:191-193): nsrc * (n_grid/2) floats each; either may be NULL */
+int clr_srcs_get_skewers(clr_ctx *ctx, int ipop, float *dg_skw, float *v_skw);
+
+/* ---- maps (imap.c, kappa.c, isw.c, cstm.c, beaming.c) --------------------------------------------- */
 /* imap_set_cartesian_single (imap.c:135-245): data[nr*12*nside^2], nadd likewise (full sky) */
 int clr_imap_set_cartesian(clr_ctx *ctx, int ipop, float *data, int32_t *nadd);
 /* kappa_beams_preproc + kappa_get_beam_properties (kappa.c:39-175) for the pixels `pos`
@@ -183,6 +201,10 @@ int clr_kappa_get_beam_properties(clr_ctx *ctx, long long num_pix, const double 
 /* isw_get_beam_properties (isw.c:78-147) */
 int clr_isw_get_beam_properties(clr_ctx *ctx, long long num_pix, const double *pos3, int nplanes,
                                 const float *rf, float *data);
+
+/* cstm_beams_preproc + cstm_get_beam_properties (cstm.c:38-145): data[num_pix] = dr * sum_r K(r) (bias_model(delta_CIC,
+ * b(r)) norm(r) - 1) for the pixels `pos` (unit vectors); several GPUs: summed over the slabs */
+int clr_cstm_get_beam_properties(clr_ctx *ctx, int ipop, long long num_pix, const double *pos3, float *data);
 
 /* ---- timing helpers for bench.py (CUDA events on the context's stream) -------------------- */
 int clr_timer_start(clr_ctx *ctx);

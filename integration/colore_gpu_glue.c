@@ -1,10 +1,11 @@
 /* Reference-side binding of the colore_b200 C ABI.
  *
- * This ONE translation unit replaces fourier.c, density.c, srcs.c, imap.c, kappa.c, isw.c and
+ * This ONE translation unit replaces fourier.c, density.c, srcs.c, imap.c, kappa.c, isw.c, cstm.c and
  * beaming.c of damonge/CoLoRe in the link line: it defines exactly the functions those files export
  * through common.h (464-543) and forwards them to include/colore_b200.h. main.c, io.c, cosmo.c,
- * cosmo_mad.c, common.c, healpix_extra.c, predictions.c, fftlog.c (and cstm.c / lensing.c) are
- * linked UNCHANGED, so `./CoLoRe param.cfg` stays the entry point (main.c:24-154).
+ * cosmo_mad.c, common.c, healpix_extra.c, predictions.c, fftlog.c (and lensing.c, whose hooks are only
+ * reached under _USE_FAST_LENSING) are linked UNCHANGED, so `./CoLoRe param.cfg` stays the entry point
+ * (main.c:24-154).
  *
  * It is compiled against the reference's own common.h (-I<reference>/src); it contains no code of
  * the reference. One process drives one GPU; COLORE_B200_NGPUS=P makes the executable fork into P ranks (see
@@ -175,6 +176,7 @@ void allocate_fftw(ParamCoLoRe *par)
   chk(clr_set_option(g_ctx, "lpt_interp_type", par->lpt_interp_type));
   chk(clr_set_option(g_ctx, "keep_particles", par->output_lpt));
   for (i = 0; i < par->n_srcs; i++) chk(clr_set_srcs(g_ctx, i, par->srcs_nz_arr[i], par->srcs_bz_arr[i]));
+  for (i = 0; i < par->n_cstm; i++) chk(clr_set_cstm(g_ctx, i, par->cstm_kz_arr[i], par->cstm_bz_arr[i]));
   par->grid_dens_f = NULL; par->grid_dens = NULL;
   par->grid_npot_f = NULL; par->grid_npot = NULL;
   if (par->output_density) { /* io.c:565-595 reads par->grid_dens on the host */
@@ -286,7 +288,12 @@ void compute_density_normalization(ParamCoLoRe *par)
     par->norm_imap_0[i] = ends[0]; par->norm_imap_f[i] = ends[1];
   }
   par->z0_norm = zends[0]; par->zf_norm = zends[1];
-  if (par->n_cstm > 0) report_error(1, "custom maps are not on the GPU path\n");
+  for (i = 0; i < par->n_cstm; i++) { /* density.c:1315-1354 */
+    double ends[2];
+    par->cstm_norm_arr[i] = my_malloc(NA * sizeof(double));
+    chk(clr_get_norm(g_ctx, 2, i, par->cstm_norm_arr[i], ends, zends));
+    par->norm_cstm_0[i] = ends[0]; par->norm_cstm_f[i] = ends[1];
+  }
   if (NodeThis == 0) timer(2);
   print_info("\n");
 }
@@ -298,8 +305,6 @@ void srcs_set_cartesian(ParamCoLoRe *par)
   print_info("*** Getting point sources (GPU)\n");
   for (ipop = 0; ipop < par->n_srcs; ipop++) {
     long long n = 0;
-    if (par->lensing_srcs[ipop] || par->skw_srcs[ipop])
-      report_error(1, "per-source lensing / skewers are not on the GPU path\n");
     if (NodeThis == 0) timer(0);
     chk(clr_srcs_set_cartesian(g_ctx, ipop, par->seed_rng, &n));
     par->nsources_c_this[ipop] = (long)n;
@@ -348,12 +353,17 @@ void srcs_get_local_properties(ParamCoLoRe *par)
 
 void srcs_beams_preproc(ParamCoLoRe *par) { (void)par; }
 void srcs_get_beam_properties(ParamCoLoRe *par)
-{ /* srcs.c:452-632, RSD part: dz_rsd from the CIC-interpolated potential gradient */
+{ /* srcs.c:425-744: dz_rsd from the CIC-interpolated potential gradient, per-source lensing, skewers */
   int ipop;
   for (ipop = 0; ipop < par->n_srcs; ipop++) {
-    if (!g_by_pixel) chk(clr_srcs_beam_rsd(g_ctx, ipop));      /* routed by pixel: already done before the exchange */
-    if (par->cats[ipop]->nsrc > 0)
-      chk(clr_srcs_get_local_properties(g_ctx, ipop, (float *)par->cats[ipop]->srcs));
+    Catalog *cat = par->cats[ipop];
+    /* routed by pixel: dz_rsd was evaluated before the exchange, on the slab that holds the potential */
+    chk(clr_srcs_get_beam_properties(g_ctx, ipop, par->lensing_srcs[ipop], par->skw_srcs[ipop], par->skw_gauss[ipop],
+                                     g_by_pixel));
+    if (cat->nsrc > 0) {
+      chk(clr_srcs_get_local_properties(g_ctx, ipop, (float *)cat->srcs));
+      if (cat->has_skw) chk(clr_srcs_get_skewers(g_ctx, ipop, cat->skw_gauss ? cat->g_skw : cat->d_skw, cat->v_skw));
+    }
   }
 }
 void srcs_beams_postproc(ParamCoLoRe *par) { (void)par; }
@@ -415,12 +425,34 @@ void isw_get_beam_properties(ParamCoLoRe *par)
 }
 void isw_beams_postproc(ParamCoLoRe *par) { (void)par; }
 
+/* ------------------------------------------------------------------ cstm.c */
+void cstm_set_cartesian(ParamCoLoRe *par) { (void)par; }
+void cstm_distribute(ParamCoLoRe *par) { (void)par; }
+void cstm_get_local_properties(ParamCoLoRe *par) { (void)par; }
+void cstm_beams_preproc(ParamCoLoRe *par)
+{ /* cstm.c:38-66 */
+  int ipop;
+  long i;
+  for (ipop = 0; ipop < par->n_cstm; ipop++)
+    for (i = 0; i < par->cstm[ipop]->num_pix; i++) { par->cstm[ipop]->data[i] = 0; par->cstm[ipop]->nadd[i] = 1; }
+}
+void cstm_get_beam_properties(ParamCoLoRe *par)
+{ /* cstm.c:68-152; on several GPUs the map comes back summed over the slabs and rank 0 writes it (io.c:754-806
+   * without _HAVE_MPI), like the kappa / ISW maps */
+  int ipop;
+  for (ipop = 0; ipop < par->n_cstm; ipop++) {
+    HealpixShells *m = par->cstm[ipop];
+    chk(clr_cstm_get_beam_properties(g_ctx, ipop, m->num_pix, m->pos, m->data));
+  }
+}
+void cstm_beams_postproc(ParamCoLoRe *par) { (void)par; }
+
 /* ------------------------------------------------------------------ beaming.c */
 int interpolate_from_grid(ParamCoLoRe *par, double *x, flouble *d, flouble v[3], flouble t[6], flouble *pd,
                           flouble *g, int flag_return, int interp_type)
-{ /* beaming.c:120-268 is only reached from the CPU tracers cstm.c / lensing.c, which are out of scope */
+{ /* beaming.c:120-268 is only reached from lensing.c under _USE_FAST_LENSING (every other caller is replaced above) */
   (void)par; (void)x; (void)d; (void)v; (void)t; (void)pd; (void)g; (void)flag_return; (void)interp_type;
-  report_error(1, "interpolate_from_grid: the grids live on the GPU; cstm / lensing tracers are not supported\n");
+  report_error(1, "interpolate_from_grid: the grids live on the GPU; build without _USE_FAST_LENSING\n");
   return 0;
 }
 
@@ -431,11 +463,12 @@ void get_beam_properties(ParamCoLoRe *par)
   if (par->do_kappa) kappa_beams_preproc(par);
   if (par->do_isw) isw_beams_preproc(par);
   if (par->do_srcs) srcs_beams_preproc(par);
+  if (par->do_cstm) cstm_beams_preproc(par);
   if (NodeThis == 0) timer(0);
   if (par->do_kappa) kappa_get_beam_properties(par);
   if (par->do_isw) isw_get_beam_properties(par);
   if (par->do_srcs) srcs_get_beam_properties(par);
-  if (par->do_cstm) report_error(1, "custom maps are not on the GPU path\n");
+  if (par->do_cstm) cstm_get_beam_properties(par);
   if (NodeThis == 0) timer(2);
   print_info("\n");
 }

@@ -449,6 +449,69 @@ def test_beam_rsd_vs_oracle(case):
     assert np.all(after[:, 4:6] == 0)
 
 
+@pytest.mark.parametrize("name", ["ref_n32_lensing", "ref_n32_gskw"])
+def test_srcs_lensing_and_skewers_vs_oracle(golden_dir, name):
+    """srcs.c:425-744: per-source shear / convergence / deflection from the NGP tidal + velocity stencils
+    along every ray, density or Gaussian skewers (CIC) and their post-processing, on the GPU's own catalogue against the
+    oracle, which reproduces the unmodified reference bit for bit on these two configurations (CPU suite)."""
+    g, t = _load(golden_dir, name)
+    flags = g["s6_srcs_flags_0"].astype(int)
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    par = _par(t)
+    _setup_sources(g, t, par)
+    par.set_sigma2_gauss(g["s1_sigma2_gauss"][0])
+    o.set_halo(g["s1_npot"])
+    cb.srcs_set_cartesian(par)
+    pos, _ = cb.srcs_get_cartesian(par, 0)
+    assert pos.shape[0] > 3000
+    before = cb.srcs_get_local_properties(par, 0)
+    srcs, dg, vs = cb.srcs_get_beam_properties(par, 0, lensing=bool(flags[0]), skewers=bool(flags[1]),
+                                               gaussian_skewers=bool(flags[2]))
+    ref = before.copy()
+    ref[:, 6:] = 0
+    ref, rdg, rvs = o.srcs_beam_full(g["s2_dens"], g["s1_npot"], pos, ref, g["s1_sigma2_gauss"][0], lensing=flags[0],
+                                     skewers=flags[1], gaussian=flags[2])
+    assert np.array_equal(srcs[:, :3], ref[:, :3])                                  # ra, dec, z0 untouched
+    np.testing.assert_allclose(srcs[:, 3], ref[:, 3], rtol=1e-5, atol=1e-9)         # dz_rsd
+    if flags[0]:
+        for col in range(4, 9):                                                     # e1, e2, kappa, dra, ddec
+            np.testing.assert_allclose(srcs[:, col], ref[:, col], rtol=2e-5, atol=2e-6 * np.abs(ref[:, col]).max())
+        assert np.abs(ref[:, 6]).max() > 0
+    else:
+        assert np.all(srcs[:, 4:6] == 0)
+    if flags[1]:
+        # sources beyond r_max - dr/2 exist, so the overrun of srcs.c:726 into the next skewer is exercised
+        r = np.sqrt((pos[:, :3].astype(np.float64) ** 2).sum(1))
+        nr = o.n // 2
+        assert ((r * nr / t["r_max"] + 0.5).astype(int) > nr - 1).any()
+        np.testing.assert_allclose(dg, rdg, rtol=2e-6, atol=2e-6 * np.abs(rdg).max())
+        np.testing.assert_allclose(vs, rvs, rtol=1e-5, atol=1e-6 * np.abs(rvs).max())
+        assert np.abs(rvs).max() > 0 and np.abs(rdg).max() > 0
+    par.free()
+
+
+def test_custom_map_vs_reference(golden_dir):
+    """cstm.c:38-145 against the unmodified reference's map, and the custom population's share of the
+    density normalisation (density.c:1177-1178, 1315-1354) against its table."""
+    g, t = _load(golden_dir, "ref_n32_lensing")
+    par = _par(t)
+    par.set_option("exact_math", 1)
+    par.grid_put(cb.GRID_DENS, g["s2_dens"])
+    par.set_sigma2_gauss(g["s1_sigma2_gauss"][0])
+    par.set_srcs(0, t["srcs_nz_0"], t["srcs_bz_0"])
+    par.set_cstm(0, t["cstm_kz_0"], t["cstm_bz_0"])
+    cb.compute_density_normalization(par)
+    norm, ends, _ = cb.get_norm(par, 2, 0)
+    np.testing.assert_allclose(norm, g["s3_cstm_norm_0"], rtol=1e-12)
+    np.testing.assert_allclose(ends, g["s3_cstm_norm_ends_0"], rtol=1e-12)
+    cb.set_norm(par, 2, 0, g["s3_cstm_norm_0"], g["s3_cstm_norm_ends_0"])
+    pos = g["s6_cstm_pos_0"].reshape(-1, 3)
+    data = cb.cstm_get_beam_properties(par, 0, pos)
+    ref = g["s6_cstm_data_0"]
+    np.testing.assert_allclose(data, ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+    par.free()
+
+
 # --------------------------------------------------------------------------------------- maps
 @pytest.mark.parametrize("exact", [1, 0])
 def test_maps_vs_reference(golden_dir, exact):
