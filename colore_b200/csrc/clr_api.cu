@@ -69,9 +69,10 @@ int clr_create(const clr_params *p, int device, clr_ctx **out)
   CLR_CHECK(p && out, "clr_create: null argument");
   *out = nullptr;
   CLR_CHECK(clr_device_count() > device, "clr_create: CUDA device %d not available (no CPU fallback exists)", device);
-  // the FFT (clr_fft.cu) is a power-of-two Stockham transform: fail here, not at the first transform
-  CLR_CHECK(p->n_grid >= 16 && p->n_grid <= 4096 && (p->n_grid & (p->n_grid - 1)) == 0,
-            "n_grid=%d unsupported: the GPU FFT takes powers of two in [16,4096]", p->n_grid);
+  // the FFT: power-of-two Stockham plans (clr_fft.cu) or the mixed-radix path (clr_fft_generic.cu): fail here, not at
+  // the first transform
+  CLR_CHECK(p->n_grid >= 16 && p->n_grid <= 4096 && ((p->n_grid & (p->n_grid - 1)) == 0 || clr_fft_generic_ok(p->n_grid)),
+            "n_grid=%d unsupported: the GPU FFT takes multiples of 4 in [16,4096] without prime factors above 31", p->n_grid);
   CLR_CHECK(p->nz_here > 0 && p->iz0_here >= 0 && p->iz0_here + p->nz_here <= p->n_grid, "bad slab bounds");
   CLR_CHECK(p->r_arr_r2z && p->z_arr_r2z && p->growth_d_arr && p->growth_v_arr && p->pkarr && p->logkarr,
             "clr_create: missing tables");

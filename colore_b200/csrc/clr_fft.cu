@@ -1305,7 +1305,9 @@ int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments)
     case 1024: return c2r_3d<1024>(c, g, (float)norm, d_moments);
     case 2048: return c2r_3d<2048>(c, g, (float)norm, d_moments);
     case 4096: return c2r_3d<4096>(c, g, (float)norm, d_moments);
-    default: clr_set_error("n_grid=%d: the FFT supports powers of two in [16,4096]", c->dev.n); return 1;
+    default:
+      if (clr_fft_generic_ok(c->dev.n)) return clr_fft_generic_c2r(c, g, (float)norm, d_moments);
+      clr_set_error("n_grid=%d: the FFT takes multiples of 4 in [16,4096] without prime factors above 31", c->dev.n); return 1;
   }
 }
 
@@ -1335,6 +1337,8 @@ int clr_fft_r2c_impl(clr_ctx *c, float *grid)
     case 1024: return r2c_3d<1024>(c, g);
     case 2048: return r2c_3d<2048>(c, g);
     case 4096: return r2c_3d<4096>(c, g);
-    default: clr_set_error("n_grid=%d: the FFT supports powers of two in [16,4096]", c->dev.n); return 1;
+    default:
+      if (clr_fft_generic_ok(c->dev.n)) return clr_fft_generic_r2c(c, g);
+      clr_set_error("n_grid=%d: the FFT takes multiples of 4 in [16,4096] without prime factors above 31", c->dev.n); return 1;
   }
 }

@@ -202,6 +202,10 @@ struct StageScope {
 int clr_fft_c2r_impl(clr_ctx *c, float *grid, double norm, double *d_moments);
 int clr_fft_r2c_impl(clr_ctx *c, float *grid);
 int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, bool *ran);
+// mixed-radix path for grids that are not powers of two (clr_fft_generic.cu)
+bool clr_fft_generic_ok(int n);
+int clr_fft_generic_c2r(clr_ctx *c, float2 *g, float norm, double *mom);
+int clr_fft_generic_r2c(clr_ctx *c, float2 *g);
 int clr_fields_fill(clr_ctx *c, uint32_t seed);
 int clr_fields_scale_moments(clr_ctx *c, double *out2);
 int clr_fields_lognormal(clr_ctx *c, int clip);

@@ -18,7 +18,8 @@ from oracle.oracle import RNG_MT, RNG_PHILOX, Oracle, tables_from_dump  # noqa: 
 
 # ref_n32_bias1 / ref_n32_bias3: the reference compiled with the other bias models (common.h:414-431);
 # ref_n32_nosmooth: do_smoothing = 0, smooth_potential = false on a power-of-two grid (fourier.c:347-351 skipped)
-GOLDEN = ["ref_n32_lognormal", "ref_n32_clip", "ref_n32_bias1", "ref_n32_bias3", "ref_n32_nosmooth"]
+# ref_n48_nosmooth: a grid that is not a power of two (mixed-radix transforms, division-based cell indexing)
+GOLDEN = ["ref_n32_lognormal", "ref_n32_clip", "ref_n32_bias1", "ref_n32_bias3", "ref_n32_nosmooth", "ref_n48_nosmooth"]
 
 
 def _bias_model(name):
@@ -51,7 +52,8 @@ def _real(a, n):
 
 
 # ------------------------------------------------------------------------------------------ FFT
-@pytest.mark.parametrize("n", [16, 32, 64, 128, 256])
+# 24 ... 104: the mixed-radix path (clr_fft_generic.cu): radices 3, 5, 7 and the direct-DFT stage (11, 13)
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 24, 48, 80, 112, 88, 104])
 def test_fft_c2r_r2c_vs_oracle(golden_dir, n):
     g, t = _load(golden_dir, "ref_n32_lognormal")
     o = Oracle(t, n)
@@ -95,6 +97,30 @@ def test_fft_drops_imag_of_xdc_and_nyquist(golden_dir):
     # numpy's irfftn follows the same convention (complex axes first, real axis last)
     ref = np.fft.irfftn(ck.astype(np.complex128), s=(n, n, n), axes=(0, 1, 2)) * n ** 3
     assert np.abs(a - ref).max() / ref.std() < 2e-5
+    par.free()
+
+
+@pytest.mark.parametrize("n", [300, 360])
+def test_fft_mixed_radix_vs_numpy(golden_dir, n):
+    """Grids that are not powers of two at a size where several stages of every radix run (300 = 4 * 3 * 5 * 5,
+    360 = 4 * 2 * 3 * 3 * 5), against numpy / pocketfft in double precision."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    par = cb.ParamCoLoRe(t, n)
+    rng = np.random.default_rng(n)
+    nc = n // 2 + 1
+    ck = (rng.standard_normal((n, n, nc)) + 1j * rng.standard_normal((n, n, nc))).astype(np.complex64)
+    par.grid_put(cb.GRID_DENS, ck)
+    cb.fftw_wrap_c2r(par, cb.GRID_DENS)
+    got = par.grid_get(cb.GRID_DENS)[:, :, :n]
+    ref = np.fft.irfftn(ck.astype(np.complex128), s=(n, n, n), axes=(0, 1, 2)) * float(n) ** 3
+    assert np.abs(got - ref).max() / ref.std() < 2e-5
+    x = np.zeros((n, n, 2 * nc), np.float32)
+    x[:, :, :n] = rng.standard_normal((n, n, n)).astype(np.float32)
+    par.grid_put(cb.GRID_NPOT, x)
+    cb.fftw_wrap_r2c(par, cb.GRID_NPOT)
+    gotk = par.grid_get(cb.GRID_NPOT).view(np.complex64)
+    refk = np.fft.rfftn(x[:, :, :n].astype(np.float64), axes=(0, 1, 2))
+    assert np.abs(gotk - refk).max() / np.sqrt(np.mean(np.abs(refk) ** 2)) < 2e-5
     par.free()
 
 
