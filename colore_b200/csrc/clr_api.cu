@@ -208,6 +208,7 @@ int clr_destroy(clr_ctx *c)
   clr_comm_destroy(c);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); free_pop(c->cstm[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
+  cudaFree(c->d_lens_data);
   cudaFree(c->d_coord_f); cudaFree(c->d_coord_d); cudaFree(c->d_fft_tmp); cudaFree(c->d_fft_sync); cudaFree(c->d_hist);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch); cudaFree(c->d_pkt); cudaFree(c->d_sincos);
@@ -610,6 +611,18 @@ int clr_cstm_get_beam_properties(clr_ctx *c, int ipop, long long num_pix, const 
 {
   CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX, "population index %d out of range", ipop);
   return clr_beam_cstm(c, ipop, num_pix, pos3, data);
+}
+int clr_lensing_get_beam_properties(clr_ctx *c, int nbeams, int nr_sh, float *r_sh, const long long *npp, const double *pos3,
+                                    float *data)
+{
+  if (clr_npot_ready(c)) return 1;
+  return clr_beam_lens_shells(c, nbeams, nr_sh, r_sh, npp, pos3, data);
+}
+int clr_srcs_lensing_from_shells(clr_ctx *c, int ipop, int nr_sh, const float *r_sh, const int32_t *nside_sh, int node, int nnodes,
+                                 long long *n_bad)
+{
+  CLR_CHECK(ipop >= 0 && ipop < CLR_NPOP_MAX && c->srcs[ipop].set, "population index %d out of range", ipop);
+  return clr_beam_srcs_from_shells(c, ipop, nr_sh, r_sh, nside_sh, node, nnodes, n_bad);
 }
 int clr_lpt_get_particles(clr_ctx *c, float *x, float *y, float *z) { return clr_lpt_particles(c, x, y, z); }
 int clr_lpt_exchange_counts(clr_ctx *c, long long *sent, long long *received)

@@ -329,6 +329,140 @@ cstm_kernel(const ClrDev d, const float *__restrict__ dens, const float *__restr
   }
 }
 
+
+// ---- fast-lensing shells (lensing.c:76-250, -D_USE_FAST_LENSING builds): one thread per pixel of the finest shell ----
+struct ShellPlan {
+  const double *fac0, *fac1, *fac2;     // lensing.c:118-127
+  const int *irmin, *irmax;             // sample range of every shell (lensing.c:100-116)
+  const double *inv_r_max, *inv_ratio;  // 1 / (i_r_here dr), 1 / npix_ratio
+  const long long *ratio, *npp, *off;   // fine pixels per pixel of shell ir, pixels per beam, float offset of shell ir
+  int nr_sh;
+  long long npix_hi;
+  double dr;
+  int restrict_z;
+  double za, zb;
+};
+
+__global__ void __launch_bounds__(kThreads)
+lens_shell_kernel(const ClrDev d, const float *__restrict__ npot, const double *__restrict__ pos, long long n_fine, ShellPlan pl,
+                  float *__restrict__ data)
+{
+  const double idx = (double)(d.n / d.l_box);
+  const bool whole_box = d.nz_here == d.n;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n_fine; it += (long long)gridDim.x * blockDim.x) {
+    const long long ib = it / pl.npix_hi, ip = it - ib * pl.npix_hi;
+    const double u[3] = {pos[3 * it], pos[3 * it + 1], pos[3 * it + 2]};
+    double u_x[3], u_y[3], r_k[6], r_e1[6], r_e2[6];
+    {
+      double cth = u[2], sth, cph = 1, sph = 0;
+      const double prefac = idx * idx, prefac_m = 0.5 * idx;
+      if (cth >= 1) cth = 1;
+      if (cth <= -1) cth = -1;
+      sth = sqrt((1 - cth) * (1 + cth));
+      if (sth != 0) { cph = u[0] / sth; sph = u[1] / sth; }
+      u_x[0] = cth * cph * prefac_m; u_x[1] = cth * sph * prefac_m; u_x[2] = -sth * prefac_m;
+      u_y[0] = -sph * prefac_m; u_y[1] = cph * prefac_m; u_y[2] = 0;
+      r_k[0] = (cth * cth * cph * cph + sph * sph) * prefac;
+      r_k[1] = (2 * cph * sph * (cth * cth - 1)) * prefac;
+      r_k[2] = (-2 * cth * sth * cph) * prefac;
+      r_k[3] = (cth * cth * sph * sph + cph * cph) * prefac;
+      r_k[4] = (-2 * cth * sth * sph) * prefac;
+      r_k[5] = (sth * sth) * prefac;
+      r_e1[0] = (cth * cth * cph * cph - sph * sph) * prefac;
+      r_e1[1] = (2 * cph * sph * (cth * cth + 1)) * prefac;
+      r_e1[2] = (-2 * cth * sth * cph) * prefac;
+      r_e1[3] = (cth * cth * sph * sph - cph * cph) * prefac;
+      r_e1[4] = (-2 * cth * sth * sph) * prefac;
+      r_e1[5] = (sth * sth) * prefac;
+      r_e2[0] = (-2 * cth * cph * sph) * prefac;
+      r_e2[1] = (2 * cth * (cph * cph - sph * sph)) * prefac;
+      r_e2[2] = (2 * sth * sph) * prefac;
+      r_e2[3] = (2 * cth * sph * cph) * prefac;
+      r_e2[4] = (-2 * sth * cph) * prefac;
+      r_e2[5] = 0;
+    }
+    int win_lo = 0, win_hi = 0x7fffffff;
+    if (pl.restrict_z) dev_window(u[2], pl.za, pl.zb, pl.dr, win_lo, win_hi);
+    double dx_0 = 0, dx_1 = 0, dy_0 = 0, dy_1 = 0, kappa_1 = 0, kappa_2 = 0, s1_1 = 0, s1_2 = 0, s2_1 = 0, s2_2 = 0;
+    for (int ish = 0; ish < pl.nr_sh; ish++) {
+      const int irmin = max(__ldg(pl.irmin + ish), win_lo), irmax = min(__ldg(pl.irmax + ish), win_hi);
+      for (int irr = irmin; irr <= irmax; irr++) {
+        const double rm = (irr + 0.5) * pl.dr;
+        double xn[3];
+        int c[3];
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) xn[ax] = (rm * u[ax] + d.pos_obs[ax]) * idx;
+        if (!dev_ngp(d, xn, c)) continue;
+        float t[6], v[3];
+        dev_tidal(d, npot, c[0], c[1], c[2], t);
+        dev_vel_element(d, npot, c[0], c[1], c[2], whole_box, v);
+        double dotk = 0, dote1 = 0, dote2 = 0, dotvx = 0, dotvy = 0;
+#pragma unroll
+        for (int ax = 0; ax < 6; ax++) { dote1 += r_e1[ax] * t[ax]; dote2 += r_e2[ax] * t[ax]; dotk += r_k[ax] * t[ax]; }
+#pragma unroll
+        for (int ax = 0; ax < 3; ax++) { dotvx += u_x[ax] * v[ax]; dotvy += u_y[ax] * v[ax]; }
+        const double f0 = __ldg(pl.fac0 + irr), f1 = __ldg(pl.fac1 + irr), f2 = __ldg(pl.fac2 + irr);
+        dx_0 += dotvx * f0; dx_1 += dotvx * f1;
+        dy_0 += dotvy * f0; dy_1 += dotvy * f1;
+        kappa_1 += dotk * f1; kappa_2 += dotk * f2;
+        s1_1 += dote1 * f1; s1_2 += dote1 * f2;
+        s2_1 += dote2 * f1; s2_2 += dote2 * f2;
+      }
+      // several fine pixels share a pixel of a coarser shell (lensing.c:219-227): atomic float sums
+      const double irm = __ldg(pl.inv_r_max + ish), w = __ldg(pl.inv_ratio + ish);
+      const long long npp = __ldg(pl.npp + ish);
+      float *o = data + __ldg(pl.off + ish) + ib * 5 * npp + 5 * (ip / __ldg(pl.ratio + ish));
+      atomicAdd(o + 0, (float)((s1_1 - irm * s1_2) * w));
+      atomicAdd(o + 1, (float)((s2_1 - irm * s2_2) * w));
+      atomicAdd(o + 2, (float)((kappa_1 - irm * kappa_2) * w));
+      atomicAdd(o + 3, (float)(2 * (dx_0 - irm * dx_1) * w));
+      atomicAdd(o + 4, (float)(2 * (dy_0 - irm * dy_1) * w));
+    }
+  }
+}
+
+// srcs.c:666-723: shear / convergence / deflection of the sources interpolated between the two shells that bracket them
+struct ShellLookup {
+  const float *r_sh;          // snapped shell radii (lensing.c:233-236)
+  const int *nside_sh;
+  const long long *npp, *off;
+  int nr_sh, nbeams, node, nnodes;
+};
+__device__ __forceinline__ long long dev_vec2pix_nest(int nside, double x, double y, double z)
+{
+  const double vlen = sqrt(x * x + y * y + z * z);
+  return clr_ring2nest(nside, (int)clr_ang2pix_ring_zphi(nside, z / vlen, atan2(y, x)));
+}
+__global__ void __launch_bounds__(kThreads)
+src_shell_lens_kernel(const ClrDev d, const float4 *__restrict__ pos, float *__restrict__ srcs, long long nsrc, ShellLookup L,
+                      const float *__restrict__ data, unsigned long long *__restrict__ bad)
+{
+  for (long long ii = blockIdx.x * (long long)blockDim.x + threadIdx.x; ii < nsrc; ii += (long long)gridDim.x * blockDim.x) {
+    float *o = srcs + 9 * ii;
+    const double r = clr_r_of_z(d, (double)o[2]);
+    // get_r_index_lensing (srcs.c:24-64): r_sh[i] <= r < r_sh[i+1], clamped to [0, nr-2]
+    int ir = 0;
+    while (ir < L.nr_sh - 2 && r >= (double)__ldg(L.r_sh + ir + 1)) ir++;
+    const float ra = __ldg(L.r_sh + ir), rb = __ldg(L.r_sh + ir + 1);
+    const double h = (r - (double)ra) / (double)(rb - ra);
+    const float4 p = pos[ii];
+    const long long ibase = dev_vec2pix_nest(d.nside_base, p.x, p.y, p.z);
+    const long long npl = __ldg(L.npp + ir), npu = __ldg(L.npp + ir + 1);
+    const long long ipl = dev_vec2pix_nest(__ldg(L.nside_sh + ir), p.x, p.y, p.z) - ibase * npl;
+    const long long ipu = dev_vec2pix_nest(__ldg(L.nside_sh + ir + 1), p.x, p.y, p.z) - ibase * npu;
+    if (ibase % L.nnodes != L.node || ipl < 0 || ipl >= npl || ipu < 0 || ipu >= npu) { atomicAdd(bad, 1ULL); continue; }
+    const long long ibh = (ibase - L.node) / L.nnodes;
+    const float *lo = data + __ldg(L.off + ir) + ibh * 5 * npl + 5 * ipl;
+    const float *up = data + __ldg(L.off + ir + 1) + ibh * 5 * npu + 2 * ipu;    // stride 2, not 5: srcs.c:710-714 as is
+    const double g1 = (double)lo[0] * (1 - h) + (double)up[0] * h, g2 = (double)lo[1] * (1 - h) + (double)up[1] * h;
+    const double kp = (double)lo[2] * (1 - h) + (double)up[2] * h;
+    const double dxv = (double)lo[3] * (1 - h) + (double)up[3] * h, dyv = (double)lo[4] * (1 - h) + (double)up[4] * h;
+    o[4] = (float)g1; o[5] = (float)g2; o[6] = (float)kp;
+    o[7] = (float)((double)(float)dyv * kRtod);
+    o[8] = (float)((double)(float)dxv * kRtod);
+  }
+}
+
 double host_lerp(const clr_ctx *c, double r, const std::vector<double> &f, double f0, double ff)
 {
   if (r <= 0) return f0;
@@ -402,6 +536,109 @@ int clr_beam_cstm(clr_ctx *c, int ipop, long long num_pix, const double *h_pos, 
   if (clr_comm_allreduce_f32(c, b_data.as<float>(), (size_t)num_pix)) return 1;
   CLR_CUDA(cudaMemcpyAsync(h_data, b_data.p, (size_t)num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+
+// lensing_beams_preproc + lensing_get_beam_properties (lensing.c:39-250). r_sh: shell radii, sorted ascending on entry,
+// snapped to the radial sampling on exit. npp[ir]: pixels per beam of shell ir; pos: unit vectors of the finest shell,
+// [nbeams][npp[nr-1]][3]. data (host, may be NULL): shells concatenated, shell ir = [nbeams][5 * npp[ir]]. The result
+// also stays on the device for clr_beam_srcs_from_shells.
+int clr_beam_lens_shells(clr_ctx *c, int nbeams, int nr_sh, float *r_sh, const long long *npp, const double *h_pos, float *h_data)
+{
+  CLR_CHECK(nbeams > 0 && nr_sh >= 2 && nr_sh <= 4096, "lensing shells: bad beam / shell count");
+  const int nr = c->p.n_grid / 2;
+  const double dr = c->p.r_max / nr, idr = 1. / dr;
+  const long long npix_hi = npp[nr_sh - 1], n_fine = (long long)nbeams * npix_hi;
+  std::vector<int> ir(2 * (size_t)nr_sh);
+  std::vector<double> dd(2 * (size_t)nr_sh + 3 * (size_t)nr);
+  std::vector<long long> ll(3 * (size_t)nr_sh);
+  int *irmin = ir.data(), *irmax = irmin + nr_sh;
+  double *inv_r_max = dd.data(), *inv_ratio = inv_r_max + nr_sh, *fac = inv_ratio + nr_sh;
+  long long *ratio = ll.data(), *nppv = ratio + nr_sh, *off = nppv + nr_sh, total = 0;
+  for (int i = 0; i < nr_sh; i++) {                   // lensing.c:100-116
+    CLR_CHECK(npp[i] > 0 && npix_hi % npp[i] == 0, "lensing shells: shell %d does not nest into the finest one", i);
+    int i_r_here = (int)(r_sh[i] * idr + 0.5);
+    inv_r_max[i] = 1. / (i_r_here * dr);
+    irmax[i] = std::min(i_r_here, nr - 1);
+    ratio[i] = npix_hi / npp[i];
+    inv_ratio[i] = 1. / ((double)ratio[i]);
+    nppv[i] = npp[i];
+    off[i] = total;
+    total += 5LL * nbeams * npp[i];
+  }
+  irmin[0] = 0;
+  for (int i = 1; i < nr_sh; i++) irmin[i] = irmax[i - 1] + 1;
+  for (int i = 0; i < nr; i++) {                      // lensing.c:118-127
+    double rm = (i + 0.5) * dr;
+    double pg = host_lerp(c, rm, c->h_d1, 1, c->h_d1[CLR_NA - 1]) * (1 + host_lerp(c, rm, c->h_z, 0, c->h_z[CLR_NA - 1]));
+    fac[i] = pg * dr; fac[nr + i] = rm * pg * dr; fac[2 * nr + i] = rm * rm * pg * dr;
+  }
+  DevBuf b_i, b_d, b_l, b_pos;
+  CLR_CUDA(cudaMalloc(&b_i.p, ir.size() * sizeof(int)));
+  CLR_CUDA(cudaMalloc(&b_d.p, dd.size() * sizeof(double)));
+  CLR_CUDA(cudaMalloc(&b_l.p, ll.size() * sizeof(long long)));
+  CLR_CUDA(cudaMalloc(&b_pos.p, (size_t)3 * n_fine * sizeof(double)));
+  cudaFree(c->d_lens_data); c->d_lens_data = nullptr; c->lens_total = 0;
+  CLR_CUDA(cudaMalloc(&c->d_lens_data, (size_t)total * sizeof(float)));
+  c->lens_total = total; c->lens_nbeams = nbeams;
+  c->lens_npp.assign(npp, npp + nr_sh);
+  CLR_CUDA(cudaMemcpyAsync(b_i.p, ir.data(), ir.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(b_d.p, dd.data(), dd.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(b_l.p, ll.data(), ll.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(b_pos.p, h_pos, (size_t)3 * n_fine * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemsetAsync(c->d_lens_data, 0, (size_t)total * sizeof(float), c->stream));
+  ShellPlan pl;
+  pl.fac0 = b_d.as<double>() + 2 * nr_sh; pl.fac1 = pl.fac0 + nr; pl.fac2 = pl.fac1 + nr;
+  pl.irmin = b_i.as<int>(); pl.irmax = pl.irmin + nr_sh;
+  pl.inv_r_max = b_d.as<double>(); pl.inv_ratio = pl.inv_r_max + nr_sh;
+  pl.ratio = b_l.as<long long>(); pl.npp = pl.ratio + nr_sh; pl.off = pl.npp + nr_sh;
+  pl.nr_sh = nr_sh; pl.npix_hi = npix_hi; pl.dr = dr;
+  pl.restrict_z = slab_window(c, nr, dr, 0.5, &pl.za, &pl.zb) ? 1 : 0;
+  {
+    StageScope sc(c, "lensing_shells", 1);
+    lens_shell_kernel<<<blocks_for(c, n_fine, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, b_pos.as<double>(), n_fine, pl, c->d_lens_data);
+    CLR_CUDA(cudaGetLastError());
+  }
+  if (clr_comm_allreduce_f32(c, c->d_lens_data, (size_t)total)) return 1;
+  if (h_data) CLR_CUDA(cudaMemcpyAsync(h_data, c->d_lens_data, (size_t)total * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CLR_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < nr_sh; i++) r_sh[i] = (float)(1. / inv_r_max[i]);     // lensing.c:233-236
+  return 0;
+}
+
+// the lensing part of srcs_beams_postproc under _USE_FAST_LENSING (srcs.c:666-723) from the shells of the last
+// clr_beam_lens_shells; beam ib holds base pixel ib * nnodes + node. *n_bad: sources outside the held base pixels.
+int clr_beam_srcs_from_shells(clr_ctx *c, int ipop, int nr_sh, const float *r_sh, const int *nside_sh, int node, int nnodes,
+                              long long *n_bad)
+{
+  clr_ctx::Pop &P = c->srcs[ipop];
+  CLR_CHECK(c->d_lens_data && (int)c->lens_npp.size() == nr_sh, "no lensing shells on the device (clr_lensing_get_beam_properties first)");
+  CLR_CHECK(nnodes >= 1 && node >= 0 && node < nnodes, "bad node layout");
+  if (n_bad) *n_bad = 0;
+  if (P.nsrc == 0) return 0;
+  std::vector<long long> ll(2 * (size_t)nr_sh);
+  long long total = 0;
+  for (int i = 0; i < nr_sh; i++) { ll[i] = c->lens_npp[i]; ll[nr_sh + i] = total; total += 5LL * c->lens_nbeams * c->lens_npp[i]; }
+  DevBuf b_r, b_ns, b_l;
+  CLR_CUDA(cudaMalloc(&b_r.p, nr_sh * sizeof(float)));
+  CLR_CUDA(cudaMalloc(&b_ns.p, nr_sh * sizeof(int)));
+  CLR_CUDA(cudaMalloc(&b_l.p, ll.size() * sizeof(long long)));
+  CLR_CUDA(cudaMemcpyAsync(b_r.p, r_sh, nr_sh * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(b_ns.p, nside_sh, nr_sh * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CLR_CUDA(cudaMemcpyAsync(b_l.p, ll.data(), ll.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  if (clr_ensure_scratch(c, sizeof(unsigned long long))) return 1;
+  unsigned long long *d_bad = reinterpret_cast<unsigned long long *>(c->d_scratch), h_bad = 0;
+  CLR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+  ShellLookup L{b_r.as<float>(), b_ns.as<int>(), b_l.as<long long>(), b_l.as<long long>() + nr_sh, nr_sh, c->lens_nbeams, node, nnodes};
+  {
+    StageScope sc(c, "srcs_shell_lensing", 1);
+    src_shell_lens_kernel<<<blocks_for(c, P.nsrc, 8), kThreads, 0, c->stream>>>(c->dev, reinterpret_cast<const float4 *>(P.d_pos), P.d_srcs,
+                                                                                 P.nsrc, L, c->d_lens_data, d_bad);
+    CLR_CUDA(cudaGetLastError());
+  }
+  if (clr_read_small(c, &h_bad, d_bad, sizeof(h_bad))) return 1;
+  if (n_bad) *n_bad = (long long)h_bad;
   return 0;
 }
 

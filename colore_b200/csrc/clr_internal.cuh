@@ -104,6 +104,8 @@ struct clr_ctx {
     long long skw_n = -1; int skw_nr = 0;
   } srcs[CLR_NPOP_MAX], imap[CLR_NPOP_MAX], cstm[CLR_NPOP_MAX];   // cstm: h_a = K(z) table (cosmo.c:659-664)
   double z0_norm = 0, zf_norm = 0;
+  // fast-lensing shells of the last clr_lensing_get_beam_properties (clr_beam.cu), kept for the source interpolation
+  float *d_lens_data = nullptr; long long lens_total = 0; int lens_nbeams = 0; std::vector<long long> lens_npp;
   // multi-GPU
   int rank = 0, nranks = 1;
   void *nccl_comm = nullptr;
@@ -222,6 +224,9 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
 int clr_beam_cstm(clr_ctx *c, int ipop, long long num_pix, const double *h_pos, float *h_data);
 int clr_beam_srcs(clr_ctx *c, int ipop, int has_lensing, int has_skw, int skw_gauss, int rsd_done);
 int clr_beam_get_skewers(clr_ctx *c, int ipop, float *h_dg, float *h_v);
+int clr_beam_lens_shells(clr_ctx *c, int nbeams, int nr_sh, float *r_sh, const long long *npp, const double *h_pos, float *h_data);
+int clr_beam_srcs_from_shells(clr_ctx *c, int ipop, int nr_sh, const float *r_sh, const int *nside_sh, int node, int nnodes,
+                              long long *n_bad);
 int clr_halo_update(clr_ctx *c);
 int clr_npot_ready(clr_ctx *c);     // main stream waits for the potential pipeline, then exchanges the z halo
 void clr_use_set(clr_ctx *c, int set);   // select the staging buffer / barrier flags (and stream) of pipeline 0 / 1

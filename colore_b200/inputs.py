@@ -60,6 +60,10 @@ class RunConfig:
     srcs_skewers: bool = False      # store_skewers (srcs.c:507-529)
     gaussian_skewers: bool = False  # srcsN.gaussian_skewers (beaming.c:55-66)
     cstm_nside: int = 0             # 0 -> no custom projected map (cstm.c)
+    lensing_n: int = 0              # > 0 -> "lensing" section (io.c:398-419; only read by -D_USE_FAST_LENSING builds)
+    lensing_nside: int = 16
+    lensing_spacing: str = "r"      # "r" or "log(1+z)" (cosmo.c:851-868)
+    lensing_write: bool = True
     cosmo: Cosmology = field(default_factory=Cosmology)
 
 
@@ -157,6 +161,9 @@ def write_param_file(fname: str, cfg: RunConfig, paths: dict, prefix_out: str) -
                   f'  tbak_filename= "{paths["tz"]}"', f'  bias_filename= "{paths["bz_im"]}"',
                   f'  freq_list= "{paths["nu"]}"', "  freq_rest= 1420.405",
                   f"  nside= {cfg.imap_nside}", "}"]
+    if cfg.lensing_n > 0:
+        lines += ["lensing:", "{", f"  n_lensing= {cfg.lensing_n}", f'  spacing_type= "{cfg.lensing_spacing}"',
+                  f"  nside= {cfg.lensing_nside}", f"  write= {b(cfg.lensing_write)}", "}"]
     zs = ", ".join(repr(float(v)) for v in cfg.z_out)
     if cfg.kappa_nside > 0:
         lines += ["kappa:", "{", f"  z_out= [{zs}]", f"  nside= {cfg.kappa_nside}", "}"]

@@ -328,6 +328,30 @@ def cstm_get_beam_properties(par: ParamCoLoRe, ipop: int, pos: np.ndarray) -> np
     return data
 
 
+def lensing_get_beam_properties(par: ParamCoLoRe, r_sh, npp, pos: np.ndarray):
+    """lensing.c:39-250 (fast-lensing shells). ``pos``: unit vectors of the finest shell [nbeams * npp[-1], 3]. Returns
+    (data flat: shell ir = [nbeams][5 * npp[ir]], r_sh snapped to the radial sampling)."""
+    r_sh = np.ascontiguousarray(r_sh, np.float32).copy()
+    npp = np.ascontiguousarray(npp, np.int64)
+    pos = np.ascontiguousarray(pos, np.float64)
+    nbeams = pos.shape[0] // int(npp[-1])
+    data = np.zeros(5 * nbeams * int(npp.sum()), np.float32)
+    check(par.lib.clr_lensing_get_beam_properties(par.ctx, C.c_int(nbeams), C.c_int(len(r_sh)), _vp(r_sh), _vp(npp), _vp(pos),
+                                                  _vp(data)))
+    return data, r_sh
+
+
+def srcs_lensing_from_shells(par: ParamCoLoRe, ipop: int, r_sh, nside_sh, node: int = 0, nnodes: int = 1):
+    """srcs.c:666-723: lensing of the sources from the shells of the last lensing_get_beam_properties. Returns
+    (srcs[n,9], number of sources outside the held base pixels)."""
+    r_sh = np.ascontiguousarray(r_sh, np.float32)
+    nside_sh = np.ascontiguousarray(nside_sh, np.int32)
+    bad = C.c_longlong()
+    check(par.lib.clr_srcs_lensing_from_shells(par.ctx, C.c_int(ipop), C.c_int(len(r_sh)), _vp(r_sh), _vp(nside_sh),
+                                               C.c_int(node), C.c_int(nnodes), C.byref(bad)))
+    return srcs_get_local_properties(par, ipop), int(bad.value)
+
+
 def imap_set_cartesian(par: ParamCoLoRe, ipop: int = 0):
     """imap.c:135-245 -> (data[nr,npix], nadd[nr,npix]); the written map is data/nadd (io.c:738-741)."""
     nside, nr = par.imap_shells[ipop]

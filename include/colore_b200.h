@@ -206,6 +206,21 @@ int clr_isw_get_beam_properties(clr_ctx *ctx, long long num_pix, const double *p
  * b(r)) norm(r) - 1) for the pixels `pos` (unit vectors); several GPUs: summed over the slabs */
 int clr_cstm_get_beam_properties(clr_ctx *ctx, int ipop, long long num_pix, const double *pos3, float *data);
 
+/* Fast-lensing shells (reference builds with -D_USE_FAST_LENSING): lensing_beams_preproc + lensing_get_beam_properties
+ * (lensing.c:39-250). nr_sh shells of radii r_sh (sorted ascending on entry, snapped to the radial sampling on exit,
+ * lensing.c:233-236) with npp[ir] pixels per base pixel ("beam", hp_shell_adaptive_alloc common.c:452-504); pos3: unit
+ * vectors of the finest shell, [nbeams][npp[nr_sh-1]][3]. data (may be NULL): shells concatenated, shell ir =
+ * [nbeams][5 * npp[ir]] = {gamma1, gamma2, kappa, dx, dy} per pixel, summed over the slabs on several GPUs. The shells
+ * also stay on the device for clr_srcs_lensing_from_shells. */
+int clr_lensing_get_beam_properties(clr_ctx *ctx, int nbeams, int nr_sh, float *r_sh, const long long *npp,
+                                    const double *pos3, float *data);
+/* The lensing branch of srcs_beams_postproc under _USE_FAST_LENSING (srcs.c:666-723): e1, e2, kappa, dra, ddec of every
+ * source interpolated in radius between the two shells that bracket it (including the reference's stride-2 read of the
+ * upper shell, srcs.c:710-714). nside_sh: resolution of every shell; beam ib = base pixel ib * nnodes + node.
+ * *n_bad: sources whose base pixel is not held (the reference stops with "Bad base"). */
+int clr_srcs_lensing_from_shells(clr_ctx *ctx, int ipop, int nr_sh, const float *r_sh, const int32_t *nside_sh, int node,
+                                 int nnodes, long long *n_bad);
+
 /* ---- timing helpers for bench.py (CUDA events on the context's stream) -------------------- */
 int clr_timer_start(clr_ctx *ctx);
 int clr_timer_stop_ms(clr_ctx *ctx, float *ms);

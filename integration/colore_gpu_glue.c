@@ -3,9 +3,9 @@
  * This ONE translation unit replaces fourier.c, density.c, srcs.c, imap.c, kappa.c, isw.c, cstm.c and
  * beaming.c of damonge/CoLoRe in the link line: it defines exactly the functions those files export
  * through common.h (464-543) and forwards them to include/colore_b200.h. main.c, io.c, cosmo.c,
- * cosmo_mad.c, common.c, healpix_extra.c, predictions.c, fftlog.c (and lensing.c, whose hooks are only
- * reached under _USE_FAST_LENSING) are linked UNCHANGED, so `./CoLoRe param.cfg` stays the entry point
- * (main.c:24-154).
+ * cosmo_mad.c, common.c, healpix_extra.c, predictions.c, fftlog.c are linked UNCHANGED, so `./CoLoRe param.cfg`
+ * stays the entry point (main.c:24-154). lensing.c: linked unchanged in the default build (its hooks are never
+ * called); with -D_USE_FAST_LENSING (make FASTLENS=1) it is left out and its hooks are defined here as well.
  *
  * It is compiled against the reference's own common.h (-I<reference>/src); it contains no code of
  * the reference. One process drives one GPU; COLORE_B200_NGPUS=P makes the executable fork into P ranks (see
@@ -357,9 +357,21 @@ void srcs_get_beam_properties(ParamCoLoRe *par)
   int ipop;
   for (ipop = 0; ipop < par->n_srcs; ipop++) {
     Catalog *cat = par->cats[ipop];
+    int lens_rays = par->lensing_srcs[ipop];
+#ifdef _USE_FAST_LENSING
+    lens_rays = 0;   /* srcs.c:531 is compiled out: the sources read the shells of lensing.c instead (srcs.c:666-721) */
+#endif
     /* routed by pixel: dz_rsd was evaluated before the exchange, on the slab that holds the potential */
-    chk(clr_srcs_get_beam_properties(g_ctx, ipop, par->lensing_srcs[ipop], par->skw_srcs[ipop], par->skw_gauss[ipop],
-                                     g_by_pixel));
+    chk(clr_srcs_get_beam_properties(g_ctx, ipop, lens_rays, par->skw_srcs[ipop], par->skw_gauss[ipop], g_by_pixel));
+#ifdef _USE_FAST_LENSING
+    if (par->lensing_srcs[ipop] && cat->nsrc > 0) {
+      /* every rank holds full-sky shells (they were allocated while NNodes was still 1): beam ib = base pixel ib */
+      HealpixShellsAdaptive *m = par->smap;
+      long long bad = 0;
+      chk(clr_srcs_lensing_from_shells(g_ctx, ipop, m->nr, m->r, m->nside, 0, 1, &bad));
+      if (bad) report_error(1, "Bad base!!\n");      /* srcs.c:684-685 */
+    }
+#endif
     if (cat->nsrc > 0) {
       chk(clr_srcs_get_local_properties(g_ctx, ipop, (float *)cat->srcs));
       if (cat->has_skw) chk(clr_srcs_get_skewers(g_ctx, ipop, cat->skw_gauss ? cat->g_skw : cat->d_skw, cat->v_skw));
@@ -447,12 +459,47 @@ void cstm_get_beam_properties(ParamCoLoRe *par)
 }
 void cstm_beams_postproc(ParamCoLoRe *par) { (void)par; }
 
+#ifdef _USE_FAST_LENSING
+/* ------------------------------------------------------------------ lensing.c (this build leaves it out of the link) */
+void lensing_set_cartesian(ParamCoLoRe *par) { (void)par; }
+void lensing_distribute(ParamCoLoRe *par) { (void)par; }
+void lensing_get_local_properties(ParamCoLoRe *par) { (void)par; }
+void lensing_beams_preproc(ParamCoLoRe *par)
+{ /* lensing.c:39-74: radii in ascending order; the library zeroes the maps */
+  HealpixShellsAdaptive *m = par->smap;
+  int ir, *order = ind_sort(m->nr, m->r);
+  flouble *r = my_malloc(m->nr * sizeof(flouble));
+  memcpy(r, m->r, m->nr * sizeof(flouble));
+  for (ir = 0; ir < m->nr; ir++) m->r[ir] = r[order[ir]];
+  free(r); free(order);
+}
+void lensing_get_beam_properties(ParamCoLoRe *par)
+{ /* lensing.c:76-244 for all beams at once; on several GPUs the shells come back summed over the slabs */
+  HealpixShellsAdaptive *m = par->smap;
+  long ib, ir, npix_hi = m->num_pix_per_beam[m->nr - 1];
+  long long total = 0, off = 0, *npp = my_malloc(m->nr * sizeof(long long));
+  double *pos = my_malloc((size_t)m->nbeams * npix_hi * 3 * sizeof(double));
+  float *data;
+  for (ir = 0; ir < m->nr; ir++) { npp[ir] = m->num_pix_per_beam[ir]; total += 5LL * m->nbeams * npp[ir]; }
+  for (ib = 0; ib < m->nbeams; ib++) memcpy(pos + ib * npix_hi * 3, m->pos[ib], npix_hi * 3 * sizeof(double));
+  data = my_malloc(total * sizeof(float));
+  chk(clr_lensing_get_beam_properties(g_ctx, m->nbeams, m->nr, m->r, npp, pos, data));
+  for (ir = 0; ir < m->nr; ir++)
+    for (ib = 0; ib < m->nbeams; ib++) {
+      memcpy(m->data[ib][ir], data + off, 5 * npp[ir] * sizeof(float));
+      off += 5 * npp[ir];
+    }
+  free(data); free(pos); free(npp);
+}
+void lensing_beams_postproc(ParamCoLoRe *par) { (void)par; }
+#endif
+
 /* ------------------------------------------------------------------ beaming.c */
 int interpolate_from_grid(ParamCoLoRe *par, double *x, flouble *d, flouble v[3], flouble t[6], flouble *pd,
                           flouble *g, int flag_return, int interp_type)
-{ /* beaming.c:120-268 is only reached from lensing.c under _USE_FAST_LENSING (every other caller is replaced above) */
+{ /* beaming.c:120-268: every caller in the reference (kappa, isw, srcs, cstm, lensing) is replaced above */
   (void)par; (void)x; (void)d; (void)v; (void)t; (void)pd; (void)g; (void)flag_return; (void)interp_type;
-  report_error(1, "interpolate_from_grid: the grids live on the GPU; build without _USE_FAST_LENSING\n");
+  report_error(1, "interpolate_from_grid: the grids live on the GPU\n");
   return 0;
 }
 
@@ -466,6 +513,9 @@ void get_beam_properties(ParamCoLoRe *par)
   if (par->do_cstm) cstm_beams_preproc(par);
   if (NodeThis == 0) timer(0);
   if (par->do_kappa) kappa_get_beam_properties(par);
+#ifdef _USE_FAST_LENSING
+  if (par->do_lensing) { lensing_beams_preproc(par); lensing_get_beam_properties(par); }   /* before the sources read them */
+#endif
   if (par->do_isw) isw_get_beam_properties(par);
   if (par->do_srcs) srcs_get_beam_properties(par);
   if (par->do_cstm) cstm_get_beam_properties(par);

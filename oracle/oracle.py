@@ -225,6 +225,27 @@ class Oracle:
                                               C.c_int(int(pre)), C.c_int(int(post)))
         return srcs, dg_skw, v_skw
 
+    def lensing_shells(self, npot, r_sh, npp, pos, nbeams, data=None, snap=True):
+        """lensing.c:76-250. Returns (data flat, r_sh snapped). data: shells concatenated, [nbeams][5*npp[ir]] each."""
+        r_sh = np.ascontiguousarray(r_sh, np.float32).copy()
+        npp = np.ascontiguousarray(npp, np.int64)
+        if data is None:
+            data = np.zeros(5 * nbeams * int(npp.sum()), np.float32)
+        self.lib.orc_lensing_get_beam_properties(self.pp, _fp(npot), C.c_int(nbeams), C.c_int(len(r_sh)), _fp(r_sh),
+                                                 npp.ctypes.data_as(C.c_void_p), _dp(pos), _fp(data), C.c_int(int(snap)))
+        return data, r_sh
+
+    def srcs_fast_lensing(self, r_sh, nside_sh, npp, data, nbeams, pos, srcs, node=0, nnodes=1):
+        """srcs.c:666-723: interpolation of the shell quantities onto the sources (updates srcs columns 4-8)."""
+        r_sh = np.ascontiguousarray(r_sh, np.float32)
+        nside_sh = np.ascontiguousarray(nside_sh, np.int64)
+        npp = np.ascontiguousarray(npp, np.int64)
+        self.lib.orc_srcs_fast_lensing.restype = C.c_long
+        bad = self.lib.orc_srcs_fast_lensing(self.pp, C.c_int(len(r_sh)), _fp(r_sh), nside_sh.ctypes.data_as(C.c_void_p),
+                                             npp.ctypes.data_as(C.c_void_p), _fp(data), C.c_int(nbeams), C.c_int(node),
+                                             C.c_int(nnodes), _fp(pos), C.c_long(pos.shape[0]), _fp(srcs))
+        return srcs, int(bad)
+
     def cstm(self, dens, kz_tab, bz_tab, norm_tab, norm_0, norm_f, pos, data=None):
         """cstm.c:68-145: custom projected map for the unit vectors pos[npix][3]."""
         npix = pos.shape[0]

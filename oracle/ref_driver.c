@@ -187,6 +187,27 @@ int main(int argc, char **argv)
         }
       }
     }
+#ifdef _USE_FAST_LENSING
+    if (par->do_lensing) { /* lensing.c:76-250: adaptive shells, 5 quantities per pixel */
+      HealpixShellsAdaptive *m = par->smap;
+      long nside[256], ir, ib, npix_hi = m->num_pix_per_beam[m->nr - 1];
+      double *pos = my_malloc(m->nbeams * npix_hi * 3 * sizeof(double));
+      for (ir = 0; ir < m->nr; ir++) nside[ir] = m->nside[ir];
+      dump_f32(d, "s6_lens_r", m->r, m->nr);
+      dump_i64(d, "s6_lens_nside", nside, m->nr);
+      dump_i64(d, "s6_lens_npp", m->num_pix_per_beam, m->nr);
+      for (ib = 0; ib < m->nbeams; ib++) memcpy(pos + ib * npix_hi * 3, m->pos[ib], npix_hi * 3 * sizeof(double));
+      dump_f64(d, "s6_lens_pos", pos, m->nbeams * npix_hi * 3);
+      free(pos);
+      for (ir = 0; ir < m->nr; ir++) {
+        long n5 = 5 * m->num_pix_per_beam[ir];
+        flouble *buf = my_malloc(m->nbeams * n5 * sizeof(flouble));
+        for (ib = 0; ib < m->nbeams; ib++) memcpy(buf + ib * n5, m->data[ib][ir], n5 * sizeof(flouble));
+        sprintf(nm, "s6_lens_data_%03ld", ir); dump_f32(d, nm, buf, m->nbeams * n5);
+        free(buf);
+      }
+    }
+#endif
     if (par->do_cstm) { /* cstm.c:68-145 */
       for (i = 0; i < par->n_cstm; i++) {
         HealpixShells *m = par->cstm[i];

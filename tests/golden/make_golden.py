@@ -47,6 +47,10 @@ CASES = {
     # Gaussian skewers (beaming.c:55-66), no lensing
     "ref_n32_gskw": RunConfig(n_grid=32, dens_type=0, nz_amplitude=15.0, srcs_skewers=True, gaussian_skewers=True,
                               seed=43),
+    # -D_USE_FAST_LENSING build (driver ref_driver_bmfl): adaptive-resolution lensing shells (lensing.c:76-250) and the
+    # interpolation of shear / convergence / deflection onto the sources (srcs.c:666-721)
+    "ref_n32_fastlens": RunConfig(n_grid=32, dens_type=0, nz_amplitude=25.0, nz_zcut=0.40, srcs_lensing=True, lensing_n=6,
+                                  lensing_nside=16, seed=47),
     # the other compile-time bias models of common.h:414-431 (drivers built by `make -C oracle refbm`):
     # model 1 = pow(1+d,b) (no flag), model 3 = max(1+b d, 0) (-D_BIAS_MODEL_3)
     "ref_n32_bias1": RunConfig(n_grid=32, dens_type=0, nz_amplitude=60.0, imap_nside=8, imap_nchannels=4, seed=21),
@@ -55,7 +59,7 @@ CASES = {
 # fixtures whose catalogue is too large to commit: arrays above 65536 elements are replaced by
 # <key>__sha256 (digest of the raw bytes), <key>__size and <key>__head (first 4096 elements); tests compare digests
 COMPACT = {"ref_n32_dense"}
-DRIVER = {"ref_n32_bias1": "ref_driver_bm1", "ref_n32_bias3": "ref_driver_bm3"}
+DRIVER = {"ref_n32_bias1": "ref_driver_bm1", "ref_n32_bias3": "ref_driver_bm3", "ref_n32_fastlens": "ref_driver_bmfl"}
 
 
 def compact(arrs):

@@ -16,6 +16,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B200 = os.path.join(ROOT, "integration", "_build", "CoLoRe_b200")
 REF = os.path.join(ROOT, "oracle", "_ref", "CoLoRe_ref")
+# the reference's -D_USE_FAST_LENSING variant (Makefile:16): drop-in built with `make -C integration FASTLENS=1`
+B200_FL = os.path.join(ROOT, "integration", "_build_fl", "CoLoRe_b200_fl")
+REF_FL = os.path.join(ROOT, "oracle", "_ref", "CoLoRe_ref_fl")
 
 
 def _read_dens(fname):
@@ -258,3 +261,34 @@ def test_native_fits_writer_header_equals_io_c():
     a, b = cards(ref), cards(mine)
     diff = [(x, y) for x, y in zip(a, b) if x != y]
     assert all(x.startswith("NAXIS2") and y.startswith("NAXIS2") for x, y in diff), diff
+
+
+@pytest.mark.skipif(not (os.path.exists(B200_FL) and os.path.exists(REF_FL)), reason="fast-lensing binaries not built")
+def test_dropin_fast_lensing_matches_reference_statistically():
+    """SURVEY 8(f)-4 through the executable built with -D_USE_FAST_LENSING: the `lensing` section makes lensing.c's
+    adaptive shells (here: the glue + clr_lensing_get_beam_properties), the sources read their shear / convergence /
+    deflection from them (srcs.c:666-721) and the unchanged io.c writes the shells (write_lensing, io.c:881-945)."""
+    from colore_b200.inputs import RunConfig
+    cfg = RunConfig(n_grid=64, dens_type=0, nz_amplitude=60.0, nz_zcut=0.40, srcs_lensing=True, lensing_n=5, lensing_nside=32,
+                    seed=55)
+    with tempfile.TemporaryDirectory() as tmp:
+        out = _run(B200_FL, tmp, "gpu", cfg)
+        _run(REF_FL, tmp, "ref", cfg)
+        assert "(GPU)" in out
+        cg = np.loadtxt(os.path.join(tmp, "out_gpu_srcs_s1_0.txt"))
+        cr = np.loadtxt(os.path.join(tmp, "out_ref_srcs_s1_0.txt"))
+        assert cg.shape[1] == cr.shape[1] == 10 and cg.shape[0] > 1000
+        mad = lambda x: np.median(np.abs(x - np.median(x)))  # noqa: E731
+        for col, name in ((5, "e1"), (6, "e2"), (7, "kappa"), (8, "dra"), (9, "ddec")):
+            assert np.isfinite(cg[:, col]).all() and 0.6 < mad(cg[:, col]) / mad(cr[:, col]) < 1.6, name
+        # shells: same radii file, same map layout (resolution adapts to the radius), same one-point statistics
+        rg = np.loadtxt(os.path.join(tmp, "out_gpu_lensing_r.txt"))
+        rr = np.loadtxt(os.path.join(tmp, "out_ref_lensing_r.txt"))
+        np.testing.assert_allclose(rg, rr, rtol=1e-6)
+        for i in range(cfg.lensing_n):
+            a, b = (os.path.join(tmp, f"out_{tag}_lensing_z{i:03d}.fits") for tag in ("gpu", "ref"))
+            assert os.path.getsize(a) == os.path.getsize(b) > 2880
+            ma, mb = _read_healpix_map(a), _read_healpix_map(b)
+            assert ma.shape == mb.shape and np.isfinite(ma).all()
+            if i >= 2:          # the innermost shells hold a handful of modes of the 64^3 box
+                assert 0.5 < ma.std() / mb.std() < 2.0, (i, ma.std(), mb.std())

@@ -516,6 +516,40 @@ def test_srcs_lensing_and_skewers_vs_oracle(golden_dir, name):
     par.free()
 
 
+def test_fast_lensing_shells_and_sources_vs_reference(golden_dir):
+    """lensing.c:39-250 + srcs.c:666-723 (reference builds with -D_USE_FAST_LENSING): the adaptive shells
+    against the unmodified reference's, then the interpolation onto the GPU's own catalogue against the oracle (which
+    reproduces the reference bit for bit, CPU suite) fed with the same shells."""
+    g, t = _load(golden_dir, "ref_n32_fastlens")
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    par = _par(t)
+    _setup_sources(g, t, par)
+    npp, nside_sh = g["s6_lens_npp"], g["s6_lens_nside"]
+    nr = len(npp)
+    pos_sh = g["s6_lens_pos"].reshape(-1, 3)
+    nbeams = pos_sh.shape[0] // int(npp[-1])
+    r0 = ((np.arange(nr) + 1) * np.float32(np.float32(t["r_max"]) / np.float32(nr))).astype(np.float32)   # cosmo.c:851-860
+    data, r_snap = cb.lensing_get_beam_properties(par, r0, npp, pos_sh)
+    assert np.array_equal(r_snap, g["s6_lens_r"])
+    ref = np.concatenate([g[f"s6_lens_data_{i:03d}"] for i in range(nr)])
+    assert data.shape == ref.shape
+    # fine pixels are summed into the coarse shells with float atomics: summation order differs
+    np.testing.assert_allclose(data, ref, rtol=2e-5, atol=2e-6 * np.abs(ref).max())
+    cb.srcs_set_cartesian(par)
+    pos, _ = cb.srcs_get_cartesian(par, 0)
+    cb.srcs_beams(par)
+    before = cb.srcs_get_local_properties(par, 0)
+    srcs, bad = cb.srcs_lensing_from_shells(par, 0, r_snap, nside_sh)
+    assert bad == 0 and pos.shape[0] > 3000
+    want = before.copy()
+    want, bad_o = o.srcs_fast_lensing(r_snap, nside_sh, npp, data, nbeams, pos, want)
+    assert bad_o == 0
+    assert np.array_equal(srcs[:, :4], want[:, :4])
+    np.testing.assert_allclose(srcs[:, 4:], want[:, 4:], rtol=1e-6, atol=1e-7 * np.abs(want[:, 4:]).max())
+    assert np.abs(want[:, 6]).max() > 0
+    par.free()
+
+
 def test_custom_map_vs_reference(golden_dir):
     """cstm.c:38-145 against the unmodified reference's map, and the custom population's share of the
     density normalisation (density.c:1177-1178, 1315-1354) against its table."""

@@ -17,6 +17,7 @@ CASES = ["ref_n32_lognormal", "ref_n32_clip", "ref_n48_nosmooth", "ref_n32_1lpt_
          "ref_n32_bias1", "ref_n32_bias3",       # the reference compiled with the other bias models (common.h:414-431)
          "ref_n32_nosmooth",                     # power-of-two grid without smoothing (runs on the GPU too)
          "ref_n32_lensing",                      # per-source lensing + density skewers + custom map (srcs.c:506-615, cstm.c)
+         "ref_n32_fastlens",                     # -D_USE_FAST_LENSING build: lensing.c shells + srcs.c:666-721
          "ref_n32_gskw",                         # Gaussian skewers (beaming.c:55-66)
          "ref_n32_dense"]                        # ~120 sources per cell: gsl_ran_poisson's mu > 10 branch (common.c:187)
 
@@ -119,7 +120,17 @@ def test_sources_bit_exact(case):
             full[:, :6] = srcs[:, :6]
             assert _same(full, g, f"s5_srcs_cat_{ipop}")
         flags = g.get(f"s6_srcs_flags_{ipop}", np.zeros(3)).astype(int)
-        if f"s6_srcs_cat_{ipop}" in g and not flags.any():
+        if "s6_lens_r" in g:
+            # fast-lensing build: RSD as usual, then shear / convergence / deflection interpolated from the shells
+            o.srcs_beam_rsd(npot, pos, srcs)
+            npp = g["s6_lens_npp"]
+            nbeams = g["s6_lens_pos"].size // (3 * int(npp[-1]))
+            data = np.concatenate([g[f"s6_lens_data_{i:03d}"] for i in range(len(npp))])
+            srcs[:, 6:] = 0
+            srcs, bad = o.srcs_fast_lensing(g["s6_lens_r"], g["s6_lens_nside"], npp, data, nbeams, pos, srcs)
+            assert bad == 0
+            assert np.array_equal(srcs, g[f"s6_srcs_cat_{ipop}"].reshape(-1, 9))
+        elif f"s6_srcs_cat_{ipop}" in g and not flags.any():
             o.srcs_beam_rsd(npot, pos, srcs)
             assert np.array_equal(srcs[:, :6], g[f"s6_srcs_cat_{ipop}"].reshape(-1, 9)[:, :6])
         elif f"s6_srcs_cat_{ipop}" in g:
@@ -133,6 +144,30 @@ def test_sources_bit_exact(case):
             if flags[1]:
                 assert np.array_equal(dg.ravel(), g[f"s6_srcs_dgskw_{ipop}"])
                 assert np.array_equal(vs.ravel(), g[f"s6_srcs_vskw_{ipop}"])
+
+
+def test_fast_lensing_shells_bit_exact(case):
+    g, t, o = case
+    if "s6_lens_r" not in g:
+        pytest.skip("case has no lensing shells")
+    o.set_halo(g["s1_npot"])
+    npp = g["s6_lens_npp"]
+    nr = len(npp)
+    npix_hi = int(npp[-1])
+    pos = g["s6_lens_pos"].reshape(-1, 3)
+    nbeams = pos.shape[0] // npix_hi
+    # the shell radii before the run: compute_lensing_spacing (cosmo.c:851-868), spacing in r
+    r0 = ((np.arange(nr) + 1) * np.float32(np.float32(t["r_max"]) / np.float32(nr))).astype(np.float32)
+    data, r_snap = o.lensing_shells(g["s1_npot"], r0, npp, pos, nbeams)
+    assert np.array_equal(r_snap, g["s6_lens_r"])
+    off = 0
+    for i in range(nr):
+        n5 = 5 * nbeams * int(npp[i])
+        assert np.array_equal(data[off:off + n5], g[f"s6_lens_data_{i:03d}"]), i
+        off += n5
+    # pixel centres of the finest shell: NEST order inside each base pixel (common.c:493-502)
+    lp, pp = o.shell_pixels(int(g["s6_lens_nside"][-1]))
+    assert np.array_equal(pp, pos)
 
 
 def test_custom_map_bit_exact(case):
