@@ -5,7 +5,7 @@ include/colore_b200.h, built into ``libcolore_b200.so``), the ctypes binding, th
 of the reference's run flow (``pipeline``), the slab decomposition (``dist``), host table
 construction (``cosmo``) and synthetic inputs (``inputs``). There is no CPU fallback.
 """
-from . import cosmo, dist, healpix, inputs  # noqa: F401
+from . import cosmo, dist, healpix, inputs, predictions  # noqa: F401
 from ._lib import ColoreError, declared_symbols, load  # noqa: F401
 from .pipeline import *  # noqa: F401,F403
 from .pipeline import ParamCoLoRe  # noqa: F401

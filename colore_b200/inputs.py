@@ -64,6 +64,9 @@ class RunConfig:
     lensing_nside: int = 16
     lensing_spacing: str = "r"      # "r" or "log(1+z)" (cosmo.c:851-868)
     lensing_write: bool = True
+    write_pred: bool = False        # global.write_pred / pred_dz / just_write_pred (io.c:283-289, predictions.c)
+    pred_dz: float = 0.1
+    just_write_pred: bool = False
     cosmo: Cosmology = field(default_factory=Cosmology)
 
 
@@ -135,7 +138,7 @@ def write_param_file(fname: str, cfg: RunConfig, paths: dict, prefix_out: str) -
         f"  output_density= {b(cfg.output_density)}",
         f'  pk_filename= "{paths["pk"]}"',
         f"  z_min= {cfg.z_min!r}", f"  z_max= {cfg.z_max!r}", f"  seed= {cfg.seed}",
-        "  write_pred=false", "  pred_dz=0.1", "  just_write_pred= false", "}",
+        f"  write_pred={b(cfg.write_pred)}", f"  pred_dz={cfg.pred_dz!r}", f"  just_write_pred= {b(cfg.just_write_pred)}", "}",
         "field_par:", "{",
         f"  r_smooth= {float(cfg.r_smooth)!r}",
         f"  smooth_potential= {b(cfg.smooth_potential)}",
