@@ -72,6 +72,7 @@ extern "C" int clr_comm_init(clr_ctx *c, int rank, int nranks, const void *id128
   ClrDev &d = c->dev;
   if (nranks == 1) { d.nyl = d.n; d.ky0 = 0; return 0; }
   CLR_CHECK(d.n % nranks == 0, "n_grid=%d is not divisible by the number of GPUs %d", d.n, nranks);
+  CLR_CHECK(d.log2n >= 6 && d.n <= 4096, "n_grid=%d: the distributed FFT takes powers of two in [64,4096]", d.n);
   CLR_CHECK(d.nz_here == d.n / nranks && d.iz0_here == rank * (d.n / nranks),
             "slab bounds (nz_here=%d, iz0_here=%d) do not match rank %d of %d", d.nz_here, d.iz0_here, rank, nranks);
   if (load_nccl()) return 1;
