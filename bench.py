@@ -350,6 +350,8 @@ def north_star_run(cb, torch, dist, rank, world, local, allsum, allmax, barrier,
         m = fn(par, pos, rf)
         wall = allmax(time.perf_counter() - t0)
         kms, _ = par.stage_ms(name)
+        if name == "kappa_los":
+            kms += par.stage_ms("kappa_tidal")[0]           # the Hessian precompute pass belongs to the kappa stage
         par.set_profiling(False)
         out[name] = {"nside": 1024, "kernel_ms_max": allmax(kms), "api_wall_ms": wall * 1e3,
                      "finite": bool(np.isfinite(m).all()), "map_rms": float(m.astype(np.float64).std())}

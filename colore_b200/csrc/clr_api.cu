@@ -406,6 +406,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
   if (!strcmp(name, "srcs_compact")) { c->srcs_compact = value; return 0; }
   if (!strcmp(name, "fft_fused")) { c->fft_fused = value; return 0; }
+  if (!strcmp(name, "los_precompute")) { c->los_precompute = value; return 0; }
   if (!strcmp(name, "fill_fused")) { c->fill_fused = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
   if (!strcmp(name, "fft_overlap")) { if (clr_npot_ready(c)) return 1; c->fft_overlap = value; return 0; }

@@ -277,10 +277,30 @@ struct LosPlan {
   double za, zb;
 };
 
+// Hessian of the potential at every cell of the slab, computed ONCE (dev_tidal, the reference's float expressions) and
+// stored as 8 floats per cell {xx, xy, xz, yy | yz, zz, -, -}: at nside 1024 on a 1024^3 grid ~11 samples of ~11
+// different pixels land in every cell, so the kappa rays then fetch two 16-byte words per sample instead of the
+// 19-point stencil. Cells no ray reaches (r > r_reach) are skipped.
+__global__ void __launch_bounds__(kThreads)
+tidal_field_kernel(const ClrDev d, const float *__restrict__ npot, float4 *__restrict__ H, float r_reach)
+{
+  const long long n_cells = (long long)d.nz_here * d.n * d.n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
+    int ix, iy, iz;
+    clr_cell(d, i, ix, iy, iz);
+    const float x = __ldg(d.cf[0] + ix), y = __ldg(d.cf[1] + iy), z = __ldg(d.cf[2] + iz + d.iz0_here);
+    if (x * x + y * y + z * z > r_reach * r_reach) continue;
+    float t[6];
+    dev_tidal(d, npot, ix, iy, iz, t);
+    H[2 * i] = make_float4(t[0], t[1], t[2], t[3]);
+    H[2 * i + 1] = make_float4(t[4], t[5], 0.f, 0.f);
+  }
+}
+
 template <bool KAPPA>
 __global__ void __launch_bounds__(kThreads)
-los_kernel(const ClrDev d, const float *__restrict__ npot, const double *__restrict__ pos, long long num_pix, LosPlan pl,
-           float *__restrict__ data)
+los_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__restrict__ H, const double *__restrict__ pos,
+           long long num_pix, LosPlan pl, float *__restrict__ data)
 {
   const double idx = (double)(d.n / d.l_box);
   for (long long ip = blockIdx.x * (long long)blockDim.x + threadIdx.x; ip < num_pix; ip += (long long)gridDim.x * blockDim.x) {
@@ -316,16 +336,31 @@ los_kernel(const ClrDev d, const float *__restrict__ npot, const double *__restr
     }
     for (int ipl = 0; ipl < pl.nplanes; ipl++) {
       int irmin = max(__ldg(pl.irmin + ipl), win_lo), irmax = min(__ldg(pl.irmax + ipl), win_hi);
-      for (int irr = irmin; irr <= irmax; irr++) {
-        double rm = (irr + 0.5) * pl.dr;
-        double xn[3];
+      double ri = irmin + 0.5;                     // (irr + 0.5), exact in double: no int -> double conversion per sample
+      for (int irr = irmin; irr <= irmax; irr++, ri += 1.0) {
+        const double rm = ri * pl.dr;
         int c[3];
+        bool in = true;
 #pragma unroll
-        for (int ax = 0; ax < 3; ax++) xn[ax] = (rm * u[ax] + d.pos_obs[ax]) * idx;
-        if (dev_ngp(d, xn, c)) {
+        for (int ax = 0; ax < 3; ax++) {
+          // beaming.c:148-157: (long)(x + 0.5) with one periodic wrap; x stays within (-n, 2n), so the 32-bit
+          // truncating conversion gives the same integer
+          int v = __double2int_rz((rm * u[ax] + d.pos_obs[ax]) * idx + 0.5);
+          if (v >= d.n) v -= d.n; else if (v < 0) v += d.n;
+          c[ax] = v;
+        }
+        c[2] -= d.iz0_here;
+        in = c[2] >= 0 && c[2] < d.nz_here;
+        if (in) {
           if (KAPPA) {
             float t[6];
-            dev_tidal(d, npot, c[0], c[1], c[2], t);
+            if (H) {
+              const long long cell = c[0] + (long long)d.n * (c[1] + (long long)d.n * c[2]);
+              const float4 a = __ldg(H + 2 * cell), b = __ldg(H + 2 * cell + 1);
+              t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y;
+            } else {
+              dev_tidal(d, npot, c[0], c[1], c[2], t);
+            }
             double dotp = 0;
 #pragma unroll
             for (int ax = 0; ax < 6; ax++) dotp += rot[ax] * t[ax];
@@ -469,12 +504,25 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
       pl.zb = (c->dev.iz0_here + c->dev.nz_here - 0.5) / idx - c->p.pos_obs[2];
     }
   }
+  // kappa: Hessian of every cell once (32 B / cell) when the rays oversample the grid and the memory is there;
+  // otherwise the rays evaluate the 19-point stencil themselves
+  float4 *d_H = nullptr;
+  const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
+  if (which == 0 && c->los_precompute && (double)num_pix * nr * (c->dev.nz_here / (double)c->dev.n) > 2.0 * (double)n_cells) {
+    if (cudaMalloc(&d_H, (size_t)n_cells * 32) != cudaSuccess) { cudaGetLastError(); d_H = nullptr; }
+  }
+  if (d_H) {
+    StageScope sc(c, "kappa_tidal", 1);
+    const float dxf = c->p.l_box / c->p.n_grid;
+    tidal_field_kernel<<<grid_for(c, n_cells, 16), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_H, (float)(nr * dr) + 2.f * dxf);
+    CLR_CUDA(cudaGetLastError());
+  }
   {
     StageScope sc(c, which == 0 ? "kappa_los" : "isw_los", 1);
     if (which == 0)
-      los_kernel<true><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_pos, num_pix, pl, d_data);
+      los_kernel<true><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_H, d_pos, num_pix, pl, d_data);
     else
-      los_kernel<false><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_pos, num_pix, pl, d_data);
+      los_kernel<false><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, nullptr, d_pos, num_pix, pl, d_data);
     CLR_CUDA(cudaGetLastError());
   }
   // slab-local ray segments: the accumulators are linear in the field, so the partial maps add up to the
@@ -482,6 +530,6 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
   if (clr_comm_allreduce_f32(c, d_data, (size_t)nplanes * num_pix)) return 1;
   CLR_CUDA(cudaMemcpyAsync(h_data, d_data, (size_t)nplanes * num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_pos); cudaFree(d_fac); cudaFree(d_inv); cudaFree(d_ir); cudaFree(d_data);
+  cudaFree(d_pos); cudaFree(d_fac); cudaFree(d_inv); cudaFree(d_ir); cudaFree(d_data); cudaFree(d_H);
   return 0;
 }

@@ -603,6 +603,32 @@ def test_maps_vs_reference(golden_dir, exact):
     par.free()
 
 
+def test_kappa_precomputed_hessian_equals_stencil(golden_dir):
+    """When the rays oversample the grid (nside 1024 on 1024^3: ~11 samples per cell) kappa_get_beam_properties evaluates
+    the Hessian once per cell and the rays fetch it (tidal_field_kernel). Same float expressions: the maps must equal
+    the per-sample 19-point stencil path bit for bit, and the oracle to fp32 rounding."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]))
+    par = _par(t)
+    par.grid_put(cb.GRID_NPOT, g["s1_npot"])
+    par.update_halo()
+    o.set_halo(g["s1_npot"])
+    _, pos = cb.healpix.hp_shell_pixels(64, int(t["nside_base"]))          # 49152 rays x 16 samples >> 32768 cells
+    rf = g["s6_kappa_rf"]
+    a = cb.kappa_get_beam_properties(par, pos, rf)
+    assert par.stage_ms("kappa_tidal")[1] == 0                              # (profiling off: no stage record)
+    par.set_profiling(True)
+    a2 = cb.kappa_get_beam_properties(par, pos, rf)
+    assert par.stage_ms("kappa_tidal")[1] == 1                              # the precompute pass really ran
+    par.set_profiling(False)
+    par.set_option("los_precompute", 0)
+    b = cb.kappa_get_beam_properties(par, pos, rf)
+    assert np.array_equal(a, b) and np.array_equal(a, a2)
+    ref = o.kappa(g["s1_npot"], pos, rf)
+    np.testing.assert_allclose(a, ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+    par.free()
+
+
 def test_imap_fast_painter_equals_exact(golden_dir):
     """The fp32-screened painter defers every sub-cell that is close to a pixel / shell edge to the double
     path, so hit counts must be IDENTICAL to the all-double kernel (imap.c:135-245) at any size."""

@@ -193,6 +193,8 @@ def main():
             m = fn(par, pos, rf)
             wall = allmax(time.perf_counter() - t0)
             kms, _ = par.stage_ms(name)
+            if name == "kappa_los":
+                kms += par.stage_ms("kappa_tidal")[0]       # the Hessian precompute pass belongs to the kappa stage
             par.set_profiling(False)
             assert np.isfinite(m).all() and m.std() > 0
             out[name] = {"nside": args.kappa_nside, "kernel_ms_max": allmax(kms), "api_wall_ms": wall * 1e3,
