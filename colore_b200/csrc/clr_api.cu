@@ -208,7 +208,7 @@ int clr_destroy(clr_ctx *c)
   clr_comm_destroy(c);
   for (int i = 0; i < CLR_NPOP_MAX; i++) { free_pop(c->srcs[i]); free_pop(c->imap[i]); free_pop(c->cstm[i]); }
   cudaFree(c->d_dens); cudaFree(c->d_npot); cudaFree(c->d_tables); cudaFree(c->d_tables_f); cudaFree(c->d_pk);
-  cudaFree(c->d_lens_data);
+  cudaFree(c->d_lens_data); cudaFree(c->d_los_hess);
   cudaFree(c->d_coord_f); cudaFree(c->d_coord_d); cudaFree(c->d_fft_tmp); cudaFree(c->d_fft_sync); cudaFree(c->d_hist);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lpt_pos[i]);
   cudaFree(c->d_twiddle); cudaFree(c->d_scratch); cudaFree(c->d_pkt); cudaFree(c->d_sincos);
@@ -406,7 +406,11 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   if (!strcmp(name, "async_results")) { c->async_results = value; return 0; }
   if (!strcmp(name, "srcs_compact")) { c->srcs_compact = value; return 0; }
   if (!strcmp(name, "fft_fused")) { c->fft_fused = value; return 0; }
-  if (!strcmp(name, "los_precompute")) { c->los_precompute = value; return 0; }
+  if (!strcmp(name, "los_precompute")) {
+    c->los_precompute = value;
+    if (!value) { cudaFree(c->d_los_hess); c->d_los_hess = nullptr; c->los_hess_bytes = 0; }
+    return 0;
+  }
   if (!strcmp(name, "fill_fused")) { c->fill_fused = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
   if (!strcmp(name, "fft_overlap")) { if (clr_npot_ready(c)) return 1; c->fft_overlap = value; return 0; }

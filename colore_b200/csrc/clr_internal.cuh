@@ -67,6 +67,8 @@ struct clr_ctx {
   void *d_fft_tmp = nullptr; size_t fft_tmp_bytes = 0;
   unsigned *d_fft_sync = nullptr;
   int srcs_compact = 1;                              // option "srcs_compact": 0 = dense per-cell counts + full-array expansion
+  size_t los_hess_bytes = 0;
+  void *d_los_hess = nullptr;                        // per-cell Hessian of the potential for the kappa rays (clr_maps.cu), 32 B / cell
   int los_precompute = 1;                            // option "los_precompute": 0 = kappa rays evaluate the Hessian stencil per sample
   int fft_fused = 1;                                 // option "fft_fused": 0 = three separate axis passes
   int fill_fused = 1;                                // option "fill_fused": 0 = stand-alone mode fill + z pass

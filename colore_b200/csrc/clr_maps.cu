@@ -11,6 +11,7 @@
 #include "clr_internal.cuh"
 #include "clr_stencil.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
@@ -275,30 +276,64 @@ struct LosPlan {
   // is set when no sample of any ray can wrap around the box, so the bound is safe
   int restrict_z;
   double za, zb;
+  // kappa with the precomputed Hessian: H holds the local planes [zc0, zc1) only (a chunk of the slab); the partial
+  // sums of the chunks are collected in double (accd) and rounded once at the end
+  int zc0, zc1;
+  double *accd;
 };
 
 // Hessian of the potential at every cell of the slab, computed ONCE (dev_tidal, the reference's float expressions) and
 // stored as 8 floats per cell {xx, xy, xz, yy | yz, zz, -, -}: at nside 1024 on a 1024^3 grid ~11 samples of ~11
 // different pixels land in every cell, so the kappa rays then fetch two 16-byte words per sample instead of the
 // 19-point stencil. Cells no ray reaches (r > r_reach) are skipped.
+constexpr int kTidalZ = 32;      // planes per CTA column
 __global__ void __launch_bounds__(kThreads)
-tidal_field_kernel(const ClrDev d, const float *__restrict__ npot, float4 *__restrict__ H, float r_reach)
+tidal_field_kernel(const ClrDev d, const float *__restrict__ npot, float4 *__restrict__ H, float r_reach, int zc0, int zc1)
 {
-  const long long n_cells = (long long)d.nz_here * d.n * d.n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_cells; i += (long long)gridDim.x * blockDim.x) {
-    int ix, iy, iz;
-    clr_cell(d, i, ix, iy, iz);
-    const float x = __ldg(d.cf[0] + ix), y = __ldg(d.cf[1] + iy), z = __ldg(d.cf[2] + iz + d.iz0_here);
-    if (x * x + y * y + z * z > r_reach * r_reach) continue;
-    float t[6];
-    dev_tidal(d, npot, ix, iy, iz, t);
-    H[2 * i] = make_float4(t[0], t[1], t[2], t[3]);
-    H[2 * i + 1] = make_float4(t[4], t[5], 0.f, 0.f);
+  // 2.5-D blocking: a CTA owns a 32 (x) x 8 (y) column of cells and marches kTidalZ planes up z with a three-plane
+  // register window {centre, x-, x+, y-, y+ (, the four xy diagonals of the middle plane)}: 9 loads per cell instead of
+  // 19, every potential plane is fetched from DRAM once (+ 2 / kTidalZ), x / y neighbours come from L1. Same float
+  // expressions as dev_tidal (beaming.c:85-116). The 32 B / cell of output are streaming stores.
+  const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int z0 = zc0 + blockIdx.z * kTidalZ, z1 = min(z0 + kTidalZ, zc1);       // local planes of this chunk
+  if (ix >= d.n || iy >= d.n) return;
+  const long long ngx = d.pitch, plane = ngx * d.n;
+  const int xh = ix + 1 == d.n ? 0 : ix + 1, xl = ix == 0 ? d.n - 1 : ix - 1;
+  const long long y0 = (long long)iy * ngx, yh = (long long)(iy + 1 == d.n ? 0 : iy + 1) * ngx, yl = (long long)(iy == 0 ? d.n - 1 : iy - 1) * ngx;
+  const float x = __ldg(d.cf[0] + ix), y = __ldg(d.cf[1] + iy);
+  const float rr = r_reach * r_reach, xy2 = x * x + y * y;
+  if (xy2 > rr) return;
+  // storage index of local plane lz in [-1, nz]: the slab, then the halo planes behind it ([nz] = -1, [nz+1] = nz)
+  auto pz = [&](int lz) -> const float * { return npot + (lz < 0 ? (long long)d.nz_here : lz >= d.nz_here ? (long long)d.nz_here + 1 : (long long)lz) * plane; };
+  struct P5 { float c, xm, xp, ym, yp; };
+  auto load5 = [&](const float *g) { P5 p; p.c = g[ix + y0]; p.xm = g[xl + y0]; p.xp = g[xh + y0]; p.ym = g[ix + yl]; p.yp = g[ix + yh]; return p; };
+  struct D4 { float pp, mm, pm, mp; };
+  auto load4 = [&](const float *g) { D4 q; q.pp = g[xh + yh]; q.mm = g[xl + yl]; q.pm = g[xh + yl]; q.mp = g[xl + yh]; return q; };
+  P5 lo = load5(pz(z0 - 1)), mid = load5(pz(z0));
+  D4 dmid = load4(pz(z0));
+  for (int iz = z0; iz < z1; iz++) {
+    const float *gh = pz(iz + 1);
+    const P5 hi = load5(gh);
+    const D4 dhi = iz + 1 < z1 ? load4(gh) : D4{0.f, 0.f, 0.f, 0.f};
+    const float z = __ldg(d.cf[2] + iz + d.iz0_here);
+    if (xy2 + z * z <= rr) {
+      const float c = mid.c;
+      const float t0 = (mid.xp + mid.xm - 2 * c);
+      const float t3 = (mid.yp + mid.ym - 2 * c);
+      const float t1 = (float)(0.25 * (double)(dmid.pp + dmid.mm - dmid.pm - dmid.mp));
+      const float t5 = (hi.c + lo.c - 2 * c);
+      const float t2 = (float)(0.25 * (double)(hi.xp + lo.xm - lo.xp - hi.xm));
+      const float t4 = (float)(0.25 * (double)(hi.yp + lo.ym - lo.yp - hi.ym));
+      const long long i = ix + (long long)d.n * (iy + (long long)d.n * (iz - zc0));
+      __stcs(H + 2 * i, make_float4(t0, t1, t2, t3));
+      __stcs(H + 2 * i + 1, make_float4(t4, t5, 0.f, 0.f));
+    }
+    lo = mid; mid = hi; dmid = dhi;
   }
 }
 
 template <bool KAPPA>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 los_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__restrict__ H, const double *__restrict__ pos,
            long long num_pix, LosPlan pl, float *__restrict__ data)
 {
@@ -334,33 +369,62 @@ los_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__restr
       win_lo = lo < 0 ? 0 : (lo > 2e9 ? 0x7fffffff : (int)lo);
       win_hi = hi < 0 ? -1 : (hi > 2e9 ? 0x7fffffff : (int)hi);
     }
-    for (int ipl = 0; ipl < pl.nplanes; ipl++) {
-      int irmin = max(__ldg(pl.irmin + ipl), win_lo), irmax = min(__ldg(pl.irmax + ipl), win_hi);
-      double ri = irmin + 0.5;                     // (irr + 0.5), exact in double: no int -> double conversion per sample
-      for (int irr = irmin; irr <= irmax; irr++, ri += 1.0) {
-        const double rm = ri * pl.dr;
-        int c[3];
-        bool in = true;
+    // NGP cell of sample ri = irr + 0.5 (beaming.c:148-157: (long)(x + 0.5) with one periodic wrap; x stays within
+    // (-n, 2n), so the 32-bit truncating conversion gives the same integer); false when the plane is not in this slab
+    auto ngp = [&](double ri, int c[3]) -> bool {
+      const double rm = ri * pl.dr;
 #pragma unroll
-        for (int ax = 0; ax < 3; ax++) {
-          // beaming.c:148-157: (long)(x + 0.5) with one periodic wrap; x stays within (-n, 2n), so the 32-bit
-          // truncating conversion gives the same integer
-          int v = __double2int_rz((rm * u[ax] + d.pos_obs[ax]) * idx + 0.5);
-          if (v >= d.n) v -= d.n; else if (v < 0) v += d.n;
-          c[ax] = v;
+      for (int ax = 0; ax < 3; ax++) {
+        int v = __double2int_rz((rm * u[ax] + d.pos_obs[ax]) * idx + 0.5);
+        if (v >= d.n) v -= d.n; else if (v < 0) v += d.n;
+        c[ax] = v;
+      }
+      c[2] -= d.iz0_here;
+      return c[2] >= pl.zc0 && c[2] < pl.zc1;
+    };
+    for (int ipl = 0; ipl < pl.nplanes; ipl++) {
+      const int irmin = max(__ldg(pl.irmin + ipl), win_lo), irmax = min(__ldg(pl.irmax + ipl), win_hi);
+      double ri = irmin + 0.5;                     // (irr + 0.5), exact in double: no int -> double conversion per sample
+      if (KAPPA && H) {
+        // software pipeline: the two 16-byte words of sample irr + 1 are requested before sample irr is consumed
+        float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+        bool nin = false;
+        if (irmin <= irmax) {
+          int c[3];
+          nin = ngp(ri, c);
+          if (nin) {
+            const long long cell = c[0] + (long long)d.n * (c[1] + (long long)d.n * (c[2] - pl.zc0));
+            na = __ldg(H + 2 * cell); nb = __ldg(H + 2 * cell + 1);
+          }
         }
-        c[2] -= d.iz0_here;
-        in = c[2] >= 0 && c[2] < d.nz_here;
-        if (in) {
+        for (int irr = irmin; irr <= irmax; irr++) {
+          const float4 a = na, b = nb;
+          const bool in = nin;
+          ri += 1.0;
+          if (irr < irmax) {
+            int c[3];
+            nin = ngp(ri, c);
+            if (nin) {
+              const long long cell = c[0] + (long long)d.n * (c[1] + (long long)d.n * (c[2] - pl.zc0));
+              na = __ldg(H + 2 * cell); nb = __ldg(H + 2 * cell + 1);
+            }
+          }
+          if (in) {
+            const float t[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+            double dotp = 0;
+#pragma unroll
+            for (int ax = 0; ax < 6; ax++) dotp += rot[ax] * t[ax];
+            acc1 += dotp * __ldg(pl.fac1 + irr);
+            acc2 += dotp * __ldg(pl.fac2 + irr);
+          }
+        }
+      } else {
+        for (int irr = irmin; irr <= irmax; irr++, ri += 1.0) {
+          int c[3];
+          if (!ngp(ri, c)) continue;
           if (KAPPA) {
             float t[6];
-            if (H) {
-              const long long cell = c[0] + (long long)d.n * (c[1] + (long long)d.n * c[2]);
-              const float4 a = __ldg(H + 2 * cell), b = __ldg(H + 2 * cell + 1);
-              t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y;
-            } else {
-              dev_tidal(d, npot, c[0], c[1], c[2], t);
-            }
+            dev_tidal(d, npot, c[0], c[1], c[2], t);
             double dotp = 0;
 #pragma unroll
             for (int ax = 0; ax < 6; ax++) dotp += rot[ax] * t[ax];
@@ -372,11 +436,21 @@ los_kernel(const ClrDev d, const float *__restrict__ npot, const float4 *__restr
           }
         }
       }
-      float *o = data + (long long)ipl * num_pix + ip;
       double add = KAPPA ? (acc1 - __ldg(pl.inv_r_max + ipl) * acc2) : acc1;
-      *o = (float)((double)(*o) + add);
+      if (KAPPA && pl.accd) pl.accd[(long long)ipl * num_pix + ip] += add;
+      else {
+        float *o = data + (long long)ipl * num_pix + ip;
+        *o = (float)((double)(*o) + add);
+      }
     }
   }
+}
+
+__global__ void __launch_bounds__(kThreads)
+los_round_kernel(const double *__restrict__ accd, float *__restrict__ data, long long n)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    data[i] = (float)((double)data[i] + accd[i]);
 }
 
 int grid_for(clr_ctx *c, long long items, int per_sm)
@@ -492,35 +566,74 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
   CLR_CUDA(cudaMemcpyAsync(d_ir, irmin.data(), nplanes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CLR_CUDA(cudaMemcpyAsync(d_ir + nplanes, irmax.data(), nplanes * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CLR_CUDA(cudaMemsetAsync(d_data, 0, (size_t)nplanes * num_pix * sizeof(float), c->stream));
-  LosPlan pl{d_fac, d_fac + nr, d_ir, d_ir + nplanes, d_inv, nplanes, dr, 0, 0., 0.};
-  if (c->nranks > 1) {
-    // NGP plane of a sample = (long)((r*u_z + pos_obs_z)*idx + 0.5) (beaming.c:148-157); it lies in this slab iff
-    // r*u_z in [(iz0-0.5)/idx - pos_obs_z, (iz0+nz-0.5)/idx - pos_obs_z) provided no sample wraps around the box
-    const double idx = (double)(c->p.n_grid / c->p.l_box);
-    double far = (nr * dr + fabs(c->p.pos_obs[2])) * idx + 0.5, near = (c->p.pos_obs[2] - nr * dr) * idx + 0.5;
-    if (far < c->p.n_grid && near >= 0) {
-      pl.restrict_z = 1;
-      pl.za = (c->dev.iz0_here - 0.5) / idx - c->p.pos_obs[2];
-      pl.zb = (c->dev.iz0_here + c->dev.nz_here - 0.5) / idx - c->p.pos_obs[2];
+  LosPlan pl{d_fac, d_fac + nr, d_ir, d_ir + nplanes, d_inv, nplanes, dr, 0, 0., 0., 0, c->dev.nz_here, nullptr};
+  // NGP plane of a sample = (long)((r*u_z + pos_obs_z)*idx + 0.5) (beaming.c:148-157); it lies in the local planes
+  // [p0, p1) iff r*u_z in [(iz0+p0-0.5)/idx - pos_obs_z, (iz0+p1-0.5)/idx - pos_obs_z) provided no sample wraps around the box
+  const double idx = (double)(c->p.n_grid / c->p.l_box);
+  const double far = (nr * dr + fabs(c->p.pos_obs[2])) * idx + 0.5, near = (c->p.pos_obs[2] - nr * dr) * idx + 0.5;
+  const bool no_wrap = far < c->p.n_grid && near >= 0;
+  auto window = [&](int p0, int p1) {
+    pl.restrict_z = 1;
+    pl.za = (c->dev.iz0_here + p0 - 0.5) / idx - c->p.pos_obs[2];
+    pl.zb = (c->dev.iz0_here + p1 - 0.5) / idx - c->p.pos_obs[2];
+  };
+  if (c->nranks > 1 && no_wrap) window(0, c->dev.nz_here);
+  // kappa: Hessian of every cell once (32 B / cell, tidal_field_kernel) when the rays oversample the grid; the rays then
+  // fetch two 16-byte words per sample instead of the 19-point stencil. The Hessian lives in scratch memory the context
+  // already owns (the z-pass buffer of the single-GPU transforms / the staging slab of the distributed ones: allocating
+  // tens of GB would cost more than the kernels), so the slab is processed in chunks of planes that fit; the partial
+  // sums of the chunks are collected in double and rounded once.
+  const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
+  const size_t plane_bytes = (size_t)c->dev.n * c->dev.n * 32;
+  float4 *d_H = nullptr;
+  size_t h_bytes = 0;
+  double *d_accd = nullptr;
+  if (which == 0 && c->los_precompute && (double)num_pix * nr * (c->dev.nz_here / (double)c->dev.n) > 2.0 * (double)n_cells) {
+    if (c->d_fft_tmp && c->fft_tmp_bytes >= plane_bytes) { d_H = reinterpret_cast<float4 *>(c->d_fft_tmp); h_bytes = c->fft_tmp_bytes; }
+    else if (c->d_stage && c->stage_floats * sizeof(float) >= plane_bytes) { d_H = reinterpret_cast<float4 *>(c->d_stage); h_bytes = c->stage_floats * sizeof(float); }
+    else {
+      // no scratch around (fields uploaded by the caller): own buffer of at most 1/8 of the slab, kept with the context
+      const size_t want = plane_bytes * (size_t)std::max(1, std::min(c->dev.nz_here, std::max(8, c->dev.nz_here / 8)));
+      if (c->d_los_hess && c->los_hess_bytes < want) { cudaFree(c->d_los_hess); c->d_los_hess = nullptr; }
+      if (!c->d_los_hess) {
+        if (cudaMalloc(&c->d_los_hess, want) == cudaSuccess) c->los_hess_bytes = want;
+        else { cudaGetLastError(); c->d_los_hess = nullptr; c->los_hess_bytes = 0; }
+      }
+      d_H = reinterpret_cast<float4 *>(c->d_los_hess); h_bytes = c->los_hess_bytes;
     }
   }
-  // kappa: Hessian of every cell once (32 B / cell) when the rays oversample the grid and the memory is there;
-  // otherwise the rays evaluate the 19-point stencil themselves
-  float4 *d_H = nullptr;
-  const long long n_cells = (long long)c->dev.nz_here * c->dev.n * c->dev.n;
-  if (which == 0 && c->los_precompute && (double)num_pix * nr * (c->dev.nz_here / (double)c->dev.n) > 2.0 * (double)n_cells) {
-    if (cudaMalloc(&d_H, (size_t)n_cells * 32) != cudaSuccess) { cudaGetLastError(); d_H = nullptr; }
+  const int ppc = d_H ? (int)std::min<size_t>((size_t)c->dev.nz_here, h_bytes / plane_bytes) : 0;
+  const int n_chunks = d_H ? (c->dev.nz_here + ppc - 1) / ppc : 0;
+  if (n_chunks > 1 && !no_wrap) d_H = nullptr;                       // the chunk windows need rays that do not wrap
+  if (d_H && n_chunks > 1) {
+    if (cudaMalloc(&d_accd, (size_t)nplanes * num_pix * sizeof(double)) != cudaSuccess) { cudaGetLastError(); d_H = nullptr; }
+    else CLR_CUDA(cudaMemsetAsync(d_accd, 0, (size_t)nplanes * num_pix * sizeof(double), c->stream));
   }
   if (d_H) {
-    StageScope sc(c, "kappa_tidal", 1);
     const float dxf = c->p.l_box / c->p.n_grid;
-    tidal_field_kernel<<<grid_for(c, n_cells, 16), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_H, (float)(nr * dr) + 2.f * dxf);
-    CLR_CUDA(cudaGetLastError());
-  }
-  {
+    pl.accd = d_accd;
+    for (int ch = 0; ch < n_chunks; ch++) {
+      pl.zc0 = ch * ppc; pl.zc1 = std::min(c->dev.nz_here, pl.zc0 + ppc);
+      if (n_chunks > 1) window(pl.zc0, pl.zc1);
+      {
+        StageScope sc(c, "kappa_tidal", 1);
+        dim3 tg((c->dev.n + 31) / 32, (c->dev.n + 7) / 8, (pl.zc1 - pl.zc0 + kTidalZ - 1) / kTidalZ);
+        tidal_field_kernel<<<tg, kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_H, (float)(nr * dr) + 2.f * dxf, pl.zc0, pl.zc1);
+        CLR_CUDA(cudaGetLastError());
+      }
+      StageScope sc(c, "kappa_los", 1);
+      los_kernel<true><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_H, d_pos, num_pix, pl, d_data);
+      CLR_CUDA(cudaGetLastError());
+    }
+    if (d_accd) {
+      StageScope sc(c, "kappa_los", 1);
+      los_round_kernel<<<grid_for(c, (long long)nplanes * num_pix, 8), kThreads, 0, c->stream>>>(d_accd, d_data, (long long)nplanes * num_pix);
+      CLR_CUDA(cudaGetLastError());
+    }
+  } else {
     StageScope sc(c, which == 0 ? "kappa_los" : "isw_los", 1);
     if (which == 0)
-      los_kernel<true><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, d_H, d_pos, num_pix, pl, d_data);
+      los_kernel<true><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, nullptr, d_pos, num_pix, pl, d_data);
     else
       los_kernel<false><<<grid_for(c, num_pix, 8), kThreads, 0, c->stream>>>(c->dev, c->d_npot, nullptr, d_pos, num_pix, pl, d_data);
     CLR_CUDA(cudaGetLastError());
@@ -530,6 +643,6 @@ int clr_maps_los(clr_ctx *c, int which, long long num_pix, const double *h_pos, 
   if (clr_comm_allreduce_f32(c, d_data, (size_t)nplanes * num_pix)) return 1;
   CLR_CUDA(cudaMemcpyAsync(h_data, d_data, (size_t)nplanes * num_pix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CLR_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_pos); cudaFree(d_fac); cudaFree(d_inv); cudaFree(d_ir); cudaFree(d_data); cudaFree(d_H);
+  cudaFree(d_pos); cudaFree(d_fac); cudaFree(d_inv); cudaFree(d_ir); cudaFree(d_data); cudaFree(d_accd);
   return 0;
 }

@@ -63,9 +63,9 @@ def main():
             ms, nl = par.stage_ms(name)
             tid, _ = par.stage_ms("kappa_tidal") if name == "kappa_los" else (0.0, 0)     # Hessian precompute pass
             par.set_profiling(False)
-            ms = (ms + tid) / max(nl, 1)
+            ms = (ms + tid) / args.steps                  # per call (kappa runs one pair of launches per chunk of planes)
             out[name] = {"nside": args.nside, "npix": npix, "planes": len(rf), "samples": samples, "kernel_ms": ms,
-                         "of_which_hessian_precompute_ms": tid / max(nl, 1),
+                         "of_which_hessian_precompute_ms": tid / args.steps, "launches_per_call": nl / args.steps,
                          "Gsamples_per_s": samples / ms / 1e6, "api_wall_ms": wall * 1e3,
                          "map_rms": float(m.astype(np.float64).std())}
 
