@@ -375,6 +375,8 @@ def main():
                          "of the GPU arm defaults to 512 (a bounded sample)")
     ap.add_argument("--no-north-star", action="store_true", help="skip the 2048^3 run that --gpus 8 appends")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="clr_set_option before the run (kernel-variant experiments, e.g. --opt fill_w=4)")
     ap.add_argument("--writer", action="store_true",
                     help="also time clr_write_catalog (ASCII + FITS, all host threads) on the last catalogue; off by default "
                          "because it writes ~2.4 GB into the temporary directory")
@@ -423,6 +425,8 @@ def main():
     cb.dist.init_comm(par, rank, world)
     nz_tab, bz_tab = tabs["srcs_nz_0"], tabs["srcs_bz_0"]
     par.set_srcs(0, nz_tab, bz_tab)
+    for o in args.opt:
+        par.set_option(o.split("=")[0], int(o.split("=")[1]))
 
     # ---- device-resident timing (value) ------------------------------------------------------
     # nvidia-smi takes ~100 ms to deliver its first line: start it before the warm-up and count only the

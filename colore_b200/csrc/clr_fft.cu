@@ -307,7 +307,10 @@ struct LineAddr {
   // tile-major staging layout of the distributed c2r (see c2r_3d_dist): [source][z-pass tile][z_local][T]
   int tiled = 0, tile_rows = 0;
   // kx-tile layout of the single-GPU c2r (see yx_fused_kernel): the z pass stores point z of line (ky, kx) at
-  // [z / G][kx / 8][ky][z % G][kx % 8], so that the G*8 lines a y tile needs are ONE contiguous block of n*G*64 bytes
+  // [kx / 8][z / G][ky][z % G][kx % 8], so that the G*8 lines a y tile needs are ONE contiguous block of n*G*64 bytes.
+  // kx / 8 is the SLOWEST index: the n points of a z line then sit n*64 bytes apart (16 / 32 planes per 2 MB page at
+  // n = 2048 / 1024) instead of one full plane apart (one page per point: the translation misses of that layout
+  // cost the z pass half its bandwidth at 2048^3), and the blocks of one kx tile are consecutive for consecutive z
   int tile8 = 0, t8_g_log2 = 0, t8_nkt = 0, t8_n = 0;
   __device__ __forceinline__ long long off(int e) const
   { return (long long)(e >> lo_bits) * hi_stride + (long long)(e & ((1 << lo_bits) - 1)) * lo_stride; }
@@ -403,8 +406,8 @@ struct StridedTile {
       const int inner = (int)(tile - (tile / tiles_per_outer) * tiles_per_outer) * T + l;
       const int b = inner >> 3, ky = b / aout.t8_nkt, kxt = b - ky * aout.t8_nkt;
       const int gl = aout.t8_g_log2;
-      float2 *bo = gout + (((long long)kxt * aout.t8_n + ky) << (gl + 3)) + (inner & 7);
-      const long long zstep = ((long long)aout.t8_nkt * aout.t8_n) << (gl + 3);      // one group of G planes
+      float2 *bo = gout + ((((long long)kxt * (M >> gl)) * aout.t8_n + ky) << (gl + 3)) + (inner & 7);
+      const long long zstep = (long long)aout.t8_n << (gl + 3);                       // one group of G planes
 #pragma unroll
       for (int i = 0; i < P::E; i++) {
         const int e = j + i * P::TPL;
@@ -614,7 +617,7 @@ fft_r2c_x_kernel(float2 *__restrict__ g, const float2 *__restrict__ W, int wn, l
 // output and one write of the real field (8 B/cell) instead of two reads and two writes (measured with copy kernels
 // of the same shape, tools/membench.cu: 1.76 ms against 3.50 ms for a 1024^3 field).
 //
-// Input `src`: z-pass output in the kx-tile layout [z / G][kx / 8][ky][z % G][kx % 8] (LineAddr::tile8), so a y tile
+// Input `src`: z-pass output in the kx-tile layout [kx / 8][z / G][ky][z % G][kx % 8] (LineAddr::tile8), so a y tile
 // (G*8 lines x n points) is one contiguous block of n*G*64 bytes, fetched by the TMA engine with bulk copies
 // (cp.async.bulk ... mbarrier::complete_tx) straight into the padded Stockham layout. Output `dst`: the real field in
 // the usual layout [z][y][pitch].
@@ -703,7 +706,7 @@ yx_fused_kernel(const YxArgs a)
     const int st = (int)(t / per), r = (int)(t - (unsigned)st * per);
     if (r < a.nkt) {
       if (st >= np) return true;
-      const float2 *blk = a.src + ((long long)st * a.nkt + r) * ((long long)N * C::TY);
+      const float2 *blk = a.src + ((long long)r * np + st) * ((long long)N * C::TY);
       if (tid == 0) { fence_proxy_async(); mbar_expect_tx(bar, (uint32_t)N * C::TY * 8u); }
       __syncwarp();
       for (unsigned c = tid; c < YCHUNKS; c += 32)
@@ -812,16 +815,19 @@ yx_fused_kernel(const YxArgs a)
         const float2 d = cmul(make_float2(x0.x - x1.x, x0.y + x1.y), wx[k]);
         v[i] = make_float2(e.x - d.y, e.y + d.x);
       }
-      __syncthreads();                                       // everybody has its inputs: s is the exchange buffer now
+      // a row belongs to the PX::TPL <= 32 threads of ONE warp (tid = lx * TPL + jx) and its exchange stays inside the
+      // row's own stretch of s: warp barriers are enough until the buffer is handed back to the bulk loads
+      static_assert(PX::TPL <= 32 && 32 % PX::TPL == 0, "x rows must not straddle warps");
+      __syncwarp();                                          // the row's inputs are in registers: s is the exchange buffer now
       stage_math<M, +1, 0>(v, tw_x, jx);
       stage_store<M, false, C::XR, 0>(v, s, jx, lx);
-      __syncthreads();
+      __syncwarp();
       stage_load<M, false, C::XR>(v, s, jx, lx);
       if constexpr (PX::NST >= 3) {
         stage_math<M, +1, 1>(v, tw_x, jx);
-        __syncthreads();
+        __syncwarp();
         stage_store<M, false, C::XR, 1>(v, s, jx, lx);
-        __syncthreads();
+        __syncwarp();
         stage_load<M, false, C::XR>(v, s, jx, lx);
       }
       __syncthreads();
@@ -862,19 +868,22 @@ yx_fused_kernel(const YxArgs a)
 // arithmetic of clr_fill.cuh), two thread groups transform one buffer each along z, and only the z-pass OUTPUT goes
 // to HBM, in the kx-tile layout the fused y+x pass reads. Saves the 8 B/cell write of the stand-alone fill and the
 // 8 B/cell read of two z passes; the kernel is bound by instruction issue (Philox + transcendentals + butterflies).
-template <int N> struct FzCfg {
-  using P = FftPlan<N>;
-  static constexpr int W = 8;                                   // lines (kx) per tile and field
+template <int N, int WW> struct FzCfg {
+  static constexpr int NP = N == 2048 ? (N | kWide) : N;        // 32 points per thread at every size
+  using P = FftPlan<NP>;
+  static constexpr int W = WW;                                  // lines (kx) per tile and field: 8, or 4 (half a kx tile)
+  static constexpr int H = 8 / W;                               // tiles per 64-byte run of the output layout
   static constexpr int GT = W * P::TPL;                         // threads of one field group
   static constexpr int THREADS = 2 * GT;
   static constexpr int BUF = P::LSTRIDE * W;                    // float2 per field
   static constexpr size_t SMEM = ((size_t)2 * BUF + P::NTW) * sizeof(float2);
-  static constexpr int MIN_CTAS = THREADS >= 512 ? 1 : (512 / THREADS > 4 ? 4 : 512 / THREADS);
+  static constexpr int MIN_CTAS = (THREADS >= 512 || SMEM > 110 * 1024) ? 1 : (512 / THREADS > 4 ? 4 : 512 / THREADS);
   static_assert(P::NST >= 2, "fused fill + z pass needs n >= 64");
+  static_assert(W == 4 || W == 8, "tile width");
 };
 
 struct FzArgs {
-  float2 *out_d, *out_p;            // z-pass output of delta / phi, kx-tile layout [z][kx/8][ky_local][kx%8]
+  float2 *out_d, *out_p;            // z-pass output of delta / phi, kx-tile layout [kx/8][z][ky_local][kx%8]
   const float2 *W; int wn;
   const float2 *pkt, *sct;
   uint32_t seed;
@@ -882,13 +891,13 @@ struct FzArgs {
   FillFastK k;
 };
 
-template <int N>
-__global__ void __launch_bounds__(FzCfg<N>::THREADS, FzCfg<N>::MIN_CTAS)
+template <int N, int WW>
+__global__ void __launch_bounds__(FzCfg<N, WW>::THREADS, FzCfg<N, WW>::MIN_CTAS)
 fill_z_kernel(const __grid_constant__ FzArgs a)
 {
-  using C = FzCfg<N>;
+  using C = FzCfg<N, WW>;
   using P = typename C::P;
-  constexpr int W = C::W;
+  constexpr int W = C::W, H = C::H, NP = C::NP;
   extern __shared__ float2 smem[];
   float2 *tw = smem + 2 * C::BUF;
   const int tid = threadIdx.x;
@@ -896,13 +905,16 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
   const int j = tg / W, l = tg % W;
   float2 *sg = smem + grp * C::BUF;
   float2 *outg = grp ? a.out_p : a.out_d;
-  load_twiddles<N, +1>(tw, a.W, a.wn);
+  load_twiddles<NP, +1>(tw, a.W, a.wn);
   const int npair_row = (a.nc + 1) / 2;
-  const long long n_tiles = (long long)a.nkt * a.nyl;
-  const long long zstep = (long long)a.nkt * a.nyl * 8;          // one z plane of the kx-tile layout
+  const long long n_tiles = (long long)a.nkt * a.nyl * H;
+  const long long zstep = (long long)a.nyl * 8;                  // one z plane inside a kx tile of the kx-tile layout
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // consecutive tiles = consecutive ky of the same kx tile: their 64-byte output runs are neighbours in memory
-    const int kxt = (int)(tile / a.nyl), kyl = (int)(tile - (long long)kxt * a.nyl);
+    // consecutive tiles = the H pieces of one 64-byte output run, then consecutive ky of the same kx tile: pieces and
+    // neighbouring runs are written at about the same time by neighbouring CTAs and meet in L2
+    const long long run = tile / H;
+    const int half = (int)(tile - run * H);
+    const int kxt = (int)(run / a.nyl), kyl = (int)(run - (long long)kxt * a.nyl);
     const int jj = a.ky0 + kyl;
     const int mj = (2 * jj <= N ? jj : N - jj);
     // ---- fill: W/2 mode pairs per kz
@@ -911,7 +923,7 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
       const int kz = q / (W / 2), pr = q - kz * (W / 2);
       const int mi = (2 * kz <= N ? kz : N - kz);
       const int m_row = mj * mj + mi * mi;
-      const int kk0 = kxt * 8 + 2 * pr;
+      const int kk0 = kxt * 8 + half * W + 2 * pr;
       const unsigned long long gidx = (unsigned long long)(kk0 >> 1) + (unsigned long long)npair_row * ((unsigned long long)jj + (unsigned long long)N * kz);
       float2 dk2[2], pk2[2];
       uint32_t w[4];
@@ -921,29 +933,29 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
         const int kk = kk0 + h, m = kk * kk + m_row;            // beyond the Nyquist column: padding lines, zero
         clr_fill_mode(a.k, a.pkt, a.sct, m, kk < a.nc && m > 0, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
       }
-      const int si = sidx<N, true, W>(kz, 2 * pr);
+      const int si = sidx<NP, true, W>(kz, 2 * pr);
       *reinterpret_cast<float4 *>(smem + si) = make_float4(dk2[0].x, dk2[0].y, dk2[1].x, dk2[1].y);
       *reinterpret_cast<float4 *>(smem + C::BUF + si) = make_float4(pk2[0].x, pk2[0].y, pk2[1].x, pk2[1].y);
     }
     __syncthreads();
     // ---- transform along z: group 0 = delta_k, group 1 = phi_k
     float2 v[P::E];
-    stage_load<N, true, W>(v, sg, j, l);
-    stage_math<N, +1, 0>(v, tw, j);
+    stage_load<NP, true, W>(v, sg, j, l);
+    stage_math<NP, +1, 0>(v, tw, j);
     __syncthreads();
-    stage_store<N, true, W, 0>(v, sg, j, l);
+    stage_store<NP, true, W, 0>(v, sg, j, l);
     __syncthreads();
-    stage_load<N, true, W>(v, sg, j, l);
+    stage_load<NP, true, W>(v, sg, j, l);
     if constexpr (P::NST >= 3) {
-      stage_math<N, +1, 1>(v, tw, j);
+      stage_math<NP, +1, 1>(v, tw, j);
       __syncthreads();
-      stage_store<N, true, W, 1>(v, sg, j, l);
+      stage_store<NP, true, W, 1>(v, sg, j, l);
       __syncthreads();
-      stage_load<N, true, W>(v, sg, j, l);
+      stage_load<NP, true, W>(v, sg, j, l);
     }
     __syncthreads();                                             // buffers free: the next fill may overwrite them
-    stage_math<N, +1, P::NST - 1>(v, tw, j);
-    float2 *o = outg + ((long long)kxt * a.nyl + kyl) * 8 + l;
+    stage_math<NP, +1, P::NST - 1>(v, tw, j);
+    float2 *o = outg + ((long long)kxt * N * a.nyl + kyl) * 8 + half * W + l;
 #pragma unroll
     for (int i = 0; i < P::E; i++) o[(long long)(j + i * P::TPL) * zstep] = v[i];
   }
@@ -1232,10 +1244,10 @@ int r2c_3d(clr_ctx *c, float2 *g)
   return run_strided<N, -1, Cfg<N>::T_Z>(c, g, 1, 0, (long long)N * nc, (int)(N * nc));
 }
 
-template <int N>
+template <int N, int W>
 int run_fill_c2r(clr_ctx *c, uint32_t seed, float norm, double *mom)
 {
-  using C = FzCfg<N>;
+  using C = FzCfg<N, W>;
   if (ensure_fft_tmp(c)) return 1;
   FzArgs a;
   if (clr_fill_fast_setup(c, &a.k)) return 1;
@@ -1247,9 +1259,9 @@ int run_fill_c2r(clr_ctx *c, uint32_t seed, float norm, double *mom)
   a.W = c->d_twiddle; a.wn = c->dev.n; a.pkt = c->d_pkt; a.sct = c->d_sincos; a.seed = seed;
   a.n = N; a.nc = c->dev.nc; a.nyl = c->dev.nyl; a.ky0 = c->dev.ky0; a.nkt = c->dev.ncp / 8;
   { StageScope sc(c, "fill_fft_z", 1);
-    auto k = fill_z_kernel<N>;
+    auto k = fill_z_kernel<N, W>;
     int grid;
-    if (launch_cfg(c, k, C::THREADS, C::SMEM, (long long)a.nkt * a.nyl, &grid)) return 1;
+    if (launch_cfg(c, k, C::THREADS, C::SMEM, (long long)a.nkt * a.nyl * C::H, &grid)) return 1;
     k<<<grid, C::THREADS, C::SMEM, c->stream>>>(a);
     CLR_CUDA(cudaGetLastError()); }
   StageScope sc(c, "fft_yx", 2);
@@ -1262,17 +1274,22 @@ int run_fill_c2r(clr_ctx *c, uint32_t seed, float norm, double *mom)
 
 // create_grids_fourier + both fftw_wrap_c2r of create_cartesian_fields (fourier.c:285-359, 81-102, 394-397) with the
 // mode fill fused into the z pass. *ran = false when this path does not apply (multi-GPU slab, exact_math, sizes outside
-// [128,1024]): the caller then runs the stand-alone fill and two transforms.
+// [128,2048]): the caller then runs the stand-alone fill and two transforms.
 int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, bool *ran)
 {
   *ran = false;
   if (c->nranks > 1 || !c->fft_fused || !c->fill_fused || !clr_fill_fast_ok(c)) return 0;
   *ran = true;
   switch (c->dev.n) {
-    case 128: return run_fill_c2r<128>(c, seed, (float)norm, d_moments);
-    case 256: return run_fill_c2r<256>(c, seed, (float)norm, d_moments);
-    case 512: return run_fill_c2r<512>(c, seed, (float)norm, d_moments);
-    case 1024: return run_fill_c2r<1024>(c, seed, (float)norm, d_moments);
+    case 128: return run_fill_c2r<128, 8>(c, seed, (float)norm, d_moments);
+    case 256: return c->fill_w == 4 ? run_fill_c2r<256, 4>(c, seed, (float)norm, d_moments)       // (oracle-sized test of W = 4)
+                                    : run_fill_c2r<256, 8>(c, seed, (float)norm, d_moments);
+    case 512: return run_fill_c2r<512, 8>(c, seed, (float)norm, d_moments);
+    // option "fill_w": 4 = half-width tiles (two CTAs per SM: the fill of one overlaps the butterflies / stores of the other)
+    case 1024: return c->fill_w == 4 ? run_fill_c2r<1024, 4>(c, seed, (float)norm, d_moments)
+                                     : run_fill_c2r<1024, 8>(c, seed, (float)norm, d_moments);
+    // 2048: two fields x 8 lines x 2048 points do not fit shared memory, 4 lines do
+    case 2048: return run_fill_c2r<2048, 4>(c, seed, (float)norm, d_moments);
     default: *ran = false; return 0;
   }
 }

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--imap-nside", type=int, default=0)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--skip-roundtrip", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="clr_set_option before the run")
     args = ap.parse_args()
     import ctypes as C
 
@@ -77,6 +78,8 @@ def main():
     par = cb.ParamCoLoRe(t, n, dens_type=args.dens_type, seed=cfg.seed, device=local, nz_here=nzl, iz0_here=iz0)
     cb.dist.init_comm(par, rank, world)
     par.set_srcs(0, t["srcs_nz_0"], t["srcs_bz_0"])
+    for o in args.opt:
+        par.set_option(o.split("=")[0], int(o.split("=")[1]))
     out = {"n_grid": n, "n_gpus": world, "dens_type": args.dens_type,
            "transpose": cb.dist.transpose_mode(par) if world > 1 else "none"}
     pitch = par.grid_pitch()
@@ -154,7 +157,7 @@ def main():
         step(100 + s)
     ms = allmax(par.timer_stop_ms()) / args.steps
     stages = {}
-    for nm in ("fill_modes", "fft_z", "fft_a2a", "fft_y", "fft_x", "halo", "lognormal", "lpt_kspace", "lpt_upsilon",
+    for nm in ("fill_modes", "fill_fft_z", "fft_z", "fft_a2a", "fft_y", "fft_x", "fft_yx", "halo", "lognormal", "lpt_kspace", "lpt_upsilon",
                "lpt_positions", "lpt_deposit", "lpt_route", "lpt_exchange", "lpt_finalize", "norm_hist", "srcs_poisson",
                "srcs_scan", "srcs_expand", "srcs_place", "srcs_local"):
         m, nl = par.stage_ms(nm)
@@ -167,10 +170,16 @@ def main():
     out["stages"] = stages
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    fft_ms = sum(stages[k]["ms_per_step"] for k in ("fft_z", "fft_y", "fft_x") if k in stages)
-    nfft = stages["fft_x"]["launches_per_step"]
-    out["fft_hbm_gbs_per_gpu"] = nfft * 24.0 * cells_rank / (fft_ms * 1e-3) / 1e9
-    out["fft_frac_of_hbm_peak"] = out["fft_hbm_gbs_per_gpu"] / peak
+    fft_ms = sum(stages[k]["ms_per_step"] for k in ("fft_z", "fft_y", "fft_x", "fft_yx") if k in stages)
+    nfft = stages["fft_x" if "fft_x" in stages else "fft_yx"]["launches_per_step"] if fft_ms else 0
+    if fft_ms and "fill_fft_z" not in stages:      # 3-D c2r as kernels of its own: 24 B/cell per transform
+        out["fft_hbm_gbs_per_gpu"] = nfft * 24.0 * cells_rank / (fft_ms * 1e-3) / 1e9
+        out["fft_frac_of_hbm_peak"] = out["fft_hbm_gbs_per_gpu"] / peak
+    # mode fill + both transforms (8 + 2 x 24 B/cell), whichever kernels carried them (the fill is fused into the z pass
+    # on one GPU up to n_grid = 1024)
+    ff_ms = fft_ms + sum(stages[k]["ms_per_step"] for k in ("fill_modes", "fill_fft_z") if k in stages)
+    out["fill_plus_fft_hbm_gbs_per_gpu"] = 56.0 * cells_rank / (ff_ms * 1e-3) / 1e9
+    out["fill_plus_fft_frac_of_hbm_peak"] = out["fill_plus_fft_hbm_gbs_per_gpu"] / peak
     if "lognormal" in stages:
         out["lognormal_hbm_gbs_per_gpu"] = 8.0 * cells_rank / (stages["lognormal"]["ms_per_step"] * 1e-3) / 1e9
         out["lognormal_frac_of_hbm_peak"] = out["lognormal_hbm_gbs_per_gpu"] / peak
