@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line summary of an ncu report: instructions executed and stall samples.
 
-usage: ncu_lines.py report.ncu-rep kernel_regex [top_n]
+usage: ncu_lines.py report.ncu-rep kernel_regex [top_n [samples]]   (samples: sort by stall samples)
 Runs `ncu -i report --page source --csv --print-source cuda,sass -k regex:<kernel_regex>` and
 aggregates the rows that carry a CUDA line number.
 """
@@ -29,7 +29,8 @@ def main():
     tot_i = sum(l[0] for l in lines) or 1
     tot_s = sum(l[1] for l in lines) or 1
     print(f"total warp-inst {tot_i}  samples {tot_s}")
-    for inst, smp, f, ln, src in sorted(lines, reverse=True)[:top]:
+    by_samples = len(sys.argv) > 4 and sys.argv[4] == "samples"
+    for inst, smp, f, ln, src in sorted(lines, key=lambda l: (l[1], l[0]) if by_samples else l, reverse=True)[:top]:
         print(f"{100*inst/tot_i:5.1f}%i {100*smp/tot_s:5.1f}%s  {f}:{ln}  {src}")
 
 if __name__ == "__main__":
