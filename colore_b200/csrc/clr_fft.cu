@@ -962,6 +962,84 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Several GPUs: mode fill fused into the z pass WITH the slab transpose (create_grids_fourier, fourier.c:285-359, + the
+// first axis of fftw_wrap_c2r, fourier.c:81-102, + FFTW-MPI's transpose). One field per launch: a CTA generates the
+// T lines x n kz modes of its tile (the same Philox blocks and arithmetic as the stand-alone fill, clr_fill.cuh),
+// transforms them along z and stores plane z straight into the staging buffer of rank z / nz_local over NVLink
+// (StridedTile::store_peer, natural or tile-major staging). The pass is bound by NVLink, so the fill arithmetic hides
+// under the transfer: the stand-alone fill (8 B/cell written) and the 8 B/cell read of the z pass disappear.
+// Tiles = T consecutive lines of the flattened (ky_local, kx) index with the row pitch ncp, like fft_strided_kernel.
+struct FpArgs {
+  LineAddr aout; int tiles_per_outer, n_inner;
+  const float2 *W; int wn;
+  const float2 *pkt, *sct;
+  uint32_t seed;
+  int nc, ncp, ky0;                 // n/2+1, complex row pitch, first ky of this rank's slab
+  FillFastK k;
+};
+
+template <int N, int T, int FIELD>
+__global__ void __launch_bounds__(T * FftPlan<N>::TPL, (T * FftPlan<N>::TPL * FftPlan<N>::E <= 8192) ? 2 : 1)
+fill_peer_kernel(const __grid_constant__ FpArgs a, long long n_tiles, const __grid_constant__ PeerPtrs peers)
+{
+  using P = FftPlan<N>;
+  constexpr int THREADS = T * P::TPL, HP = T / 2;                // mode pairs per kz of a tile
+  static_assert(THREADS % HP == 0 && T % 2 == 0, "a thread keeps its pair of lines for the whole tile");
+  extern __shared__ float2 smem[];
+  float2 *s = smem;
+  float2 *tw = smem + P::LSTRIDE * T;
+  const int tid = threadIdx.x;
+  StridedTile<N, +1, T> tl{nullptr, nullptr, a.aout, a.aout, a.tiles_per_outer, a.n_inner, tid / T, tid % T};
+  const int j = tl.j, l = tl.l;
+  load_twiddles<N, +1>(tw, a.W, a.wn);
+  const int npair_row = (a.nc + 1) / 2;
+  const int pr = tid % HP, kz0 = tid / HP;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- fill: this thread's pair of lines (flattened index inner, inner + 1: same ky, kx even)
+    const long long inner = tile * T + 2 * pr;
+    const int kyl = (int)(inner / a.ncp), kk0 = (int)(inner - (long long)kyl * a.ncp);
+    const int jj = a.ky0 + kyl;
+    const int mj = (2 * jj <= N ? jj : N - jj);
+    const bool row_ok = inner < a.n_inner;
+#pragma unroll 2
+    for (int kz = kz0; kz < N; kz += THREADS / HP) {
+      const int mi = (2 * kz <= N ? kz : N - kz);
+      const int m_row = mj * mj + mi * mi;
+      const unsigned long long gidx = (unsigned long long)(kk0 >> 1) + (unsigned long long)npair_row * ((unsigned long long)jj + (unsigned long long)N * kz);
+      float2 dk2[2], pk2[2];
+      uint32_t w[4];
+      clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, a.seed, 0u, w);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int kk = kk0 + h, m = kk * kk + m_row;            // beyond the Nyquist column: padding, zero
+        clr_fill_mode(a.k, a.pkt, a.sct, m, row_ok && kk < a.nc && m > 0, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
+      }
+      const float2 v0 = FIELD ? pk2[0] : dk2[0], v1 = FIELD ? pk2[1] : dk2[1];
+      *reinterpret_cast<float4 *>(s + sidx<N, true, T>(kz, 2 * pr)) = make_float4(v0.x, v0.y, v1.x, v1.y);
+    }
+    __syncthreads();
+    // ---- transform along z, peer stores
+    float2 v[P::E];
+    stage_load<N, true, T>(v, s, j, l);
+    stage_math<N, +1, 0>(v, tw, j);
+    __syncthreads();
+    stage_store<N, true, T, 0>(v, s, j, l);
+    __syncthreads();
+    stage_load<N, true, T>(v, s, j, l);
+    if constexpr (P::NST >= 3) {
+      stage_math<N, +1, 1>(v, tw, j);
+      __syncthreads();
+      stage_store<N, true, T, 1>(v, s, j, l);
+      __syncthreads();
+      stage_load<N, true, T>(v, s, j, l);
+    }
+    __syncthreads();                                             // buffer free: the next fill may overwrite it
+    stage_math<N, +1, P::NST - 1>(v, tw, j);
+    tl.store_peer(tile, v, peers);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host-side dispatch
 template <int M> struct Cfg {   // lines per CTA tile, per transform length
   static constexpr int TPL = FftPlan<M>::TPL;
@@ -1042,12 +1120,43 @@ int ilog2_host(int v) { int b = 0; while ((1 << b) < v) b++; return b; }
 template <int M, bool MOM> int run_c2r_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c, float norm, double *mom);
 template <int M> int run_r2c_x(clr_ctx *c, float2 *g, long long n_rows, int pitch_c);
 
+// z pass of the distributed c2r with the mode fill fused in (fill_peer_kernel): field 0 = delta_k, 1 = phi_k
+struct FillSpec { uint32_t seed; int field; };
+
 template <int N>
-int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
+int run_fill_peer(clr_ctx *c, const FillSpec &fs, LineAddr aout, int n_inner, const PeerPtrs &pp)
+{
+  constexpr int T = Cfg<N>::T_STRIDED;
+  using P = FftPlan<N>;
+  constexpr int threads = T * P::TPL;
+  const size_t smem = ((size_t)P::LSTRIDE * T + P::NTW) * sizeof(float2);
+  FpArgs a;
+  if (clr_fill_fast_setup(c, &a.k)) return 1;
+  a.aout = aout; a.n_inner = n_inner; a.tiles_per_outer = (n_inner + T - 1) / T;
+  a.W = c->d_twiddle; a.wn = c->dev.n; a.pkt = c->d_pkt; a.sct = c->d_sincos; a.seed = fs.seed;
+  a.nc = c->dev.nc; a.ncp = c->dev.ncp; a.ky0 = c->dev.ky0;
+  const long long n_tiles = a.tiles_per_outer;
+  int grid;
+  if (fs.field) {
+    auto k = fill_peer_kernel<N, T, 1>;
+    if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
+    k<<<grid, threads, smem, c->stream>>>(a, n_tiles, pp);
+  } else {
+    auto k = fill_peer_kernel<N, T, 0>;
+    if (launch_cfg(c, k, threads, smem, n_tiles, &grid)) return 1;
+    k<<<grid, threads, smem, c->stream>>>(a, n_tiles, pp);
+  }
+  CLR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom, const FillSpec *fs = nullptr)
 {
   const long long nc = c->dev.ncp;     // complex PITCH of a row (>= N/2+1, multiple of 8)
   const int P = c->nranks, nzl = N / P, nyl = N / P;
   float2 *stage = reinterpret_cast<float2 *>(c->d_stage);
+  CLR_CHECK(!fs || (c->p2p && c->p2p_enabled), "fused fill + transpose needs the peer-memory transpose");
   // tile-major staging pays when the remote runs of the natural layout are short (T = 8 lines = 64 bytes at
   // n_grid = 2048: 346 -> 496 GB/s per direction on 8 GPUs, step 46.2 -> 42.5 ms) and most of the output leaves the
   // GPU; with 128-byte runs (n_grid = 1024) or 2 GPUs the gather it forces on the y pass costs more than it saves
@@ -1064,7 +1173,8 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
       LineAddr ain{0, 0, (long long)nyl * nc, 31};
       LineAddr aout{0, 0, (long long)nyl * nc, ilog2_host(nzl)};
       aout.tiled = 1;
-      if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
+      if (fs ? run_fill_peer<N>(c, *fs, aout, (int)(nyl * nc), pp)
+             : run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
       if (clr_comm_barrier(c)) return 1;
       if (c->ev_after_z) CLR_CUDA(cudaEventRecord(c->ev_after_z, c->stream));
       c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1); }
@@ -1083,7 +1193,8 @@ int c2r_3d_dist(clr_ctx *c, float2 *g, float norm, double *mom)
     PeerPtrs pp = peer_blocks(c, (size_t)nzl * nyl * nc);
     LineAddr ain{0, 0, (long long)nyl * nc, 31};
     LineAddr aout{0, 0, (long long)nyl * nc, ilog2_host(nzl)};
-    if (run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
+    if (fs ? run_fill_peer<N>(c, *fs, aout, (int)(nyl * nc), pp)
+           : run_strided2<N, +1>(c, g, nullptr, ain, aout, 1, (int)(nyl * nc), &pp)) return 1;
     if (clr_comm_barrier(c)) return 1;
     if (c->ev_after_z) CLR_CUDA(cudaEventRecord(c->ev_after_z, c->stream));
     c->a2a_bytes += (double)nzl * nyl * nc * 8 * (c->nranks - 1);
@@ -1273,12 +1384,28 @@ int run_fill_c2r(clr_ctx *c, uint32_t seed, float norm, double *mom)
 }  // namespace
 
 // create_grids_fourier + both fftw_wrap_c2r of create_cartesian_fields (fourier.c:285-359, 81-102, 394-397) with the
-// mode fill fused into the z pass. *ran = false when this path does not apply (multi-GPU slab, exact_math, sizes outside
-// [128,2048]): the caller then runs the stand-alone fill and two transforms.
+// mode fill fused into the z pass. *ran = false when this path does not apply (exact_math, no peer-memory transpose on
+// several GPUs, sizes outside [128,2048] on one GPU): the caller then runs the stand-alone fill and two transforms.
 int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, bool *ran)
 {
   *ran = false;
-  if (c->nranks > 1 || !c->fft_fused || !c->fill_fused || !clr_fill_fast_ok(c)) return 0;
+  if (!c->fill_fused || !clr_fill_fast_ok(c)) return 0;
+  if (c->nranks > 1) {
+    // several GPUs: the fill rides on the NVLink-bound z pass of each transform (fill_peer_kernel); density first (its
+    // moments), then the potential, like the separate passes
+    if (!(c->p2p && c->p2p_enabled) || c->fft_overlap) return 0;
+    float2 *dens = reinterpret_cast<float2 *>(c->d_dens), *npot = reinterpret_cast<float2 *>(c->d_npot);
+    const FillSpec fd{seed, 0}, fp{seed, 1};
+    *ran = true;
+    switch (c->dev.n) {
+#define CLR_FILL_DIST(NN) case NN: return c2r_3d_dist<NN>(c, dens, (float)norm, d_moments, &fd) || c2r_3d_dist<NN>(c, npot, (float)norm, nullptr, &fp);
+      CLR_FILL_DIST(64) CLR_FILL_DIST(128) CLR_FILL_DIST(256) CLR_FILL_DIST(512) CLR_FILL_DIST(1024) CLR_FILL_DIST(2048)
+      CLR_FILL_DIST(4096)
+#undef CLR_FILL_DIST
+      default: *ran = false; return 0;
+    }
+  }
+  if (!c->fft_fused) return 0;
   *ran = true;
   switch (c->dev.n) {
     case 128: return run_fill_c2r<128, 8>(c, seed, (float)norm, d_moments);

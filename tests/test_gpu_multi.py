@@ -35,3 +35,11 @@ def test_slab_decomposed_path_other_transposes(mode):
     """the same checks through the tile-major staging layout of the fused transpose and through the NCCL
     all-to-all fallback (what runs when a peer's staging buffer cannot be mapped)"""
     _run_worker(64, {"COLORE_B200_P2P_TILED": "1"} if mode == "tiled" else {"COLORE_B200_P2P": "0"})
+
+
+@pytest.mark.parametrize("n,tiled", [(64, 0), (128, 0), (128, 1)])
+def test_slab_decomposed_path_fused_fill(n, tiled):
+    """default (fp32) field kernels: the mode fill is generated inside the z pass that stores the slab transpose into
+    the peers' staging buffers (fill_peer_kernel, natural and tile-major staging) -- fields against the oracle's
+    Philox fill + transforms to 2e-5 sigma, everything downstream as in the other cases"""
+    _run_worker(n, {"CLR_TEST_EXACT": "0", "COLORE_B200_P2P_TILED": str(tiled)})
