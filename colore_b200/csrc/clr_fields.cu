@@ -460,7 +460,8 @@ __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
 // XFORM: the walk first applies lognormalize / densclip (density.c:1034-1103, the arithmetic of lognormal_fast_kernel) to
 // the Gaussian cell, stores it, and bins the transformed value: one read of the field for both stages, radius and table
 // position computed once.
-template <int NPOP, bool XFORM>
+// BM: bias model fixed at compile time (2 = the reference's default build, common.h:414-431), 0 = d.bias_model
+template <int NPOP, bool XFORM, int BM>
 __global__ void __launch_bounds__(kThreads)
 norm_hist_fast_kernel(const ClrDev d, float *__restrict__ dens, NormPopsF pops, int nz, double idz,
                       unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b,
@@ -567,7 +568,7 @@ norm_hist_fast_kernel(const ClrDev d, float *__restrict__ dens, NormPopsF pops, 
             float bi;
             if (ip == 0) bi = past ? 1.f : fmaf(tz.w, fr, tz.z);
             else { float2 t = __ldg(pops.bt[ip] + ir); bi = past ? 1.f : fmaf(t.y, fr, t.x); }
-            bm2[h][ip] = bias_model_f(d.bias_model, dl, bi);
+            bm2[h][ip] = bias_model_f(BM ? BM : d.bias_model, dl, bi);
           }
         }
       }
@@ -805,9 +806,11 @@ static int launch_hist_walk(clr_ctx *c, int npop, const double *const *d_bz, int
   int grid = (int)(ranges * groups);
   const size_t smem = nd * sizeof(double);
   XformArgs x0{nullptr, 0.f, 0.f, 0};
-#define CLR_HIST(NP)                                                                                                              \
-  if (xf) norm_hist_fast_kernel<NP, true><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf); \
-  else norm_hist_fast_kernel<NP, false><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, x0)
+#define CLR_HIST(NP)                                                                                                                 \
+  if (xf && c->dev.bias_model == 2)                                                                                                  \
+    norm_hist_fast_kernel<NP, true, 2><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf);     \
+  else if (xf) norm_hist_fast_kernel<NP, true, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf); \
+  else norm_hist_fast_kernel<NP, false, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, x0)
   switch (npop) {
     case 0: CLR_HIST(0); break;
     case 1: CLR_HIST(1); break;
