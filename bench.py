@@ -282,7 +282,13 @@ def ncu_traffic_table():
                 "lognormal_hist_kernel": "lognormal", "lognormal_fast_kernel": "lognormal", "norm_hist_fast_kernel": "norm_hist",
                 "poisson_kernel": "srcs_poisson", "expand_kernel": "srcs_expand", "place_src_kernel": "srcs_place"}
     tab, src = {}, {}
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*_full.csv"))):      # later rounds override earlier ones
+    def order(f):                                  # round, then the _vN tag of the capture: later captures override earlier ones
+        b = os.path.basename(f)
+        v = re.search(r"_v(\d+)_", b)
+        return (int(re.match(r"r(\d+)_", b).group(1)), int(v.group(1)) if v else 0, b)
+    files = [f for f in glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*_full.csv"))
+             if "_1024_" in os.path.basename(f) and re.match(r"r\d+_", os.path.basename(f))]
+    for f in sorted(files, key=order):
         try:
             for row in csv.DictReader(open(f)):
                 name = row.get("kernel", "")
@@ -293,6 +299,8 @@ def ncu_traffic_table():
                             return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
                         tab[st] = gb(row["dram__bytes_read.sum"]) + gb(row["dram__bytes_write.sum"])
                         src[st] = os.path.basename(f)
+                        if key == "norm_hist_fast_kernel" and "1, 1>" in name.replace("1, 1, 2>", "1, 1>"):
+                            tab["lognormal"], src["lognormal"] = tab[st], src[st]     # the fused lognormal + histogram walk
         except Exception:  # noqa: BLE001
             continue
     return tab, src

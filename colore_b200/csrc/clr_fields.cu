@@ -461,7 +461,7 @@ __device__ __forceinline__ float bias_model_f(int model, float dl, float bi)
 // the Gaussian cell, stores it, and bins the transformed value: one read of the field for both stages, radius and table
 // position computed once.
 // BM: bias model fixed at compile time (2 = the reference's default build, common.h:414-431), 0 = d.bias_model
-template <int NPOP, bool XFORM, int BM>
+template <int NPOP, int XFORM, int BM>      // XFORM: 0 = histogram only, 1 = lognormalize first, 2 = densclip first
 __global__ void __launch_bounds__(kThreads)
 norm_hist_fast_kernel(const ClrDev d, float *__restrict__ dens, NormPopsF pops, int nz, double idz,
                       unsigned long long *__restrict__ g_n, double *__restrict__ g_z, double *__restrict__ g_b,
@@ -548,7 +548,7 @@ norm_hist_fast_kernel(const ClrDev d, float *__restrict__ dens, NormPopsF pops, 
         if (XFORM) {
           const float2 e = __ldg(xf.d1_t + ir);
           const float dg = past ? xf.dlast : fmaf(e.y, fr, e.x);
-          dl = xf.clip ? fmaxf(fmaf(dg, dl, 1.f), 0.f) - 1.f : clr_ex2_fast(1.4426950408889634f * dg * fmaf(-xf.hs2, dg, dl)) - 1.f;
+          dl = XFORM == 2 ? fmaxf(fmaf(dg, dl, 1.f), 0.f) - 1.f : clr_ex2_fast(1.4426950408889634f * dg * fmaf(-xf.hs2, dg, dl)) - 1.f;
           xo[h] = dl;
         }
         const float zf = past ? zlastf : fmaf(tz.y, fr, tz.x);
@@ -807,10 +807,11 @@ static int launch_hist_walk(clr_ctx *c, int npop, const double *const *d_bz, int
   const size_t smem = nd * sizeof(double);
   XformArgs x0{nullptr, 0.f, 0.f, 0};
 #define CLR_HIST(NP)                                                                                                                 \
-  if (xf && c->dev.bias_model == 2)                                                                                                  \
-    norm_hist_fast_kernel<NP, true, 2><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf);     \
-  else if (xf) norm_hist_fast_kernel<NP, true, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf); \
-  else norm_hist_fast_kernel<NP, false, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, x0)
+  if (xf && !xf->clip && c->dev.bias_model == 2)                                                                                     \
+    norm_hist_fast_kernel<NP, 1, 2><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf);        \
+  else if (xf && !xf->clip) norm_hist_fast_kernel<NP, 1, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf); \
+  else if (xf) norm_hist_fast_kernel<NP, 2, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, *xf); \
+  else norm_hist_fast_kernel<NP, 0, 0><<<grid, kThreads, smem, c->stream>>>(c->dev, c->d_dens, pf, nz, idz, g_n, g_z, g_b, x0)
   switch (npop) {
     case 0: CLR_HIST(0); break;
     case 1: CLR_HIST(1); break;
