@@ -1399,8 +1399,8 @@ int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, 
     *ran = true;
     switch (c->dev.n) {
 #define CLR_FILL_DIST(NN) case NN: return c2r_3d_dist<NN>(c, dens, (float)norm, d_moments, &fd) || c2r_3d_dist<NN>(c, npot, (float)norm, nullptr, &fp);
+      // (4096^3 keeps the stand-alone fill: that size has only been run through the separate passes)
       CLR_FILL_DIST(64) CLR_FILL_DIST(128) CLR_FILL_DIST(256) CLR_FILL_DIST(512) CLR_FILL_DIST(1024) CLR_FILL_DIST(2048)
-      CLR_FILL_DIST(4096)
 #undef CLR_FILL_DIST
       default: *ran = false; return 0;
     }
