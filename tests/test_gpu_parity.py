@@ -14,6 +14,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 import colore_b200 as cb  # noqa: E402
+from colore_b200._lib import check  # noqa: E402
 from oracle.oracle import RNG_MT, RNG_PHILOX, Oracle, tables_from_dump  # noqa: E402
 
 # ref_n32_bias1 / ref_n32_bias3: the reference compiled with the other bias models (common.h:414-431);
@@ -478,6 +479,69 @@ def test_async_results_match_sync(case):
     par.set_option("async_results", 0)
     assert np.array_equal(out, want)
     assert np.array_equal(cb.srcs_get_local_properties(par, 0), want)
+
+
+def test_three_populations_one_of_them_empty(golden_dir, tmp_path):
+    """Several populations at once (srcs.c:285-294 loops over n_srcs; density.c:1128-1393 normalises them in ONE walk:
+    the NPOP = 3 instantiation of the histogram kernel) and a population without sources (n(z) = 0): normalisation
+    tables against the oracle, per-cell counts and pixels bit-exact per population (each on its own Philox streams),
+    an empty catalogue through every read-back and through the writer (header only, as io.c writes it)."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    o = Oracle(t, int(t["n_grid"]), nside_base=int(t["nside_base"]), bias_model=2)
+    par = _par(t, bias_model=2)
+    try:
+        nz0, bz0 = t["srcs_nz_0"], t["srcs_bz_0"]
+        pops = [(nz0, bz0), (0.5 * nz0, bz0 + 0.3), (np.zeros_like(nz0), bz0)]
+        par.grid_put(cb.GRID_DENS, g["s2_dens"])
+        par.grid_put(cb.GRID_NPOT, g["s1_npot"])
+        par.update_halo()
+        for i, (nz, bz) in enumerate(pops):
+            par.set_srcs(i, nz, bz)
+        cb.compute_density_normalization(par)
+        nm = o.density_normalization(g["s2_dens"].copy(), [bz for _, bz in pops])
+        o.set_halo(g["s1_npot"])
+        seed = int(t["seed"])
+        nsrc = cb.srcs_set_cartesian(par)
+        for i, (nz, bz) in enumerate(pops):
+            norm, ends, _ = cb.get_norm(par, 0, i)
+            np.testing.assert_allclose(norm, nm["norm"][i], rtol=1e-6)
+            ns, tot = o.srcs_poisson(g["s2_dens"], nz, bz, norm, ends[0], ends[1], RNG_PHILOX, seed, i)
+            assert nsrc[i] == tot and np.array_equal(cb.srcs_get_counts(par, i), ns)
+            pos_ref, ipix_ref = o.srcs_place(g["s1_npot"], ns, RNG_PHILOX, seed, i)
+            pos, ipix = cb.srcs_get_cartesian(par, i)
+            assert np.array_equal(ipix, ipix_ref) and np.array_equal(pos[:, :3], pos_ref[:, :3])
+        assert nsrc[0] > 0 and 0 < nsrc[1] < nsrc[0] and nsrc[2] == 0
+        assert cb.srcs_get_local_properties(par, 2).shape == (0, 9)
+        cb.srcs_beams(par)                                  # no-op on the empty catalogue
+        fa = str(tmp_path / "empty.txt")
+        cb.write_catalog(par, 2, fa, "ascii")
+        assert open(fa).read() == "#[1]type [2]RA, [3]dec, [4]z0, [5]dz_RSD \n"
+        ff = str(tmp_path / "empty.fits")
+        cb.write_catalog(par, 2, ff, "fits")
+        raw = open(ff, "rb").read()
+        assert len(raw) == 5760 and b"NAXIS2  =                    0" in raw
+    finally:
+        par.free()
+
+
+def test_bad_arguments_fail_loudly(golden_dir):
+    """Error behaviour of the boundary: every ABI call returns non-zero + clr_last_error (mapped to report_error(1, ...)
+    by the glue, common.c:290-306) instead of computing something else."""
+    g, t = _load(golden_dir, "ref_n32_lognormal")
+    for n in (30, 4 * 37):                                  # not a multiple of 4; a prime factor above 31
+        with pytest.raises(cb.ColoreError):
+            cb.ParamCoLoRe(t, n)
+    par = _par(t)
+    try:
+        with pytest.raises(cb.ColoreError, match="unknown option"):
+            par.set_option("no_such_option", 1)
+        with pytest.raises(cb.ColoreError, match="out of range"):
+            check(par.lib.clr_srcs_distribute(par.ctx, 99, 0, None))          # population index
+        par.set_srcs(0, t["srcs_nz_0"], t["srcs_bz_0"])
+        with pytest.raises(cb.ColoreError, match="open file"):
+            cb.write_catalog(par, 0, "/nonexistent_dir/x.txt", "ascii")        # common.c:58-62 error_open_file
+    finally:
+        par.free()
 
 
 def test_beam_rsd_vs_oracle(case):
