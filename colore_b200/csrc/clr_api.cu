@@ -413,6 +413,7 @@ int clr_set_option(clr_ctx *c, const char *name, int value)
   }
   if (!strcmp(name, "fill_fused")) { c->fill_fused = value; return 0; }
   if (!strcmp(name, "fill_w")) { c->fill_w = value; return 0; }
+  if (!strcmp(name, "fill_cluster")) { c->fill_cluster = value; return 0; }
   if (!strcmp(name, "p2p_fused")) { c->p2p_enabled = value; return 0; }
   if (!strcmp(name, "fft_overlap")) { if (clr_npot_ready(c)) return 1; c->fft_overlap = value; return 0; }
   if (!strcmp(name, "p2p_tiled")) { c->p2p_tiled = value; return 0; }

@@ -24,6 +24,7 @@
 //    squares needed by compute_sigma_dens (fourier.c:24-79, 394-397).
 #include "clr_internal.cuh"
 #include "clr_fill.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <utility>
 
@@ -962,6 +963,103 @@ fill_z_kernel(const __grid_constant__ FzArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// The same fusion on a CLUSTER OF TWO CTAs, for grids whose tile (two fields x 8 lines x n points) does not fit the
+// shared memory of one SM (n = 2048: 2 x 135 KB). CTA 0 of the pair transforms delta_k, CTA 1 phi_k, each with its own
+// 8-line tile in its own shared memory. The fill is shared work: every CTA generates the modes of HALF of the kz range
+// for BOTH fields (one Philox block and one P(k) / phase evaluation per mode pair, as in fill_z_kernel), keeps its own
+// field's values and pushes the other field's values into the partner's shared memory through distributed shared
+// memory (st.shared::cluster via cluster.map_shared_rank). Cluster barriers: "tile complete" (release / acquire over
+// both CTAs' stores) before the transforms, and a split "buffer free" barrier -- arrive after the last read of the
+// exchange buffer, wait at the top of the next fill -- so the partner never overwrites a tile that is still being read.
+// Output runs are 64 bytes (8 lines) instead of the 32 bytes of the 4-line tiles of fill_z_kernel<2048, 4>.
+template <int N> struct FzcCfg {
+  static constexpr int NP = N == 2048 ? (N | kWide) : N;
+  using P = FftPlan<NP>;
+  static constexpr int W = 8;
+  static constexpr int THREADS = W * P::TPL;                    // one field per CTA
+  static constexpr int BUF = P::LSTRIDE * W;
+  static constexpr size_t SMEM = ((size_t)BUF + P::NTW) * sizeof(float2);
+  static_assert(P::NST >= 2 && N % 2 == 0, "cluster fill + z pass needs n >= 64");
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FzcCfg<N>::THREADS, 1)
+fill_z_cluster_kernel(const __grid_constant__ FzArgs a)
+{
+  using C = FzcCfg<N>;
+  using P = typename C::P;
+  constexpr int W = C::W, NP = C::NP;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float2 smem[];
+  float2 *tw = smem + C::BUF;
+  const int tid = threadIdx.x;
+  const unsigned field = cluster.block_rank();                   // 0: this CTA transforms delta_k, 1: phi_k
+  float2 *mine = smem;
+  float2 *theirs = cluster.map_shared_rank(smem, field ^ 1u);    // the partner's tile (distributed shared memory)
+  float2 *buf_d = field == 0 ? mine : theirs, *buf_p = field == 0 ? theirs : mine;
+  const int j = tid / W, l = tid % W;
+  float2 *outg = field ? a.out_p : a.out_d;
+  load_twiddles<NP, +1>(tw, a.W, a.wn);
+  const int npair_row = (a.nc + 1) / 2;
+  const long long n_tiles = (long long)a.nkt * a.nyl;
+  const long long zstep = (long long)a.nyl * 8;
+  const int n_cl = gridDim.x >> 1;
+  const int kz_lo = (int)field * (N / 2);                        // this CTA fills kz in [kz_lo, kz_lo + N/2)
+  cluster_arrive();                                              // opens the first "buffer free" phase
+  for (long long tile = blockIdx.x >> 1; tile < n_tiles; tile += n_cl) {
+    const int kxt = (int)(tile / a.nyl), kyl = (int)(tile - (long long)kxt * a.nyl);
+    const int jj = a.ky0 + kyl;
+    const int mj = (2 * jj <= N ? jj : N - jj);
+    cluster_wait();                                              // both CTAs have read their previous tile back
+#pragma unroll 2
+    for (int q = tid; q < (N / 2) * (W / 2); q += C::THREADS) {
+      const int kz = kz_lo + q / (W / 2), pr = q % (W / 2);
+      const int mi = (2 * kz <= N ? kz : N - kz);
+      const int m_row = mj * mj + mi * mi;
+      const int kk0 = kxt * 8 + 2 * pr;
+      const unsigned long long gidx = (unsigned long long)(kk0 >> 1) + (unsigned long long)npair_row * ((unsigned long long)jj + (unsigned long long)N * kz);
+      float2 dk2[2], pk2[2];
+      uint32_t w[4];
+      clr_philox((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, a.seed, 0u, w);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int kk = kk0 + h, m = kk * kk + m_row;            // beyond the Nyquist column: padding lines, zero
+        clr_fill_mode(a.k, a.pkt, a.sct, m, kk < a.nc && m > 0, w[2 * h], w[2 * h + 1], dk2[h], pk2[h]);
+      }
+      const int si = sidx<NP, true, W>(kz, 2 * pr);
+      *reinterpret_cast<float4 *>(buf_d + si) = make_float4(dk2[0].x, dk2[0].y, dk2[1].x, dk2[1].y);
+      *reinterpret_cast<float4 *>(buf_p + si) = make_float4(pk2[0].x, pk2[0].y, pk2[1].x, pk2[1].y);
+    }
+    cluster_arrive();                                            // tile complete: my stores (local and remote) are released ...
+    cluster_wait();                                              // ... and the partner's half has arrived
+    float2 v[P::E];
+    stage_load<NP, true, W>(v, mine, j, l);
+    stage_math<NP, +1, 0>(v, tw, j);
+    __syncthreads();
+    stage_store<NP, true, W, 0>(v, mine, j, l);
+    __syncthreads();
+    stage_load<NP, true, W>(v, mine, j, l);
+    if constexpr (P::NST >= 3) {
+      stage_math<NP, +1, 1>(v, tw, j);
+      __syncthreads();
+      stage_store<NP, true, W, 1>(v, mine, j, l);
+      __syncthreads();
+      stage_load<NP, true, W>(v, mine, j, l);
+    }
+    cluster_arrive();                                            // buffer free (waited for at the top of the next fill)
+    stage_math<NP, +1, P::NST - 1>(v, tw, j);
+    float2 *o = outg + ((long long)kxt * N * a.nyl + kyl) * 8 + l;
+#pragma unroll
+    for (int i = 0; i < P::E; i++) o[(long long)(j + i * P::TPL) * zstep] = v[i];
+  }
+  cluster_wait();                                                // pair up the last arrive: no CTA leaves while its partner may still push
+}
+
+// ------------------------------------------------------------------------------------------
 // Several GPUs: mode fill fused into the z pass WITH the slab transpose (create_grids_fourier, fourier.c:285-359, + the
 // first axis of fftw_wrap_c2r, fourier.c:81-102, + FFTW-MPI's transpose). One field per launch: a CTA generates the
 // T lines x n kz modes of its tile (the same Philox blocks and arithmetic as the stand-alone fill, clr_fill.cuh),
@@ -1381,6 +1479,44 @@ int run_fill_c2r(clr_ctx *c, uint32_t seed, float norm, double *mom)
   return run_yx_fused<N, 1, false>(c, tmp, dens, norm, nullptr);
 }
 
+// the cluster variant: one field per CTA of a pair (fill_z_cluster_kernel)
+template <int N>
+int run_fill_c2r_cluster(clr_ctx *c, uint32_t seed, float norm, double *mom)
+{
+  using C = FzcCfg<N>;
+  if (ensure_fft_tmp(c)) return 1;
+  FzArgs a;
+  if (clr_fill_fast_setup(c, &a.k)) return 1;
+  float2 *tmp = reinterpret_cast<float2 *>(c->d_fft_tmp), *dens = reinterpret_cast<float2 *>(c->d_dens),
+         *npot = reinterpret_cast<float2 *>(c->d_npot);
+  a.out_d = tmp; a.out_p = dens;
+  a.W = c->d_twiddle; a.wn = c->dev.n; a.pkt = c->d_pkt; a.sct = c->d_sincos; a.seed = seed;
+  a.n = N; a.nc = c->dev.nc; a.nyl = c->dev.nyl; a.ky0 = c->dev.ky0; a.nkt = c->dev.ncp / 8;
+  { StageScope sc(c, "fill_fft_z", 1);
+    auto k = fill_z_cluster_kernel<N>;
+    static int clusters = 0;                       // co-resident CTA pairs (a pair shares a GPC): asked once
+    if (!clusters) {
+      CLR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * c->sm_count); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      CLR_CUDA(cudaOccupancyMaxActiveClusters(&n, k, &cfg));
+      CLR_CHECK(n > 0, "fill + z pass on CTA pairs does not fit this device (threads=%d smem=%zu)", C::THREADS, C::SMEM);
+      clusters = n;
+    }
+    const long long n_tiles = (long long)a.nkt * a.nyl;
+    const int grid = 2 * (int)std::min<long long>(clusters, n_tiles);
+    k<<<grid, C::THREADS, C::SMEM, c->stream>>>(a);
+    CLR_CUDA(cudaGetLastError()); }
+  StageScope sc(c, "fft_yx", 2);
+  if (run_yx_fused<N, 1, false>(c, dens, npot, norm, nullptr)) return 1;
+  if (mom) return run_yx_fused<N, 1, true>(c, tmp, dens, norm, mom);
+  return run_yx_fused<N, 1, false>(c, tmp, dens, norm, nullptr);
+}
+
 }  // namespace
 
 // create_grids_fourier + both fftw_wrap_c2r of create_cartesian_fields (fourier.c:285-359, 81-102, 394-397) with the
@@ -1409,14 +1545,18 @@ int clr_fft_fill_c2r(clr_ctx *c, uint32_t seed, double norm, double *d_moments, 
   *ran = true;
   switch (c->dev.n) {
     case 128: return run_fill_c2r<128, 8>(c, seed, (float)norm, d_moments);
-    case 256: return c->fill_w == 4 ? run_fill_c2r<256, 4>(c, seed, (float)norm, d_moments)       // (oracle-sized test of W = 4)
-                                    : run_fill_c2r<256, 8>(c, seed, (float)norm, d_moments);
+    case 256: return c->fill_cluster > 0 ? run_fill_c2r_cluster<256>(c, seed, (float)norm, d_moments)   // (oracle-sized tests)
+                     : c->fill_w == 4 ? run_fill_c2r<256, 4>(c, seed, (float)norm, d_moments)
+                                      : run_fill_c2r<256, 8>(c, seed, (float)norm, d_moments);
     case 512: return run_fill_c2r<512, 8>(c, seed, (float)norm, d_moments);
     // option "fill_w": 4 = half-width tiles (two CTAs per SM: the fill of one overlaps the butterflies / stores of the other)
-    case 1024: return c->fill_w == 4 ? run_fill_c2r<1024, 4>(c, seed, (float)norm, d_moments)
-                                     : run_fill_c2r<1024, 8>(c, seed, (float)norm, d_moments);
-    // 2048: two fields x 8 lines x 2048 points do not fit shared memory, 4 lines do
-    case 2048: return run_fill_c2r<2048, 4>(c, seed, (float)norm, d_moments);
+    case 1024: return c->fill_cluster > 0 ? run_fill_c2r_cluster<1024>(c, seed, (float)norm, d_moments)
+                      : c->fill_w == 4 ? run_fill_c2r<1024, 4>(c, seed, (float)norm, d_moments)
+                                       : run_fill_c2r<1024, 8>(c, seed, (float)norm, d_moments);
+    // 2048: two fields x 8 lines x 2048 points do not fit the shared memory of one SM: a CTA pair with one field each
+    // (option "fill_cluster" = 0: 4-line tiles on single CTAs instead)
+    case 2048: return c->fill_cluster != 0 ? run_fill_c2r_cluster<2048>(c, seed, (float)norm, d_moments)
+                                           : run_fill_c2r<2048, 4>(c, seed, (float)norm, d_moments);
     default: *ran = false; return 0;
   }
 }

@@ -72,6 +72,7 @@ struct clr_ctx {
   int los_precompute = 1;                            // option "los_precompute": 0 = kappa rays evaluate the Hessian stencil per sample
   int fft_fused = 1;                                 // option "fft_fused": 0 = three separate axis passes
   int fill_fused = 1;                                // option "fill_fused": 0 = stand-alone mode fill + z pass
+  int fill_cluster = -1;                             // option "fill_cluster": fused fill + z pass on CTA pairs (-1: where needed, i.e. n = 2048)
   int fill_w = 8;                                    // option "fill_w": kx lines per tile of the fused fill + z pass at n = 1024 (8 or 4)
   size_t scratch_bytes = 0;
   double sigma2_gauss = 0, mean_gauss = 0;

@@ -201,11 +201,12 @@ def test_fft_large_vs_cufft(golden_dir, n, fused):
     par.free()
 
 
-@pytest.mark.parametrize("n,fill_w", [(128, 8), (256, 8), (256, 4)])
-def test_fused_fields_vs_oracle(golden_dir, n, fill_w):
+@pytest.mark.parametrize("n,fill_w,cluster", [(128, 8, 0), (256, 8, 0), (256, 4, 0), (256, 8, 1)])
+def test_fused_fields_vs_oracle(golden_dir, n, fill_w, cluster):
     """n >= 128 on one GPU: the mode fill is fused into the z pass and the y + x passes run as one kernel through L2
     (clr_fft.cu: fill_z_kernel, yx_fused_kernel). Same Philox stream in the oracle -> fields to 2e-5 sigma.
-    fill_w = 4: the half-width tiles of the fused fill (the only variant at 2048^3, optional at 1024^3)."""
+    fill_w = 4: half-width tiles (optional at 1024^3); cluster: one field per CTA of a pair, the fill shared through
+    distributed shared memory (fill_z_cluster_kernel, what runs at 2048^3)."""
     g, t = _load(golden_dir, "ref_n32_lognormal")
     t = dict(t)
     t["l_box"] = float(np.float32(2 * t["r_max"] * (1 + 2. / n)))
@@ -213,6 +214,7 @@ def test_fused_fields_vs_oracle(golden_dir, n, fill_w):
     o = Oracle(t, n)
     par = cb.ParamCoLoRe(t, n, seed=77)
     par.set_option("fill_w", fill_w)
+    par.set_option("fill_cluster", cluster)
     dk, pk = o.fill_modes(RNG_PHILOX, 77)
     dens, npot = o.c2r(dk), o.c2r(pk)
     o.normalize_fields(dens, npot)
@@ -225,8 +227,9 @@ def test_fused_fields_vs_oracle(golden_dir, n, fill_w):
     par.free()
 
 
-@pytest.mark.parametrize("n,fill_w", [(128, 8), (512, 8), (1024, 8), (1024, 4), (2048, 4)])
-def test_fused_fields_match_separate_passes(golden_dir, n, fill_w):
+@pytest.mark.parametrize("n,fill_w,cluster", [(128, 8, 0), (512, 8, 0), (1024, 8, 0), (1024, 4, 0), (1024, 8, 1), (2048, 8, 1),
+                                              (2048, 4, 0)])
+def test_fused_fields_match_separate_passes(golden_dir, n, fill_w, cluster):
     """Full-size consistency of the two code paths of create_cartesian_fields: fused (fill + z pass, y + x pass) against
     stand-alone fill + three separate axis passes, same seed. Both evaluate the same butterflies in fp32.
     At 2048^3 (two 34 GB grids + scratch) every 16th plane is kept for the comparison, plus the sum of every plane."""
@@ -239,6 +242,7 @@ def test_fused_fields_match_separate_passes(golden_dir, n, fill_w):
     t["pos_obs"] = 0.5 * t["l_box"]
     par = cb.ParamCoLoRe(t, n, seed=5)
     par.set_option("fill_w", fill_w)
+    par.set_option("fill_cluster", cluster)
     zs = 16 if n >= 2048 else 1
 
     def snapshot(grid):
