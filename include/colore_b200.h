@@ -127,7 +127,16 @@ int clr_set_sigma2_gauss(clr_ctx *ctx, double sigma2);
  * "keep_particles" = 1 keeps the LPT particles resident for clr_lpt_get_particles.
  * "async_results" = 1 makes clr_srcs_get_local_properties return as soon as the device-to-host copy is
  * queued on a separate copy stream (the host buffer must be pinned and is valid after clr_synchronize);
- * the next run overlaps the copy and only waits for it before it reuses the catalogue buffers. */
+ * the next run overlaps the copy and only waits for it before it reuses the catalogue buffers.
+ * Kernel-path switches (all default to the fast path; the tests use them to compare one path against another):
+ * "fill_fused" = 0: stand-alone mode fill instead of the fill fused into the z pass of the transforms (one GPU) /
+ * into the peer-store z pass of the slab transpose (several GPUs); "fft_fused" = 0: three separate axis passes
+ * instead of the fused y + x pass; "fill_w" = 4 / 8: kx lines per tile of the fused fill at n_grid = 1024;
+ * "fill_cluster" = 1 / 0 / -1: fused fill + z pass on pairs of CTAs of a thread-block cluster (default -1: where one
+ * SM cannot hold both fields' tiles, i.e. n_grid = 2048); "hist_fused" = 0: lognormal transform and normalisation
+ * histogram as separate passes; "srcs_compact" = 0: dense per-cell counts; "los_precompute" = 0: kappa rays evaluate
+ * the Hessian stencil per sample; "p2p_fused" = 0: NCCL all-to-all instead of peer-memory stores for the slab
+ * transpose; "p2p_tiled" = 0 / 1: staging layout of that transpose; "fft_overlap" = 1: second transform pipeline. */
 int clr_set_option(clr_ctx *ctx, const char *name, int value);
 /* refresh the z-halo planes of the potential after clr_grid_put (fourier.c:401-414) */
 int clr_update_halo(clr_ctx *ctx);
