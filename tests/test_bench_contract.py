@@ -33,3 +33,18 @@ def test_reference_arm_other_ranks_are_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_roofline_traffic_comes_from_the_newest_committed_capture():
+    """bench.py's roofline.traffic = DRAM bytes per launch of the dominant kernel from the committed `ncu --set full`
+    summaries of THIS workload (1024^3, one GPU): the newest capture (round, then _vN tag) wins, captures of other grid
+    sizes are ignored."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tab, src = bench.ncu_traffic_table()
+    assert "_1024_" in src["fill_fft_z"] and "_1024_" in src["fft_yx"]
+    assert src["fill_fft_z"] == "r2_ncu_fft_1024_v6_full.csv"
+    # the fused fill + z pass only WRITES its output: two half-spectra of 1024^2 x 520 complex64 = 8.7 GB
+    assert 8.6e9 < tab["fill_fft_z"] < 8.8e9
+    # one fused y + x pass reads one half-spectrum and writes one real field
+    assert 8.6e9 < tab["fft_yx"] < 8.8e9
