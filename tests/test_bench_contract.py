@@ -43,7 +43,7 @@ def test_roofline_traffic_comes_from_the_newest_committed_capture():
     import bench
     tab, src = bench.ncu_traffic_table()
     assert "_1024_" in src["fill_fft_z"] and "_1024_" in src["fft_yx"]
-    assert src["fill_fft_z"] == "r2_ncu_fft_1024_v6_full.csv"
+    assert src["fill_fft_z"] >= "r2_ncu_fft_1024_v6_full.csv"      # that capture or a later one
     # the fused fill + z pass only WRITES its output: two half-spectra of 1024^2 x 520 complex64 = 8.7 GB
     assert 8.6e9 < tab["fill_fft_z"] < 8.8e9
     # one fused y + x pass reads one half-spectrum and writes one real field
