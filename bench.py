@@ -172,7 +172,9 @@ def reference_arm(args):
         return
     threads = os.cpu_count() or 1
     n_s = args.ref_n_grid or args.n_grid
-    budget_s = float(os.environ.get("CLR_REF_BUDGET_S", "1200"))
+    # ~35 s per run at n_grid=1024 on 16 cores: a 7-minute budget (warm-up included) keeps the arm "a few minutes" long
+    # whatever --steps asks for; the line says how many runs were averaged
+    budget_s = float(os.environ.get("CLR_REF_BUDGET_S", "420"))
     try:
         t_start = time.time()
         vals, stages, done = [], {}, 0
