@@ -22,6 +22,15 @@
 //    gathers the per-stage, per-thread factors once into shared memory (persistent CTAs).
 //  * The last pass of the c2r optionally fuses the (sqrt(2 pi)/L)^3 scaling and the sum / sum of
 //    squares needed by compute_sigma_dens (fourier.c:24-79, 394-397).
+//
+// Kernels of the product path (each described where it is defined):
+//    one GPU      fill_z_kernel (mode fill + z pass of both fields, n <= 1024) / fill_z_cluster_kernel (the same on
+//                 CTA pairs with distributed shared memory, n = 2048) -> yx_fused_kernel (y + x passes through L2,
+//                 TMA bulk loads); fft_strided_kernel + fft_c2r_x_kernel / fft_r2c_x_kernel for grids handed in by the
+//                 caller, the r2c, n < 128 and n = 4096
+//    several GPUs fill_peer_kernel (mode fill + z pass + slab transpose as NVLink peer stores, one field per launch) or
+//                 fft_strided_kernel<PEER> (the same pass on a grid that already holds modes) -> y pass out of the
+//                 staging buffer -> x pass
 #include "clr_internal.cuh"
 #include "clr_fill.cuh"
 #include <cooperative_groups.h>
