@@ -111,6 +111,27 @@ def r2c_dist_numpy(rslab: np.ndarray, rank: int, nranks: int, alltoall) -> np.nd
     return np.fft.fft(full_z, axis=0)
 
 
+def fill_tile_modes(tile: int, t_lines: int, n: int, nranks: int, rank: int):
+    """Modes a CTA of the fused fill + transpose pass (clr_fft.cu: fill_peer_kernel) generates for z-pass tile ``tile``:
+    lines = ``t_lines`` consecutive values of the flattened index ky_local * ncp + kx (ncp = row pitch: n/2+1 rounded up
+    to a multiple of 8), a thread owns a PAIR of lines (same ky, kx even / odd) and draws ONE Philox block per pair and
+    kz. Returns (ky_global[lines], kx[lines], live[lines], block_index[pairs, n]) with block_index the counter the
+    oracle uses for the pair: kx // 2 + ceil((n/2+1)/2) * (ky + n * kz) (DESIGN.md section 4). Padding columns
+    (kx >= n/2+1) and lines past the end of the slab are not live (the kernel writes zeros there)."""
+    nc = n // 2 + 1
+    ncp = (nc + 7) // 8 * 8
+    nyl = n // nranks
+    inner = tile * t_lines + np.arange(t_lines)
+    kyl, kx = inner // ncp, inner % ncp
+    ky = rank * nyl + kyl
+    live = (inner < nyl * ncp) & (kx < nc)
+    npair_row = (nc + 1) // 2
+    pair = np.arange(0, t_lines, 2)
+    kz = np.arange(n)
+    block = (kx[pair] // 2)[:, None] + npair_row * (ky[pair][:, None] + n * kz[None, :])
+    return ky, kx, live, block
+
+
 # ---- numpy restatement of the LPT particle routing (test support) ----------------------------------
 
 def lpt_planes_numpy(z: np.ndarray, interp: int, n: int, l_box: float) -> np.ndarray:

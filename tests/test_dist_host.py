@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from colore_b200.dist import c2r_dist_numpy, kspace_slab, r2c_dist_numpy, slab_bounds
+from colore_b200.dist import c2r_dist_numpy, fill_tile_modes, kspace_slab, r2c_dist_numpy, slab_bounds
 
 
 def _free_port():
@@ -118,6 +118,37 @@ def test_lpt_routing_covers_every_plane_once(interp):
             mine = (pl // nzl) == h                                     # the deposit's slab check
             np.add.at(total, pl[mine], 1)
     assert np.array_equal(total, ref)
+
+
+@pytest.mark.parametrize("n,nranks,t_lines", [(64, 2, 32), (64, 4, 32), (128, 2, 32), (1024, 8, 16), (2048, 8, 8)])
+def test_fused_fill_tiles_cover_every_mode_once(n, nranks, t_lines):
+    """fill_peer_kernel (several GPUs, mode fill inside the transpose pass): over all ranks and tiles every mode
+    (kz, ky, kx) of the half-spectrum is generated exactly once, a pair of lines never straddles a row (so the two modes
+    of a Philox block are the neighbours kx = 2p, 2p + 1 of one row, as in the stand-alone fill and the oracle), and the
+    block counters of all pairs are distinct."""
+    nc = n // 2 + 1
+    ncp = (nc + 7) // 8 * 8
+    nyl = n // nranks
+    seen = np.zeros((n, nc), np.int32)                       # (ky, kx) lines; every line carries all n kz
+    blocks = []
+    for rank in range(nranks):
+        n_tiles = (nyl * ncp + t_lines - 1) // t_lines
+        tiles = range(n_tiles) if n <= 128 else list(range(3)) + [n_tiles // 2, n_tiles - 1]
+        for tile in tiles:
+            ky, kx, live, block = fill_tile_modes(tile, t_lines, n, nranks, rank)
+            assert np.all(ky[0::2] == ky[1::2]) and np.all(kx[0::2] % 2 == 0) and np.all(kx[1::2] == kx[0::2] + 1)
+            np.add.at(seen, (ky[live], kx[live]), 1)
+            keep = live[0::2]                                # pairs whose even line is a real mode
+            blocks.append(block[keep][:, [0, 1, n - 1]].ravel())
+            # the oracle's counter of the pair (DESIGN.md section 4), evaluated independently for kz = 1
+            want = kx[0::2][keep] // 2 + ((nc + 1) // 2) * (ky[0::2][keep] + n * 1)
+            assert np.array_equal(block[keep][:, 1], want)
+    if n <= 128:
+        assert np.all(seen == 1)                             # every (ky, kx) line exactly once over ranks and tiles
+    else:
+        assert seen.max() == 1
+    allb = np.concatenate(blocks)
+    assert len(np.unique(allb)) == len(allb)
 
 
 def test_slab_bounds():
