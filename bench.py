@@ -349,9 +349,18 @@ def north_star_run(cb, torch, dist, rank, world, local, allsum, allmax, barrier,
         zname = "fill_fft_z" if "fill_fft_z" in st else "fft_z"
         sent = 2 * 8.0 * n * n * (n // 2 + 1) / world * (world - 1) / world
         out["nvlink_gbs_per_direction_during_fused_pass"] = sent / (st[zname]["ms_per_step_max"] * 1e-3) / 1e9
-    # kappa + ISW maps at nside 1024 on two planes
+    out.update(maps_run(cb, par, tabs, allmax, barrier))
+    par.free()
+    return out
+
+
+def maps_run(cb, par, tabs, allmax, barrier, nside=1024):
+    """kappa + ISW HEALPix maps (kappa.c:39-175, isw.c:78-147) at ``nside`` on two source planes from the fields ``par``
+    holds: kernel time (max over ranks; kappa includes its Hessian precompute pass) and wall time of the API call with
+    the host pixel list going in and the all-reduced map coming out. BASELINE config 3 at the bench's n_grid."""
+    out = {}
     rf = np.interp([0.2, 0.4], tabs["z"], tabs["r"]).astype(np.float32)
-    _, pos = cb.healpix.hp_shell_pixels(1024, 2)
+    _, pos = cb.healpix.hp_shell_pixels(nside, 2)
     for name, fn in (("kappa_los", cb.kappa_get_beam_properties), ("isw_los", cb.isw_get_beam_properties)):
         fn(par, pos[:1024], rf)
         barrier()
@@ -363,9 +372,8 @@ def north_star_run(cb, torch, dist, rank, world, local, allsum, allmax, barrier,
         if name == "kappa_los":
             kms += par.stage_ms("kappa_tidal")[0]           # the Hessian precompute pass belongs to the kappa stage
         par.set_profiling(False)
-        out[name] = {"nside": 1024, "kernel_ms_max": allmax(kms), "api_wall_ms": wall * 1e3,
+        out[name] = {"nside": nside, "kernel_ms_max": allmax(kms), "api_wall_ms": wall * 1e3,
                      "finite": bool(np.isfinite(m).all()), "map_rms": float(m.astype(np.float64).std())}
-    par.free()
     return out
 
 
@@ -385,6 +393,7 @@ def main():
                          "of the GPU arm defaults to 512 (a bounded sample)")
     ap.add_argument("--no-north-star", action="store_true", help="skip the 2048^3 run that --gpus 8 appends")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-maps", action="store_true", help="skip the kappa / ISW maps (nside 1024) appended under \"maps\"")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="clr_set_option before the run (kernel-variant experiments, e.g. --opt fill_w=4)")
     ap.add_argument("--writer", action="store_true",
@@ -580,6 +589,14 @@ def main():
     # ---- correctness bits of this very configuration (after the timed regions) ------------------
     parity = parity_checks(cb, torch, par, tabs, n, local, allsum, allmax)
     transpose = cb.dist.transpose_mode(par) if world > 1 else "none"
+    # ---- BASELINE config 3: kappa + ISW maps at nside 1024 from the fields of this configuration (outside the step) ----
+    maps = None
+    if not args.no_maps:
+        try:
+            run_step(cb, par, 1000, tabs)
+            maps = maps_run(cb, par, tabs, allmax, barrier)
+        except Exception as e:  # noqa: BLE001
+            maps = {"failed": str(e)[:300]}
     par.free()
     par = None
     north = None
@@ -598,7 +615,7 @@ def main():
             "parallelism": f"{world} z-slab(s), one process per GPU, FFT slab transpose: {transpose}",
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "fft_hbm_gbs": fft_gbs, "nvlink": nvlink, "stages": stages, "parity": parity,
-            "north_star": north, "writer": writer, "cpu_baseline": cpu,
+            "maps": maps, "north_star": north, "writer": writer, "cpu_baseline": cpu,
         }))
     if par is not None:
         par.free()
