@@ -389,3 +389,19 @@ def write_catalog(par: ParamCoLoRe, ipop: int, fname: str, fmt: str = "ascii", n
     check(par.lib.clr_write_catalog(par.ctx, C.c_int(ipop), fname.encode(), C.c_int({"ascii": 0, "fits": 1}[fmt]),
                                     C.c_int(ipop), C.c_int(n_threads), C.byref(sec)))
     return sec.value
+
+
+def write_healpix_map(fname: str, data, nside: int, nest: bool = False, nadd=None, listpix=None, n_threads: int = 0) -> float:
+    """he_write_healpix_map (healpix_extra.c:4-57) + the shell loops of write_kappa / write_isw / write_imap
+    (io.c:697-1017) through clr_write_healpix_map: ``data`` [num_pix] float32 (with ``listpix``: the local pixels of a
+    shell, ``nadd``: their hit counts), NEST -> RING when ``nest``. Returns the wall time in seconds. No GPU needed."""
+    from ._lib import load
+    lib = load()
+    data = np.ascontiguousarray(data, np.float32)
+    nadd_c = None if nadd is None else np.ascontiguousarray(nadd, np.int32)
+    list_c = None if listpix is None else np.ascontiguousarray(listpix, np.int32)
+    sec = C.c_double()
+    check(lib.clr_write_healpix_map(_vp(data), None if nadd_c is None else _vp(nadd_c), None if list_c is None else _vp(list_c),
+                                    C.c_longlong(data.shape[0]), C.c_long(nside), C.c_int(int(nest)), fname.encode(),
+                                    C.c_int(n_threads), C.byref(sec)))
+    return sec.value

@@ -177,6 +177,14 @@ int clr_srcs_get_local_properties(clr_ctx *ctx, int ipop, float *srcs9);
 #define CLR_FORMAT_ASCII 0
 #define CLR_FORMAT_FITS 1
 int clr_write_catalog(clr_ctx *ctx, int ipop, const char *fname, int format, int type_id, int n_threads, double *seconds);
+/* One HEALPix map file as he_write_healpix_map writes it (healpix_extra.c:4-57: BINTABLE column "map 1" 1E, ORDERING RING,
+ * NSIDE, COORDSYS G), preceded -- when nadd / listpix are given -- by the shell loops of write_imap / write_kappa /
+ * write_isw (io.c:697-1017): map[listpix[i]] += data[i], hits[listpix[i]] += nadd[i] over num_pix local pixels
+ * (listpix NULL: pixel i, num_pix must then be 12 nside^2), map /= hits where hits > 0. isnest: the pixel indices are
+ * NEST, the file is RING (he_nest2ring_inplace). The NEST -> RING gather and the big-endian conversion run on n_threads
+ * host threads (<= 0: all cores). Host arrays in, no device involved; a leading '!' of fname is skipped. */
+int clr_write_healpix_map(const float *data, const int *nadd, const int *listpix, long long num_pix, long nside, int isnest,
+                          const char *fname, int n_threads, double *seconds);
 /* srcs_distribute_single (srcs.c:296-373), several GPUs: route every source to rank ipix % nranks, order preserved
  * (blocks received from rank-1, rank-2, ..., own sources last). beam_first != 0: evaluate the RSD-under-beaming
  * estimator (srcs.c:486-504) first, on the slab that holds the potential around each source, and carry it along.
