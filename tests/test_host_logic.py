@@ -44,19 +44,21 @@ def test_cosmo_tables_match_reference():
     cfg = RunConfig(n_grid=32, dens_type=0, nz_amplitude=60.0, imap_nside=8, imap_nchannels=4, kappa_nside=8,
                     isw_nside=8, seed=1003)                       # the fixture's configuration (make_golden.py)
     t = _tables_like_golden(cfg)
-    for key, tab, rtol in (("r", "tab_r", 1e-6), ("z", "tab_z", 1e-5), ("d1", "tab_d1", 1e-5), ("d2", "tab_d2", 1e-4),
-                           ("v1", "tab_v1", 1e-4), ("pd", "tab_pd", 1e-3), ("ih", "tab_ih", 1e-5),
-                           ("a2r_r", "tab_a2r_r", 1e-5)):
+    # measured agreement: ~1e-8 of the table's largest entry (two quadrature implementations of the same integrals); pd =
+    # D H (f - 1) cancels at high redshift, where f -> 1: 3e-5
+    for key, tab, rtol in (("r", "tab_r", 1e-7), ("z", "tab_z", 1e-7), ("d1", "tab_d1", 2e-7), ("d2", "tab_d2", 2e-7),
+                           ("v1", "tab_v1", 2e-7), ("pd", "tab_pd", 1e-4), ("ih", "tab_ih", 1e-7),
+                           ("a2r_r", "tab_a2r_r", 1e-7)):
         ref = g[tab]
         np.testing.assert_allclose(t[key], ref, rtol=rtol, atol=rtol * np.abs(ref).max(), err_msg=key)
     # P(k) table normalised to sigma_8 (pk_linear_set, cosmo.c:310-422)
     np.testing.assert_allclose(t["pk_logk"], g["pk_logk"], rtol=1e-12)
-    np.testing.assert_allclose(t["pk_pk"], g["pk_pk"], rtol=2e-5)
+    np.testing.assert_allclose(t["pk_pk"], g["pk_pk"], rtol=1e-6)       # sigma_8 integral: 4e-8 between the two quadratures
     # population tables: dN/dz dOmega -> n(r), b(r), T(r) (cosmo.c:549-629)
     for key, tab in (("srcs_nz_0", "tab_srcs_nz_0"), ("srcs_bz_0", "tab_srcs_bz_0"), ("imap_tz_0", "tab_imap_tz_0"),
                      ("imap_bz_0", "tab_imap_bz_0")):
         ref = g[tab]
-        np.testing.assert_allclose(np.nan_to_num(t[key]), np.nan_to_num(ref), rtol=2e-4, atol=2e-4 * np.abs(np.nan_to_num(ref)).max(),
+        np.testing.assert_allclose(np.nan_to_num(t[key]), np.nan_to_num(ref), rtol=1e-7, atol=1e-7 * np.abs(np.nan_to_num(ref)).max(),
                                    err_msg=key)
 
 
