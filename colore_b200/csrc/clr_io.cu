@@ -195,7 +195,7 @@ std::string healpix_header(long long npix, long nside)
 //   map[listpix[i]] += data[i], hits[listpix[i]] += nadd[i] over the num_pix local pixels (listpix NULL: i itself),
 //   map[p] /= hits[p] where hits[p] > 0, then -- isnest -- NEST -> RING, float32 big endian, one BINTABLE column.
 // A leading '!' of fname (cfitsio: overwrite) is skipped. No device is involved: the maps are host arrays at the boundary.
-extern "C" int clr_write_healpix_map(const float *data, const int *nadd, const int *listpix, long long num_pix, long nside,
+extern "C" int clr_write_healpix_map(const float *data, const int *nadd, const long *listpix, long long num_pix, long nside,
                                      int isnest, const char *fname, int n_threads, double *seconds)
 {
   CLR_CHECK(nside > 0 && (nside & (nside - 1)) == 0 && nside <= (1L << 15), "HEALPix nside %ld is not a power of two <= 32768", nside);

@@ -399,7 +399,7 @@ def write_healpix_map(fname: str, data, nside: int, nest: bool = False, nadd=Non
     lib = load()
     data = np.ascontiguousarray(data, np.float32)
     nadd_c = None if nadd is None else np.ascontiguousarray(nadd, np.int32)
-    list_c = None if listpix is None else np.ascontiguousarray(listpix, np.int32)
+    list_c = None if listpix is None else np.ascontiguousarray(listpix, np.int64)      # `long *listpix` (common.h:211)
     sec = C.c_double()
     check(lib.clr_write_healpix_map(_vp(data), None if nadd_c is None else _vp(nadd_c), None if list_c is None else _vp(list_c),
                                     C.c_longlong(data.shape[0]), C.c_long(nside), C.c_int(int(nest)), fname.encode(),

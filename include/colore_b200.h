@@ -182,8 +182,9 @@ int clr_write_catalog(clr_ctx *ctx, int ipop, const char *fname, int format, int
  * write_isw (io.c:697-1017): map[listpix[i]] += data[i], hits[listpix[i]] += nadd[i] over num_pix local pixels
  * (listpix NULL: pixel i, num_pix must then be 12 nside^2), map /= hits where hits > 0. isnest: the pixel indices are
  * NEST, the file is RING (he_nest2ring_inplace). The NEST -> RING gather and the big-endian conversion run on n_threads
- * host threads (<= 0: all cores). Host arrays in, no device involved; a leading '!' of fname is skipped. */
-int clr_write_healpix_map(const float *data, const int *nadd, const int *listpix, long long num_pix, long nside, int isnest,
+ * host threads (<= 0: all cores). Host arrays in (data / nadd / listpix typed as in HealpixShells, common.h:207-218), no
+ * device involved; a leading '!' of fname is skipped. */
+int clr_write_healpix_map(const float *data, const int *nadd, const long *listpix, long long num_pix, long nside, int isnest,
                           const char *fname, int n_threads, double *seconds);
 /* srcs_distribute_single (srcs.c:296-373), several GPUs: route every source to rank ipix % nranks, order preserved
  * (blocks received from rank-1, rank-2, ..., own sources last). beam_first != 0: evaluate the RSD-under-beaming

@@ -75,7 +75,7 @@ def test_shell_loops_of_write_kappa(tmp_path):
     nside = 8
     npix = 12 * nside * nside
     rng = np.random.default_rng(5)
-    listpix = rng.permutation(npix)[: npix - 50].astype(np.int32)          # 50 pixels nobody owns
+    listpix = rng.permutation(npix)[: npix - 50].astype(np.int64)          # 50 pixels nobody owns
     data = rng.normal(size=listpix.size).astype(np.float32)
     nadd = rng.integers(0, 4, size=listpix.size).astype(np.int32)
     f = str(tmp_path / "k.fits")
